@@ -1,0 +1,34 @@
+# Builds libdxmc_b200.so (CUDA sm_100a product library) and the CPU oracle (test infrastructure).
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX  ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+CSRC := opendxmc_b200/csrc
+LIBDIR := opendxmc_b200/lib
+NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
+
+LIB := $(LIBDIR)/libdxmc_b200.so
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/context.o
+
+all: $(LIB) oracle
+
+$(LIB): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+build/%.o: $(CSRC)/%.cpp $(CSRC)/physics.hpp $(CSRC)/internal.hpp include/dxb.h
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/kernels.hpp include/dxb.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+oracle: oracle/liboracle.so
+oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -shared -pthread -o $@ oracle/oracle.cpp
+
+clean:
+	rm -rf build $(LIB) oracle/liboracle.so
+
+.PHONY: all oracle clean

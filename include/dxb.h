@@ -1,0 +1,359 @@
+/*
+ * dxb.h — C ABI of libdxmc_b200: the B200-native replacement for the DXMClib
+ * `dxmc::Transport` photon-history path that OpenDXMC drives.
+ *
+ * Citation convention: R:path:line = /root/reference/path:line (OpenDXMC).
+ *
+ * OpenDXMC has no FFI layer for this path: it instantiates DXMClib's C++
+ * templates inside libopendxmc (R:src/libopendxmc/simulationpipeline.cpp:124-235).
+ * This header is the boundary a replacement must export; the C++ shim headers
+ * under include/dxmc/ re-create the consumed C++ names on top of it, and
+ * opendxmc_b200/ (Python, ctypes) mirrors the same names for tests and bench.
+ *
+ * Rules of the ABI
+ *  - plain C, no exceptions cross it; every call returns a dxb_status (or a value).
+ *  - caller owns every array it passes in (the reference hands `const&` to
+ *    DataContainer vectors, R:src/libopendxmc/simulationpipeline.cpp:147-149);
+ *    outputs are caller-allocated.
+ *  - one dxb_run at a time per context; progress/stop are lock-free and may be
+ *    touched from other threads (R:src/libopendxmc/simulationpipeline.cpp:112-122,259-262).
+ *  - there is NO CPU fallback: without a CUDA device dxb_create fails with DXB_ECUDA.
+ *
+ * Units follow the reference: lengths cm (R:src/libopendxmc/datacontainer.cpp:241-253),
+ * energies keV, density g/cm3, angles rad, dose mGy.
+ */
+#ifndef DXB_H
+#define DXB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DXB_ABI_VERSION 1
+
+typedef enum dxb_status {
+    DXB_OK = 0,
+    DXB_EINVAL = 1,    /* bad argument */
+    DXB_EMATERIAL = 2, /* Material::byWeight -> nullopt (R:src/libopendxmc/simulationpipeline.cpp:136-141) */
+    DXB_ECUDA = 3,     /* CUDA error / no device / extension not usable */
+    DXB_ESTATE = 4,    /* call order violated (e.g. run before set_grid) */
+    DXB_ECANCELLED = 5,/* stop flag observed; the reference conflates this with "finished" (:119-121,:234) */
+    DXB_ENOMEM = 6
+} dxb_status;
+
+/* ---- physics modes: the CORRECTION template argument of AAVoxelGrid<5,CORRECTION,255>
+ *      (R:src/libopendxmc/simulationpipeline.cpp:127,247-255; GUI default 1,
+ *      R:src/libopendxmc/simulationwidget.cpp:70-75) */
+#define DXB_PHYSICS_NONE 0      /* free-electron Klein-Nishina, Thomson Rayleigh */
+#define DXB_PHYSICS_LIVERMORE 1 /* scatter function S(q) and form factor F(q) */
+#define DXB_PHYSICS_IA 2        /* impulse approximation: shell binding, Doppler, fluorescence */
+
+/* ====================================================================== */
+/* Materials  (dxmc::Material<5>, dxmc::NISTMaterials, dxmc::AtomHandler)  */
+/* ====================================================================== */
+
+typedef struct dxb_material dxb_material; /* opaque, immutable after creation */
+
+/* Material<5>::byWeight(map<Z,weight>) — R:src/libopendxmc/simulationpipeline.cpp:136.
+ * Weights need not be normalised (ICRP media are mass-%, the appended air is a
+ * fraction, R:src/libopendxmc/icrpphantomimportpipeline.cpp:273,300).
+ * Fails with DXB_EMATERIAL for Z outside 1..92, non-positive total weight, n == 0. */
+int dxb_material_by_weight(dxb_material** out, uint32_t n, const uint32_t* Z, const double* weight);
+/* Material<5>::byNistName — R:src/libopendxmc/ctsegmentationpipeline.cpp:73-75,83-85 */
+int dxb_material_by_nist_name(dxb_material** out, const char* name);
+/* Material<5>::byChemicalFormula ("H2O", "C5O2H8") */
+int dxb_material_by_chemical_formula(dxb_material** out, const char* formula);
+void dxb_material_destroy(dxb_material*);
+
+/* attenuationValues(E): mass attenuation [cm2/g] {photoelectric, incoherent, coherent}.
+ * `physics_mode` 0 gives the free-electron incoherent and Thomson-type coherent
+ * values that mode samples from; 1 and 2 the form-factor/scatter-function ones. */
+int dxb_material_attenuation(const dxb_material*, double energy_kev, double out_pic[3]);
+double dxb_material_mass_energy_transfer(const dxb_material*, double energy_kev); /* mu_tr/rho [cm2/g] */
+double dxb_material_effective_z(const dxb_material*);
+double dxb_material_form_factor(const dxb_material*, double x_inv_angstrom);     /* F(x), x = sin(theta/2)/lambda */
+double dxb_material_scatter_factor(const dxb_material*, double x_inv_angstrom);  /* S(x)/Z_total in [0,1] */
+
+/* dxmc::NISTMaterials — R:src/libopendxmc/ctsegmentationpipeline.cpp:74-76,
+ * R:src/libopendxmc/otherphantomimportpipeline.cpp:87-93 */
+int dxb_nist_count(void);
+const char* dxb_nist_name(int index);
+double dxb_nist_density(const char* name); /* g/cm3, <0 if unknown */
+/* composition: returns element count, fills up to cap entries (mass fractions) */
+int dxb_nist_composition(const char* name, uint32_t* Z, double* weight, int cap);
+/* dxmc::AtomHandler::toSymbol(Z) — R:src/libopendxmc/hdf5wrapper.cpp:429 */
+const char* dxb_atom_symbol(uint32_t Z);
+double dxb_atom_weight(uint32_t Z);
+double dxb_atom_standard_density(uint32_t Z);
+
+/* The interaction tables of one material, exactly as the device consumes them
+ * (double precision master copy).  This is also what tests hand to the CPU oracle
+ * so that both sides run on identical data.
+ * All arrays are owned by the material. */
+#define DXB_MAX_SHELLS 5
+typedef struct dxb_shell {
+    double binding_energy_kev;
+    double n_electrons;         /* electrons per "molecule-average atom" in this shell group */
+    double n_electrons_fraction;/* share of all electrons of the material */
+    double photo_fraction_above;/* probability that a photoelectric event above the edge ionises this shell */
+    double fluor_yield;         /* probability of a fluorescence photon after ionisation */
+    double fluor_energy_kev;    /* mean line energy */
+    double compton_j0;          /* Compton profile J(0) [1/(m_e c alpha)] for the analytic profile */
+} dxb_shell;
+
+typedef struct dxb_material_tables {
+    uint32_t n_energy;      /* nodes of the log-uniform energy grid */
+    double   e_min_kev, e_max_kev;
+    const double* photo;    /* [n_energy] cm2/g */
+    const double* incoh;    /* [n_energy] Livermore (S(q)-weighted) */
+    const double* coh;      /* [n_energy] form-factor Rayleigh */
+    const double* incoh_kn; /* [n_energy] free-electron Klein-Nishina (mode 0) */
+    const double* coh_thomson; /* [n_energy] mode-0 value (== coh: DXMClib keeps the cross-section, changes only the angular law) */
+    const double* etr;      /* [n_energy] mass energy-transfer coefficient (kerma; CT/DX calibration) */
+    uint32_t n_x;           /* nodes of the log-uniform momentum-transfer grid x [1/Angstrom] */
+    double   x_min, x_max;
+    const double* ff_cdf;   /* [n_x] A(x_k) = integral_0^{x_k^2} F(t)^2 d(t) / Z^2, t = x^2 */
+    const double* sf;       /* [n_x] S(x_k)/Z */
+    uint32_t n_shells;      /* <= DXB_MAX_SHELLS, most tightly bound first */
+    dxb_shell shells[DXB_MAX_SHELLS];
+    double   rest_electrons_fraction; /* electrons not covered by `shells` (treated as free, mode 2) */
+    double   electrons_per_gram;
+    double   effective_z;
+} dxb_material_tables;
+int dxb_material_tables_get(const dxb_material*, dxb_material_tables* out);
+/* library-wide table geometry */
+uint32_t dxb_table_n_energy(void);
+double   dxb_table_e_min(void);
+double   dxb_table_e_max(void);
+
+/* ====================================================================== */
+/* Tube  (dxmc::Tube) — R:src/libopendxmc/ctsegmentationpipeline.cpp:66-71, */
+/*                       R:src/libopendxmc/beamsettingsmodel.cpp:257-346    */
+/* ====================================================================== */
+#define DXB_TUBE_MAX_FILT 8
+typedef struct dxb_tube_desc {
+    double voltage_kv;       /* clamped to [20,150] like the GUI */
+    double anode_angle_deg;  /* default 12 */
+    double energy_resolution_kev; /* default 1 */
+    uint32_t n_filt;
+    uint32_t filt_Z[DXB_TUBE_MAX_FILT];
+    double   filt_mm[DXB_TUBE_MAX_FILT];
+} dxb_tube_desc;
+/* Tube::getEnergy(): number of bins; fills up to cap */
+int dxb_tube_energies(const dxb_tube_desc*, double* energy_kev, int cap);
+/* Tube::getSpecter(energies, normalize) */
+int dxb_tube_spectrum(const dxb_tube_desc*, const double* energy_kev, int n, int normalize, double* weight);
+double dxb_tube_mean_energy(const dxb_tube_desc*);
+double dxb_tube_al_half_value_layer_mm(const dxb_tube_desc*);
+
+/* ====================================================================== */
+/* Beams                                                                    */
+/* ====================================================================== */
+typedef enum dxb_beam_type {
+    DXB_BEAM_DX = 0,            /* dxmc::DXBeam<false> (+ OpenDXMC subclass, R:src/libopendxmc/dxmc_specialization.cpp:22-90) */
+    DXB_BEAM_CT_SPIRAL = 1,     /* dxmc::CTSpiralBeam<false>          R:src/libopendxmc/beamsettingsmodel.cpp:1158-1378 */
+    DXB_BEAM_CT_SPIRAL_DUAL = 2,/* dxmc::CTSpiralDualEnergyBeam<false> R:...:1413-1832 */
+    DXB_BEAM_CBCT = 3,          /* dxmc::CBCTBeam<false>              R:...:730-895 */
+    DXB_BEAM_CT_SEQUENTIAL = 4, /* dxmc::CTSequentialBeam<false>      R:...:921-1131 */
+    DXB_BEAM_PENCIL = 5,        /* dxmc::PencilBeam<false>            R:...:637-711 */
+    DXB_BEAM_CTDI = 6           /* DXMClib-internal axial beam used by CT calibration */
+} dxb_beam_type;
+
+typedef struct dxb_spectrum { /* (E[], w[]) as produced by Tube — SURVEY.md §8a row a10 */
+    uint32_t n;               /* n == 1: mono-energetic */
+    const double* energy_kev; /* ascending, uniform step */
+    const double* weight;     /* any positive scale */
+} dxb_spectrum;
+
+typedef struct dxb_bowtie {   /* dxmc::BowtieFilter(vector<pair<angle,weight>>) R:src/libopendxmc/bowtiefilterreader.cpp:74-93 */
+    uint32_t n;               /* 0: no filter (weight 1) */
+    const double* angle_rad;  /* unsorted, sign ignored */
+    const double* weight;
+} dxb_bowtie;
+
+typedef struct dxb_aec {      /* dxmc::CTAECFilter(start, stop, weights) R:src/libopendxmc/datacontainer.cpp:37,59 */
+    uint32_t n;               /* < 2: empty (weight 1) */
+    double start[3], stop[3];
+    const double* weights;
+} dxb_aec;
+
+typedef struct dxb_organ_aec { /* dxmc::CTOrganAECFilter R:src/libopendxmc/beamsettingsmodel.cpp:349-437 */
+    int32_t use_filter;
+    int32_t compensate_outside;
+    double start_angle, stop_angle, ramp_angle; /* rad */
+    double low_weight;
+} dxb_organ_aec;
+
+typedef struct dxb_beam_desc {
+    int32_t  type;                    /* dxb_beam_type */
+    int32_t  reserved0;
+    uint64_t n_exposures;             /* DX, PENCIL: explicit; CT/CBCT: ignored (derived) */
+    uint64_t particles_per_exposure;
+    /* --- geometry --- */
+    double position[3];               /* DX/PENCIL source position; CT_SEQUENTIAL/CTDI first slice centre */
+    double direction[3];              /* PENCIL direction; CT_SEQUENTIAL scan normal; CBCT rotation axis */
+    double cosines[2][3];             /* DX direction cosines */
+    double half_angles[2];            /* DX, CBCT collimation half angles [rad] (stored value, see a2) */
+    double start[3], stop[3];         /* CT_SPIRAL(_DUAL) */
+    double isocenter[3];              /* CBCT */
+    double sdd;                       /* source-detector distance */
+    double fov;                       /* scan field of view (tube A) */
+    double fov_b;                     /* tube B */
+    double collimation;               /* total z collimation at isocentre */
+    double pitch;
+    double start_angle, step_angle;   /* rad */
+    double stop_angle;                /* CBCT */
+    uint64_t n_slices;                /* CT_SEQUENTIAL */
+    double slice_spacing;
+    double tube_b_offset_angle;       /* CT_SPIRAL_DUAL */
+    double relative_mas_a, relative_mas_b;
+    /* --- calibration --- */
+    double ctdi;                      /* CTDIvol (spiral) or CTDIw (sequential) [mGy] */
+    double ctdi_diameter;             /* phantom diameter [cm], default 32 */
+    double dap;                       /* DX/CBCT dose-area product [mGy cm2] */
+    double air_kerma;                 /* PENCIL [mGy] */
+    double energy;                    /* PENCIL photon energy */
+    /* --- per-tube data --- */
+    dxb_spectrum spectrum[2];
+    dxb_bowtie   bowtie[2];
+    dxb_aec      aec;
+    dxb_organ_aec organ_aec;
+} dxb_beam_desc;
+
+void dxb_beam_desc_init(dxb_beam_desc*, int type); /* zero + reference defaults for `type` */
+
+/* Beam::numberOfExposures(), ::numberOfParticles(), ::exposure(i) — the geometry the GUI
+ * reads at R:src/libopendxmc/beamactorcontainer.cpp:113-195 */
+typedef struct dxb_exposure {
+    double position[3];
+    double cosines[2][3];
+    double direction[3];      /* cross(cosines[0], cosines[1]) */
+    double half_angles[2];
+    double weight;            /* AEC * organ-AEC * relative mAs */
+    uint64_t n_particles;
+    int32_t tube;             /* 0 = A, 1 = B (selects spectrum/bowtie) */
+    int32_t reserved;
+} dxb_exposure;
+uint64_t dxb_beam_number_of_exposures(const dxb_beam_desc*);
+uint64_t dxb_beam_number_of_particles(const dxb_beam_desc*);
+int dxb_beam_exposure(const dxb_beam_desc*, uint64_t index, dxb_exposure* out);
+/* evaluate the (normalised) filters the way the kernels do */
+double dxb_bowtie_weight(const dxb_bowtie*, double angle_rad);
+double dxb_aec_weight(const dxb_aec*, const double position[3]);
+double dxb_organ_aec_weight(const dxb_organ_aec*, double angle_rad);
+double dxb_organ_aec_max_weight(const dxb_organ_aec*);
+/* dose-per-history scale for non-CT beams: mGy per (keV/g) (DAP / air-kerma calibration) */
+double dxb_beam_analytic_calibration(const dxb_beam_desc*);
+
+/* ====================================================================== */
+/* Progress (dxmc::TransportProgress) — R:src/libopendxmc/simulationpipeline.cpp:37,114-119,139,169,234,261 */
+/* ====================================================================== */
+typedef struct dxb_progress dxb_progress;
+dxb_progress* dxb_progress_create(void);
+void dxb_progress_destroy(dxb_progress*);
+void dxb_progress_read(const dxb_progress*, uint64_t* done, uint64_t* total);
+void dxb_progress_stop(dxb_progress*);            /* setStopSimulation() */
+int  dxb_progress_continue(const dxb_progress*);  /* continueSimulation() */
+void dxb_progress_reset(dxb_progress*);
+/* message(): copies a NUL-terminated text ("hh:mm:ss remaining") into buf */
+int  dxb_progress_message(const dxb_progress*, char* buf, int cap);
+
+/* ====================================================================== */
+/* Context = World<AAVoxelGrid<5,C,255>> + Transport on one or more GPUs    */
+/* ====================================================================== */
+typedef struct dxb_ctx dxb_ctx;
+
+/* cuda_devices == NULL && n_devices == 0: use the current device. */
+int  dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices);
+void dxb_destroy(dxb_ctx*);
+const char* dxb_last_error(const dxb_ctx*); /* text of the last failure on this context */
+
+/* AAVoxelGrid::setData(materials part) — R:src/libopendxmc/simulationpipeline.cpp:134-149 */
+int dxb_set_materials(dxb_ctx*, uint32_t n, const dxb_material* const* materials);
+/* AAVoxelGrid::setData(dims, density, material) + setSpacing + World::build():
+ * index order x fastest: i + j*nx + k*nx*ny (R:src/libopendxmc/otherphantomimportpipeline.cpp:44);
+ * grid centred on the origin (R:src/libopendxmc/datacontainer.cpp:174-178).
+ * Copies to the device, packs voxels, builds the per-energy majorant. Clears all dose. */
+int dxb_set_grid(dxb_ctx*, const uint64_t dim[3], const double spacing_cm[3],
+                 const double* density, const uint8_t* material);
+int dxb_set_grid_center(dxb_ctx*, const double center_cm[3]); /* default origin */
+
+/* Transport knobs */
+int dxb_set_seed(dxb_ctx*, uint64_t seed);                    /* Philox key; default 0x0DDC0FFEE */
+int dxb_set_history_range(dxb_ctx*, uint64_t rank, uint64_t world); /* this context runs block `rank` of `world` of every exposure (multi-process sharding) */
+int dxb_set_calibration_histories(dxb_ctx*, uint64_t n);      /* nested CTDI run size */
+int dxb_set_stream(dxb_ctx*, void* cuda_stream);              /* launch on a caller-owned stream (device 0 of the ctx) */
+int dxb_set_option(dxb_ctx*, const char* key, double value);  /* tuning knobs, see DESIGN.md */
+
+/* Transport::operator()(world, beam, progress, useBeamCalibration) — R:src/libopendxmc/simulationpipeline.cpp:165.
+ * Blocking. Clears the energy tallies, runs all histories of the beam, reduces across the
+ * context's devices, converts energy to dose and ACCUMULATES into the dose score, exactly like
+ * repeated transport() calls on one world. */
+int dxb_run(dxb_ctx*, const dxb_beam_desc*, int physics_mode, int use_beam_calibration, dxb_progress*);
+
+/* Split form of dxb_run for multi-process sharding (one process per GPU):
+ *   dxb_run_transport  — tallies only (no energy->dose), may be called on every rank;
+ *   the caller sums the tally buffer across ranks (NCCL, int64 sum) in place;
+ *   dxb_finish_beam    — calibration factor + energy->dose on the summed tallies. */
+int dxb_run_transport(dxb_ctx*, const dxb_beam_desc*, int physics_mode, dxb_progress*);
+int dxb_finish_beam(dxb_ctx*, const dxb_beam_desc*, int physics_mode, int use_beam_calibration, double* factor_out);
+/* device pointer + element count (int64 words) of the raw fixed-point tally buffer of device 0 */
+int dxb_tally_buffer(dxb_ctx*, void** device_ptr, uint64_t* n_words);
+
+/* doseScored(i).dose()/variance()/numberOfEvents() for all i — R:src/libopendxmc/simulationpipeline.cpp:174-219.
+ * Any pointer may be NULL. dose [mGy], variance [mGy^2]. */
+int dxb_get_dose(dxb_ctx*, double* dose, double* variance, uint64_t* n_events);
+/* the per-beam energy tallies of the LAST beam (keV, keV^2, count) */
+int dxb_get_energy_scored(dxb_ctx*, double* energy, double* energy_sq, uint64_t* n_events);
+int dxb_clear_dose(dxb_ctx*);
+
+/* The reference's post-processing at R:src/libopendxmc/simulationpipeline.cpp:174-232 done on the
+ * device before the copy-out: air mask (material==0 -> 0) and the uGy rescale.
+ * units_out receives "mGy" or "uGy". */
+int dxb_get_dose_postprocessed(dxb_ctx*, int delete_air_dose, double* dose, double* variance,
+                               double* n_events, char units_out[4]);
+
+/* Per-organ mass-weighted mean dose, R:src/libopendxmc/dosetablepipeline.cpp:60-84. */
+int dxb_organ_dose(dxb_ctx*, const uint8_t* organ, uint32_t n_organs,
+                   double* dose_out, double* mass_out, uint64_t* n_voxels_out, double* variance_out);
+
+/* Run statistics of the last dxb_run / dxb_run_transport on this context. */
+typedef struct dxb_run_stats {
+    uint64_t histories;       /* histories simulated by this context */
+    uint64_t steps;           /* tentative Woodcock steps (voxel fetches) */
+    uint64_t interactions;    /* accepted (real) interactions */
+    uint64_t deposits;        /* energy-depositing events (tally updates) */
+    uint64_t kernel_launches; /* transport kernel launches */
+    double   transport_ms;    /* device time of the transport kernels (CUDA events) */
+    double   total_ms;        /* device time incl. reduce + energy->dose */
+    double   calibration_ms;  /* nested CTDI run */
+    double   calibration_factor;
+    double   energy_emitted_kev;   /* sum of E*w over sampled histories */
+    double   energy_deposited_kev; /* sum over tallies */
+} dxb_run_stats;
+int dxb_get_run_stats(const dxb_ctx*, dxb_run_stats* out);
+
+/* Device-side table lookups, for the "lookups within 1e-6" parity test: evaluates
+ * {photo, incoh, coh, total}*1 [cm2/g] of material `m` at n energies with the kernels' own
+ * float code path. */
+int dxb_device_attenuation(dxb_ctx*, uint32_t material_index, int physics_mode,
+                           const double* energy_kev, uint32_t n, float* out4);
+/* majorant mu_max(E) [1/cm] as the kernels interpolate it */
+int dxb_device_majorant(dxb_ctx*, const double* energy_kev, uint32_t n, float* out);
+
+/* CT segmentation, SURVEY §8f-1: HU -> (material, density)
+ * R:src/libopendxmc/ctsegmentationpipeline.cpp:113-169 */
+int dxb_segment_ct(dxb_ctx*, const double* hu, uint64_t n, const dxb_tube_desc* tube,
+                   uint8_t* material_out, double* density_out,
+                   dxb_material** materials_out /* [5], caller destroys */);
+
+int dxb_abi_version(void);
+int dxb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXB_H */

@@ -1,0 +1,1335 @@
+// context.cu — dxb_ctx: World<AAVoxelGrid<5,C,255>> + Transport on one or more B200s.
+//
+// Mirrors the driver at R:src/libopendxmc/simulationpipeline.cpp:124-235:
+//   setData/setSpacing/build  -> dxb_set_materials + dxb_set_grid (pack voxels, per-energy majorant)
+//   transport(world, beam, progress, true) -> dxb_run (tallies -> reduce -> calibration -> dose)
+//   doseScored(i).dose()/variance()/numberOfEvents() -> dxb_get_dose
+#include "kernels.hpp"
+#include "physics.hpp"
+#include "internal.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace dxb;
+
+static_assert(kDevNE == static_cast<int>(kNEnergy), "energy grid mismatch");
+static_assert(kDevNX == static_cast<int>(kNX), "x grid mismatch");
+static_assert(kDevEPerOctave == static_cast<int>(kENodesPerOctave), "energy grid mismatch");
+static_assert(kDevXPerOctave == static_cast<int>(kXNodesPerOctave), "x grid mismatch");
+static_assert(sizeof(ExposureDev) == 64, "ExposureDev must be 64 bytes");
+
+struct dxb_progress {
+    std::atomic<uint64_t> done { 0 }, total { 0 };
+    std::atomic<int> stop { 0 };
+    std::atomic<int64_t> start_ns { 0 };
+};
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int device = -1;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (device >= 0)
+                cudaSetDevice(device);
+            cudaFree(p);
+            cudaSetDevice(cur);
+        }
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count, int dev)
+    {
+        if (p && n == count && device == dev)
+            return cudaSuccess;
+        release();
+        device = dev;
+        if (count == 0)
+            return cudaSuccess;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+        if (e == cudaSuccess)
+            n = count;
+        return e;
+    }
+    template <typename H>
+    cudaError_t upload(const std::vector<H>& h, int dev, cudaStream_t s)
+    {
+        static_assert(sizeof(H) == sizeof(T), "size mismatch");
+        cudaError_t e = alloc(h.size(), dev);
+        if (e != cudaSuccess || h.empty())
+            return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+// One voxel world resident on one device: grid + the tables of its materials.
+struct World {
+    int device = 0;
+    uint64_t dim[3] = { 0, 0, 0 };
+    double spacing[3] = { 1, 1, 1 };
+    double center[3] = { 0, 0, 0 };
+    size_t nvox = 0;
+    int n_mat = 0;
+    DevBuf<uint2> voxels;
+    DevBuf<unsigned long long> tally; // 4 words / voxel
+    DevBuf<float4> att;
+    DevBuf<float> tot, etr, majorant, ffcdf, sf;
+    DevBuf<ShellDev> shells;
+    DevBuf<int> nshells;
+    DevBuf<unsigned int> maxDensityBits; // [256]
+    bool hasGrid = false, hasTables = false;
+
+    GridDev gridDev() const
+    {
+        GridDev g;
+        g.nx = static_cast<int>(dim[0]);
+        g.ny = static_cast<int>(dim[1]);
+        g.nz = static_cast<int>(dim[2]);
+        const double hx = 0.5 * dim[0] * spacing[0], hy = 0.5 * dim[1] * spacing[1], hz = 0.5 * dim[2] * spacing[2];
+        g.x0 = static_cast<float>(center[0] - hx);
+        g.y0 = static_cast<float>(center[1] - hy);
+        g.z0 = static_cast<float>(center[2] - hz);
+        g.x1 = static_cast<float>(center[0] + hx);
+        g.y1 = static_cast<float>(center[1] + hy);
+        g.z1 = static_cast<float>(center[2] + hz);
+        g.inv_dx = static_cast<float>(1.0 / spacing[0]);
+        g.inv_dy = static_cast<float>(1.0 / spacing[1]);
+        g.inv_dz = static_cast<float>(1.0 / spacing[2]);
+        g.voxels = voxels.p;
+        g.tally = tally.p;
+        return g;
+    }
+    TablesDev tablesDev() const
+    {
+        TablesDev t;
+        t.n_mat = n_mat;
+        t.att = att.p;
+        t.tot = tot.p;
+        t.etr = etr.p;
+        t.majorant = majorant.p;
+        t.ffcdf = ffcdf.p;
+        t.sf = sf.p;
+        t.shells = shells.p;
+        t.n_shells = nshells.p;
+        return t;
+    }
+};
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    World world;                 // the patient grid
+    std::unique_ptr<World> ctdi; // nested calibration phantom (device 0 only)
+    double ctdiDiameter = 0;
+    DevBuf<double> dose, variance;
+    DevBuf<unsigned long long> events;
+    DevBuf<ExposureDev> exposures;
+    DevBuf<float> specProb[2], bowAngle[2], bowWeight[2];
+    DevBuf<unsigned short> specAlias[2];
+    DevBuf<unsigned long long> counters; // [0] work cursor, [8..12] stats
+    cudaEvent_t evStart = nullptr, evTransport = nullptr, evEnd = nullptr;
+};
+
+struct Options {
+    uint64_t batch = 1ull << 27; // local histories per launch
+    int threads = 256;
+    int blocksPerSm = 0;         // 0: occupancy query
+    int tableInSmem = 1;
+};
+
+} // namespace
+
+struct dxb_ctx {
+    std::vector<std::unique_ptr<DeviceState>> devs;
+    std::vector<std::shared_ptr<Material>> materials;
+    uint64_t seed = 0x0DDC0FFEEull;
+    uint64_t rank = 0, world = 1;
+    uint64_t calibHistories = 36000000ull;
+    Options opt;
+    std::string error;
+    dxb_run_stats stats {};
+    float scaleE = 16777216.0f, scaleE2 = 65536.0f; // 2^24, 2^16 fixed-point quanta per keV, keV^2
+    int smCount = 148;
+    bool tallyValid = false;
+};
+
+namespace {
+
+int fail(dxb_ctx* c, int code, const std::string& msg)
+{
+    if (c)
+        c->error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return fail(ctx, DXB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+        }                                                                                          \
+    } while (0)
+
+// Vose's alias method (DXMClib RandomDistribution; restated independently in oracle/oracle.cpp)
+void buildAlias(const std::vector<double>& w, std::vector<float>& prob, std::vector<unsigned short>& alias)
+{
+    const size_t n = w.size();
+    prob.assign(n, 1.0f);
+    alias.resize(n);
+    double sum = 0;
+    for (double v : w)
+        sum += std::max(0.0, v);
+    std::vector<double> q(n);
+    std::vector<size_t> small, large;
+    for (size_t i = 0; i < n; ++i) {
+        q[i] = sum > 0 ? std::max(0.0, w[i]) / sum * static_cast<double>(n) : 1.0;
+        alias[i] = static_cast<unsigned short>(i);
+    }
+    for (size_t i = 0; i < n; ++i)
+        (q[i] < 1.0 ? small : large).push_back(i);
+    while (!small.empty() && !large.empty()) {
+        const size_t s = small.back();
+        small.pop_back();
+        const size_t l = large.back();
+        large.pop_back();
+        prob[s] = static_cast<float>(q[s]);
+        alias[s] = static_cast<unsigned short>(l);
+        q[l] = (q[l] + q[s]) - 1.0;
+        (q[l] < 1.0 ? small : large).push_back(l);
+    }
+    for (size_t i : small)
+        prob[i] = 1.0f;
+    for (size_t i : large)
+        prob[i] = 1.0f;
+}
+
+int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Material>>& mats, cudaStream_t s)
+{
+    const int n = static_cast<int>(mats.size());
+    std::vector<float4> att(static_cast<size_t>(n) * kDevNE);
+    std::vector<float> tot(att.size()), etr(att.size());
+    std::vector<float> ff(static_cast<size_t>(n) * kDevNX), sf(ff.size());
+    std::vector<ShellDev> shells(static_cast<size_t>(n) * kMaxShells);
+    std::vector<int> nsh(n);
+    for (int m = 0; m < n; ++m) {
+        const Material& M = *mats[m];
+        for (int i = 0; i < kDevNE; ++i) {
+            const double p = M.photo[i], in = M.incoh[i], co = M.coh[i];
+            // the total is rounded from the double sum (what the oracle uses), not re-summed in float
+            att[static_cast<size_t>(m) * kDevNE + i] = make_float4(static_cast<float>(p), static_cast<float>(in),
+                static_cast<float>(co), static_cast<float>(p + in + co));
+            tot[static_cast<size_t>(m) * kDevNE + i] = static_cast<float>(p + in + co);
+            etr[static_cast<size_t>(m) * kDevNE + i] = static_cast<float>(M.etr[i]);
+        }
+        for (int i = 0; i < kDevNX; ++i) {
+            ff[static_cast<size_t>(m) * kDevNX + i] = static_cast<float>(M.ffCdf[i]);
+            sf[static_cast<size_t>(m) * kDevNX + i] = static_cast<float>(M.sf[i]);
+        }
+        nsh[m] = static_cast<int>(M.nShells);
+        for (uint32_t k = 0; k < M.nShells; ++k) {
+            ShellDev& d = shells[static_cast<size_t>(m) * kMaxShells + k];
+            const dxb_shell& h = M.shells[k];
+            d.binding = static_cast<float>(h.binding_energy_kev);
+            d.nel_fraction = static_cast<float>(h.n_electrons_fraction);
+            d.photo_fraction = static_cast<float>(h.photo_fraction_above);
+            d.fluor_yield = static_cast<float>(h.fluor_yield);
+            d.fluor_energy = static_cast<float>(h.fluor_energy_kev);
+            d.j0 = static_cast<float>(h.compton_j0);
+            d.pad0 = d.pad1 = 0.0f;
+        }
+    }
+    w.n_mat = n;
+    CUDA_TRY(c, w.att.upload(att, w.device, s));
+    CUDA_TRY(c, w.tot.upload(tot, w.device, s));
+    CUDA_TRY(c, w.etr.upload(etr, w.device, s));
+    CUDA_TRY(c, w.ffcdf.upload(ff, w.device, s));
+    CUDA_TRY(c, w.sf.upload(sf, w.device, s));
+    CUDA_TRY(c, w.shells.upload(shells, w.device, s));
+    CUDA_TRY(c, w.nshells.upload(nsh, w.device, s));
+    CUDA_TRY(c, w.majorant.alloc(kDevNE, w.device));
+    CUDA_TRY(c, cudaStreamSynchronize(s)); // host vectors go out of scope
+    w.hasTables = true;
+    return DXB_OK;
+}
+
+int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing[3], const double* density,
+    const uint8_t* material, cudaStream_t s)
+{
+    const size_t n = static_cast<size_t>(dim[0]) * dim[1] * dim[2];
+    for (int i = 0; i < 3; ++i) {
+        w.dim[i] = dim[i];
+        w.spacing[i] = spacing[i];
+    }
+    w.nvox = n;
+    CUDA_TRY(c, w.voxels.alloc(n, w.device));
+    CUDA_TRY(c, w.tally.alloc(n * 4, w.device));
+    CUDA_TRY(c, w.maxDensityBits.alloc(256, w.device));
+    // staging buffers for the caller's f64 density + u8 material; freed after packing
+    DevBuf<double> dDens;
+    DevBuf<unsigned char> dMat;
+    CUDA_TRY(c, dDens.alloc(n, w.device));
+    CUDA_TRY(c, dMat.alloc(n, w.device));
+    CUDA_TRY(c, cudaMemcpyAsync(dDens.p, density, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(dMat.p, material, n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemsetAsync(w.maxDensityBits.p, 0, 256 * sizeof(unsigned int), s));
+    launchPackVoxels(dDens.p, dMat.p, w.voxels.p, n, w.maxDensityBits.p, s);
+    CUDA_TRY(c, cudaGetLastError());
+    launchMajorant(w.tot.p, w.maxDensityBits.p, w.n_mat, w.majorant.p, s);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, n * 4 * sizeof(unsigned long long), s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    w.hasGrid = true;
+    return DXB_OK;
+}
+
+struct PreparedBeam {
+    std::vector<ExposureDev> exposures;
+    uint64_t ppe = 0, nTotal = 0;
+    std::vector<float> prob[2], bowA[2], bowW[2];
+    std::vector<unsigned short> alias[2];
+    int specN[2] = { 1, 1 };
+    float specE0[2] = { 0, 0 }, specStep[2] = { 1, 1 };
+    double maxWeight = 1.0;
+};
+
+int prepareBeam(dxb_ctx* c, const dxb_beam_desc& b, PreparedBeam& out)
+{
+    const uint64_t nExp = beamNumberOfExposures(b);
+    if (nExp == 0 || b.particles_per_exposure == 0)
+        return fail(c, DXB_EINVAL, "beam has no exposures or no particles");
+    if (nExp > (1ull << 26))
+        return fail(c, DXB_EINVAL, "too many exposures");
+    const AecTable aec = makeAec(b.aec);
+    out.exposures.resize(nExp);
+    double wmax = 0;
+    for (uint64_t i = 0; i < nExp; ++i) {
+        dxb_exposure e;
+        if (beamExposure(b, i, aec, e) != DXB_OK)
+            return fail(c, DXB_EINVAL, "bad exposure");
+        ExposureDev& d = out.exposures[i];
+        for (int k = 0; k < 3; ++k) {
+            d.pos[k] = static_cast<float>(e.position[k]);
+            d.c0[k] = static_cast<float>(e.cosines[0][k]);
+            d.c1[k] = static_cast<float>(e.cosines[1][k]);
+            d.dir[k] = static_cast<float>(e.direction[k]);
+        }
+        d.hx = static_cast<float>(e.half_angles[0]);
+        d.hy = static_cast<float>(e.half_angles[1]);
+        d.weight = static_cast<float>(e.weight);
+        d.tube = e.tube;
+        wmax = std::max(wmax, e.weight);
+    }
+    out.ppe = b.particles_per_exposure;
+    out.nTotal = nExp * b.particles_per_exposure;
+    const int nTubes = (b.type == DXB_BEAM_CT_SPIRAL_DUAL || (b.type == DXB_BEAM_CTDI && b.spectrum[1].n > 0)) ? 2 : 1;
+    double bowMax = 1.0;
+    for (int t = 0; t < 2; ++t) {
+        const dxb_spectrum& s = b.spectrum[t < nTubes ? t : 0];
+        if (b.type == DXB_BEAM_PENCIL) {
+            out.specN[t] = 1;
+            out.specE0[t] = static_cast<float>(b.energy);
+            out.specStep[t] = 0;
+            out.prob[t].assign(1, 1.0f);
+            out.alias[t].assign(1, 0);
+        } else {
+            if (s.n == 0 || !s.energy_kev || !s.weight)
+                return fail(c, DXB_EINVAL, "beam spectrum missing");
+            if (s.n > 60000)
+                return fail(c, DXB_EINVAL, "spectrum too long");
+            out.specN[t] = static_cast<int>(s.n);
+            out.specE0[t] = static_cast<float>(s.energy_kev[0]);
+            out.specStep[t] = s.n > 1 ? static_cast<float>(s.energy_kev[1] - s.energy_kev[0]) : 0.0f;
+            std::vector<double> w(s.weight, s.weight + s.n);
+            buildAlias(w, out.prob[t], out.alias[t]);
+        }
+        const BowtieTable bt = makeBowtie(b.bowtie[t < nTubes ? t : 0]);
+        out.bowA[t].clear();
+        out.bowW[t].clear();
+        if (!bt.empty() && b.type != DXB_BEAM_PENCIL && b.type != DXB_BEAM_DX && b.type != DXB_BEAM_CBCT) {
+            for (size_t i = 0; i < bt.angle.size(); ++i) {
+                out.bowA[t].push_back(static_cast<float>(bt.angle[i]));
+                out.bowW[t].push_back(static_cast<float>(bt.weight[i]));
+                bowMax = std::max(bowMax, bt.weight[i]);
+            }
+        }
+    }
+    out.maxWeight = std::max(1.0, wmax) * bowMax / (1.0 - 0.9);
+    return DXB_OK;
+}
+
+int uploadBeam(dxb_ctx* c, DeviceState& d, const PreparedBeam& pb)
+{
+    CUDA_TRY(c, d.exposures.upload(pb.exposures, d.device, d.stream));
+    for (int t = 0; t < 2; ++t) {
+        CUDA_TRY(c, d.specProb[t].upload(pb.prob[t], d.device, d.stream));
+        CUDA_TRY(c, d.specAlias[t].upload(pb.alias[t], d.device, d.stream));
+        CUDA_TRY(c, d.bowAngle[t].upload(pb.bowA[t], d.device, d.stream));
+        CUDA_TRY(c, d.bowWeight[t].upload(pb.bowW[t], d.device, d.stream));
+    }
+    return DXB_OK;
+}
+
+// number of local linear indices owned by shard (rank, world) for nTotal global histories
+uint64_t localCount(uint64_t nTotal, uint64_t rank, uint64_t world)
+{
+    const uint64_t nBlocks = (nTotal + kShardBlock - 1) / kShardBlock;
+    // blocks rank, rank+world, ...
+    if (rank >= nBlocks)
+        return 0;
+    const uint64_t mine = (nBlocks - rank + world - 1) / world;
+    return mine * kShardBlock; // padded; the kernel skips ids >= nTotal
+}
+
+struct TransportResult {
+    double ms = 0;
+    uint64_t launches = 0;
+    uint64_t stats[5] = { 0, 0, 0, 0, 0 };
+    bool cancelled = false;
+};
+
+// Runs the histories of one prepared beam through `world` on device state d for shard (rank, world).
+int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, int mode, bool calib, int scoreMaterial,
+    uint64_t rank, uint64_t world, dxb_progress* progress, bool asyncOnly, TransportResult* res)
+{
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    RunParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.grid = w.gridDev();
+    P.tab = w.tablesDev();
+    for (int t = 0; t < 2; ++t) {
+        P.spec[t].n = pb.specN[t];
+        P.spec[t].e0 = pb.specE0[t];
+        P.spec[t].step = pb.specStep[t];
+        P.spec[t].prob = d.specProb[t].p;
+        P.spec[t].alias = d.specAlias[t].p;
+        P.bow[t].n = static_cast<int>(pb.bowA[t].size());
+        P.bow[t].angle = d.bowAngle[t].p;
+        P.bow[t].weight = d.bowWeight[t].p;
+    }
+    P.exposures = d.exposures.p;
+    P.n_exposures = pb.exposures.size();
+    P.ppe = pb.ppe;
+    P.n_total = pb.nTotal;
+    P.world = static_cast<unsigned int>(world);
+    P.rank = static_cast<unsigned int>(rank);
+    P.seed_lo = static_cast<unsigned int>(c->seed);
+    P.seed_hi = static_cast<unsigned int>(c->seed >> 32);
+    P.tally_scale_e = c->scaleE;
+    P.tally_scale_e2 = c->scaleE2;
+    P.score_material = calib ? scoreMaterial : -1;
+    P.work_counter = d.counters.p;
+    P.stats = d.counters.p + 8;
+
+    LaunchConfig cfg;
+    cfg.threads = c->opt.threads;
+    const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
+    cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
+    cfg.smem = cfg.table_in_smem ? tableBytes : 0;
+    int perSm = c->opt.blocksPerSm;
+    if (perSm <= 0) {
+        perSm = transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
+        if (perSm <= 0)
+            return fail(c, DXB_ECUDA, "transport kernel cannot be resident (occupancy 0)");
+    }
+    cfg.blocks = c->smCount * perSm;
+
+    const uint64_t nLocal = localCount(pb.nTotal, rank, world);
+    CUDA_TRY(c, cudaMemsetAsync(d.counters.p + 8, 0, 8 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(c, cudaEventRecord(d.evStart, d.stream));
+    uint64_t launches = 0;
+    bool cancelled = false;
+    for (uint64_t begin = 0; begin < nLocal; begin += c->opt.batch) {
+        if (progress && progress->stop.load(std::memory_order_relaxed)) {
+            cancelled = true;
+            break;
+        }
+        const uint64_t end = std::min(nLocal, begin + c->opt.batch);
+        P.local_begin = begin;
+        P.local_end = end;
+        CUDA_TRY(c, cudaMemsetAsync(d.counters.p, 0, sizeof(unsigned long long), d.stream));
+        CUDA_TRY(c, launchTransport(P, mode, calib, cfg, d.stream));
+        ++launches;
+        if (progress && !asyncOnly && end < nLocal) {
+            // stop must be observed within one batch; progress is published per batch
+            CUDA_TRY(c, cudaStreamSynchronize(d.stream));
+            progress->done.fetch_add(end - begin, std::memory_order_relaxed);
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(d.evTransport, d.stream));
+    if (res) {
+        res->launches = launches;
+        res->cancelled = cancelled;
+    }
+    return DXB_OK;
+}
+
+int collectStats(dxb_ctx* c, DeviceState& d, TransportResult& res)
+{
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    CUDA_TRY(c, cudaStreamSynchronize(d.stream));
+    unsigned long long h[5];
+    CUDA_TRY(c, cudaMemcpy(h, d.counters.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i)
+        res.stats[i] = h[i];
+    float ms = 0;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, d.evStart, d.evTransport));
+    res.ms = ms;
+    return DXB_OK;
+}
+
+void chooseScales(dxb_ctx* c, const PreparedBeam& pb, bool kerma)
+{
+    // largest power-of-two quanta such that nTotal * Emax * wmax cannot overflow 2^63
+    const double worstE = static_cast<double>(pb.nTotal) * 150.0 * pb.maxWeight * (kerma ? 50.0 : 1.0);
+    int se = 24;
+    while (se > 0 && worstE * std::ldexp(1.0, se) > 4.0e18)
+        --se;
+    const double worstE2 = static_cast<double>(pb.nTotal) * 150.0 * 150.0 * pb.maxWeight * pb.maxWeight * (kerma ? 2500.0 : 1.0);
+    int s2 = 16;
+    while (s2 > -20 && worstE2 * std::ldexp(1.0, s2) > 4.0e18)
+        --s2;
+    c->scaleE = static_cast<float>(std::ldexp(1.0, se));
+    c->scaleE2 = static_cast<float>(std::ldexp(1.0, s2));
+}
+
+// ---- nested CTDI calibration (CTSpiralBeam/CTSequentialBeam::calibrationFactor, recalled) ----
+// A PMMA cylinder (diameter = beam.ctdi_diameter, length 15 cm) with five 1.31 cm air holes, voxelised at
+// 0.2 x 0.2 x 0.5 cm; one axial rotation of the same tube/bowtie/collimation; air kerma in the central 10 cm
+// of the holes from a collision estimator; CTDIw = 1/3 centre + 2/3 periphery.
+struct CtdiPhantom {
+    uint64_t dim[3];
+    double spacing[3];
+    std::vector<double> density;
+    std::vector<uint8_t> material; // 0 air, 1 PMMA, 2 measurement air
+    std::vector<int> hole;         // per voxel: -1 or hole id 0..4 (central 10 cm only)
+    std::vector<std::shared_ptr<Material>> mats;
+};
+
+void buildCtdiPhantom(double diameter, CtdiPhantom& ph)
+{
+    const double sxy = 0.2, sz = 0.5;
+    const int nxy = static_cast<int>(std::ceil((diameter + 4.0) / sxy / 2.0)) * 2;
+    const int nz = 30; // 15 cm
+    ph.dim[0] = ph.dim[1] = nxy;
+    ph.dim[2] = nz;
+    ph.spacing[0] = ph.spacing[1] = sxy;
+    ph.spacing[2] = sz;
+    const size_t n = static_cast<size_t>(nxy) * nxy * nz;
+    ph.density.assign(n, 0.0);
+    ph.material.assign(n, 0);
+    ph.hole.assign(n, -1);
+    const double airRho = nistFind("Air, Dry (near sea level)")->density;
+    const double pmmaRho = nistFind("Polymethyl Methacralate (Lucite, Perspex)")->density;
+    const double R = 0.5 * diameter, rh = 0.655, off = R - 1.0;
+    const double hx[5] = { 0, off, -off, 0, 0 }, hy[5] = { 0, 0, 0, off, -off };
+    for (int k = 0; k < nz; ++k) {
+        const double z = (k + 0.5) * sz - 0.5 * nz * sz;
+        for (int j = 0; j < nxy; ++j) {
+            const double y = (j + 0.5) * sxy - 0.5 * nxy * sxy;
+            for (int i = 0; i < nxy; ++i) {
+                const double x = (i + 0.5) * sxy - 0.5 * nxy * sxy;
+                const size_t idx = (static_cast<size_t>(k) * nxy + j) * nxy + i;
+                ph.density[idx] = airRho;
+                if (x * x + y * y <= R * R) {
+                    ph.density[idx] = pmmaRho;
+                    ph.material[idx] = 1;
+                    for (int h = 0; h < 5; ++h) {
+                        const double ddx = x - hx[h], ddy = y - hy[h];
+                        if (ddx * ddx + ddy * ddy <= rh * rh) {
+                            ph.density[idx] = airRho;
+                            ph.material[idx] = 0;
+                            if (std::fabs(z) <= 5.0) {
+                                ph.material[idx] = 2;
+                                ph.hole[idx] = h;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ph.mats = { Material::byNistName("Air, Dry (near sea level)"), Material::byNistName("Polymethyl Methacralate (Lucite, Perspex)"),
+        Material::byNistName("Air, Dry (near sea level)") };
+}
+
+bool isCtBeam(int type)
+{
+    return type == DXB_BEAM_CT_SPIRAL || type == DXB_BEAM_CT_SPIRAL_DUAL || type == DXB_BEAM_CT_SEQUENTIAL;
+}
+
+int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOut, double* msOut)
+{
+    DeviceState& d = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    const double diameter = b.ctdi_diameter > 0 ? b.ctdi_diameter : 32.0;
+    CtdiPhantom ph;
+    buildCtdiPhantom(diameter, ph);
+    if (!d.ctdi || d.ctdiDiameter != diameter) {
+        d.ctdi = std::make_unique<World>();
+        d.ctdi->device = d.device;
+        int rc = uploadTables(c, *d.ctdi, ph.mats, d.stream);
+        if (rc != DXB_OK)
+            return rc;
+        rc = uploadGrid(c, *d.ctdi, ph.dim, ph.spacing, ph.density.data(), ph.material.data(), d.stream);
+        if (rc != DXB_OK)
+            return rc;
+        d.ctdiDiameter = diameter;
+    }
+    World& w = *d.ctdi;
+    CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, w.nvox * 4 * sizeof(unsigned long long), d.stream));
+
+    // the internal axial beam: same tube(s), bowtie(s), collimation, SDD and FOV; 1 degree steps, no AEC
+    dxb_beam_desc cb = b;
+    cb.type = DXB_BEAM_CTDI;
+    cb.position[0] = cb.position[1] = cb.position[2] = 0;
+    cb.direction[0] = cb.direction[1] = 0;
+    cb.direction[2] = 1;
+    cb.step_angle = kPi / 180.0;
+    cb.start_angle = 0;
+    cb.n_slices = 1;
+    cb.aec.n = 0;
+    cb.organ_aec.use_filter = 0;
+    if (b.type != DXB_BEAM_CT_SPIRAL_DUAL)
+        cb.spectrum[1].n = 0;
+    const uint64_t nExp = beamNumberOfExposures(cb);
+    cb.particles_per_exposure = std::max<uint64_t>(1, c->calibHistories / nExp);
+
+    PreparedBeam pb;
+    int rc = prepareBeam(c, cb, pb);
+    if (rc != DXB_OK)
+        return rc;
+    const float saveE = c->scaleE, saveE2 = c->scaleE2;
+    chooseScales(c, pb, true);
+    rc = uploadBeam(c, d, pb);
+    TransportResult tr;
+    if (rc == DXB_OK)
+        rc = runOnDevice(c, d, w, pb, mode, true, 2, 0, 1, nullptr, true, &tr);
+    if (rc == DXB_OK)
+        rc = collectStats(c, d, tr);
+    const double invE = 1.0 / c->scaleE;
+    c->scaleE = saveE;
+    c->scaleE2 = saveE2;
+    if (rc != DXB_OK)
+        return rc;
+    if (msOut)
+        *msOut = tr.ms;
+    // read back the kerma tallies of the hole voxels
+    std::vector<unsigned long long> tally(w.nvox * 4);
+    CUDA_TRY(c, cudaMemcpy(tally.data(), w.tally.p, tally.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double sum[5] = { 0, 0, 0, 0, 0 };
+    size_t cnt[5] = { 0, 0, 0, 0, 0 };
+    for (size_t i = 0; i < w.nvox; ++i) {
+        const int h = ph.hole[i];
+        if (h >= 0) {
+            sum[h] += static_cast<double>(tally[i * 4]) * invE;
+            ++cnt[h];
+        }
+    }
+    const double vol = ph.spacing[0] * ph.spacing[1] * ph.spacing[2];
+    double kerma[5];
+    for (int h = 0; h < 5; ++h)
+        kerma[h] = cnt[h] ? sum[h] / (cnt[h] * vol) : 0.0; // keV/g, mean over the 10 cm chamber length
+    // CTDI100 = (1/NT) * integral_{-5}^{5} K dz = Kmean * 10 cm / collimation
+    const double ctdi100c = kerma[0] * 10.0 / b.collimation;
+    const double ctdi100p = 0.25 * (kerma[1] + kerma[2] + kerma[3] + kerma[4]) * 10.0 / b.collimation;
+    const double ctdiwSim = ctdi100c / 3.0 + 2.0 * ctdi100p / 3.0; // keV/g for pb.nTotal histories in ONE rotation
+    if (!(ctdiwSim > 0))
+        return fail(c, DXB_EINVAL, "CTDI calibration run scored nothing");
+    const double perHistory = ctdiwSim / static_cast<double>(pb.nTotal);
+    // histories the main beam spends per rotation
+    const double step = std::fabs(b.step_angle) > 0 ? std::fabs(b.step_angle) : kPi / 180.0;
+    double perRot = static_cast<double>(b.particles_per_exposure) * (2.0 * kPi / step);
+    if (b.type == DXB_BEAM_CT_SPIRAL_DUAL)
+        perRot *= 2.0;
+    const double target = b.type == DXB_BEAM_CT_SEQUENTIAL ? b.ctdi : b.ctdi * b.pitch; // CTDIw [mGy] per rotation
+    *factorOut = target / (perHistory * perRot);
+    return DXB_OK;
+}
+
+int initDevice(dxb_ctx* c, DeviceState& d)
+{
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaEventCreate(&d.evStart));
+    CUDA_TRY(c, cudaEventCreate(&d.evTransport));
+    CUDA_TRY(c, cudaEventCreate(&d.evEnd));
+    CUDA_TRY(c, d.counters.alloc(16, d.device));
+    CUDA_TRY(c, cudaMemset(d.counters.p, 0, 16 * sizeof(unsigned long long)));
+    d.world.device = d.device;
+    return DXB_OK;
+}
+
+} // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int dxb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices)
+{
+    if (!out)
+        return DXB_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return DXB_ECUDA; // no CPU fallback
+    }
+    auto c = std::make_unique<dxb_ctx>();
+    std::vector<int> devices;
+    if (!cuda_devices || n_devices <= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        devices.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; ++i) {
+            if (cuda_devices[i] < 0 || cuda_devices[i] >= count)
+                return DXB_EINVAL;
+            devices.push_back(cuda_devices[i]);
+        }
+    }
+    for (int dev : devices) {
+        auto d = std::make_unique<DeviceState>();
+        d->device = dev;
+        if (initDevice(c.get(), *d) != DXB_OK)
+            return DXB_ECUDA;
+        c->devs.push_back(std::move(d));
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, devices[0]) == cudaSuccess)
+        c->smCount = prop.multiProcessorCount;
+    // peer access for the in-process tally reduce
+    for (size_t i = 1; i < c->devs.size(); ++i) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, c->devs[0]->device, c->devs[i]->device);
+        if (can) {
+            cudaSetDevice(c->devs[0]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[i]->device, 0);
+            if (e != cudaSuccess)
+                cudaGetLastError();
+        }
+    }
+    cudaSetDevice(devices[0]);
+    *out = c.release();
+    return DXB_OK;
+}
+
+void dxb_destroy(dxb_ctx* c)
+{
+    if (!c)
+        return;
+    for (auto& d : c->devs) {
+        cudaSetDevice(d->device);
+        cudaStreamSynchronize(d->stream);
+        if (d->evStart)
+            cudaEventDestroy(d->evStart);
+        if (d->evTransport)
+            cudaEventDestroy(d->evTransport);
+        if (d->evEnd)
+            cudaEventDestroy(d->evEnd);
+        if (d->ownStream && d->stream)
+            cudaStreamDestroy(d->stream);
+    }
+    delete c;
+}
+
+const char* dxb_last_error(const dxb_ctx* c) { return c ? c->error.c_str() : "null context"; }
+
+int dxb_set_materials(dxb_ctx* c, uint32_t n, const dxb_material* const* materials)
+{
+    if (!c || n == 0 || n > 255 || !materials)
+        return fail(c, DXB_EINVAL, "set_materials: need 1..255 materials");
+    std::vector<std::shared_ptr<Material>> mats;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!materials[i] || !materials[i]->m)
+            return fail(c, DXB_EMATERIAL, "set_materials: null material");
+        mats.push_back(materials[i]->m);
+    }
+    c->materials = mats;
+    for (auto& d : c->devs) {
+        CUDA_TRY(c, cudaSetDevice(d->device));
+        int rc = uploadTables(c, d->world, mats, d->stream);
+        if (rc != DXB_OK)
+            return rc;
+        d->world.hasGrid = false; // majorant depends on the tables
+    }
+    return DXB_OK;
+}
+
+int dxb_set_grid(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], const double* density, const uint8_t* material)
+{
+    if (!c || !dim || !spacing_cm || !density || !material)
+        return fail(c, DXB_EINVAL, "set_grid: null argument");
+    if (c->materials.empty())
+        return fail(c, DXB_ESTATE, "set_grid: call dxb_set_materials first");
+    const uint64_t n = dim[0] * dim[1] * dim[2];
+    if (n == 0 || n >= (1ull << 32) || dim[0] >= (1u << 20) || dim[1] >= (1u << 20) || dim[2] >= (1u << 20))
+        return fail(c, DXB_EINVAL, "set_grid: bad dimensions");
+    for (int i = 0; i < 3; ++i)
+        if (!(spacing_cm[i] > 0))
+            return fail(c, DXB_EINVAL, "set_grid: spacing must be positive");
+    // the reference checks max(material) < n_materials before running (R:...simulationpipeline.cpp:54-57)
+    uint8_t mmax = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        mmax = std::max(mmax, material[i]);
+    if (mmax >= c->materials.size())
+        return fail(c, DXB_EINVAL, "set_grid: material index out of range");
+    for (auto& d : c->devs) {
+        CUDA_TRY(c, cudaSetDevice(d->device));
+        int rc = uploadGrid(c, d->world, dim, spacing_cm, density, material, d->stream);
+        if (rc != DXB_OK)
+            return rc;
+    }
+    // dose score lives on device 0
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    CUDA_TRY(c, d0.dose.alloc(n, d0.device));
+    CUDA_TRY(c, d0.variance.alloc(n, d0.device));
+    CUDA_TRY(c, d0.events.alloc(n, d0.device));
+    c->tallyValid = false;
+    return dxb_clear_dose(c);
+}
+
+int dxb_set_grid_center(dxb_ctx* c, const double center_cm[3])
+{
+    if (!c || !center_cm)
+        return DXB_EINVAL;
+    for (auto& d : c->devs)
+        for (int i = 0; i < 3; ++i)
+            d->world.center[i] = center_cm[i];
+    return DXB_OK;
+}
+
+int dxb_clear_dose(dxb_ctx* c)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "clear_dose: no grid");
+    DeviceState& d0 = *c->devs[0];
+    const size_t n = d0.world.nvox;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    CUDA_TRY(c, cudaMemsetAsync(d0.dose.p, 0, n * sizeof(double), d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(d0.variance.p, 0, n * sizeof(double), d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(d0.events.p, 0, n * sizeof(unsigned long long), d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_set_seed(dxb_ctx* c, uint64_t seed)
+{
+    if (!c)
+        return DXB_EINVAL;
+    c->seed = seed;
+    return DXB_OK;
+}
+
+int dxb_set_history_range(dxb_ctx* c, uint64_t rank, uint64_t world)
+{
+    if (!c || world == 0 || rank >= world || world > 65535)
+        return fail(c, DXB_EINVAL, "set_history_range: need rank < world");
+    c->rank = rank;
+    c->world = world;
+    return DXB_OK;
+}
+
+int dxb_set_calibration_histories(dxb_ctx* c, uint64_t n)
+{
+    if (!c || n == 0)
+        return DXB_EINVAL;
+    c->calibHistories = n;
+    return DXB_OK;
+}
+
+int dxb_set_stream(dxb_ctx* c, void* cuda_stream)
+{
+    if (!c || c->devs.empty())
+        return DXB_EINVAL;
+    DeviceState& d = *c->devs[0];
+    cudaSetDevice(d.device);
+    cudaStreamSynchronize(d.stream);
+    if (d.ownStream && d.stream)
+        cudaStreamDestroy(d.stream);
+    if (cuda_stream) {
+        d.stream = static_cast<cudaStream_t>(cuda_stream);
+        d.ownStream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(c, DXB_ECUDA, "stream create failed");
+        d.ownStream = true;
+    }
+    return DXB_OK;
+}
+
+int dxb_set_option(dxb_ctx* c, const char* key, double value)
+{
+    if (!c || !key)
+        return DXB_EINVAL;
+    const std::string k(key);
+    if (k == "batch_histories") {
+        if (value < 1024)
+            return DXB_EINVAL;
+        c->opt.batch = static_cast<uint64_t>(value);
+    } else if (k == "threads_per_block") {
+        const int t = static_cast<int>(value);
+        if (t < 32 || t > 256 || (t % 32))
+            return DXB_EINVAL;
+        c->opt.threads = t;
+    } else if (k == "blocks_per_sm") {
+        c->opt.blocksPerSm = static_cast<int>(value);
+    } else if (k == "table_in_smem") {
+        c->opt.tableInSmem = value != 0;
+    } else {
+        return fail(c, DXB_EINVAL, "unknown option " + k);
+    }
+    return DXB_OK;
+}
+
+int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, dxb_progress* progress)
+{
+    if (!c || !beam)
+        return DXB_EINVAL;
+    if (physics_mode < 0 || physics_mode > 2)
+        return fail(c, DXB_EINVAL, "physics_mode must be 0, 1 or 2");
+    if (c->devs.empty() || !c->devs[0]->world.hasGrid || !c->devs[0]->world.hasTables)
+        return fail(c, DXB_ESTATE, "run: set materials and grid first");
+    PreparedBeam pb;
+    int rc = prepareBeam(c, *beam, pb);
+    if (rc != DXB_OK)
+        return rc;
+    chooseScales(c, pb, false);
+    const uint64_t nDev = c->devs.size();
+    const uint64_t effWorld = c->world * nDev;
+    if (progress) {
+        uint64_t mine = 0;
+        for (uint64_t i = 0; i < nDev; ++i)
+            mine += std::min(localCount(pb.nTotal, c->rank * nDev + i, effWorld), pb.nTotal);
+        progress->total.store(std::min(mine, pb.nTotal));
+        progress->done.store(0);
+        progress->start_ns.store(std::chrono::duration_cast<std::chrono::nanoseconds>(
+            std::chrono::steady_clock::now().time_since_epoch()).count());
+    }
+    c->stats = dxb_run_stats {};
+    c->tallyValid = false;
+    std::vector<TransportResult> results(nDev);
+    // clear tallies, upload the beam and launch on every device (launches are asynchronous, so the devices run concurrently)
+    for (uint64_t i = 0; i < nDev; ++i) {
+        DeviceState& d = *c->devs[i];
+        CUDA_TRY(c, cudaSetDevice(d.device));
+        CUDA_TRY(c, cudaMemsetAsync(d.world.tally.p, 0, d.world.nvox * 4 * sizeof(unsigned long long), d.stream));
+        rc = uploadBeam(c, d, pb);
+        if (rc != DXB_OK)
+            return rc;
+    }
+    for (uint64_t i = 0; i < nDev; ++i) {
+        rc = runOnDevice(c, *c->devs[i], c->devs[i]->world, pb, physics_mode, false, -1, c->rank * nDev + i, effWorld, progress,
+            nDev > 1, &results[i]);
+        if (rc != DXB_OK)
+            return rc;
+    }
+    bool cancelled = false;
+    double msMax = 0;
+    for (uint64_t i = 0; i < nDev; ++i) {
+        rc = collectStats(c, *c->devs[i], results[i]);
+        if (rc != DXB_OK)
+            return rc;
+        cancelled = cancelled || results[i].cancelled;
+        msMax = std::max(msMax, results[i].ms);
+        c->stats.steps += results[i].stats[0];
+        c->stats.interactions += results[i].stats[1];
+        c->stats.deposits += results[i].stats[2];
+        c->stats.energy_emitted_kev += static_cast<double>(results[i].stats[3]) / 65536.0;
+        c->stats.histories += results[i].stats[4];
+        c->stats.kernel_launches += results[i].launches;
+    }
+    c->stats.transport_ms = msMax;
+    if (progress)
+        progress->done.store(progress->total.load());
+    if (cancelled)
+        return fail(c, DXB_ECANCELLED, "cancelled");
+    // in-process reduce: device 0 pulls the peers' tallies over NVLink peer memory
+    if (nDev > 1) {
+        DeviceState& d0 = *c->devs[0];
+        CUDA_TRY(c, cudaSetDevice(d0.device));
+        std::vector<const unsigned long long*> peers;
+        for (uint64_t i = 1; i < nDev; ++i)
+            peers.push_back(c->devs[i]->world.tally.p);
+        DevBuf<const unsigned long long*> dPeers;
+        CUDA_TRY(c, dPeers.upload(peers, d0.device, d0.stream));
+        launchPeerReduce(d0.world.tally.p, dPeers.p, static_cast<int>(peers.size()), d0.world.nvox * 4, d0.stream);
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    }
+    c->tallyValid = true;
+    return DXB_OK;
+}
+
+int dxb_finish_beam(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int use_beam_calibration, double* factor_out)
+{
+    if (!c || !beam)
+        return DXB_EINVAL;
+    if (!c->tallyValid)
+        return fail(c, DXB_ESTATE, "finish_beam: no tallies (call dxb_run_transport first)");
+    DeviceState& d0 = *c->devs[0];
+    double factor = kKeVperGramToMilliGray;
+    double calibMs = 0;
+    if (use_beam_calibration) {
+        if (isCtBeam(beam->type)) {
+            int rc = ctCalibration(c, *beam, physics_mode, &factor, &calibMs);
+            if (rc != DXB_OK)
+                return rc;
+        } else {
+            factor = beamAnalyticCalibration(*beam);
+        }
+    }
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    World& w = d0.world;
+    const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
+    launchEnergyToDose(w.tally.p, w.voxels.p, d0.dose.p, d0.variance.p, d0.events.p, w.nvox, 1.0 / c->scaleE, 1.0 / c->scaleE2,
+        factor, vol, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    c->stats.calibration_factor = factor;
+    c->stats.calibration_ms = calibMs;
+    if (factor_out)
+        *factor_out = factor;
+    return DXB_OK;
+}
+
+int dxb_run(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int use_beam_calibration, dxb_progress* progress)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = dxb_run_transport(c, beam, physics_mode, progress);
+    if (rc != DXB_OK)
+        return rc;
+    if (c->world > 1)
+        return fail(c, DXB_ESTATE, "dxb_run on a sharded context: use run_transport + external reduce + finish_beam");
+    rc = dxb_finish_beam(c, beam, physics_mode, use_beam_calibration, nullptr);
+    if (rc != DXB_OK)
+        return rc;
+    c->stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return DXB_OK;
+}
+
+int dxb_tally_buffer(dxb_ctx* c, void** device_ptr, uint64_t* n_words)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "tally_buffer: no grid");
+    if (device_ptr)
+        *device_ptr = c->devs[0]->world.tally.p;
+    if (n_words)
+        *n_words = c->devs[0]->world.nvox * 4;
+    return DXB_OK;
+}
+
+int dxb_get_dose(dxb_ctx* c, double* dose, double* variance, uint64_t* n_events)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_dose: no grid");
+    DeviceState& d0 = *c->devs[0];
+    const size_t n = d0.world.nvox;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    if (dose)
+        CUDA_TRY(c, cudaMemcpyAsync(dose, d0.dose.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    if (variance)
+        CUDA_TRY(c, cudaMemcpyAsync(variance, d0.variance.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    if (n_events)
+        CUDA_TRY(c, cudaMemcpyAsync(n_events, d0.events.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_get_energy_scored(dxb_ctx* c, double* energy, double* energy_sq, uint64_t* n_events)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_energy_scored: no grid");
+    DeviceState& d0 = *c->devs[0];
+    World& w = d0.world;
+    const size_t n = w.nvox;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    DevBuf<double> e, e2;
+    DevBuf<unsigned long long> cnt;
+    if (energy)
+        CUDA_TRY(c, e.alloc(n, d0.device));
+    if (energy_sq)
+        CUDA_TRY(c, e2.alloc(n, d0.device));
+    if (n_events)
+        CUDA_TRY(c, cnt.alloc(n, d0.device));
+    launchTallyToEnergy(w.tally.p, e.p, e2.p, cnt.p, n, 1.0 / c->scaleE, 1.0 / c->scaleE2, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    if (energy)
+        CUDA_TRY(c, cudaMemcpyAsync(energy, e.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    if (energy_sq)
+        CUDA_TRY(c, cudaMemcpyAsync(energy_sq, e2.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    if (n_events)
+        CUDA_TRY(c, cudaMemcpyAsync(n_events, cnt.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_get_dose_postprocessed(dxb_ctx* c, int delete_air_dose, double* dose, double* variance, double* n_events, char units_out[4])
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_dose_postprocessed: no grid");
+    DeviceState& d0 = *c->devs[0];
+    World& w = d0.world;
+    const size_t n = w.nvox;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    // max(dose) < 1 mGy -> report uGy (dose x 1e3, variance x 1e6), R:src/libopendxmc/simulationpipeline.cpp:187-195,227-229
+    DevBuf<unsigned long long> dMax;
+    CUDA_TRY(c, dMax.alloc(1, d0.device));
+    CUDA_TRY(c, cudaMemsetAsync(dMax.p, 0, sizeof(unsigned long long), d0.stream));
+    launchMax(d0.dose.p, w.voxels.p, n, delete_air_dose, dMax.p, d0.stream);
+    unsigned long long bits = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&bits, dMax.p, sizeof(bits), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    double maxDose;
+    std::memcpy(&maxDose, &bits, sizeof(double));
+    const bool micro = maxDose < 1.0;
+    if (units_out)
+        std::memcpy(units_out, micro ? "uGy" : "mGy", 4);
+    DevBuf<double> tmp;
+    CUDA_TRY(c, tmp.alloc(n, d0.device));
+    if (dose) {
+        launchPostprocess(d0.dose.p, w.voxels.p, tmp.p, n, delete_air_dose, micro ? 1e3 : 1.0, d0.stream);
+        CUDA_TRY(c, cudaMemcpyAsync(dose, tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    }
+    if (n_events) {
+        launchU64ToDouble(d0.events.p, w.voxels.p, tmp.p, n, delete_air_dose, d0.stream);
+        CUDA_TRY(c, cudaMemcpyAsync(n_events, tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    }
+    if (variance) {
+        launchPostprocess(d0.variance.p, w.voxels.p, tmp.p, n, delete_air_dose, micro ? 1e6 : 1.0, d0.stream);
+        CUDA_TRY(c, cudaMemcpyAsync(variance, tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    }
+    return DXB_OK;
+}
+
+int dxb_organ_dose(dxb_ctx* c, const uint8_t* organ, uint32_t n_organs, double* dose_out, double* mass_out,
+    uint64_t* n_voxels_out, double* variance_out)
+{
+    if (!c || !organ || n_organs == 0 || n_organs > 256)
+        return fail(c, DXB_EINVAL, "organ_dose: bad arguments");
+    if (c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "organ_dose: no grid");
+    DeviceState& d0 = *c->devs[0];
+    World& w = d0.world;
+    const size_t n = w.nvox;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    DevBuf<unsigned char> dOrg;
+    DevBuf<double> acc; // energy[256], mass[256], var[256]
+    DevBuf<unsigned long long> cnt;
+    CUDA_TRY(c, dOrg.alloc(n, d0.device));
+    CUDA_TRY(c, acc.alloc(768, d0.device));
+    CUDA_TRY(c, cnt.alloc(256, d0.device));
+    CUDA_TRY(c, cudaMemcpyAsync(dOrg.p, organ, n, cudaMemcpyHostToDevice, d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(acc.p, 0, 768 * sizeof(double), d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(cnt.p, 0, 256 * sizeof(unsigned long long), d0.stream));
+    const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
+    launchOrganDose(d0.dose.p, d0.variance.p, w.voxels.p, dOrg.p, n, vol, acc.p, acc.p + 256, cnt.p, acc.p + 512, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    double h[768];
+    unsigned long long hc[256];
+    CUDA_TRY(c, cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaMemcpyAsync(hc, cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    for (uint32_t o = 0; o < n_organs; ++o) {
+        const double mass = h[256 + o];
+        if (dose_out)
+            dose_out[o] = mass > 0 ? h[o] / mass : 0.0;
+        if (mass_out)
+            mass_out[o] = mass;
+        if (n_voxels_out)
+            n_voxels_out[o] = hc[o];
+        if (variance_out)
+            variance_out[o] = mass > 0 ? h[512 + o] / (mass * mass) : 0.0;
+    }
+    return DXB_OK;
+}
+
+int dxb_get_run_stats(const dxb_ctx* c, dxb_run_stats* out)
+{
+    if (!c || !out)
+        return DXB_EINVAL;
+    *out = c->stats;
+    return DXB_OK;
+}
+
+int dxb_device_attenuation(dxb_ctx* c, uint32_t material_index, int physics_mode, const double* energy_kev, uint32_t n, float* out4)
+{
+    (void)physics_mode;
+    if (!c || !energy_kev || !out4 || n == 0)
+        return DXB_EINVAL;
+    if (c->devs.empty() || !c->devs[0]->world.hasTables || material_index >= static_cast<uint32_t>(c->devs[0]->world.n_mat))
+        return fail(c, DXB_ESTATE, "device_attenuation: no tables / bad material");
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    std::vector<float> e(n);
+    for (uint32_t i = 0; i < n; ++i)
+        e[i] = static_cast<float>(energy_kev[i]);
+    DevBuf<float> dE, dOut;
+    CUDA_TRY(c, dE.upload(e, d0.device, d0.stream));
+    CUDA_TRY(c, dOut.alloc(static_cast<size_t>(n) * 4, d0.device));
+    launchAttenuationProbe(d0.world.tablesDev(), static_cast<int>(material_index), dE.p, static_cast<int>(n), dOut.p, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out4, dOut.p, static_cast<size_t>(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_device_majorant(dxb_ctx* c, const double* energy_kev, uint32_t n, float* out)
+{
+    if (!c || !energy_kev || !out || n == 0)
+        return DXB_EINVAL;
+    if (c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "device_majorant: no grid");
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    std::vector<float> e(n);
+    for (uint32_t i = 0; i < n; ++i)
+        e[i] = static_cast<float>(energy_kev[i]);
+    DevBuf<float> dE, dOut;
+    CUDA_TRY(c, dE.upload(e, d0.device, d0.stream));
+    CUDA_TRY(c, dOut.alloc(n, d0.device));
+    launchMajorantProbe(d0.world.majorant.p, dE.p, static_cast<int>(n), dOut.p, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(out, dOut.p, n * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+// CT segmentation, SURVEY §8f-1 — R:src/libopendxmc/ctsegmentationpipeline.cpp:61-169
+int dxb_segment_ct(dxb_ctx* c, const double* hu, uint64_t n, const dxb_tube_desc* tube, uint8_t* material_out,
+    double* density_out, dxb_material** materials_out)
+{
+    if (!c || !hu || n == 0 || !tube || !material_out || !density_out)
+        return fail(c, DXB_EINVAL, "segment_ct: null argument");
+    static const char* names[5] = { "Air, Dry (near sea level)", "Adipose Tissue (ICRP)", "Tissue, Soft (ICRP)", "Muscle, Skeletal",
+        "Bone, Cortical (ICRP)" };
+    std::vector<std::shared_ptr<Material>> mats;
+    std::vector<double> dens;
+    for (const char* nm : names) {
+        auto m = Material::byNistName(nm);
+        if (!m)
+            return fail(c, DXB_EMATERIAL, "segment_ct: material");
+        mats.push_back(m);
+        dens.push_back(nistFind(nm)->density);
+    }
+    dens.back() = 1.09; // "Density for bone is to high", R:...ctsegmentationpipeline.cpp:126-127
+    const auto en = tubeEnergies(*tube);
+    const auto sw = tubeSpectrum(*tube, en, true);
+    auto air = mats[0];
+    auto water = Material::byNistName("Water, Liquid");
+    const double airD = nistFind("Air, Dry (near sea level)")->density, waterD = 1.0;
+    std::vector<double> HU(5, 0.0), att(5, 0.0);
+    double attW = 0, attA = 0;
+    for (size_t k = 0; k < en.size(); ++k) {
+        const double e = std::clamp(en[k], kEMin, kEMax);
+        const double uw = water->total(e), ua = air->total(e);
+        attW += sw[k] * uw;
+        attA += sw[k] * ua;
+        for (int i = 0; i < 5; ++i) {
+            const double um = mats[i]->total(e);
+            att[i] += sw[k] * um;
+            HU[i] += 1000.0 * sw[k] * (um * dens[i] - uw * waterD) / (uw * waterD - ua * airD);
+        }
+    }
+    std::vector<double> sep;
+    for (int i = 0; i < 4; ++i)
+        sep.push_back(0.5 * (HU[i] + HU[i + 1]));
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    DevBuf<double> dHu, dSep, dAtt, dDens;
+    DevBuf<unsigned char> dMat;
+    CUDA_TRY(c, dHu.alloc(n, d0.device));
+    CUDA_TRY(c, dDens.alloc(n, d0.device));
+    CUDA_TRY(c, dMat.alloc(n, d0.device));
+    CUDA_TRY(c, dSep.upload(sep, d0.device, d0.stream));
+    CUDA_TRY(c, dAtt.upload(att, d0.device, d0.stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dHu.p, hu, n * sizeof(double), cudaMemcpyHostToDevice, d0.stream));
+    launchSegment(dHu.p, n, dSep.p, 4, dAtt.p, attW * waterD, attA * airD, dMat.p, dDens.p, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(material_out, dMat.p, n, cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaMemcpyAsync(density_out, dDens.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    if (materials_out)
+        for (int i = 0; i < 5; ++i)
+            materials_out[i] = new dxb_material { mats[i] };
+    return DXB_OK;
+}
+
+// -------------------------------------------------------------------------- progress
+dxb_progress* dxb_progress_create(void) { return new dxb_progress(); }
+void dxb_progress_destroy(dxb_progress* p) { delete p; }
+void dxb_progress_read(const dxb_progress* p, uint64_t* done, uint64_t* total)
+{
+    if (!p)
+        return;
+    if (done)
+        *done = p->done.load(std::memory_order_relaxed);
+    if (total)
+        *total = p->total.load(std::memory_order_relaxed);
+}
+void dxb_progress_stop(dxb_progress* p)
+{
+    if (p)
+        p->stop.store(1, std::memory_order_relaxed);
+}
+int dxb_progress_continue(const dxb_progress* p) { return p ? !p->stop.load(std::memory_order_relaxed) : 1; }
+void dxb_progress_reset(dxb_progress* p)
+{
+    if (!p)
+        return;
+    p->stop.store(0);
+    p->done.store(0);
+    p->total.store(0);
+}
+int dxb_progress_message(const dxb_progress* p, char* buf, int cap)
+{
+    if (!p || !buf || cap <= 0)
+        return DXB_EINVAL;
+    const uint64_t done = p->done.load(), total = p->total.load();
+    const int64_t now = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    const double elapsed = (now - p->start_ns.load()) * 1e-9;
+    if (done == 0 || total == 0) {
+        std::snprintf(buf, cap, "Starting simulation");
+    } else {
+        const double remaining = elapsed * static_cast<double>(total - done) / static_cast<double>(done);
+        const int s = static_cast<int>(remaining);
+        std::snprintf(buf, cap, "Remaining time %02d:%02d:%02d", s / 3600, (s / 60) % 60, s % 60);
+    }
+    return DXB_OK;
+}
+
+} // extern "C"

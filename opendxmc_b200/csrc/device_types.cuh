@@ -1,0 +1,98 @@
+// device_types.cuh — PODs shared between the host context and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dxb {
+
+// table geometry, mirrors physics.hpp (static_asserted in context.cu)
+constexpr int kDevNE = 465;
+constexpr int kDevEPerOctave = 64;
+constexpr int kDevNX = 259;
+constexpr int kDevXPerOctave = 24;
+constexpr float kDevXMinInv = 128.0f;
+constexpr int kMaxShells = 5;
+
+// HBM layout of the voxel grid (x fastest, like the reference: i + j*nx + k*nx*ny,
+// R:src/libopendxmc/otherphantomimportpipeline.cpp:44).
+//   voxels : uint2 {float density bits, material index}      8 B / voxel
+//   tally  : 4 x u64 {sum E, sum E^2, events, pad}           32 B / voxel = one DRAM sector,
+//            64-bit fixed point so that sums are order independent
+//   dose   : 3 x f64 {dose, variance, events} accumulated over beams (DoseScore)
+struct GridDev {
+    int nx, ny, nz;
+    float x0, y0, z0; // min corner [cm]
+    float x1, y1, z1; // max corner
+    float inv_dx, inv_dy, inv_dz;
+    const uint2* __restrict__ voxels;
+    unsigned long long* __restrict__ tally;
+};
+
+struct ShellDev {
+    float binding, nel_fraction, photo_fraction, fluor_yield, fluor_energy, j0, pad0, pad1;
+};
+
+struct TablesDev {
+    int n_mat;
+    const float4* __restrict__ att;   // [n_mat*NE] {photo, incoh, coh, total} cm2/g
+    const float* __restrict__ tot;    // [n_mat*NE] total, staged in shared memory by the kernel
+    const float* __restrict__ etr;    // [n_mat*NE] mass energy-transfer (kerma estimator)
+    const float* __restrict__ majorant; // [NE] mu_max [1/cm]
+    const float* __restrict__ ffcdf;  // [n_mat*NX]
+    const float* __restrict__ sf;     // [n_mat*NX]
+    const ShellDev* __restrict__ shells; // [n_mat*kMaxShells]
+    const int* __restrict__ n_shells; // [n_mat]
+};
+
+struct SpectrumDev {
+    int n;             // 1: mono-energetic
+    float e0, step;    // energy[i] = e0 + i*step
+    const float* __restrict__ prob;           // alias acceptance
+    const unsigned short* __restrict__ alias;
+};
+
+struct BowtieDev {
+    int n; // 0: none
+    const float* __restrict__ angle;
+    const float* __restrict__ weight;
+};
+
+struct ExposureDev { // 64 B
+    float pos[3];
+    float c0[3];
+    float c1[3];
+    float dir[3];
+    float hx, hy;
+    float weight;
+    int tube;
+};
+
+struct RunParams {
+    GridDev grid;
+    TablesDev tab;
+    SpectrumDev spec[2];
+    BowtieDev bow[2];
+    const ExposureDev* __restrict__ exposures;
+    unsigned long long n_exposures;
+    unsigned long long ppe;         // particles per exposure
+    unsigned long long n_total;     // histories of the whole beam (all ranks)
+    unsigned long long local_begin; // this launch covers local indices [local_begin, local_end)
+    unsigned long long local_end;
+    unsigned int world, rank;       // history sharding: 65536-history blocks dealt round-robin
+    unsigned int seed_lo, seed_hi;  // Philox key
+    float tally_scale_e, tally_scale_e2;
+    int score_material;             // calibration: kerma collision estimator in this material (-1: off)
+    unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
+    unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
+};
+
+constexpr unsigned int kShardBlock = 65536; // histories per sharding block
+
+// launch wrappers (transport.cu)
+struct LaunchConfig {
+    int blocks, threads;
+    size_t smem;
+    bool table_in_smem;
+};
+
+} // namespace dxb
