@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py — histories/s of the dxmc::Transport hot path on the BASELINE.json workload (C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--histories H] [--impl ours|reference]
+
+A *step* is one full beam: H histories (default 1e9 = BASELINE.json configs[1]) of the 120 kV spiral CT beam with
+bowtie through the synthetic 512x512x300 patient volume.  Every step uses a fresh Philox key, so nothing is cached.
+
+  value  histories/s with the voxel grid, tables and beam already resident in HBM (timed region: tally clear +
+         transport kernels + [N>1: NCCL reduce of the fixed-point tallies to rank 0] + energy->dose), CUDA events,
+         barrier + synchronize on both sides, max over ranks.
+  e2e    the same metric through the reference-facing C ABI with HOST buffers: dxb_set_grid (H2D of the f64 density
+         and u8 material arrays from pinned memory) + dxb_run_transport/dxb_finish_beam + dxb_get_dose (D2H of dose,
+         variance, event count), i.e. what R:src/libopendxmc/simulationpipeline.cpp:145-219 does around transport().
+  roofline  the transport kernel: algorithmic bytes/history A = S*5 + D*48 (S, D counted by the
+         kernel in the same run) x histories / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (restated DXMClib algorithm, std::thread on all host cores; "port": the real
+         DXMClib is absent from the reference tree) on a bounded sample of the same workload.
+
+Inputs (630 MB f64 density + 79 MB material -> 629 MB packed voxels + 2.5 GB tallies) are far larger than the
+126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED0 = 0x0DDC0FFEE
+METRIC = "histories/sec (512x512x300 CT, 120 kV spiral)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--histories", type=float, default=1e9, help="histories per step (whole job)")
+    ap.add_argument("--scale", type=int, default=1, help="grid coarsening (1 = the BASELINE 512x512x300 volume)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median of the samples taken under load (power above the idle floor)
+        pmax = max(power)
+        load = sorted(s for s, p in zip(sm, power) if p >= 0.5 * pmax) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": pmax}
+
+
+def make_workload(args):
+    import opendxmc_b200 as dx
+    return dx.workloads.ct_spiral_patient(scale=args.scale, histories=int(args.histories))
+
+
+def config_dict(args, wl, extra=None):
+    c = {"workload": "C2 synthetic CT patient %dx%dx%d, 120 kV spiral CT, bowtie, pitch 1, %d exposures" % (
+        wl.dim[0], wl.dim[1], wl.dim[2], wl.beam.numberOfExposures()),
+        "histories_per_step": wl.beam.numberOfParticles(), "physics_mode": 1,
+        "l2": "inputs larger than L2 (0.63 GB voxels + 2.5 GB tallies vs 126 MB), no flush needed"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------------------- CPU oracle legs
+def cpu_oracle_rate(args, wl, target_seconds):
+    """Times the CPU oracle (all host cores) on a bounded sample of the workload.  bench.py is one of the few places
+    allowed to execute oracle/ (as the measured *baseline*, never as the product)."""
+    from oracle import oracle_py as orc
+    import opendxmc_b200 as dx
+    ow = orc.OracleWorld.from_workload(wl)
+    nexp = wl.beam.numberOfExposures()
+    full_ppe = wl.beam.numberOfParticlesPerExposure()
+    # probe
+    wl.beam.setNumberOfParticlesPerExposure(max(1, 200_000 // nexp))
+    _, _, _, st = ow.run(wl.beam, 1, SEED0, 0)
+    rate = st["histories"] / max(st["seconds"], 1e-9)
+    ppe = max(1, int(rate * target_seconds / nexp))
+    wl.beam.setNumberOfParticlesPerExposure(ppe)
+    _, _, _, st = ow.run(wl.beam, 1, SEED0 + 1, 0)
+    wl.beam.setNumberOfParticlesPerExposure(full_ppe)
+    return {"value": st["histories"] / st["seconds"], "unit": "histories/s", "cores": int(st["threads"]), "kind": "port",
+            "sample": "%d histories (%d per exposure x %d exposures) of the same beam through the full volume, %.1f s" % (
+                st["histories"], ppe, nexp, st["seconds"]),
+            "steps_per_history": st["steps"] / st["histories"], "deposits_per_history": st["deposits"] / st["histories"]}, ow
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = make_workload(args)
+    from oracle import oracle_py as orc
+    ow = orc.OracleWorld.from_workload(wl)
+    nexp = wl.beam.numberOfExposures()
+    full = wl.beam.numberOfParticles()
+    wl.beam.setNumberOfParticlesPerExposure(max(1, 200_000 // nexp))
+    _, _, _, st = ow.run(wl.beam, 1, SEED0, 0)
+    rate = st["histories"] / max(st["seconds"], 1e-9)
+    per_step_seconds = min(20.0, 180.0 / max(1, args.steps + args.warmup))
+    ppe = max(1, int(rate * per_step_seconds / nexp))
+    wl.beam.setNumberOfParticlesPerExposure(ppe)
+    for i in range(args.warmup):
+        ow.run(wl.beam, 1, SEED0 + i, 0)
+    hist, secs, threads = 0, 0.0, 0
+    for i in range(args.steps):
+        _, _, _, st = ow.run(wl.beam, 1, SEED0 + 100 + i, 0)
+        hist += st["histories"]
+        secs += st["seconds"]
+        threads = st["threads"]
+    value = hist / secs
+    sample = "%d histories per step (%d per exposure x %d exposures) of the %d-history beam, full volume" % (ppe * nexp, ppe, nexp, full)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": config_dict(args, wl, {"reference": "CPU oracle = in-repo restatement of the DXMClib algorithm (DXMClib is not in "
+                                                           "/root/reference and cannot be built offline), std::thread on all host cores"}),
+           "cpu_baseline": {"value": value, "unit": "histories/s", "cores": int(threads), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class _DevView:
+    """exposes a raw device pointer to torch through __cuda_array_interface__ (int64 words)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import opendxmc_b200 as dx
+    from opendxmc_b200 import _capi as K
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libdxmc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = K.load()
+
+    wl = make_workload(args)
+    n_hist = wl.beam.numberOfParticles()
+    nvox = wl.n_voxels
+    # pinned host copies of the caller-owned arrays (the reference hands in std::vector<double>/<uint8_t>)
+    dens_pin = torch.empty(nvox, dtype=torch.float64).pin_memory()
+    mat_pin = torch.empty(nvox, dtype=torch.uint8).pin_memory()
+    dens_pin.numpy()[:] = wl.density
+    mat_pin.numpy()[:] = wl.material
+    wl.density, wl.material = dens_pin.numpy(), mat_pin.numpy()
+    out_pin = [torch.empty(nvox, dtype=torch.float64).pin_memory(), torch.empty(nvox, dtype=torch.float64).pin_memory(),
+               torch.empty(nvox, dtype=torch.int64).pin_memory()] if rank == 0 else None
+
+    world = wl.build_world(1, [local_rank])
+    ctx = world.ctx()
+    world.set_history_range(rank, world_size)
+    stream = torch.cuda.Stream(device=local_rank)
+    K.load().dxb_set_stream(ctx, C.c_void_p(stream.cuda_stream))
+    tr = dx.Transport()
+    desc = wl.beam.desc()
+    ptr, nwords = C.c_void_p(), C.c_uint64()
+    lib.dxb_tally_buffer(ctx, C.byref(ptr), C.byref(nwords))
+    tally = torch.as_tensor(_DevView(ptr.value, nwords.value), device=f"cuda:{local_rank}")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, timed_stats=None):
+        """one beam with everything resident: tallies -> (reduce) -> dose."""
+        lib.dxb_set_seed(ctx, SEED0 + 7919 * (i + 1))
+        rc = lib.dxb_run_transport(ctx, C.byref(desc), 1, None)
+        assert rc == 0, lib.dxb_last_error(ctx)
+        if timed_stats is not None:
+            timed_stats.append(world.run_stats())
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)
+            stream.synchronize()
+        if rank == 0:
+            rc = lib.dxb_finish_beam(ctx, C.byref(desc), 1, 0, None)
+            assert rc == 0, lib.dxb_last_error(ctx)
+
+    def e2e_step(i):
+        """the reference-facing call sequence with host buffers: setData/build -> transport -> read dose."""
+        dim = (C.c_uint64 * 3)(*wl.dim)
+        sp = (C.c_double * 3)(*wl.spacing)
+        rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
+        assert rc == 0, lib.dxb_last_error(ctx)
+        step(1000 + i)
+        if rank == 0:
+            rc = lib.dxb_get_dose(ctx, C.cast(out_pin[0].data_ptr(), K.c_double_p), C.cast(out_pin[1].data_ptr(), K.c_double_p),
+                                  C.cast(out_pin[2].data_ptr(), K.c_u64_p))
+            assert rc == 0, lib.dxb_last_error(ctx)
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local_rank)
+    stats = []
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i, stats)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    tms = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total = float(tms[0])
+    # per-rank kernel statistics -> global S, D and the slowest rank's kernel time
+    k = torch.tensor([sum(s["histories"] for s in stats), sum(s["steps"] for s in stats), sum(s["deposits"] for s in stats),
+                      sum(s["kernel_launches"] for s in stats)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    kms = torch.tensor([sum(s["transport_ms"] for s in stats)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(k, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    hist_done, steps_done, deps_done, launches = [float(v) for v in k]
+    kernel_ms = float(kms[0])
+
+    # ---- e2e
+    e2e = None
+    if not args.no_e2e:
+        e2e_step(-1)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 2))
+        for i in range(n_e2e):
+            e2e_step(i)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_hist * n_e2e / float(te[0]), "unit": "histories/s",
+               "h2d_bytes_per_step": int(nvox * 9 * world_size), "d2h_bytes_per_step": int(nvox * 24),
+               "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e,
+               "note": "host-clock around dxb_set_grid + dxb_run_transport + NCCL reduce + dxb_finish_beam + dxb_get_dose, pinned host buffers"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    S = steps_done / hist_done
+    D = deps_done / hist_done
+    a_hist = S * 5.0 + D * 48.0
+    # per-GPU roofline of the transport kernel: this rank's share of the histories over the slowest rank's kernel time
+    achieved = (hist_done / world_size) * a_hist / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "transportKernel<1,false,true>", "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": D,
+                "sector_bytes_per_history": (S + 3 * D) * 32.0,
+                "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / ms_total}
+    value = n_hist * args.steps / (ms_total * 1e-3)
+    out = {"metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl, {"parallelism": "histories sharded over %d GPU(s), "
+                                                                                 "int64 tally reduce" % world_size}),
+           "clocks": clocks, "gpu_launches": int(launches + args.steps),  # transport kernels (all ranks) + energyToDose on rank 0
+           "roofline": roofline}
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        world.close()
+        cb, _ = cpu_oracle_rate(args, wl, args.cpu_seconds)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
