@@ -154,6 +154,8 @@ struct Options {
     int threads = 256;
     int blocksPerSm = 0;         // 0: occupancy query
     int tableInSmem = 1;
+    int refillThreshold = 6;     // warp phase machine (transport.cu)
+    int interactThreshold = 12;
 };
 
 } // namespace
@@ -437,6 +439,8 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.tally_scale_e = c->scaleE;
     P.tally_scale_e2 = c->scaleE2;
     P.score_material = calib ? scoreMaterial : -1;
+    P.refill_threshold = std::clamp(c->opt.refillThreshold, 1, 32);
+    P.interact_threshold = std::clamp(c->opt.interactThreshold, 1, 32);
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -444,7 +448,8 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.threads = c->opt.threads;
     const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
-    cfg.smem = cfg.table_in_smem ? tableBytes : 0;
+    const size_t bufBytes = static_cast<size_t>(cfg.threads / 32) * kSourceBufWords * 32 * sizeof(float);
+    cfg.smem = bufBytes + (cfg.table_in_smem ? tableBytes : 0);
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
         perSm = transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
@@ -894,9 +899,9 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         return DXB_EINVAL;
     const std::string k(key);
     if (k == "batch_histories") {
-        if (value < 1024)
+        if (value < kShardBlock)
             return DXB_EINVAL;
-        c->opt.batch = static_cast<uint64_t>(value);
+        c->opt.batch = static_cast<uint64_t>(value) / kShardBlock * kShardBlock; // launches start on shard-block boundaries
     } else if (k == "threads_per_block") {
         const int t = static_cast<int>(value);
         if (t < 32 || t > 256 || (t % 32))
@@ -906,6 +911,10 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.blocksPerSm = static_cast<int>(value);
     } else if (k == "table_in_smem") {
         c->opt.tableInSmem = value != 0;
+    } else if (k == "refill_threshold") {
+        c->opt.refillThreshold = static_cast<int>(value);
+    } else if (k == "interact_threshold") {
+        c->opt.interactThreshold = static_cast<int>(value);
     } else {
         return fail(c, DXB_EINVAL, "unknown option " + k);
     }

@@ -12,6 +12,7 @@ constexpr int kDevNX = 259;
 constexpr int kDevXPerOctave = 24;
 constexpr float kDevXMinInv = 128.0f;
 constexpr int kMaxShells = 5;
+constexpr int kSourceBufWords = 13; // words per entry of the per-warp source buffer (transport.cu)
 
 // HBM layout of the voxel grid (x fastest, like the reference: i + j*nx + k*nx*ny,
 // R:src/libopendxmc/otherphantomimportpipeline.cpp:44).
@@ -82,6 +83,8 @@ struct RunParams {
     unsigned int seed_lo, seed_hi;  // Philox key
     float tally_scale_e, tally_scale_e2;
     int score_material;             // calibration: kerma collision estimator in this material (-1: off)
+    int refill_threshold;           // dead lanes per warp that trigger a refill phase
+    int interact_threshold;         // waiting lanes per warp that trigger an interaction phase
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
 };

@@ -158,33 +158,28 @@ __device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float c
 }
 
 // ------------------------------------------------------------------ scoring
-// Warp-aggregated fixed-point tally update: lanes of the same warp that hit the same voxel in the
-// same iteration are merged (exact integer sums, so the result does not depend on the merge).
-__device__ __forceinline__ void scoreEnergy(unsigned long long* __restrict__ tally, unsigned int voxel, float edep,
+// Warp-aggregated fixed-point tally update.  `mask` = the lanes that score in this phase (all of them call
+// this function together); lanes of the mask that hit the same voxel are merged before the atomics (exact
+// integer sums, so the result does not depend on the merge or on arrival order).
+__device__ __forceinline__ void scoreEnergy(unsigned int mask, unsigned long long* __restrict__ tally, unsigned int voxel, float edep,
     float scale_e, float scale_e2)
 {
     unsigned long long e = static_cast<unsigned long long>(__float2ll_rn(edep * scale_e));
     unsigned long long e2 = static_cast<unsigned long long>(__float2ll_rn(edep * edep * scale_e2));
     unsigned int n = 1;
-    const unsigned int active = __activemask();
-    const unsigned int peers = __match_any_sync(active, voxel);
+    const unsigned int peers = __match_any_sync(mask, voxel);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     if (peers != (1u << lane)) {
-        // rare path: several lanes on one voxel; everyone walks the peer set
-        unsigned int rest = peers & ~(1u << leader);
+        // rare path: several lanes on one voxel; every peer walks the peer set
         unsigned long long se = 0, se2 = 0;
-        // all peers must execute the shuffles together
         unsigned int walk = peers;
         while (walk) {
             const int src = __ffs(walk) - 1;
             walk &= walk - 1;
-            const unsigned long long pe = __shfl_sync(peers, e, src);
-            const unsigned long long pe2 = __shfl_sync(peers, e2, src);
-            se += pe;
-            se2 += pe2;
+            se += __shfl_sync(peers, e, src);
+            se2 += __shfl_sync(peers, e2, src);
         }
-        (void)rest;
         e = se;
         e2 = se2;
         n = __popc(peers);
@@ -305,6 +300,18 @@ __device__ __forceinline__ void rayleighScatter(Rng& rng, const TablesDev& tab, 
 }
 
 // ------------------------------------------------------------------ the history kernel
+//
+// Warp-level phase machine.  Every lane owns at most one photon and is in one of three states:
+//   STEP  tentative Woodcock steps (cheap, executed by most lanes every iteration),
+//   WAIT  a tentative collision was accepted as real; the (expensive, divergent) interaction sampler has
+//         not run yet,
+//   DEAD  no photon; waiting for a new history.
+// Each iteration the warp picks ONE phase by vote: the interaction sampler only runs once `interact_threshold`
+// lanes wait for it (or nobody can step), dead lanes are only refilled once `refill_threshold` of them are dead.
+// Source sampling is warp-cooperative: all 32 lanes sample one history each (full SIMD efficiency, independent
+// of how many lanes are dead), photons that hit the grid are compacted into a per-warp shared-memory buffer,
+// and dead lanes pop from it.  This replaces the one-lane-at-a-time refill/interaction of the first version,
+// whose ncu capture showed 5.4 of 32 lanes active per instruction (profiles/r01_transport_v1.md).
 struct Photon {
     float px, py, pz;
     float dx, dy, dz;
@@ -312,10 +319,19 @@ struct Photon {
     float remaining; // distance to the grid exit along the current direction
 };
 
+constexpr int kStStep = 0, kStWait = 1, kStDead = 2;
+constexpr int kWarpBufFloats = kSourceBufWords * 32; // px py pz dx dy dz E w remaining histOffset epos.i epos.f muMax
+static_assert(kSourceBufWords == 13, "source buffer layout");
+
 template <int MODE, bool CALIB, bool SMEM_TABLE>
-__global__ void __launch_bounds__(256) transportKernel(const __grid_constant__ RunParams P)
+__global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant__ RunParams P)
 {
-    extern __shared__ float s_tot[]; // [n_mat * NE] total mass attenuation
+    extern __shared__ float s_dyn[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nWarps = blockDim.x >> 5;
+    float* __restrict__ sbuf = s_dyn + warp * kWarpBufFloats; // SoA: word f of entry k at sbuf[f * 32 + k]
+    float* __restrict__ s_tot = s_dyn + nWarps * kWarpBufFloats;
     if (SMEM_TABLE) {
         const int n = P.tab.n_mat * kDevNE;
         for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -324,236 +340,318 @@ __global__ void __launch_bounds__(256) transportKernel(const __grid_constant__ R
     }
     const float* __restrict__ totTable = SMEM_TABLE ? s_tot : P.tab.tot;
     const GridDev& G = P.grid;
-    const int lane = threadIdx.x & 31;
+    const unsigned int laneLt = (1u << lane) - 1u;
 
-    // warp-level pool of local history indices
+    // warp-level pool of local history indices (carved from the global cursor in 256-history pieces)
     unsigned long long poolNext = 0, poolEnd = 0;
     bool drained = false;
+    int bufCount = 0;                 // entries in the warp's source buffer
+    unsigned long long bufBase = 0;   // global history id of buffer offset 0
 
     Rng rng;
     Photon ph;
-    bool alive = false;
-    TabPos epos;        // energy grid position of ph.E
+    int status = kStDead;
+    TabPos epos;
     float muMax = 1.0f, muMaxInv = 1.0f;
+    unsigned int voxel = 0;
+    int mat = 0;
     epos.i = 0;
     epos.f = 0.0f;
     ph.remaining = 0.0f;
+    rng.init(P.seed_lo, P.seed_hi, 0ull);
 
     unsigned int nSteps = 0, nInter = 0, nDep = 0, nHist = 0;
     unsigned long long emitted = 0;
 
     for (;;) {
-        // ---------------- refill dead lanes from the warp pool
-        const unsigned int deadMask = __ballot_sync(0xffffffffu, !alive);
-        if (deadMask) {
-            const unsigned int need = __popc(deadMask);
-            if (poolNext == poolEnd && !drained) {
-                // pool empty: carve the next 256-history piece from the global cursor
-                constexpr unsigned long long kPiece = 256;
-                unsigned long long base = 0;
-                if (lane == 0)
-                    base = atomicAdd(P.work_counter, kPiece);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned long long start = P.local_begin + base;
-                if (start >= P.local_end) {
-                    drained = true;
-                } else {
-                    poolNext = start;
-                    poolEnd = min(start + kPiece, P.local_end);
-                }
-            }
-            const unsigned long long avail = poolEnd - poolNext;
-            if (!alive) {
-                const unsigned int rank = __popc(deadMask & ((1u << lane) - 1u));
-                if (rank < avail) {
-                    const unsigned long long local = poolNext + rank;
-                    // local index -> global history id (65536-history blocks dealt round-robin over ranks)
-                    const unsigned long long blk = local / kShardBlock;
-                    const unsigned long long h = (blk * P.world + P.rank) * kShardBlock + (local % kShardBlock);
-                    if (h < P.n_total) {
-                        // ---------------- sample the source particle of history h
-                        rng.init(P.seed_lo, P.seed_hi, h);
-                        const unsigned long long ei = h / P.ppe;
-                        const ExposureDev* ex = P.exposures + ei;
-                        const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
-                        const float angx = (2.0f * rng.uniform() - 1.0f) * hx;
-                        const float angy = (2.0f * rng.uniform() - 1.0f) * hy;
-                        const int tube = __ldg(&ex->tube);
-                        const SpectrumDev& sp = P.spec[tube];
-                        float E;
-                        if (sp.n <= 1) {
-                            E = sp.e0;
-                        } else {
-                            const float r0 = rng.uniform();
-                            int idx = min(static_cast<int>(r0 * static_cast<float>(sp.n)), sp.n - 1);
-                            const float r1 = rng.uniform();
-                            if (!(r1 < __ldg(sp.prob + idx)))
-                                idx = __ldg(sp.alias + idx);
-                            const float r2 = rng.uniform();
-                            E = sp.e0 + static_cast<float>(idx) * sp.step;
-                            if (idx < sp.n - 1)
-                                E += r2 * sp.step;
-                        }
-                        float w = __ldg(&ex->weight);
-                        const BowtieDev& bt = P.bow[tube];
-                        if (bt.n > 0) {
-                            const float a = fabsf(angx);
-                            float bw;
-                            if (a <= __ldg(bt.angle)) {
-                                bw = __ldg(bt.weight);
-                            } else if (a >= __ldg(bt.angle + bt.n - 1)) {
-                                bw = __ldg(bt.weight + bt.n - 1);
-                            } else {
-                                int i = 1;
-                                while (__ldg(bt.angle + i) < a)
-                                    ++i;
-                                const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
-                                bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
-                            }
-                            w *= bw;
-                        }
-                        float sx, sy;
-                        sx = __sinf(angx);
-                        sy = __sinf(angy);
-                        const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
-                        ph.dx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
-                        ph.dy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
-                        ph.dz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
-                        ph.px = __ldg(&ex->pos[0]);
-                        ph.py = __ldg(&ex->pos[1]);
-                        ph.pz = __ldg(&ex->pos[2]);
-                        ph.E = E;
-                        ph.w = w;
-                        ++nHist;
-                        emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
-                        // ---------------- move to the grid AABB (World::transport)
-                        const float ix = 1.0f / ph.dx, iy = 1.0f / ph.dy, iz = 1.0f / ph.dz;
-                        float tmin = 0.0f, tmax = 3.0e38f;
-                        {
-                            float t0 = (G.x0 - ph.px) * ix, t1 = (G.x1 - ph.px) * ix;
-                            if (ph.dx == 0.0f) {
-                                if (ph.px < G.x0 || ph.px > G.x1)
-                                    tmax = -1.0f;
-                            } else {
-                                tmin = fmaxf(tmin, fminf(t0, t1));
-                                tmax = fminf(tmax, fmaxf(t0, t1));
-                            }
-                            t0 = (G.y0 - ph.py) * iy;
-                            t1 = (G.y1 - ph.py) * iy;
-                            if (ph.dy == 0.0f) {
-                                if (ph.py < G.y0 || ph.py > G.y1)
-                                    tmax = -1.0f;
-                            } else {
-                                tmin = fmaxf(tmin, fminf(t0, t1));
-                                tmax = fminf(tmax, fmaxf(t0, t1));
-                            }
-                            t0 = (G.z0 - ph.pz) * iz;
-                            t1 = (G.z1 - ph.pz) * iz;
-                            if (ph.dz == 0.0f) {
-                                if (ph.pz < G.z0 || ph.pz > G.z1)
-                                    tmax = -1.0f;
-                            } else {
-                                tmin = fmaxf(tmin, fminf(t0, t1));
-                                tmax = fminf(tmax, fmaxf(t0, t1));
-                            }
-                        }
-                        if (tmax > tmin && E >= kMinEnergy) {
-                            ph.px = fmaf(ph.dx, tmin, ph.px);
-                            ph.py = fmaf(ph.dy, tmin, ph.py);
-                            ph.pz = fmaf(ph.dz, tmin, ph.pz);
-                            ph.remaining = tmax - tmin;
-                            alive = true;
-                            epos = tabPos<kDevEPerOctave, kDevNE>(ph.E);
-                            muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
-                            muMaxInv = 1.0f / muMax;
-                        }
+        const unsigned int mDead = __ballot_sync(0xffffffffu, status == kStDead);
+        const unsigned int mWait = __ballot_sync(0xffffffffu, status == kStWait);
+        const int nDead = __popc(mDead), nWait = __popc(mWait), nStep = 32 - nDead - nWait;
+        const bool canRefill = !(drained && bufCount == 0);
+        int phase; // 0 step, 1 interact, 2 refill
+        if (canRefill && nDead >= P.refill_threshold)
+            phase = 2;
+        else if (nWait >= P.interact_threshold)
+            phase = 1;
+        else if (nStep > 0)
+            phase = 0;
+        else if (nWait > 0)
+            phase = 1;
+        else if (canRefill)
+            phase = 2;
+        else
+            break;
+
+        if (phase == 2) {
+            // ------------------------------------------------------------ refill
+            if (bufCount == 0) {
+                // warp-cooperative source sampling of the next (up to) 32 histories
+                if (poolNext == poolEnd && !drained) {
+                    constexpr unsigned long long kPiece = 256;
+                    unsigned long long base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(P.work_counter, kPiece);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned long long start = P.local_begin + base;
+                    if (start >= P.local_end) {
+                        drained = true;
+                    } else {
+                        poolNext = start;
+                        poolEnd = min(start + kPiece, P.local_end);
                     }
                 }
-            }
-            poolNext += min(static_cast<unsigned long long>(need), avail);
-            if (drained && __ballot_sync(0xffffffffu, alive) == 0u)
-                break;
-        }
-
-        // ---------------- one tentative Woodcock step for every live lane
-        if (alive) {
-            const float s = -__logf(1.0f - rng.uniform()) * muMaxInv;
-            if (s >= ph.remaining) {
-                alive = false; // left the grid
-            } else {
-                ++nSteps;
-                ph.px = fmaf(ph.dx, s, ph.px);
-                ph.py = fmaf(ph.dy, s, ph.py);
-                ph.pz = fmaf(ph.dz, s, ph.pz);
-                ph.remaining -= s;
-                int vx = static_cast<int>((ph.px - G.x0) * G.inv_dx);
-                int vy = static_cast<int>((ph.py - G.y0) * G.inv_dy);
-                int vz = static_cast<int>((ph.pz - G.z0) * G.inv_dz);
-                vx = min(max(vx, 0), G.nx - 1);
-                vy = min(max(vy, 0), G.ny - 1);
-                vz = min(max(vz, 0), G.nz - 1);
-                const unsigned int voxel = (static_cast<unsigned int>(vz) * G.ny + vy) * G.nx + vx;
-                const uint2 vox = __ldg(G.voxels + voxel);
-                const float rho = __uint_as_float(vox.x);
-                const int mat = static_cast<int>(vox.y);
-                const float* tt = totTable + mat * kDevNE + epos.i;
-                const float mu = rho * lerp(tt[0], tt[1], epos.f);
-                const float r = rng.uniform();
-                if (CALIB && mat == P.score_material) {
-                    // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
-                    const float* et = P.tab.etr + mat * kDevNE + epos.i;
-                    const float k = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
-                    scoreEnergy(G.tally, voxel, k, P.tally_scale_e, P.tally_scale_e2);
+                const unsigned long long avail = poolEnd - poolNext;
+                const int nb = static_cast<int>(min(avail, 32ull));
+                // local index -> global history id (65536-history blocks dealt round-robin over ranks); a piece never
+                // straddles a shard block (256 divides 65536), so the 32 ids are consecutive
+                const unsigned long long blk = poolNext / kShardBlock;
+                bufBase = (blk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
+                const unsigned long long h = bufBase + lane;
+                bool hit = false;
+                Photon q;
+                TabPos qpos;
+                float qmu = 1.0f;
+                qpos.i = 0;
+                qpos.f = 0.0f;
+                q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = q.remaining = 0.0f;
+                if (lane < nb && h < P.n_total) {
+                    Rng srng;
+                    srng.init(P.seed_lo, P.seed_hi, h);
+                    const unsigned long long ei = h / P.ppe;
+                    const ExposureDev* ex = P.exposures + ei;
+                    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
+                    const float angx = (2.0f * srng.uniform() - 1.0f) * hx;
+                    const float angy = (2.0f * srng.uniform() - 1.0f) * hy;
+                    const int tube = __ldg(&ex->tube);
+                    const SpectrumDev& sp = P.spec[tube];
+                    float E;
+                    if (sp.n <= 1) {
+                        E = sp.e0;
+                    } else {
+                        const float r0 = srng.uniform();
+                        int idx = min(static_cast<int>(r0 * static_cast<float>(sp.n)), sp.n - 1);
+                        const float r1 = srng.uniform();
+                        if (!(r1 < __ldg(sp.prob + idx)))
+                            idx = __ldg(sp.alias + idx);
+                        const float r2 = srng.uniform();
+                        E = sp.e0 + static_cast<float>(idx) * sp.step;
+                        if (idx < sp.n - 1)
+                            E += r2 * sp.step;
+                    }
+                    float w = __ldg(&ex->weight);
+                    const BowtieDev& bt = P.bow[tube];
+                    if (bt.n > 0) {
+                        const float a = fabsf(angx);
+                        float bw;
+                        if (a <= __ldg(bt.angle)) {
+                            bw = __ldg(bt.weight);
+                        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
+                            bw = __ldg(bt.weight + bt.n - 1);
+                        } else {
+                            int i = 1;
+                            while (__ldg(bt.angle + i) < a)
+                                ++i;
+                            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
+                            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
+                        }
+                        w *= bw;
+                    }
+                    const float sx = __sinf(angx), sy = __sinf(angy);
+                    const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
+                    q.dx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
+                    q.dy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
+                    q.dz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
+                    q.px = __ldg(&ex->pos[0]);
+                    q.py = __ldg(&ex->pos[1]);
+                    q.pz = __ldg(&ex->pos[2]);
+                    q.E = E;
+                    q.w = w;
+                    ++nHist;
+                    emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
+                    // move to the grid AABB (World::transport)
+                    const float ix = 1.0f / q.dx, iy = 1.0f / q.dy, iz = 1.0f / q.dz;
+                    float tmin = 0.0f, tmax = 3.0e38f;
+                    float t0 = (G.x0 - q.px) * ix, t1 = (G.x1 - q.px) * ix;
+                    if (q.dx == 0.0f) {
+                        if (q.px < G.x0 || q.px > G.x1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    t0 = (G.y0 - q.py) * iy;
+                    t1 = (G.y1 - q.py) * iy;
+                    if (q.dy == 0.0f) {
+                        if (q.py < G.y0 || q.py > G.y1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    t0 = (G.z0 - q.pz) * iz;
+                    t1 = (G.z1 - q.pz) * iz;
+                    if (q.dz == 0.0f) {
+                        if (q.pz < G.z0 || q.pz > G.z1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    if (tmax > tmin && E >= kMinEnergy) {
+                        q.px = fmaf(q.dx, tmin, q.px);
+                        q.py = fmaf(q.dy, tmin, q.py);
+                        q.pz = fmaf(q.dz, tmin, q.pz);
+                        q.remaining = tmax - tmin;
+                        qpos = tabPos<kDevEPerOctave, kDevNE>(E);
+                        qmu = lerp(__ldg(P.tab.majorant + qpos.i), __ldg(P.tab.majorant + qpos.i + 1), qpos.f);
+                        hit = true;
+                    }
                 }
-                if (r * muMax < mu) {
-                    // ---------------- real interaction
-                    ++nInter;
-                    const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
-                    const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
-                    const float aPhoto = lerp(a.x, b.x, epos.f);
-                    const float aIncoh = lerp(a.y, b.y, epos.f);
-                    const float aTot = lerp(a.w, b.w, epos.f);
-                    const float r2 = rng.uniform() * aTot;
-                    float edep = 0.0f;
-                    bool energyChanged = false, dirChanged = false;
-                    if (r2 < aPhoto) {
-                        edep = ph.E * ph.w;
+                poolNext += nb;
+                const unsigned int mHit = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int k = __popc(mHit & laneLt);
+                    sbuf[0 * 32 + k] = q.px;
+                    sbuf[1 * 32 + k] = q.py;
+                    sbuf[2 * 32 + k] = q.pz;
+                    sbuf[3 * 32 + k] = q.dx;
+                    sbuf[4 * 32 + k] = q.dy;
+                    sbuf[5 * 32 + k] = q.dz;
+                    sbuf[6 * 32 + k] = q.E;
+                    sbuf[7 * 32 + k] = q.w;
+                    sbuf[8 * 32 + k] = q.remaining;
+                    sbuf[9 * 32 + k] = __int_as_float(lane);
+                    sbuf[10 * 32 + k] = __int_as_float(qpos.i);
+                    sbuf[11 * 32 + k] = qpos.f;
+                    sbuf[12 * 32 + k] = qmu;
+                }
+                bufCount = __popc(mHit);
+                __syncwarp();
+            }
+            // dead lanes pop from the top of the buffer
+            if (status == kStDead) {
+                const int r = __popc(mDead & laneLt);
+                if (r < bufCount) {
+                    const int k = bufCount - 1 - r;
+                    ph.px = sbuf[0 * 32 + k];
+                    ph.py = sbuf[1 * 32 + k];
+                    ph.pz = sbuf[2 * 32 + k];
+                    ph.dx = sbuf[3 * 32 + k];
+                    ph.dy = sbuf[4 * 32 + k];
+                    ph.dz = sbuf[5 * 32 + k];
+                    ph.E = sbuf[6 * 32 + k];
+                    ph.w = sbuf[7 * 32 + k];
+                    ph.remaining = sbuf[8 * 32 + k];
+                    const unsigned long long h = bufBase + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
+                    epos.i = __float_as_int(sbuf[10 * 32 + k]);
+                    epos.f = sbuf[11 * 32 + k];
+                    muMax = sbuf[12 * 32 + k];
+                    muMaxInv = 1.0f / muMax;
+                    // the transport stream of a history starts at Philox block 2 (blocks 0-1 belong to the source)
+                    rng.init(P.seed_lo, P.seed_hi, h);
+                    rng.c2 = 2u;
+                    status = kStStep;
+                }
+            }
+            bufCount -= min(nDead, bufCount);
+            __syncwarp();
+        } else if (phase == 0) {
+            // ------------------------------------------------------------ one tentative Woodcock step
+            float kerma = 0.0f;
+            if (status == kStStep) {
+                const float s = -__logf(1.0f - rng.uniform()) * muMaxInv;
+                if (s >= ph.remaining) {
+                    status = kStDead; // left the grid
+                } else {
+                    ++nSteps;
+                    ph.px = fmaf(ph.dx, s, ph.px);
+                    ph.py = fmaf(ph.dy, s, ph.py);
+                    ph.pz = fmaf(ph.dz, s, ph.pz);
+                    ph.remaining -= s;
+                    int vx = static_cast<int>((ph.px - G.x0) * G.inv_dx);
+                    int vy = static_cast<int>((ph.py - G.y0) * G.inv_dy);
+                    int vz = static_cast<int>((ph.pz - G.z0) * G.inv_dz);
+                    vx = min(max(vx, 0), G.nx - 1);
+                    vy = min(max(vy, 0), G.ny - 1);
+                    vz = min(max(vz, 0), G.nz - 1);
+                    voxel = (static_cast<unsigned int>(vz) * G.ny + vy) * G.nx + vx;
+                    const uint2 vox = __ldg(G.voxels + voxel);
+                    const float rho = __uint_as_float(vox.x);
+                    mat = static_cast<int>(vox.y);
+                    const float* tt = totTable + mat * kDevNE + epos.i;
+                    const float mu = rho * lerp(tt[0], tt[1], epos.f);
+                    const float r = rng.uniform();
+                    if (CALIB && mat == P.score_material) {
+                        // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
+                        const float* et = P.tab.etr + mat * kDevNE + epos.i;
+                        kerma = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
+                    }
+                    if (r * muMax < mu)
+                        status = kStWait;
+                }
+            }
+            if (CALIB) {
+                const unsigned int mScore = __ballot_sync(0xffffffffu, kerma > 0.0f);
+                if (kerma > 0.0f)
+                    scoreEnergy(mScore, G.tally, voxel, kerma, P.tally_scale_e, P.tally_scale_e2);
+            }
+        } else {
+            // ------------------------------------------------------------ real interactions of the waiting lanes
+            float edep = 0.0f;
+            if (status == kStWait) {
+                ++nInter;
+                const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
+                const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
+                const float aPhoto = lerp(a.x, b.x, epos.f);
+                const float aIncoh = lerp(a.y, b.y, epos.f);
+                const float aTot = lerp(a.w, b.w, epos.f);
+                const float r2 = rng.uniform() * aTot;
+                bool alive = true, energyChanged = false, dirChanged = false;
+                if (r2 < aPhoto) {
+                    edep = ph.E * ph.w;
+                    ph.E = 0.0f;
+                    alive = false;
+                } else if (r2 < aPhoto + aIncoh) {
+                    const float de = comptonScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
+                    edep = de * ph.w;
+                    energyChanged = true;
+                    dirChanged = true;
+                } else {
+                    rayleighScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
+                    dirChanged = true;
+                }
+                if (alive) {
+                    if (ph.E < kMinEnergy) {
+                        edep += ph.E * ph.w;
                         ph.E = 0.0f;
                         alive = false;
-                    } else if (r2 < aPhoto + aIncoh) {
-                        const float de = comptonScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
-                        edep = de * ph.w;
-                        energyChanged = true;
-                        dirChanged = true;
-                    } else {
-                        rayleighScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
-                        dirChanged = true;
-                    }
-                    if (alive) {
-                        if (ph.E < kMinEnergy) {
-                            edep += ph.E * ph.w;
-                            ph.E = 0.0f;
+                    } else if (ph.w < kRouletteThreshold) {
+                        if (rng.uniform() < kRouletteKill)
                             alive = false;
-                        } else if (ph.w < kRouletteThreshold) {
-                            if (rng.uniform() < kRouletteKill)
-                                alive = false;
-                            else
-                                ph.w *= 1.0f / (1.0f - kRouletteKill);
-                        }
+                        else
+                            ph.w *= 1.0f / (1.0f - kRouletteKill);
                     }
-                    if (!CALIB && edep > 0.0f) {
-                        ++nDep;
-                        scoreEnergy(G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
+                }
+                if (alive) {
+                    if (energyChanged) {
+                        epos = tabPos<kDevEPerOctave, kDevNE>(ph.E);
+                        muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
+                        muMaxInv = 1.0f / muMax;
                     }
-                    if (alive) {
-                        if (energyChanged) {
-                            epos = tabPos<kDevEPerOctave, kDevNE>(ph.E);
-                            muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
-                            muMaxInv = 1.0f / muMax;
-                        }
-                        if (dirChanged)
-                            ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
-                    }
+                    if (dirChanged)
+                        ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
+                    status = kStStep;
+                } else {
+                    status = kStDead;
+                }
+                if (CALIB)
+                    edep = 0.0f;
+            }
+            if (!CALIB) {
+                const unsigned int mScore = __ballot_sync(0xffffffffu, edep > 0.0f);
+                if (edep > 0.0f) {
+                    ++nDep;
+                    scoreEnergy(mScore, G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
                 }
             }
         }

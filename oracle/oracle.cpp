@@ -23,7 +23,8 @@
 //
 // Random-number protocol (must match opendxmc_b200/csrc/transport.cu draw for draw):
 //   stream(history) = Philox4x32-10, key = seed, counter = (history lo, history hi, block, 0),
-//   words consumed in order; uniform u = (word >> 8) * 2^-24 in [0,1).
+//   words consumed in order; uniform u = (word >> 8) * 2^-24 in [0,1); the source sampler draws from
+//   blocks 0-1, transport (Woodcock steps, interactions) starts at block 2.
 #include "oracle.h"
 
 #include <algorithm>
@@ -85,6 +86,13 @@ struct RandomState {
         ctr[1] = static_cast<uint32_t>(history >> 32);
         ctr[2] = 0;
         ctr[3] = 0;
+    }
+    // [D] the transport stream of a history starts at Philox block 2: blocks 0-1 belong to the source sampler
+    // (the device samples sources warp-cooperatively with a separate generator object, transport.cu)
+    void startTransportStream()
+    {
+        ctr[2] = 2;
+        used = 4;
     }
     double randomUniform()
     {
@@ -939,6 +947,7 @@ void runWorker(AAVoxelGrid& grid, const BeamModel& beam, int correction, uint64_
                 continue;
             RandomState state(seed, history);
             Particle p = beam.sampleParticle(exposure, state);
+            state.startTransportStream();
             ++st.histories;
             st.emitted += p.energy * p.weight;
             grid.transport(p, correction, state, st);

@@ -147,6 +147,7 @@ def test_full_transport_dose_matches_oracle(dx, orc, c1):
     assert abs(mean_gpu - mean_cpu) / mean_cpu < 0.025
     done, total = prog.progress()
     assert done == total > 0
-    # CTDIw-calibrated: dose in the phantom is of the order of the requested CTDIw (1 mGy)
-    assert 0.2 < mean_gpu < 5.0
+    # CTDIw-calibrated (1 mGy): averaged over the whole 36 cm long cylinder the dose is ~ CTDIw * collimation / length
+    expect = c1.beam.CTDIw() * c1.beam.collimation() / (c1.dim[2] * c1.spacing[2])
+    assert abs(mean_gpu - expect) / expect < 0.25, (mean_gpu, expect)
     world.close()
