@@ -105,7 +105,8 @@ typedef struct dxb_shell {
 } dxb_shell;
 
 typedef struct dxb_material_tables {
-    uint32_t n_energy;      /* nodes of the log-uniform energy grid */
+    uint32_t n_energy;      /* nodes of the semi-log energy grid: node(i) = e_min * 2^(i/P) * (1 + (i%P)/P),
+                               P = nodes_per_octave_e (uniform spacing inside each octave) */
     double   e_min_kev, e_max_kev;
     const double* photo;    /* [n_energy] cm2/g */
     const double* incoh;    /* [n_energy] Livermore (S(q)-weighted) */
@@ -113,7 +114,7 @@ typedef struct dxb_material_tables {
     const double* incoh_kn; /* [n_energy] free-electron Klein-Nishina (mode 0) */
     const double* coh_thomson; /* [n_energy] mode-0 value (== coh: DXMClib keeps the cross-section, changes only the angular law) */
     const double* etr;      /* [n_energy] mass energy-transfer coefficient (kerma; CT/DX calibration) */
-    uint32_t n_x;           /* nodes of the log-uniform momentum-transfer grid x [1/Angstrom] */
+    uint32_t n_x;           /* nodes of the semi-log momentum-transfer grid x [1/Angstrom], P = nodes_per_octave_x */
     double   x_min, x_max;
     const double* ff_cdf;   /* [n_x] A(x_k) = integral_0^{x_k^2} F(t)^2 d(t) / Z^2, t = x^2 */
     const double* sf;       /* [n_x] S(x_k)/Z */
@@ -122,6 +123,7 @@ typedef struct dxb_material_tables {
     double   rest_electrons_fraction; /* electrons not covered by `shells` (treated as free, mode 2) */
     double   electrons_per_gram;
     double   effective_z;
+    uint32_t nodes_per_octave_e, nodes_per_octave_x;
 } dxb_material_tables;
 int dxb_material_tables_get(const dxb_material*, dxb_material_tables* out);
 /* library-wide table geometry */

@@ -112,10 +112,14 @@ class Material:
         t = self.tables()
         ne, nx = t.n_energy, t.n_x
         g = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+        def nodes(vmin, n, per):
+            i = np.arange(n)
+            return vmin * np.exp2(i // per) * (1.0 + (i % per) / per)
         return {
-            "energy": t.e_min_kev * np.exp2(np.arange(ne) * np.log2(t.e_max_kev / t.e_min_kev) / (ne - 1)),
+            "energy": nodes(t.e_min_kev, ne, t.nodes_per_octave_e),
             "photo": g(t.photo, ne), "incoh": g(t.incoh, ne), "coh": g(t.coh, ne), "etr": g(t.etr, ne),
-            "x": t.x_min * np.exp2(np.arange(nx) * np.log2(t.x_max / t.x_min) / (nx - 1)),
+            "x": nodes(t.x_min, nx, t.nodes_per_octave_x),
             "ff_cdf": g(t.ff_cdf, nx), "sf": g(t.sf, nx),
         }
 

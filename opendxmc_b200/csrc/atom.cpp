@@ -285,36 +285,44 @@ void buildElement(Element& el)
 
 } // namespace
 
-double energyNode(uint32_t i)
-{
-    return kEMin * std::exp2(static_cast<double>(i) / kENodesPerOctave);
-}
-double xNode(uint32_t i)
-{
-    return kXMin * std::exp2(static_cast<double>(i) / kXNodesPerOctave);
-}
-
+// Both grids are "semi-log": P nodes per octave, uniformly spaced INSIDE each octave,
+//   node(i) = vmin * 2^(i / P) * (1 + (i % P) / P),
+// so that the grid coordinate of a value is its float exponent and leading mantissa bits (index) and the
+// remaining mantissa bits (fraction): exact in f32 and f64, no logarithm in the kernels.
 namespace {
+double semiLogNode(uint32_t i, double vmin, uint32_t perOctave)
+{
+    const uint32_t o = i / perOctave, j = i % perOctave;
+    return vmin * std::ldexp(1.0 + static_cast<double>(j) / perOctave, static_cast<int>(o));
+}
 GridPos gridPos(double v, double vmin, uint32_t perOctave, uint32_t n)
 {
-    const double u = std::log2(v / vmin) * perOctave;
     GridPos p;
-    if (!(u > 0)) {
+    const double r = v / vmin;
+    if (!(r > 1.0)) {
         p.i = 0;
         p.f = 0;
         return p;
     }
-    const uint32_t i = static_cast<uint32_t>(u);
+    int ex = 0;
+    const double m = 2.0 * std::frexp(r, &ex); // r = m * 2^(ex-1), m in [1,2)
+    const double u = (m - 1.0) * perOctave;
+    uint32_t j = static_cast<uint32_t>(u);
+    if (j >= perOctave)
+        j = perOctave - 1;
+    const uint32_t i = static_cast<uint32_t>(ex - 1) * perOctave + j;
     if (i >= n - 1) {
         p.i = n - 2;
         p.f = 1.0;
         return p;
     }
     p.i = i;
-    p.f = u - i;
+    p.f = u - j;
     return p;
 }
 }
+double energyNode(uint32_t i) { return semiLogNode(i, kEMin, kENodesPerOctave); }
+double xNode(uint32_t i) { return semiLogNode(i, kXMin, kXNodesPerOctave); }
 GridPos energyPos(double e) { return gridPos(e, kEMin, kENodesPerOctave, kNEnergy); }
 GridPos xPos(double x) { return gridPos(x, kXMin, kXNodesPerOctave, kNX); }
 double lerpTable(const std::vector<double>& t, GridPos p)

@@ -102,6 +102,8 @@ int dxb_material_tables_get(const dxb_material* m, dxb_material_tables* t)
     t->rest_electrons_fraction = M.restElectronsFraction;
     t->electrons_per_gram = M.electronsPerGram;
     t->effective_z = M.effectiveZ;
+    t->nodes_per_octave_e = kENodesPerOctave;
+    t->nodes_per_octave_x = kXNodesPerOctave;
     return DXB_OK;
 }
 uint32_t dxb_table_n_energy(void) { return kNEnergy; }

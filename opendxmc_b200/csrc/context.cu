@@ -156,6 +156,7 @@ struct Options {
     int tableInSmem = 1;
     int refillThreshold = 6;     // warp phase machine (transport.cu)
     int interactThreshold = 12;
+    int rayleighThreshold = 6;
 };
 
 } // namespace
@@ -441,6 +442,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.score_material = calib ? scoreMaterial : -1;
     P.refill_threshold = std::clamp(c->opt.refillThreshold, 1, 32);
     P.interact_threshold = std::clamp(c->opt.interactThreshold, 1, 32);
+    P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold, 1, 32);
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -915,6 +917,8 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.refillThreshold = static_cast<int>(value);
     } else if (k == "interact_threshold") {
         c->opt.interactThreshold = static_cast<int>(value);
+    } else if (k == "rayleigh_threshold") {
+        c->opt.rayleighThreshold = static_cast<int>(value);
     } else {
         return fail(c, DXB_EINVAL, "unknown option " + k);
     }

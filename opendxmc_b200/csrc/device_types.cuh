@@ -8,8 +8,8 @@ namespace dxb {
 // table geometry, mirrors physics.hpp (static_asserted in context.cu)
 constexpr int kDevNE = 465;
 constexpr int kDevEPerOctave = 64;
-constexpr int kDevNX = 259;
-constexpr int kDevXPerOctave = 24;
+constexpr int kDevNX = 353;
+constexpr int kDevXPerOctave = 32;
 constexpr float kDevXMinInv = 128.0f;
 constexpr int kMaxShells = 5;
 constexpr int kSourceBufWords = 13; // words per entry of the per-warp source buffer (transport.cu)
@@ -85,6 +85,7 @@ struct RunParams {
     int score_material;             // calibration: kerma collision estimator in this material (-1: off)
     int refill_threshold;           // dead lanes per warp that trigger a refill phase
     int interact_threshold;         // waiting lanes per warp that trigger an interaction phase
+    int rayleigh_threshold;         // lanes waiting for a Rayleigh try that trigger a Rayleigh phase
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
 };

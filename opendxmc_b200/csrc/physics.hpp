@@ -30,19 +30,20 @@ constexpr double kKeVperGramToMilliGray = 1.602176634e-10; // 1 keV/g = 1.602e-1
 constexpr double kPi = 3.14159265358979323846;
 
 // ---- table geometry (shared by every material, the device and the oracle) ---
-// Both grids are log-uniform with an INTEGER number of nodes per octave, so that the device can
-// take the integer part of the grid coordinate from the float exponent and the fraction from
-// log2 of the mantissa alone; this keeps f32 lookups within 1e-6 of the f64 ones.
+// Both grids are semi-log: a power-of-two number P of nodes per octave, uniformly spaced inside the octave,
+// node(i) = vmin * 2^(i/P) * (1 + (i%P)/P).  The device reads the grid coordinate straight from the float bit
+// pattern (exponent + top mantissa bits = index, remaining mantissa bits = fraction), which is exact, so f32
+// lookups stay within 1e-6 of the f64 ones and the hot loop needs no logarithm.
 constexpr uint32_t kENodesPerOctave = 64;
 constexpr double kEMin = 1.0;        // keV  (DXMClib MIN_ENERGY, SURVEY.md §8c "1 keV cutoff")
-constexpr double kEMax = 150.0;      // keV  (DXMClib MAX_ENERGY); grid reaches 2^7.25 = 152.2
-constexpr uint32_t kNEnergy = 7 * 64 + 16 + 1; // 465 nodes: 1 .. 2^(464/64) keV
-constexpr uint32_t kXNodesPerOctave = 24;
+constexpr double kEMax = 150.0;      // keV  (DXMClib MAX_ENERGY); grid reaches 128 * (1 + 16/64) = 160
+constexpr uint32_t kNEnergy = 7 * 64 + 16 + 1; // 465 nodes: 1 .. 160 keV
+constexpr uint32_t kXNodesPerOctave = 32;
 constexpr double kXMin = 1.0 / 128.0; // 1/Angstrom
-constexpr uint32_t kNX = 259;        // up to 2^(258/24 - 7) = 13.45 > kEMax/hc = 12.1
-constexpr double kXMax = 13.454342644059432; // kXMin * 2^(258/24)
+constexpr uint32_t kNX = 11 * 32 + 1; // 353 nodes: 2^-7 .. 2^4 = 16 > kEMax/hc = 12.1
+constexpr double kXMax = 16.0;
 
-double energyNode(uint32_t i);       // kEMin * 2^(i/kENodesPerOctave)
+double energyNode(uint32_t i);
 double xNode(uint32_t i);
 
 // ---- elements ----------------------------------------------------------------

@@ -1,17 +1,29 @@
 // transport.cu — the photon-history kernels for sm_100a.
 //
-// One launch = a batch of histories of one beam.  Every lane owns one photon; when it dies the
-// lane takes the next history id from its warp's pool (pools are carved from one global cursor in
-// 256-history pieces), so warps stay full until the batch drains and concurrently resident
-// histories belong to the same / adjacent exposures — the primary-beam slab of the voxel grid
-// then lives in the 126 MB L2.
+// One launch = a batch of histories of one beam.  Histories are handed to warps from one global cursor
+// (256-history pieces), so concurrently resident histories belong to the same / adjacent exposures and the
+// primary-beam slab of the voxel grid stays in the 126 MB L2.
 //
 // Replaces (recalled DXMClib): Transport::runWorker -> exposure.sampleParticle
 // -> World::transport -> AAVoxelGrid::woodcockTransport -> interactions::interact -> EnergyScore.
 // The algorithm and its random-number protocol are restated independently in oracle/oracle.cpp.
 //
-// No tensor cores: nothing here is a dense contraction.  The hot loop is one dependent 8-byte
-// voxel gather per tentative step (HBM/L2 sector bound) + FP32/INT issue (Philox, log, lerp).
+// No tensor cores: nothing here is a dense contraction.  The hot loop is one dependent 8-byte voxel gather
+// per tentative step (HBM/L2 sector bound) + FP32/INT issue (Philox, log, lerp); see DESIGN.md §Kernels.
+//
+// Random-number protocol (mirrored draw for draw by the oracle): stream(history) = Philox4x32-10 with
+// key = seed and counter = (history lo, history hi, block, 0).  A history consumes whole BLOCKS of four
+// 24-bit uniforms, one block per event, so that every lane of a warp that executes an event generates its
+// block at the same time (no divergent generator refills):
+//   blocks 0-1  source sampling (angles, spectrum alias lookup)
+//   then, from block 2 on, one block per
+//     step pair        w0,w1 = length / acceptance of tentative step A, w2,w3 = the same for step B
+//                      (B is only used if A was a virtual collision; otherwise w2,w3 are discarded)
+//     interaction try  w0 = channel choice (first try of an interaction only), w1,w2 = Compton candidate /
+//                      rejection test, w3 = azimuth
+//     Rayleigh try     w0 = form-factor CDF target (Thomson: rejection variable), w1 = rejection test (Thomson:
+//                      polar angle), w2 = azimuth
+//     roulette         w0
 #include "device_types.cuh"
 
 #include <cstdio>
@@ -27,57 +39,36 @@ constexpr float kRouletteThreshold = 0.1f;   // weight below which roulette is p
 constexpr float kRouletteKill = 0.9f;        // kill probability
 constexpr float kTwoPi = 6.283185307179586f;
 constexpr float kPiF = 3.14159265358979f;
+constexpr float kU24 = 5.9604644775390625e-8f; // 2^-24
 
 // ------------------------------------------------------------------ Philox4x32-10
-struct Rng {
-    unsigned int k0, k1;       // key
-    unsigned int c0, c1, c2;   // counter words: history id lo/hi, block index
-    unsigned int buf[4];
-    int have;
-
-    __device__ __forceinline__ void init(unsigned int seed_lo, unsigned int seed_hi, unsigned long long history)
-    {
-        k0 = seed_lo;
-        k1 = seed_hi;
-        c0 = static_cast<unsigned int>(history);
-        c1 = static_cast<unsigned int>(history >> 32);
-        c2 = 0;
-        have = 0;
-    }
-    __device__ __forceinline__ void refill()
-    {
-        unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = 0u;
-        unsigned int ka = k0, kb = k1;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const unsigned int hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-            const unsigned int hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-            x0 = hi1 ^ x1 ^ ka;
-            x1 = lo1;
-            x2 = hi0 ^ x3 ^ kb;
-            x3 = lo0;
-            ka += 0x9E3779B9u;
-            kb += 0xBB67AE85u;
-        }
-        buf[0] = x0;
-        buf[1] = x1;
-        buf[2] = x2;
-        buf[3] = x3;
-        ++c2;
-        have = 4;
-    }
+struct PhiloxBlock {
+    unsigned int w[4];
     // k * 2^-24, k in [0, 2^24): exactly representable, in [0,1)
-    __device__ __forceinline__ float uniform()
-    {
-        if (have == 0)
-            refill();
-        // consume in order buf[0], buf[1], buf[2], buf[3]
-        const int idx = 4 - have;
-        --have;
-        const unsigned int r = idx == 0 ? buf[0] : (idx == 1 ? buf[1] : (idx == 2 ? buf[2] : buf[3]));
-        return static_cast<float>(r >> 8) * 5.9604644775390625e-8f;
-    }
+    __device__ __forceinline__ float u(int i) const { return static_cast<float>(w[i] >> 8) * kU24; }
 };
+
+__device__ __forceinline__ PhiloxBlock philox4x32_10(unsigned int k0, unsigned int k1, unsigned int c0, unsigned int c1, unsigned int c2)
+{
+    unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        x0 = hi1 ^ x1 ^ k0;
+        x1 = lo1;
+        x2 = hi0 ^ x3 ^ k1;
+        x3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    PhiloxBlock b;
+    b.w[0] = x0;
+    b.w[1] = x1;
+    b.w[2] = x2;
+    b.w[3] = x3;
+    return b;
+}
 
 // ------------------------------------------------------------------ table coordinates
 struct TabPos {
@@ -85,25 +76,16 @@ struct TabPos {
     float f;
 };
 
-// grid coordinate of a value on a log-uniform grid with PER nodes per octave starting at 1.0:
-// integer part from the float exponent, fraction from log2(mantissa) only.
-template <int PER, int N>
+// Grid coordinate of v >= 1 on a semi-log grid with PER = 2^LOG2PER nodes per octave (uniform inside the
+// octave, physics.hpp): index = exponent and top mantissa bits, fraction = remaining mantissa bits.  Exact.
+template <int LOG2PER, int N>
 __device__ __forceinline__ TabPos tabPos(float v)
 {
     TabPos p;
-    if (!(v > 1.0f)) {
-        p.i = 0;
-        p.f = 0.0f;
-        return p;
-    }
-    const int bits = __float_as_int(v);
-    const int ex = (bits >> 23) - 127;
-    const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-    const float t = log2f(m) * static_cast<float>(PER);
-    int ti = static_cast<int>(t);
-    ti = min(ti, PER - 1);
-    int i = ex * PER + ti;
-    float f = t - static_cast<float>(ti);
+    const int bits = __float_as_int(fmaxf(v, 1.0f));
+    constexpr int SH = 23 - LOG2PER;
+    int i = (bits >> SH) - (127 << LOG2PER);
+    float f = static_cast<float>(bits & ((1 << SH) - 1)) * (1.0f / static_cast<float>(1 << SH));
     if (i >= N - 1) {
         i = N - 2;
         f = 1.0f;
@@ -112,17 +94,26 @@ __device__ __forceinline__ TabPos tabPos(float v)
     p.f = f;
     return p;
 }
+// value of grid node k (relative to the grid minimum)
+template <int LOG2PER>
+__device__ __forceinline__ float tabNode(int k)
+{
+    return __int_as_float(((127 << LOG2PER) + k) << (23 - LOG2PER));
+}
+constexpr int kLog2EPer = 6, kLog2XPer = 5;
+static_assert((1 << kLog2EPer) == kDevEPerOctave && (1 << kLog2XPer) == kDevXPerOctave, "grid geometry");
+
+__device__ __forceinline__ TabPos energyPos(float e) { return tabPos<kLog2EPer, kDevNE>(e); }
 
 __device__ __forceinline__ float lerp(float a, float b, float f) { return fmaf(f, b - a, a); }
 
 // ------------------------------------------------------------------ geometry helpers
 __device__ __forceinline__ float exitDistance(const GridDev& g, float px, float py, float pz, float dx, float dy, float dz)
 {
-    const float tx = ((dx > 0.0f ? g.x1 : g.x0) - px) / dx;
-    const float ty = ((dy > 0.0f ? g.y1 : g.y0) - py) / dy;
-    const float tz = ((dz > 0.0f ? g.z1 : g.z0) - pz) / dz;
-    // a zero direction component gives +-inf or NaN; fminf drops NaN, and -inf cannot occur for a
-    // point inside the box except exactly on a face
+    const float tx = __fdividef((dx > 0.0f ? g.x1 : g.x0) - px, dx);
+    const float ty = __fdividef((dy > 0.0f ? g.y1 : g.y0) - py, dy);
+    const float tz = __fdividef((dz > 0.0f ? g.z1 : g.z0) - pz, dz);
+    // a zero direction component gives +-inf or NaN: excluded explicitly
     float t = 3.0e38f;
     if (dx != 0.0f)
         t = fminf(t, tx);
@@ -141,8 +132,8 @@ __device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float c
     __sincosf(phi, &sinP, &cosP);
     float nx, ny, nz;
     if (fabsf(dz) < 0.99999f) {
-        const float tmp = sqrtf(1.0f - dz * dz);
-        const float inv = 1.0f / tmp;
+        const float inv = rsqrtf(1.0f - dz * dz);
+        const float tmp = (1.0f - dz * dz) * inv;
         nx = dx * cosT + sinT * (dx * dz * cosP - dy * sinP) * inv;
         ny = dy * cosT + sinT * (dy * dz * cosP + dx * sinP) * inv;
         nz = dz * cosT - tmp * sinT * cosP;
@@ -192,126 +183,104 @@ __device__ __forceinline__ void scoreEnergy(unsigned int mask, unsigned long lon
     }
 }
 
-// ------------------------------------------------------------------ interaction samplers
+// ------------------------------------------------------------------ interaction samplers (one try each)
+// Klein-Nishina candidate e = E'/E uniform in [emin, 1], accepted with g(e)/gmax; MODE >= 1 multiplies the
+// acceptance by the incoherent scatter function S(x)/Z (Livermore).  Returns true if accepted.
 template <int MODE>
-__device__ __forceinline__ float comptonScatter(Rng& rng, const TablesDev& tab, int mat, float& E, float& dx, float& dy, float& dz)
+__device__ __forceinline__ bool comptonTry(const TablesDev& tab, int mat, float E, float r1, float ra, float& e, float& cosT)
 {
-    // Klein-Nishina by rejection on g(e)/gmax with e = E'/E uniform in [emin, 1];
-    // MODE 1 multiplies the acceptance by the incoherent scatter function S(x)/Z.
     const float k = E * (1.0f / kElectronMass);
-    const float emin = 1.0f / (1.0f + 2.0f * k);
-    const float gmaxInv = emin / (1.0f + emin * emin);
-    float e, cosT;
-    bool rejected;
-    do {
-        const float r1 = rng.uniform();
-        e = r1 + (1.0f - r1) * emin;
-        const float t = fminf((1.0f - e) / (k * e), 2.0f);
-        const float sin2 = t * (2.0f - t);
-        cosT = 1.0f - t;
-        float g = (1.0f / e + e - sin2) * gmaxInv;
-        if (MODE >= 1) {
-            const float x = E * (1.0f / kHc) * sqrtf(0.5f * t); // momentum transfer [1/A]
-            float sfv;
-            const float xs = x * kDevXMinInv;
-            if (xs <= 1.0f) {
-                sfv = __ldg(tab.sf + mat * kDevNX) * xs * xs;
-            } else {
-                const TabPos p = tabPos<kDevXPerOctave, kDevNX>(xs);
-                const float* s = tab.sf + mat * kDevNX + p.i;
-                sfv = lerp(__ldg(s), __ldg(s + 1), p.f);
-            }
-            g *= sfv;
+    const float emin = __fdividef(1.0f, 1.0f + 2.0f * k);
+    const float gmaxInv = __fdividef(emin, 1.0f + emin * emin);
+    e = r1 + (1.0f - r1) * emin;
+    const float einv = __fdividef(1.0f, e);
+    const float t = fminf((1.0f - e) * einv * __fdividef(1.0f, k), 2.0f);
+    const float sin2 = t * (2.0f - t);
+    cosT = 1.0f - t;
+    float g = (einv + e - sin2) * gmaxInv;
+    if (MODE >= 1) {
+        const float xs = E * (kDevXMinInv / kHc) * sqrtf(0.5f * t); // momentum transfer in units of the grid minimum
+        float sfv;
+        if (xs <= 1.0f) {
+            sfv = __ldg(tab.sf + mat * kDevNX) * xs * xs;
+        } else {
+            const TabPos p = tabPos<kLog2XPer, kDevNX>(xs);
+            const float* s = tab.sf + mat * kDevNX + p.i;
+            sfv = lerp(__ldg(s), __ldg(s + 1), p.f);
         }
-        rejected = rng.uniform() > g;
-    } while (rejected);
-    const float phi = kTwoPi * rng.uniform();
-    deflect(dx, dy, dz, cosT, phi);
-    const float E0 = E;
-    E = E0 * e;
-    return E0 - E;
+        g *= sfv;
+    }
+    return !(ra > g);
 }
 
+// Rayleigh: MODE 0 Thomson (pdf ~ (1 + cos^2) sin(theta), rejection from a box); MODE >= 1 samples
+// q^2 ~ F(q)^2 on [0, qmax^2] from the tabulated cumulative A(x^2) (piecewise linear in x^2) and accepts with
+// (1 + cos^2)/2.  Returns true if accepted.
 template <int MODE>
-__device__ __forceinline__ void rayleighScatter(Rng& rng, const TablesDev& tab, int mat, float E, float& dx, float& dy, float& dz)
+__device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float E, float r0, float r1, float& cosT)
 {
-    float cosT;
     if (MODE == 0) {
-        // Thomson: pdf ~ (1 + cos^2) sin(theta), rejection from a box
-        bool reject;
-        do {
-            const float r1 = rng.uniform() * 1.0886621079036347f; // 4 sqrt2 / (3 sqrt3)
-            const float theta = kPiF * rng.uniform();
-            float s, c;
-            __sincosf(theta, &s, &c);
-            cosT = c;
-            reject = r1 > (2.0f - s * s) * s;
-        } while (reject);
-    } else {
-        // q^2 ~ F(q)^2 on [0, qmax^2] via the tabulated cumulative A(x^2) (piecewise linear in x^2),
-        // then accept with (1 + cos^2)/2.
-        const float xmax = E * (1.0f / kHc);
-        const float xmax2 = xmax * xmax;
-        const float* cdf = tab.ffcdf + mat * kDevNX;
-        float amax;
-        {
-            const float xs = xmax * kDevXMinInv;
-            if (xs <= 1.0f) {
-                amax = __ldg(cdf) * xs * xs; // F^2 flat below the first node: A = F0^2 x^2
-            } else {
-                const TabPos p = tabPos<kDevXPerOctave, kDevNX>(xs);
-                const float xa = exp2f(static_cast<float>(p.i) * (1.0f / kDevXPerOctave)) * (1.0f / kDevXMinInv);
-                const float xb = exp2f(static_cast<float>(p.i + 1) * (1.0f / kDevXPerOctave)) * (1.0f / kDevXMinInv);
-                const float fa = (xmax2 - xa * xa) / (xb * xb - xa * xa);
-                amax = lerp(__ldg(cdf + p.i), __ldg(cdf + p.i + 1), fminf(fmaxf(fa, 0.0f), 1.0f));
-            }
-        }
-        bool reject;
-        do {
-            const float target = rng.uniform() * amax;
-            float x2;
-            const float a0 = __ldg(cdf);
-            if (target <= a0) {
-                const float x0 = 1.0f / kDevXMinInv;
-                x2 = target / a0 * x0 * x0;
-            } else {
-                // binary search: largest i with A[i] <= target
-                int lo = 0, hi = kDevNX - 1;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(cdf + mid) <= target)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                const float al = __ldg(cdf + lo), ah = __ldg(cdf + lo + 1);
-                const float xa = exp2f(static_cast<float>(lo) * (1.0f / kDevXPerOctave)) * (1.0f / kDevXMinInv);
-                const float xb = exp2f(static_cast<float>(lo + 1) * (1.0f / kDevXPerOctave)) * (1.0f / kDevXMinInv);
-                const float f = ah > al ? (target - al) / (ah - al) : 0.0f;
-                x2 = xa * xa + f * (xb * xb - xa * xa);
-            }
-            x2 = fminf(x2, xmax2);
-            cosT = 1.0f - 2.0f * x2 / xmax2;
-            reject = (1.0f + cosT * cosT) * 0.5f < rng.uniform();
-        } while (reject);
+        const float rr = r0 * 1.0886621079036347f; // 4 sqrt2 / (3 sqrt3)
+        float s, c;
+        __sincosf(kPiF * r1, &s, &c);
+        cosT = c;
+        return !(rr > (2.0f - s * s) * s);
     }
-    const float phi = kTwoPi * rng.uniform();
-    deflect(dx, dy, dz, cosT, phi);
+    const float xmaxs = E * (kDevXMinInv / kHc); // in units of the grid minimum
+    const float xmax2 = xmaxs * xmaxs;
+    const float* cdf = tab.ffcdf + mat * kDevNX;
+    const float a0 = __ldg(cdf);
+    float amax;
+    int top; // the target lies below node `top`
+    if (xmaxs <= 1.0f) {
+        amax = a0 * xmax2; // F^2 flat below the first node: A = F0^2 x^2
+        top = 0;
+    } else {
+        const TabPos p = tabPos<kLog2XPer, kDevNX>(xmaxs);
+        const float xa = tabNode<kLog2XPer>(p.i), xb = tabNode<kLog2XPer>(p.i + 1);
+        const float fa = __fdividef(xmax2 - xa * xa, xb * xb - xa * xa);
+        amax = lerp(__ldg(cdf + p.i), __ldg(cdf + p.i + 1), fminf(fmaxf(fa, 0.0f), 1.0f));
+        top = p.i + 1;
+    }
+    const float target = r0 * amax;
+    float x2;
+    if (target <= a0) {
+        x2 = __fdividef(target, a0);
+    } else {
+        // binary search: largest i with A[i] <= target (target <= amax <= A[top])
+        int lo = 0, hi = top;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) <= target)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const float al = __ldg(cdf + lo), ah = __ldg(cdf + lo + 1);
+        const float xa = tabNode<kLog2XPer>(lo), xb = tabNode<kLog2XPer>(lo + 1);
+        const float f = ah > al ? __fdividef(target - al, ah - al) : 0.0f;
+        x2 = xa * xa + f * (xb * xb - xa * xa);
+    }
+    x2 = fminf(x2, xmax2);
+    cosT = 1.0f - 2.0f * __fdividef(x2, xmax2);
+    return !((1.0f + cosT * cosT) * 0.5f < r1);
 }
 
 // ------------------------------------------------------------------ the history kernel
 //
-// Warp-level phase machine.  Every lane owns at most one photon and is in one of three states:
-//   STEP  tentative Woodcock steps (cheap, executed by most lanes every iteration),
-//   WAIT  a tentative collision was accepted as real; the (expensive, divergent) interaction sampler has
-//         not run yet,
-//   DEAD  no photon; waiting for a new history.
-// Each iteration the warp picks ONE phase by vote: the interaction sampler only runs once `interact_threshold`
-// lanes wait for it (or nobody can step), dead lanes are only refilled once `refill_threshold` of them are dead.
-// Source sampling is warp-cooperative: all 32 lanes sample one history each (full SIMD efficiency, independent
-// of how many lanes are dead), photons that hit the grid are compacted into a per-warp shared-memory buffer,
-// and dead lanes pop from it.  This replaces the one-lane-at-a-time refill/interaction of the first version,
-// whose ncu capture showed 5.4 of 32 lanes active per instruction (profiles/r01_transport_v1.md).
+// Warp-level phase machine.  Every lane owns at most one photon and is in one of these states:
+//   STEP      tentative Woodcock steps (cheap, executed by most lanes every iteration),
+//   WAIT_NEW  a tentative collision was accepted as real; channel not chosen yet,
+//   WAIT_C    Compton chosen, previous candidate rejected; waits for the next interaction phase,
+//   WAIT_R    Rayleigh chosen; waits for a Rayleigh phase,
+//   DEAD      no photon; waiting for a new history.
+// Each iteration the warp picks ONE phase by vote: the (expensive) interaction code only runs once
+// `interact_threshold` lanes wait for it (or nobody can step); every execution of it performs exactly one
+// sampling try per lane, rejected lanes simply stay in their WAIT state, so rejection loops never run with a
+// handful of lanes.  Dead lanes are only refilled once `refill_threshold` of them are dead.  Source sampling is
+// warp-cooperative: all 32 lanes sample one history each, photons that hit the grid are compacted into a
+// per-warp shared-memory buffer, and dead lanes pop from it.  (profiles/r01_kernel_history.md has the ncu
+// numbers that drove this structure: 5.4 -> 12.8 -> ... active lanes per instruction.)
 struct Photon {
     float px, py, pz;
     float dx, dy, dz;
@@ -319,7 +288,7 @@ struct Photon {
     float remaining; // distance to the grid exit along the current direction
 };
 
-constexpr int kStStep = 0, kStWait = 1, kStDead = 2;
+constexpr int kStStep = 0, kStWaitNew = 1, kStWaitC = 2, kStWaitR = 3, kStDead = 4;
 constexpr int kWarpBufFloats = kSourceBufWords * 32; // px py pz dx dy dz E w remaining histOffset epos.i epos.f muMax
 static_assert(kSourceBufWords == 13, "source buffer layout");
 
@@ -341,6 +310,8 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     const float* __restrict__ totTable = SMEM_TABLE ? s_tot : P.tab.tot;
     const GridDev& G = P.grid;
     const unsigned int laneLt = (1u << lane) - 1u;
+    // voxel coordinate = p * inv_d + off (one FMA per axis)
+    const float offx = -G.x0 * G.inv_dx, offy = -G.y0 * G.inv_dy, offz = -G.z0 * G.inv_dz;
 
     // warp-level pool of local history indices (carved from the global cursor in 256-history pieces)
     unsigned long long poolNext = 0, poolEnd = 0;
@@ -348,8 +319,8 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     int bufCount = 0;                 // entries in the warp's source buffer
     unsigned long long bufBase = 0;   // global history id of buffer offset 0
 
-    Rng rng;
     Photon ph;
+    unsigned int hlo = 0, hhi = 0, blk = 2; // Philox counter of this lane's history
     int status = kStDead;
     TabPos epos;
     float muMax = 1.0f, muMaxInv = 1.0f;
@@ -357,32 +328,203 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     int mat = 0;
     epos.i = 0;
     epos.f = 0.0f;
-    ph.remaining = 0.0f;
-    rng.init(P.seed_lo, P.seed_hi, 0ull);
+    ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.E = ph.w = ph.remaining = 0.0f;
 
     unsigned int nSteps = 0, nInter = 0, nDep = 0, nHist = 0;
     unsigned long long emitted = 0;
 
+    // after an accepted scatter: cut-off, roulette, majorant / exit distance refresh
+    auto finishScatter = [&](float& edep, bool energyChanged) {
+        bool alive = true;
+        if (ph.E < kMinEnergy) {
+            edep += ph.E * ph.w;
+            ph.E = 0.0f;
+            alive = false;
+        } else if (ph.w < kRouletteThreshold) {
+            const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+            if (rb.u(0) < kRouletteKill)
+                alive = false;
+            else
+                ph.w *= 1.0f / (1.0f - kRouletteKill);
+        }
+        if (alive) {
+            if (energyChanged) {
+                epos = energyPos(ph.E);
+                muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
+                muMaxInv = __fdividef(1.0f, muMax);
+            }
+            ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
+            status = kStStep;
+        } else {
+            status = kStDead;
+        }
+    };
+
     for (;;) {
         const unsigned int mDead = __ballot_sync(0xffffffffu, status == kStDead);
-        const unsigned int mWait = __ballot_sync(0xffffffffu, status == kStWait);
-        const int nDead = __popc(mDead), nWait = __popc(mWait), nStep = 32 - nDead - nWait;
+        const unsigned int mInt = __ballot_sync(0xffffffffu, status == kStWaitNew || status == kStWaitC);
+        const unsigned int mRay = __ballot_sync(0xffffffffu, status == kStWaitR);
+        const int nDead = __popc(mDead), nInt = __popc(mInt), nRay = __popc(mRay), nStep = 32 - nDead - nInt - nRay;
         const bool canRefill = !(drained && bufCount == 0);
-        int phase; // 0 step, 1 interact, 2 refill
+        int phase; // 0 step, 1 interact, 2 refill, 3 rayleigh
         if (canRefill && nDead >= P.refill_threshold)
             phase = 2;
-        else if (nWait >= P.interact_threshold)
+        else if (nInt >= P.interact_threshold)
             phase = 1;
+        else if (nRay >= P.rayleigh_threshold)
+            phase = 3;
         else if (nStep > 0)
             phase = 0;
-        else if (nWait > 0)
+        else if (nInt > 0)
             phase = 1;
+        else if (nRay > 0)
+            phase = 3;
         else if (canRefill)
             phase = 2;
         else
             break;
 
-        if (phase == 2) {
+        if (phase == 0) {
+            // ------------------------------------------------------------ a pair of tentative Woodcock steps
+            float kermaA = 0.0f, kermaB = 0.0f;
+            unsigned int voxA = 0, voxB = 0;
+            if (status == kStStep) {
+                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                const float sA = -__logf(1.0f - rb.u(0)) * muMaxInv;
+                const float sB = -__logf(1.0f - rb.u(2)) * muMaxInv;
+                const bool inA = sA < ph.remaining;
+                const bool inB = inA && (sA + sB < ph.remaining);
+                const float ax = fmaf(ph.dx, sA, ph.px), ay = fmaf(ph.dy, sA, ph.py), az = fmaf(ph.dz, sA, ph.pz);
+                const float bx = fmaf(ph.dx, sB, ax), by = fmaf(ph.dy, sB, ay), bz = fmaf(ph.dz, sB, az);
+                int ix = static_cast<int>(fmaf(ax, G.inv_dx, offx));
+                int iy = static_cast<int>(fmaf(ay, G.inv_dy, offy));
+                int iz = static_cast<int>(fmaf(az, G.inv_dz, offz));
+                ix = min(max(ix, 0), G.nx - 1);
+                iy = min(max(iy, 0), G.ny - 1);
+                iz = min(max(iz, 0), G.nz - 1);
+                voxA = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
+                ix = static_cast<int>(fmaf(bx, G.inv_dx, offx));
+                iy = static_cast<int>(fmaf(by, G.inv_dy, offy));
+                iz = static_cast<int>(fmaf(bz, G.inv_dz, offz));
+                ix = min(max(ix, 0), G.nx - 1);
+                iy = min(max(iy, 0), G.ny - 1);
+                iz = min(max(iz, 0), G.nz - 1);
+                voxB = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
+                // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
+                uint2 cellA = make_uint2(0u, 0u), cellB = make_uint2(0u, 0u);
+                if (inA)
+                    cellA = __ldg(G.voxels + voxA);
+                if (inB)
+                    cellB = __ldg(G.voxels + voxB);
+                if (!inA) {
+                    status = kStDead; // left the grid
+                } else {
+                    ++nSteps;
+                    const int matA = static_cast<int>(cellA.y);
+                    const float* tt = totTable + matA * kDevNE + epos.i;
+                    const float muA = __uint_as_float(cellA.x) * lerp(tt[0], tt[1], epos.f);
+                    if (CALIB && matA == P.score_material) {
+                        // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
+                        const float* et = P.tab.etr + matA * kDevNE + epos.i;
+                        kermaA = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
+                    }
+                    if (rb.u(1) * muMax < muA) {
+                        ph.px = ax;
+                        ph.py = ay;
+                        ph.pz = az;
+                        ph.remaining -= sA;
+                        voxel = voxA;
+                        mat = matA;
+                        status = kStWaitNew;
+                    } else if (!inB) {
+                        status = kStDead;
+                    } else {
+                        ++nSteps;
+                        const int matB = static_cast<int>(cellB.y);
+                        const float* tb = totTable + matB * kDevNE + epos.i;
+                        const float muB = __uint_as_float(cellB.x) * lerp(tb[0], tb[1], epos.f);
+                        if (CALIB && matB == P.score_material) {
+                            const float* et = P.tab.etr + matB * kDevNE + epos.i;
+                            kermaB = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
+                        }
+                        ph.px = bx;
+                        ph.py = by;
+                        ph.pz = bz;
+                        ph.remaining -= sA + sB;
+                        if (rb.u(3) * muMax < muB) {
+                            voxel = voxB;
+                            mat = matB;
+                            status = kStWaitNew;
+                        }
+                    }
+                }
+            }
+            if (CALIB) {
+                unsigned int mScore = __ballot_sync(0xffffffffu, kermaA > 0.0f);
+                if (kermaA > 0.0f)
+                    scoreEnergy(mScore, G.tally, voxA, kermaA, P.tally_scale_e, P.tally_scale_e2);
+                mScore = __ballot_sync(0xffffffffu, kermaB > 0.0f);
+                if (kermaB > 0.0f)
+                    scoreEnergy(mScore, G.tally, voxB, kermaB, P.tally_scale_e, P.tally_scale_e2);
+            }
+        } else if (phase == 1) {
+            // ------------------------------------------------------------ one interaction try per waiting lane
+            float edep = 0.0f;
+            if (status == kStWaitNew || status == kStWaitC) {
+                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                bool compton = status == kStWaitC;
+                if (status == kStWaitNew) {
+                    ++nInter;
+                    const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
+                    const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
+                    const float aPhoto = lerp(a.x, b.x, epos.f);
+                    const float aIncoh = lerp(a.y, b.y, epos.f);
+                    const float aTot = lerp(a.w, b.w, epos.f);
+                    const float r2 = rb.u(0) * aTot;
+                    if (r2 < aPhoto) {
+                        edep = ph.E * ph.w;
+                        ph.E = 0.0f;
+                        status = kStDead;
+                    } else if (r2 < aPhoto + aIncoh) {
+                        compton = true;
+                    } else {
+                        status = kStWaitR;
+                    }
+                }
+                if (compton) {
+                    float e, cosT;
+                    if (comptonTry<MODE>(P.tab, mat, ph.E, rb.u(1), rb.u(2), e, cosT)) {
+                        deflect(ph.dx, ph.dy, ph.dz, cosT, kTwoPi * rb.u(3));
+                        const float E0 = ph.E;
+                        ph.E = E0 * e;
+                        edep = (E0 - ph.E) * ph.w;
+                        finishScatter(edep, true);
+                    } else {
+                        status = kStWaitC;
+                    }
+                }
+                if (CALIB)
+                    edep = 0.0f;
+            }
+            if (!CALIB) {
+                const unsigned int mScore = __ballot_sync(0xffffffffu, edep > 0.0f);
+                if (edep > 0.0f) {
+                    ++nDep;
+                    scoreEnergy(mScore, G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
+                }
+            }
+        } else if (phase == 3) {
+            // ------------------------------------------------------------ one Rayleigh try per waiting lane
+            if (status == kStWaitR) {
+                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                float cosT;
+                if (rayleighTry<MODE>(P.tab, mat, ph.E, rb.u(0), rb.u(1), cosT)) {
+                    deflect(ph.dx, ph.dy, ph.dz, cosT, kTwoPi * rb.u(2));
+                    float edep = 0.0f; // Rayleigh deposits nothing (E >= cut-off here)
+                    finishScatter(edep, false);
+                }
+            }
+        } else {
             // ------------------------------------------------------------ refill
             if (bufCount == 0) {
                 // warp-cooperative source sampling of the next (up to) 32 histories
@@ -404,8 +546,8 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                 const int nb = static_cast<int>(min(avail, 32ull));
                 // local index -> global history id (65536-history blocks dealt round-robin over ranks); a piece never
                 // straddles a shard block (256 divides 65536), so the 32 ids are consecutive
-                const unsigned long long blk = poolNext / kShardBlock;
-                bufBase = (blk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
+                const unsigned long long sblk = poolNext / kShardBlock;
+                bufBase = (sblk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
                 const unsigned long long h = bufBase + lane;
                 bool hit = false;
                 Photon q;
@@ -415,28 +557,27 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                 qpos.f = 0.0f;
                 q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = q.remaining = 0.0f;
                 if (lane < nb && h < P.n_total) {
-                    Rng srng;
-                    srng.init(P.seed_lo, P.seed_hi, h);
+                    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
+                    const PhiloxBlock s0 = philox4x32_10(P.seed_lo, P.seed_hi, qlo, qhi, 0u);
                     const unsigned long long ei = h / P.ppe;
                     const ExposureDev* ex = P.exposures + ei;
                     const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
-                    const float angx = (2.0f * srng.uniform() - 1.0f) * hx;
-                    const float angy = (2.0f * srng.uniform() - 1.0f) * hy;
+                    const float angx = (2.0f * s0.u(0) - 1.0f) * hx;
+                    const float angy = (2.0f * s0.u(1) - 1.0f) * hy;
                     const int tube = __ldg(&ex->tube);
                     const SpectrumDev& sp = P.spec[tube];
                     float E;
                     if (sp.n <= 1) {
                         E = sp.e0;
                     } else {
-                        const float r0 = srng.uniform();
-                        int idx = min(static_cast<int>(r0 * static_cast<float>(sp.n)), sp.n - 1);
-                        const float r1 = srng.uniform();
-                        if (!(r1 < __ldg(sp.prob + idx)))
+                        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(sp.n)), sp.n - 1);
+                        if (!(s0.u(3) < __ldg(sp.prob + idx)))
                             idx = __ldg(sp.alias + idx);
-                        const float r2 = srng.uniform();
                         E = sp.e0 + static_cast<float>(idx) * sp.step;
-                        if (idx < sp.n - 1)
-                            E += r2 * sp.step;
+                        if (idx < sp.n - 1) {
+                            const PhiloxBlock s1 = philox4x32_10(P.seed_lo, P.seed_hi, qlo, qhi, 1u);
+                            E += s1.u(0) * sp.step;
+                        }
                     }
                     float w = __ldg(&ex->weight);
                     const BowtieDev& bt = P.bow[tube];
@@ -502,7 +643,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                         q.py = fmaf(q.dy, tmin, q.py);
                         q.pz = fmaf(q.dz, tmin, q.pz);
                         q.remaining = tmax - tmin;
-                        qpos = tabPos<kDevEPerOctave, kDevNE>(E);
+                        qpos = energyPos(E);
                         qmu = lerp(__ldg(P.tab.majorant + qpos.i), __ldg(P.tab.majorant + qpos.i + 1), qpos.f);
                         hit = true;
                     }
@@ -546,114 +687,15 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                     epos.i = __float_as_int(sbuf[10 * 32 + k]);
                     epos.f = sbuf[11 * 32 + k];
                     muMax = sbuf[12 * 32 + k];
-                    muMaxInv = 1.0f / muMax;
-                    // the transport stream of a history starts at Philox block 2 (blocks 0-1 belong to the source)
-                    rng.init(P.seed_lo, P.seed_hi, h);
-                    rng.c2 = 2u;
+                    muMaxInv = __fdividef(1.0f, muMax);
+                    hlo = static_cast<unsigned int>(h);
+                    hhi = static_cast<unsigned int>(h >> 32);
+                    blk = 2u; // blocks 0-1 belong to the source
                     status = kStStep;
                 }
             }
             bufCount -= min(nDead, bufCount);
             __syncwarp();
-        } else if (phase == 0) {
-            // ------------------------------------------------------------ one tentative Woodcock step
-            float kerma = 0.0f;
-            if (status == kStStep) {
-                const float s = -__logf(1.0f - rng.uniform()) * muMaxInv;
-                if (s >= ph.remaining) {
-                    status = kStDead; // left the grid
-                } else {
-                    ++nSteps;
-                    ph.px = fmaf(ph.dx, s, ph.px);
-                    ph.py = fmaf(ph.dy, s, ph.py);
-                    ph.pz = fmaf(ph.dz, s, ph.pz);
-                    ph.remaining -= s;
-                    int vx = static_cast<int>((ph.px - G.x0) * G.inv_dx);
-                    int vy = static_cast<int>((ph.py - G.y0) * G.inv_dy);
-                    int vz = static_cast<int>((ph.pz - G.z0) * G.inv_dz);
-                    vx = min(max(vx, 0), G.nx - 1);
-                    vy = min(max(vy, 0), G.ny - 1);
-                    vz = min(max(vz, 0), G.nz - 1);
-                    voxel = (static_cast<unsigned int>(vz) * G.ny + vy) * G.nx + vx;
-                    const uint2 vox = __ldg(G.voxels + voxel);
-                    const float rho = __uint_as_float(vox.x);
-                    mat = static_cast<int>(vox.y);
-                    const float* tt = totTable + mat * kDevNE + epos.i;
-                    const float mu = rho * lerp(tt[0], tt[1], epos.f);
-                    const float r = rng.uniform();
-                    if (CALIB && mat == P.score_material) {
-                        // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
-                        const float* et = P.tab.etr + mat * kDevNE + epos.i;
-                        kerma = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
-                    }
-                    if (r * muMax < mu)
-                        status = kStWait;
-                }
-            }
-            if (CALIB) {
-                const unsigned int mScore = __ballot_sync(0xffffffffu, kerma > 0.0f);
-                if (kerma > 0.0f)
-                    scoreEnergy(mScore, G.tally, voxel, kerma, P.tally_scale_e, P.tally_scale_e2);
-            }
-        } else {
-            // ------------------------------------------------------------ real interactions of the waiting lanes
-            float edep = 0.0f;
-            if (status == kStWait) {
-                ++nInter;
-                const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
-                const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
-                const float aPhoto = lerp(a.x, b.x, epos.f);
-                const float aIncoh = lerp(a.y, b.y, epos.f);
-                const float aTot = lerp(a.w, b.w, epos.f);
-                const float r2 = rng.uniform() * aTot;
-                bool alive = true, energyChanged = false, dirChanged = false;
-                if (r2 < aPhoto) {
-                    edep = ph.E * ph.w;
-                    ph.E = 0.0f;
-                    alive = false;
-                } else if (r2 < aPhoto + aIncoh) {
-                    const float de = comptonScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
-                    edep = de * ph.w;
-                    energyChanged = true;
-                    dirChanged = true;
-                } else {
-                    rayleighScatter<MODE>(rng, P.tab, mat, ph.E, ph.dx, ph.dy, ph.dz);
-                    dirChanged = true;
-                }
-                if (alive) {
-                    if (ph.E < kMinEnergy) {
-                        edep += ph.E * ph.w;
-                        ph.E = 0.0f;
-                        alive = false;
-                    } else if (ph.w < kRouletteThreshold) {
-                        if (rng.uniform() < kRouletteKill)
-                            alive = false;
-                        else
-                            ph.w *= 1.0f / (1.0f - kRouletteKill);
-                    }
-                }
-                if (alive) {
-                    if (energyChanged) {
-                        epos = tabPos<kDevEPerOctave, kDevNE>(ph.E);
-                        muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
-                        muMaxInv = 1.0f / muMax;
-                    }
-                    if (dirChanged)
-                        ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
-                    status = kStStep;
-                } else {
-                    status = kStDead;
-                }
-                if (CALIB)
-                    edep = 0.0f;
-            }
-            if (!CALIB) {
-                const unsigned int mScore = __ballot_sync(0xffffffffu, edep > 0.0f);
-                if (edep > 0.0f) {
-                    ++nDep;
-                    scoreEnergy(mScore, G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
-                }
-            }
         }
     }
 
@@ -849,7 +891,7 @@ __global__ void attenuationProbeKernel(TablesDev tab, int mat, const float* __re
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    const TabPos p = tabPos<kDevEPerOctave, kDevNE>(energy[i]);
+    const TabPos p = energyPos(energy[i]);
     const float4 a = tab.att[mat * kDevNE + p.i];
     const float4 b = tab.att[mat * kDevNE + p.i + 1];
     out4[4 * i + 0] = lerp(a.x, b.x, p.f);
@@ -863,7 +905,7 @@ __global__ void majorantProbeKernel(const float* __restrict__ majorant, const fl
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    const TabPos p = tabPos<kDevEPerOctave, kDevNE>(energy[i]);
+    const TabPos p = energyPos(energy[i]);
     out[i] = lerp(majorant[p.i], majorant[p.i + 1], p.f);
 }
 

@@ -23,8 +23,12 @@
 //
 // Random-number protocol (must match opendxmc_b200/csrc/transport.cu draw for draw):
 //   stream(history) = Philox4x32-10, key = seed, counter = (history lo, history hi, block, 0),
-//   words consumed in order; uniform u = (word >> 8) * 2^-24 in [0,1); the source sampler draws from
-//   blocks 0-1, transport (Woodcock steps, interactions) starts at block 2.
+//   uniform u = (word >> 8) * 2^-24 in [0,1).  The source sampler draws sequentially from blocks 0-1; transport
+//   starts at block 2 and consumes one whole block per event:
+//     step pair        w0,w1 = length / acceptance of tentative step A, w2,w3 = the same for step B (B only if A was virtual)
+//     interaction try  w0 = channel choice (first try only), w1,w2 = Compton candidate / rejection test, w3 = azimuth
+//     Rayleigh try     w0 = CDF target (Thomson: rejection variable), w1 = rejection test (Thomson: polar angle), w2 = azimuth
+//     roulette         w0
 #include "oracle.h"
 
 #include <algorithm>
@@ -94,6 +98,15 @@ struct RandomState {
         ctr[2] = 2;
         used = 4;
     }
+    // four uniforms of the next Philox block (one block per event, see the protocol above)
+    std::array<double, 4> block()
+    {
+        philox(key, ctr, buf);
+        ++ctr[2];
+        used = 4;
+        return { static_cast<double>(buf[0] >> 8) * (1.0 / 16777216.0), static_cast<double>(buf[1] >> 8) * (1.0 / 16777216.0),
+            static_cast<double>(buf[2] >> 8) * (1.0 / 16777216.0), static_cast<double>(buf[3] >> 8) * (1.0 / 16777216.0) };
+    }
     double randomUniform()
     {
         if (used == 4) {
@@ -157,7 +170,7 @@ Vec peturb(const Vec& d, double cosTheta, double phi)
 struct OMaterial {
     uint32_t nE = 0, nX = 0;
     double eMin = 1, xMin = 1;
-    double ePerOctave = 64, xPerOctave = 24;
+    uint32_t ePerOctave = 64, xPerOctave = 32; // semi-log grids: node(i) = vmin 2^(i/P) (1 + (i%P)/P)
     std::vector<double> photo, incoh, coh, etr, ffCdf, sf;
     uint32_t nShells = 0;
     dxb_shell shells[DXB_MAX_SHELLS];
@@ -169,8 +182,8 @@ struct OMaterial {
         nX = t.n_x;
         eMin = t.e_min_kev;
         xMin = t.x_min;
-        ePerOctave = (nE - 1) / std::log2(t.e_max_kev / t.e_min_kev);
-        xPerOctave = (nX - 1) / std::log2(t.x_max / t.x_min);
+        ePerOctave = t.nodes_per_octave_e;
+        xPerOctave = t.nodes_per_octave_x;
         photo.assign(t.photo, t.photo + nE);
         incoh.assign(t.incoh, t.incoh + nE);
         coh.assign(t.coh, t.coh + nE);
@@ -193,9 +206,21 @@ struct OMaterial {
         const double f = u - static_cast<double>(i);
         return tab[i] + f * (tab[i + 1] - tab[i]);
     }
-    double eCoord(double e) const { return std::log2(e / eMin) * ePerOctave; }
-    double xCoord(double x) const { return std::log2(x / xMin) * xPerOctave; }
-    double xNode(size_t k) const { return xMin * std::exp2(static_cast<double>(k) / xPerOctave); }
+    static double semiLogCoord(double v, double vmin, uint32_t per)
+    {
+        const double r = v / vmin;
+        if (!(r > 1.0))
+            return 0.0;
+        int ex = 0;
+        const double m = 2.0 * std::frexp(r, &ex); // r = m 2^(ex-1), m in [1,2)
+        return static_cast<double>(ex - 1) * per + (m - 1.0) * per;
+    }
+    double eCoord(double e) const { return semiLogCoord(e, eMin, ePerOctave); }
+    double xCoord(double x) const { return semiLogCoord(x, xMin, xPerOctave); }
+    double xNode(size_t k) const
+    {
+        return xMin * std::ldexp(1.0 + static_cast<double>(k % xPerOctave) / xPerOctave, static_cast<int>(k / xPerOctave));
+    }
 
     struct AttenuationValues {
         double photoelectric, incoherent, coherent;
@@ -270,30 +295,54 @@ struct InteractionResult {
     bool particleDirectionChanged = false;
 };
 
-double comptonScatter(Particle& p, const OMaterial& material, int correction, RandomState& state, double* eRatio = nullptr,
-    double* cosOut = nullptr)
+// One Klein-Nishina candidate (r1) and rejection test (ra); true if accepted.
+bool comptonTry(double energy, const OMaterial& material, int correction, double r1, double ra, double& e, double& cosTheta)
 {
-    const double k = p.energy / ELECTRON_REST_MASS;
+    const double k = energy / ELECTRON_REST_MASS;
     const double emin = 1.0 / (1.0 + 2.0 * k);
     const double gmaxInv = emin / (1.0 + emin * emin);
+    e = r1 + (1.0 - r1) * emin;
+    const double t = std::min((1.0 - e) / (k * e), 2.0);
+    const double sinthetasqr = t * (2.0 - t);
+    cosTheta = 1.0 - t;
+    double g = (1.0 / e + e - sinthetasqr) * gmaxInv;
+    if (correction >= 1) {
+        // momentumTransferCosAngle(E, cos) = E/hc * sqrt((1-cos)/2)
+        const double q = energy / HC * std::sqrt(0.5 * t);
+        g *= material.scatterFactor(q);
+    }
+    return !(ra > g);
+}
+
+// One Rayleigh try; true if accepted.
+bool rayleighTry(double energy, const OMaterial& material, int correction, double r0, double r1, double& cosAngle)
+{
+    if (correction == 0) {
+        constexpr double extreme = 1.0886621079036347; // 4 sqrt2 / (3 sqrt3)
+        const double rr = r0 * extreme;
+        const double theta = PI * r1;
+        const double sinang = std::sin(theta);
+        cosAngle = std::cos(theta);
+        return !(rr > (2.0 - sinang * sinang) * sinang);
+    }
+    const double qmax = energy / HC;
+    const double qmax_squared = qmax * qmax;
+    const double amax = material.formFactorCumulative(qmax);
+    const double target = r0 * amax;
+    const double q_squared = std::min(material.sampleSquaredMomentumTransfer(target), qmax_squared);
+    cosAngle = 1.0 - 2.0 * q_squared / qmax_squared;
+    return !((1.0 + cosAngle * cosAngle) * 0.5 < r1);
+}
+
+double comptonScatter(Particle& p, const OMaterial& material, int correction, RandomState& state, const std::array<double, 4>* first,
+    double* eRatio = nullptr, double* cosOut = nullptr)
+{
+    // the first try may share its block with the channel choice (words 1..3 of *first)
+    std::array<double, 4> u = first ? *first : state.block();
     double e, cosTheta;
-    bool rejected;
-    do {
-        const double r1 = state.randomUniform();
-        e = r1 + (1.0 - r1) * emin;
-        const double t = std::min((1.0 - e) / (k * e), 2.0);
-        const double sinthetasqr = t * (2.0 - t);
-        cosTheta = 1.0 - t;
-        double g = (1.0 / e + e - sinthetasqr) * gmaxInv;
-        if (correction >= 1) {
-            // momentumTransferCosAngle(E, cos) = E/hc * sqrt((1-cos)/2)
-            const double q = p.energy / HC * std::sqrt(0.5 * t);
-            g *= material.scatterFactor(q);
-        }
-        rejected = state.randomUniform() > g;
-    } while (rejected);
-    const double phi = 2.0 * PI * state.randomUniform();
-    p.dir = peturb(p.dir, cosTheta, phi);
+    while (!comptonTry(p.energy, material, correction, u[1], u[2], e, cosTheta))
+        u = state.block();
+    p.dir = peturb(p.dir, cosTheta, 2.0 * PI * u[3]);
     const double E = p.energy;
     p.energy *= e;
     if (eRatio)
@@ -305,31 +354,11 @@ double comptonScatter(Particle& p, const OMaterial& material, int correction, Ra
 
 void rayleightScatter(Particle& p, const OMaterial& material, int correction, RandomState& state, double* cosOut = nullptr)
 {
+    std::array<double, 4> u = state.block();
     double cosAngle;
-    if (correction == 0) {
-        bool reject;
-        do {
-            constexpr double extreme = 1.0886621079036347; // 4 sqrt2 / (3 sqrt3)
-            const double r1 = state.randomUniform() * extreme;
-            const double theta = PI * state.randomUniform();
-            const double sinang = std::sin(theta);
-            cosAngle = std::cos(theta);
-            reject = r1 > (2.0 - sinang * sinang) * sinang;
-        } while (reject);
-    } else {
-        const double qmax = p.energy / HC;
-        const double qmax_squared = qmax * qmax;
-        const double amax = material.formFactorCumulative(qmax);
-        bool reject;
-        do {
-            const double target = state.randomUniform() * amax;
-            const double q_squared = std::min(material.sampleSquaredMomentumTransfer(target), qmax_squared);
-            cosAngle = 1.0 - 2.0 * q_squared / qmax_squared;
-            reject = (1.0 + cosAngle * cosAngle) * 0.5 < state.randomUniform();
-        } while (reject);
-    }
-    const double phi = 2.0 * PI * state.randomUniform();
-    p.dir = peturb(p.dir, cosAngle, phi);
+    while (!rayleighTry(p.energy, material, correction, u[0], u[1], cosAngle))
+        u = state.block();
+    p.dir = peturb(p.dir, cosAngle, 2.0 * PI * u[2]);
     if (cosOut)
         *cosOut = cosAngle;
 }
@@ -338,14 +367,15 @@ InteractionResult interact(const OMaterial::AttenuationValues& att, Particle& p,
     RandomState& state)
 {
     InteractionResult res;
-    const double r2 = state.randomUniform() * att.sum();
+    const std::array<double, 4> u = state.block();
+    const double r2 = u[0] * att.sum();
     if (r2 < att.photoelectric) {
         res.energyImparted = p.energy * p.weight;
         p.energy = 0;
         res.particleAlive = false;
         res.particleEnergyChanged = true;
     } else if (r2 < att.photoelectric + att.incoherent) {
-        res.energyImparted = comptonScatter(p, material, correction, state);
+        res.energyImparted = comptonScatter(p, material, correction, state, &u);
         res.particleEnergyChanged = true;
         res.particleDirectionChanged = true;
     } else {
@@ -358,7 +388,7 @@ InteractionResult interact(const OMaterial::AttenuationValues& att, Particle& p,
             p.energy = 0;
             res.particleAlive = false;
         } else if (p.weight < RUSSIAN_ROULETTE_THRESHOLD) {
-            if (state.randomUniform() < RUSSIAN_ROULETTE_PROBABILITY)
+            if (state.block()[0] < RUSSIAN_ROULETTE_PROBABILITY)
                 res.particleAlive = false;
             else
                 p.weight *= 1.0 / (1.0 - RUSSIAN_ROULETTE_PROBABILITY);
@@ -495,9 +525,16 @@ struct AAVoxelGrid {
                 attMaxInv = 1.0 / attMax;
                 updateAtt = false;
             }
-            const double steplen = -std::log(1.0 - state.randomUniform()) * attMaxInv;
-            const double toExit = exitDistance(p);
-            if (steplen < toExit) {
+            // one Philox block serves a pair of tentative steps; the second half is discarded if the first step
+            // was a real interaction or left the grid [D]
+            const std::array<double, 4> u = state.block();
+            for (int half = 0; half < 2 && still_inside; ++half) {
+                const double steplen = -std::log(1.0 - u[2 * half]) * attMaxInv;
+                const double toExit = exitDistance(p);
+                if (!(steplen < toExit)) {
+                    still_inside = false;
+                    break;
+                }
                 ++st.steps;
                 p.translate(steplen);
                 const size_t flat = flatIndex(p.pos);
@@ -506,12 +543,11 @@ struct AAVoxelGrid {
                 const OMaterial& mat = materials[matInd];
                 const auto att = mat.attenuationValues(p.energy);
                 const double attSum = att.sum() * dens;
-                const double r = state.randomUniform();
                 if (scoreMaterial >= 0 && matInd == scoreMaterial) {
                     // [D] collision estimator of air kerma: each tentative collision stands for 1/mu_max of track
                     scoreEnergy(flat, p.weight * p.energy * mat.massEnergyTransfer(p.energy) * attMaxInv);
                 }
-                if (r * attMax < attSum) {
+                if (u[2 * half + 1] * attMax < attSum) {
                     ++st.interactions;
                     const auto res = interact(att, p, mat, correction, state);
                     if (scoreMaterial < 0 && res.energyImparted > 0) {
@@ -520,9 +556,8 @@ struct AAVoxelGrid {
                     }
                     still_inside = res.particleAlive;
                     updateAtt = res.particleEnergyChanged;
+                    break;
                 }
-            } else {
-                still_inside = false;
             }
         }
     }
@@ -1241,7 +1276,7 @@ void orc_sample_compton(const dxb_material_tables* t, int mode, double energy, u
     for (uint64_t i = 0; i < n; ++i) {
         RandomState st(seed, i);
         Particle p { { 0, 0, 0 }, { 0, 0, 1 }, energy, 1.0 };
-        comptonScatter(p, m, mode, st, ratio ? ratio + i : nullptr, cosT ? cosT + i : nullptr);
+        comptonScatter(p, m, mode, st, nullptr, ratio ? ratio + i : nullptr, cosT ? cosT + i : nullptr);
     }
 }
 void orc_sample_rayleigh(const dxb_material_tables* t, int mode, double energy, uint64_t seed, uint64_t n, double* cosT)
