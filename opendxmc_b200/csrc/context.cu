@@ -88,7 +88,7 @@ struct World {
     double center[3] = { 0, 0, 0 };
     size_t nvox = 0;
     int n_mat = 0;
-    DevBuf<uint2> voxels;
+    DevBuf<unsigned int> voxels;
     DevBuf<unsigned long long> tally; // 4 words / voxel
     DevBuf<float4> att;
     DevBuf<float> tot, etr, majorant, ffcdf, sf;
@@ -113,6 +113,9 @@ struct World {
         g.inv_dx = static_cast<float>(1.0 / spacing[0]);
         g.inv_dy = static_cast<float>(1.0 / spacing[1]);
         g.inv_dz = static_cast<float>(1.0 / spacing[2]);
+        g.offx = -g.x0 * g.inv_dx;
+        g.offy = -g.y0 * g.inv_dy;
+        g.offz = -g.z0 * g.inv_dz;
         g.voxels = voxels.p;
         g.tally = tally.p;
         return g;
@@ -154,9 +157,9 @@ struct Options {
     int threads = 256;
     int blocksPerSm = 0;         // 0: occupancy query
     int tableInSmem = 1;
-    int refillThreshold = 6;     // warp phase machine (transport.cu)
+    int refillThreshold = 4;     // warp phase machine (transport.cu)
     int interactThreshold = 12;
-    int rayleighThreshold = 6;
+    int rayleighThreshold = 4;
 };
 
 } // namespace
@@ -437,6 +440,10 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.rank = static_cast<unsigned int>(rank);
     P.seed_lo = static_cast<unsigned int>(c->seed);
     P.seed_hi = static_cast<unsigned int>(c->seed >> 32);
+    for (unsigned int r = 0; r < 10; ++r) {
+        P.round_key[r][0] = P.seed_lo + r * 0x9E3779B9u;
+        P.round_key[r][1] = P.seed_hi + r * 0xBB67AE85u;
+    }
     P.tally_scale_e = c->scaleE;
     P.tally_scale_e2 = c->scaleE2;
     P.score_material = calib ? scoreMaterial : -1;
@@ -450,8 +457,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.threads = c->opt.threads;
     const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
-    const size_t bufBytes = static_cast<size_t>(cfg.threads / 32) * kSourceBufWords * 32 * sizeof(float);
-    cfg.smem = bufBytes + (cfg.table_in_smem ? tableBytes : 0);
+    cfg.smem = transportSmemBytes(cfg.threads, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
         perSm = transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);

@@ -16,7 +16,8 @@ constexpr int kSourceBufWords = 13; // words per entry of the per-warp source bu
 
 // HBM layout of the voxel grid (x fastest, like the reference: i + j*nx + k*nx*ny,
 // R:src/libopendxmc/otherphantomimportpipeline.cpp:44).
-//   voxels : uint2 {float density bits, material index}      8 B / voxel
+//   voxels : u32 {top 24 bits of the f32 density (round to nearest, 2^-17 relative), material index}   4 B / voxel
+//            (the 3.84 cm primary-beam slab of config C2 is then 40 MB and stays resident in the 126 MB L2)
 //   tally  : 4 x u64 {sum E, sum E^2, events, pad}           32 B / voxel = one DRAM sector,
 //            64-bit fixed point so that sums are order independent
 //   dose   : 3 x f64 {dose, variance, events} accumulated over beams (DoseScore)
@@ -25,9 +26,17 @@ struct GridDev {
     float x0, y0, z0; // min corner [cm]
     float x1, y1, z1; // max corner
     float inv_dx, inv_dy, inv_dz;
-    const uint2* __restrict__ voxels;
+    float offx, offy, offz; // voxel coordinate = p * inv_d + off
+    const unsigned int* __restrict__ voxels;
     unsigned long long* __restrict__ tally;
 };
+
+// packed voxel helpers
+__host__ __device__ inline unsigned int quantizeDensityBits(unsigned int f32bits) { return (f32bits + 0x80u) & 0xFFFFFF00u; }
+#ifdef __CUDACC__
+__device__ __forceinline__ float voxelDensity(unsigned int v) { return __uint_as_float(v & 0xFFFFFF00u); }
+__device__ __forceinline__ int voxelMaterial(unsigned int v) { return static_cast<int>(v & 0xFFu); }
+#endif
 
 struct ShellDev {
     float binding, nel_fraction, photo_fraction, fluor_yield, fluor_energy, j0, pad0, pad1;
@@ -81,6 +90,7 @@ struct RunParams {
     unsigned long long local_end;
     unsigned int world, rank;       // history sharding: 65536-history blocks dealt round-robin
     unsigned int seed_lo, seed_hi;  // Philox key
+    unsigned int round_key[10][2];  // Philox round keys (key + r * Weyl constants), read from the constant bank
     float tally_scale_e, tally_scale_e2;
     int score_material;             // calibration: kerma collision estimator in this material (-1: off)
     int refill_threshold;           // dead lanes per warp that trigger a refill phase
@@ -91,6 +101,16 @@ struct RunParams {
 };
 
 constexpr unsigned int kShardBlock = 65536; // histories per sharding block
+
+// dynamic shared memory of the transport kernel:
+//   [per warp: 4 x u64 history-pool words][per warp: source buffer, kSourceBufWords x 32 words]
+//   [per thread: kLaneCounters words][optional: total-attenuation table, n_mat x kDevNE floats]
+constexpr int kLaneCounters = 5; // interactions, deposits, histories, emitted lo, emitted hi
+__host__ __device__ inline size_t transportSmemBytes(int threads, int table_floats)
+{
+    const size_t warps = static_cast<size_t>(threads) / 32;
+    return warps * 32 + warps * kSourceBufWords * 32 * 4 + static_cast<size_t>(threads) * kLaneCounters * 4 + static_cast<size_t>(table_floats) * 4;
+}
 
 // launch wrappers (transport.cu)
 struct LaunchConfig {

@@ -5,17 +5,17 @@
 namespace dxb {
 cudaError_t launchTransport(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream);
 int transportOccupancy(int mode, bool calib, bool smemTable, int threads, size_t smem);
-void launchPackVoxels(const double* density, const unsigned char* material, uint2* out, size_t n, unsigned int* maxBits, cudaStream_t s);
+void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s);
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s);
-void launchEnergyToDose(const unsigned long long* tally, const uint2* voxels, double* dose, double* variance,
+void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,
     unsigned long long* events, size_t n, double inv_e, double inv_e2, double factor, double vol, cudaStream_t s);
 void launchTallyToEnergy(const unsigned long long* tally, double* e, double* e2, unsigned long long* cnt, size_t n,
     double inv_e, double inv_e2, cudaStream_t s);
 void launchPeerReduce(unsigned long long* dst, const unsigned long long* const* peers, int n_peers, size_t n_words, cudaStream_t s);
-void launchPostprocess(const double* in, const uint2* voxels, double* out, size_t n, int maskAir, double scale, cudaStream_t s);
-void launchU64ToDouble(const unsigned long long* in, const uint2* voxels, double* out, size_t n, int maskAir, cudaStream_t s);
-void launchMax(const double* in, const uint2* voxels, size_t n, int maskAir, unsigned long long* outBits, cudaStream_t s);
-void launchOrganDose(const double* dose, const double* variance, const uint2* voxels, const unsigned char* organ, size_t n,
+void launchPostprocess(const double* in, const unsigned int* voxels, double* out, size_t n, int maskAir, double scale, cudaStream_t s);
+void launchU64ToDouble(const unsigned long long* in, const unsigned int* voxels, double* out, size_t n, int maskAir, cudaStream_t s);
+void launchMax(const double* in, const unsigned int* voxels, size_t n, int maskAir, unsigned long long* outBits, cudaStream_t s);
+void launchOrganDose(const double* dose, const double* variance, const unsigned int* voxels, const unsigned char* organ, size_t n,
     double vol, double* energy, double* mass, unsigned long long* count, double* varEnergy, cudaStream_t s);
 void launchAttenuationProbe(const TablesDev& tab, int mat, const float* energy, int n, float* out4, cudaStream_t s);
 void launchMajorantProbe(const float* majorant, const float* energy, int n, float* out, cudaStream_t s);

@@ -48,19 +48,18 @@ struct PhiloxBlock {
     __device__ __forceinline__ float u(int i) const { return static_cast<float>(w[i] >> 8) * kU24; }
 };
 
-__device__ __forceinline__ PhiloxBlock philox4x32_10(unsigned int k0, unsigned int k1, unsigned int c0, unsigned int c1, unsigned int c2)
+// rk = the ten round keys (key + r * Weyl constants), precomputed on the host and read as constant-bank operands
+__device__ __forceinline__ PhiloxBlock philox4x32_10(const unsigned int (&rk)[10][2], unsigned int c0, unsigned int c1, unsigned int c2)
 {
     unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = 0u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const unsigned int hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
         const unsigned int hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-        x0 = hi1 ^ x1 ^ k0;
+        x0 = hi1 ^ x1 ^ rk[r][0];
         x1 = lo1;
-        x2 = hi0 ^ x3 ^ k1;
+        x2 = hi0 ^ x3 ^ rk[r][1];
         x3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     PhiloxBlock b;
     b.w[0] = x0;
@@ -288,19 +287,33 @@ struct Photon {
     float remaining; // distance to the grid exit along the current direction
 };
 
-constexpr int kStStep = 0, kStWaitNew = 1, kStWaitC = 2, kStWaitR = 3, kStDead = 4;
+// state values double as vote increments: one __reduce_add_sync gives all lane counts (dead: bits 0-7,
+// waiting for an interaction try: bits 8-15, waiting for a Rayleigh try: bits 16-23; bit 30 only tags WAIT_C)
+constexpr int kStStep = 0, kStDead = 1, kStWaitNew = 0x100, kStWaitC = 0x100 | (1 << 30), kStWaitR = 0x10000;
 constexpr int kWarpBufFloats = kSourceBufWords * 32; // px py pz dx dy dz E w remaining histOffset epos.i epos.f muMax
 static_assert(kSourceBufWords == 13, "source buffer layout");
 
 template <int MODE, bool CALIB, bool SMEM_TABLE>
-__global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant__ RunParams P)
+__global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant__ RunParams P)
 {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nWarps = blockDim.x >> 5;
+    // layout: see transportSmemBytes (device_types.cuh)
+    unsigned long long* __restrict__ spool = reinterpret_cast<unsigned long long*>(s_raw) + warp * 4; // poolNext, poolEnd, bufBase
+    float* __restrict__ s_dyn = reinterpret_cast<float*>(s_raw + nWarps * 32);
     float* __restrict__ sbuf = s_dyn + warp * kWarpBufFloats; // SoA: word f of entry k at sbuf[f * 32 + k]
-    float* __restrict__ s_tot = s_dyn + nWarps * kWarpBufFloats;
+    unsigned int* __restrict__ scnt = reinterpret_cast<unsigned int*>(s_dyn + nWarps * kWarpBufFloats) + threadIdx.x; // stride blockDim.x
+    float* __restrict__ s_tot = s_dyn + nWarps * kWarpBufFloats + blockDim.x * kLaneCounters;
+    for (int k = 0; k < kLaneCounters; ++k)
+        scnt[k * blockDim.x] = 0u;
+    if (lane == 0) {
+        spool[0] = 0ull;
+        spool[1] = 0ull;
+        spool[2] = 0ull;
+    }
+    __syncwarp();
     if (SMEM_TABLE) {
         const int n = P.tab.n_mat * kDevNE;
         for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -309,15 +322,10 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     }
     const float* __restrict__ totTable = SMEM_TABLE ? s_tot : P.tab.tot;
     const GridDev& G = P.grid;
-    const unsigned int laneLt = (1u << lane) - 1u;
-    // voxel coordinate = p * inv_d + off (one FMA per axis)
-    const float offx = -G.x0 * G.inv_dx, offy = -G.y0 * G.inv_dy, offz = -G.z0 * G.inv_dz;
-
-    // warp-level pool of local history indices (carved from the global cursor in 256-history pieces)
-    unsigned long long poolNext = 0, poolEnd = 0;
+    // the warp's pool of local history indices (carved from the global cursor in 256-history pieces) lives in
+    // shared memory (spool); only the refill phase touches it
     bool drained = false;
     int bufCount = 0;                 // entries in the warp's source buffer
-    unsigned long long bufBase = 0;   // global history id of buffer offset 0
 
     Photon ph;
     unsigned int hlo = 0, hhi = 0, blk = 2; // Philox counter of this lane's history
@@ -330,8 +338,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     epos.f = 0.0f;
     ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.E = ph.w = ph.remaining = 0.0f;
 
-    unsigned int nSteps = 0, nInter = 0, nDep = 0, nHist = 0;
-    unsigned long long emitted = 0;
+    unsigned int nSteps = 0; // the other per-lane counters live in shared memory (scnt)
 
     // after an accepted scatter: cut-off, roulette, majorant / exit distance refresh
     auto finishScatter = [&](float& edep, bool energyChanged) {
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
             ph.E = 0.0f;
             alive = false;
         } else if (ph.w < kRouletteThreshold) {
-            const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+            const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
             if (rb.u(0) < kRouletteKill)
                 alive = false;
             else
@@ -361,10 +368,8 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     };
 
     for (;;) {
-        const unsigned int mDead = __ballot_sync(0xffffffffu, status == kStDead);
-        const unsigned int mInt = __ballot_sync(0xffffffffu, status == kStWaitNew || status == kStWaitC);
-        const unsigned int mRay = __ballot_sync(0xffffffffu, status == kStWaitR);
-        const int nDead = __popc(mDead), nInt = __popc(mInt), nRay = __popc(mRay), nStep = 32 - nDead - nInt - nRay;
+        const unsigned int votes = __reduce_add_sync(0xffffffffu, static_cast<unsigned int>(status) & 0x00ffffffu);
+        const int nDead = votes & 0xff, nInt = (votes >> 8) & 0xff, nRay = (votes >> 16) & 0xff, nStep = 32 - nDead - nInt - nRay;
         const bool canRefill = !(drained && bufCount == 0);
         int phase; // 0 step, 1 interact, 2 refill, 3 rayleigh
         if (canRefill && nDead >= P.refill_threshold)
@@ -389,29 +394,29 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
             float kermaA = 0.0f, kermaB = 0.0f;
             unsigned int voxA = 0, voxB = 0;
             if (status == kStStep) {
-                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
                 const float sA = -__logf(1.0f - rb.u(0)) * muMaxInv;
                 const float sB = -__logf(1.0f - rb.u(2)) * muMaxInv;
                 const bool inA = sA < ph.remaining;
                 const bool inB = inA && (sA + sB < ph.remaining);
                 const float ax = fmaf(ph.dx, sA, ph.px), ay = fmaf(ph.dy, sA, ph.py), az = fmaf(ph.dz, sA, ph.pz);
                 const float bx = fmaf(ph.dx, sB, ax), by = fmaf(ph.dy, sB, ay), bz = fmaf(ph.dz, sB, az);
-                int ix = static_cast<int>(fmaf(ax, G.inv_dx, offx));
-                int iy = static_cast<int>(fmaf(ay, G.inv_dy, offy));
-                int iz = static_cast<int>(fmaf(az, G.inv_dz, offz));
+                int ix = static_cast<int>(fmaf(ax, G.inv_dx, G.offx));
+                int iy = static_cast<int>(fmaf(ay, G.inv_dy, G.offy));
+                int iz = static_cast<int>(fmaf(az, G.inv_dz, G.offz));
                 ix = min(max(ix, 0), G.nx - 1);
                 iy = min(max(iy, 0), G.ny - 1);
                 iz = min(max(iz, 0), G.nz - 1);
                 voxA = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
-                ix = static_cast<int>(fmaf(bx, G.inv_dx, offx));
-                iy = static_cast<int>(fmaf(by, G.inv_dy, offy));
-                iz = static_cast<int>(fmaf(bz, G.inv_dz, offz));
+                ix = static_cast<int>(fmaf(bx, G.inv_dx, G.offx));
+                iy = static_cast<int>(fmaf(by, G.inv_dy, G.offy));
+                iz = static_cast<int>(fmaf(bz, G.inv_dz, G.offz));
                 ix = min(max(ix, 0), G.nx - 1);
                 iy = min(max(iy, 0), G.ny - 1);
                 iz = min(max(iz, 0), G.nz - 1);
                 voxB = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
                 // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
-                uint2 cellA = make_uint2(0u, 0u), cellB = make_uint2(0u, 0u);
+                unsigned int cellA = 0u, cellB = 0u;
                 if (inA)
                     cellA = __ldg(G.voxels + voxA);
                 if (inB)
@@ -420,9 +425,9 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                     status = kStDead; // left the grid
                 } else {
                     ++nSteps;
-                    const int matA = static_cast<int>(cellA.y);
+                    const int matA = voxelMaterial(cellA);
                     const float* tt = totTable + matA * kDevNE + epos.i;
-                    const float muA = __uint_as_float(cellA.x) * lerp(tt[0], tt[1], epos.f);
+                    const float muA = voxelDensity(cellA) * lerp(tt[0], tt[1], epos.f);
                     if (CALIB && matA == P.score_material) {
                         // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
                         const float* et = P.tab.etr + matA * kDevNE + epos.i;
@@ -440,9 +445,9 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                         status = kStDead;
                     } else {
                         ++nSteps;
-                        const int matB = static_cast<int>(cellB.y);
+                        const int matB = voxelMaterial(cellB);
                         const float* tb = totTable + matB * kDevNE + epos.i;
-                        const float muB = __uint_as_float(cellB.x) * lerp(tb[0], tb[1], epos.f);
+                        const float muB = voxelDensity(cellB) * lerp(tb[0], tb[1], epos.f);
                         if (CALIB && matB == P.score_material) {
                             const float* et = P.tab.etr + matB * kDevNE + epos.i;
                             kermaB = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
@@ -471,10 +476,10 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
             // ------------------------------------------------------------ one interaction try per waiting lane
             float edep = 0.0f;
             if (status == kStWaitNew || status == kStWaitC) {
-                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
                 bool compton = status == kStWaitC;
                 if (status == kStWaitNew) {
-                    ++nInter;
+                    scnt[0] += 1u;
                     const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
                     const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
                     const float aPhoto = lerp(a.x, b.x, epos.f);
@@ -509,14 +514,14 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
             if (!CALIB) {
                 const unsigned int mScore = __ballot_sync(0xffffffffu, edep > 0.0f);
                 if (edep > 0.0f) {
-                    ++nDep;
+                    scnt[blockDim.x] += 1u;
                     scoreEnergy(mScore, G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
                 }
             }
         } else if (phase == 3) {
             // ------------------------------------------------------------ one Rayleigh try per waiting lane
             if (status == kStWaitR) {
-                const PhiloxBlock rb = philox4x32_10(P.seed_lo, P.seed_hi, hlo, hhi, blk++);
+                const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
                 float cosT;
                 if (rayleighTry<MODE>(P.tab, mat, ph.E, rb.u(0), rb.u(1), cosT)) {
                     deflect(ph.dx, ph.dy, ph.dz, cosT, kTwoPi * rb.u(2));
@@ -526,8 +531,10 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
             }
         } else {
             // ------------------------------------------------------------ refill
+            const unsigned int laneLt = (1u << lane) - 1u;
             if (bufCount == 0) {
                 // warp-cooperative source sampling of the next (up to) 32 histories
+                unsigned long long poolNext = spool[0], poolEnd = spool[1];
                 if (poolNext == poolEnd && !drained) {
                     constexpr unsigned long long kPiece = 256;
                     unsigned long long base = 0;
@@ -547,7 +554,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                 // local index -> global history id (65536-history blocks dealt round-robin over ranks); a piece never
                 // straddles a shard block (256 divides 65536), so the 32 ids are consecutive
                 const unsigned long long sblk = poolNext / kShardBlock;
-                bufBase = (sblk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
+                const unsigned long long bufBase = (sblk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
                 const unsigned long long h = bufBase + lane;
                 bool hit = false;
                 Photon q;
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                 q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = q.remaining = 0.0f;
                 if (lane < nb && h < P.n_total) {
                     const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
-                    const PhiloxBlock s0 = philox4x32_10(P.seed_lo, P.seed_hi, qlo, qhi, 0u);
+                    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
                     const unsigned long long ei = h / P.ppe;
                     const ExposureDev* ex = P.exposures + ei;
                     const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
@@ -575,7 +582,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                             idx = __ldg(sp.alias + idx);
                         E = sp.e0 + static_cast<float>(idx) * sp.step;
                         if (idx < sp.n - 1) {
-                            const PhiloxBlock s1 = philox4x32_10(P.seed_lo, P.seed_hi, qlo, qhi, 1u);
+                            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
                             E += s1.u(0) * sp.step;
                         }
                     }
@@ -607,8 +614,13 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                     q.pz = __ldg(&ex->pos[2]);
                     q.E = E;
                     q.w = w;
-                    ++nHist;
-                    emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
+                    scnt[2 * blockDim.x] += 1u;
+                    {
+                        const unsigned long long em = (static_cast<unsigned long long>(scnt[4 * blockDim.x]) << 32 | scnt[3 * blockDim.x])
+                            + static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
+                        scnt[3 * blockDim.x] = static_cast<unsigned int>(em);
+                        scnt[4 * blockDim.x] = static_cast<unsigned int>(em >> 32);
+                    }
                     // move to the grid AABB (World::transport)
                     const float ix = 1.0f / q.dx, iy = 1.0f / q.dy, iz = 1.0f / q.dz;
                     float tmin = 0.0f, tmax = 3.0e38f;
@@ -648,7 +660,12 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                         hit = true;
                     }
                 }
-                poolNext += nb;
+                __syncwarp();
+                if (lane == 0) {
+                    spool[0] = poolNext + nb;
+                    spool[1] = poolEnd;
+                    spool[2] = bufBase;
+                }
                 const unsigned int mHit = __ballot_sync(0xffffffffu, hit);
                 if (hit) {
                     const int k = __popc(mHit & laneLt);
@@ -670,6 +687,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                 __syncwarp();
             }
             // dead lanes pop from the top of the buffer
+            const unsigned int mDead = __ballot_sync(0xffffffffu, status == kStDead);
             if (status == kStDead) {
                 const int r = __popc(mDead & laneLt);
                 if (r < bufCount) {
@@ -683,7 +701,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
                     ph.E = sbuf[6 * 32 + k];
                     ph.w = sbuf[7 * 32 + k];
                     ph.remaining = sbuf[8 * 32 + k];
-                    const unsigned long long h = bufBase + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
+                    const unsigned long long h = spool[2] + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
                     epos.i = __float_as_int(sbuf[10 * 32 + k]);
                     epos.f = sbuf[11 * 32 + k];
                     muMax = sbuf[12 * 32 + k];
@@ -700,7 +718,8 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
     }
 
     // ---------------- statistics
-    unsigned long long v[5] = { nSteps, nInter, nDep, emitted, nHist };
+    unsigned long long v[5] = { nSteps, scnt[0], scnt[blockDim.x], static_cast<unsigned long long>(scnt[4 * blockDim.x]) << 32 | scnt[3 * blockDim.x],
+        scnt[2 * blockDim.x] };
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         unsigned long long x = v[k];
@@ -714,7 +733,7 @@ __global__ void __launch_bounds__(256, 3) transportKernel(const __grid_constant_
 
 // ------------------------------------------------------------------ grid preparation kernels
 __global__ void packVoxelsKernel(const double* __restrict__ density, const unsigned char* __restrict__ material,
-    uint2* __restrict__ out, size_t n, unsigned int* __restrict__ maxDensityBits /* [256] */)
+    unsigned int* __restrict__ out, size_t n, unsigned int* __restrict__ maxDensityBits /* [256] */)
 {
     __shared__ unsigned int s_max[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
@@ -726,8 +745,9 @@ __global__ void packVoxelsKernel(const double* __restrict__ density, const unsig
         if (!(rho > 0.0f))
             rho = 0.0f;
         const unsigned int m = material[i];
-        out[i] = make_uint2(__float_as_uint(rho), m);
-        atomicMax(&s_max[m], __float_as_uint(rho)); // non-negative floats order like their bit patterns
+        const unsigned int q = quantizeDensityBits(__float_as_uint(rho));
+        out[i] = q | m;
+        atomicMax(&s_max[m], q); // non-negative floats order like their bit patterns
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
@@ -749,7 +769,7 @@ __global__ void majorantKernel(const float* __restrict__ tot, const unsigned int
 
 // per-beam energy tallies -> accumulated dose score (DoseScore::addScoredEnergy, recalled):
 //   dose += E k / (rho V);  var += var_E (k/(rho V))^2 with var_E = sum E^2 - (sum E)^2 / n
-__global__ void energyToDoseKernel(const unsigned long long* __restrict__ tally, const uint2* __restrict__ voxels,
+__global__ void energyToDoseKernel(const unsigned long long* __restrict__ tally, const unsigned int* __restrict__ voxels,
     double* __restrict__ dose, double* __restrict__ variance, unsigned long long* __restrict__ events, size_t n,
     double inv_scale_e, double inv_scale_e2, double factor, double voxel_volume)
 {
@@ -758,7 +778,7 @@ __global__ void energyToDoseKernel(const unsigned long long* __restrict__ tally,
         const ulonglong4 t = reinterpret_cast<const ulonglong4*>(tally)[i];
         if (t.z == 0)
             continue;
-        const double rho = static_cast<double>(__uint_as_float(voxels[i].x));
+        const double rho = static_cast<double>(voxelDensity(voxels[i]));
         if (!(rho > 0.0))
             continue;
         const double e = static_cast<double>(t.x) * inv_scale_e;
@@ -807,39 +827,39 @@ __global__ void peerReduceKernel(unsigned long long* __restrict__ dst, const uns
 }
 
 // reference post-processing (R:src/libopendxmc/simulationpipeline.cpp:180-185,206-211,221-229)
-__global__ void postprocessKernel(const double* __restrict__ in, const uint2* __restrict__ voxels, double* __restrict__ out,
+__global__ void postprocessKernel(const double* __restrict__ in, const unsigned int* __restrict__ voxels, double* __restrict__ out,
     size_t n, int maskAir, double scale)
 {
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         double v = in[i];
-        if (maskAir && voxels[i].y == 0)
+        if (maskAir && voxelMaterial(voxels[i]) == 0)
             v = 0.0;
         out[i] = v * scale;
     }
 }
 
-__global__ void u64ToDoubleKernel(const unsigned long long* __restrict__ in, const uint2* __restrict__ voxels,
+__global__ void u64ToDoubleKernel(const unsigned long long* __restrict__ in, const unsigned int* __restrict__ voxels,
     double* __restrict__ out, size_t n, int maskAir)
 {
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         double v = static_cast<double>(in[i]);
-        if (maskAir && voxels[i].y == 0)
+        if (maskAir && voxelMaterial(voxels[i]) == 0)
             v = 0.0;
         out[i] = v;
     }
 }
 
 // block max reduction for the uGy decision (max(dose) < 1)
-__global__ void maxKernel(const double* __restrict__ in, const uint2* __restrict__ voxels, size_t n, int maskAir,
+__global__ void maxKernel(const double* __restrict__ in, const unsigned int* __restrict__ voxels, size_t n, int maskAir,
     unsigned long long* __restrict__ outBits)
 {
     double m = 0.0;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         double v = in[i];
-        if (maskAir && voxels[i].y == 0)
+        if (maskAir && voxelMaterial(voxels[i]) == 0)
             v = 0.0;
         m = fmax(m, v);
     }
@@ -852,7 +872,7 @@ __global__ void maxKernel(const double* __restrict__ in, const uint2* __restrict
 // per-organ mass-weighted dose (R:src/libopendxmc/dosetablepipeline.cpp:60-84):
 //   dose_o = sum(dose rho V) / sum(rho V) over voxels of organ o
 __global__ void organDoseKernel(const double* __restrict__ dose, const double* __restrict__ variance,
-    const uint2* __restrict__ voxels, const unsigned char* __restrict__ organ, size_t n, double voxel_volume,
+    const unsigned int* __restrict__ voxels, const unsigned char* __restrict__ organ, size_t n, double voxel_volume,
     double* __restrict__ energy /*[256]*/, double* __restrict__ mass /*[256]*/, unsigned long long* __restrict__ count /*[256]*/,
     double* __restrict__ varEnergy /*[256]*/)
 {
@@ -868,7 +888,7 @@ __global__ void organDoseKernel(const double* __restrict__ dose, const double* _
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const unsigned int o = organ[i];
-        const double m = static_cast<double>(__uint_as_float(voxels[i].x)) * voxel_volume;
+        const double m = static_cast<double>(voxelDensity(voxels[i])) * voxel_volume;
         atomicAdd(&s_e[o], dose[i] * m);
         atomicAdd(&s_m[o], m);
         atomicAdd(&s_v[o], variance[i] * m * m);
@@ -995,7 +1015,7 @@ int transportOccupancy(int mode, bool calib, bool smemTable, int threads, size_t
     return e == cudaSuccess ? nb : 0;
 }
 
-void launchPackVoxels(const double* density, const unsigned char* material, uint2* out, size_t n, unsigned int* maxBits, cudaStream_t s)
+void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s)
 {
     packVoxelsKernel<<<148 * 8, 256, 0, s>>>(density, material, out, n, maxBits);
 }
@@ -1003,7 +1023,7 @@ void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, fl
 {
     majorantKernel<<<(kDevNE + 127) / 128, 128, 0, s>>>(tot, maxBits, n_mat, majorant);
 }
-void launchEnergyToDose(const unsigned long long* tally, const uint2* voxels, double* dose, double* variance,
+void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,
     unsigned long long* events, size_t n, double inv_e, double inv_e2, double factor, double vol, cudaStream_t s)
 {
     energyToDoseKernel<<<148 * 8, 256, 0, s>>>(tally, voxels, dose, variance, events, n, inv_e, inv_e2, factor, vol);
@@ -1017,19 +1037,19 @@ void launchPeerReduce(unsigned long long* dst, const unsigned long long* const* 
 {
     peerReduceKernel<<<148 * 8, 256, 0, s>>>(dst, peers, n_peers, n_words);
 }
-void launchPostprocess(const double* in, const uint2* voxels, double* out, size_t n, int maskAir, double scale, cudaStream_t s)
+void launchPostprocess(const double* in, const unsigned int* voxels, double* out, size_t n, int maskAir, double scale, cudaStream_t s)
 {
     postprocessKernel<<<148 * 8, 256, 0, s>>>(in, voxels, out, n, maskAir, scale);
 }
-void launchU64ToDouble(const unsigned long long* in, const uint2* voxels, double* out, size_t n, int maskAir, cudaStream_t s)
+void launchU64ToDouble(const unsigned long long* in, const unsigned int* voxels, double* out, size_t n, int maskAir, cudaStream_t s)
 {
     u64ToDoubleKernel<<<148 * 8, 256, 0, s>>>(in, voxels, out, n, maskAir);
 }
-void launchMax(const double* in, const uint2* voxels, size_t n, int maskAir, unsigned long long* outBits, cudaStream_t s)
+void launchMax(const double* in, const unsigned int* voxels, size_t n, int maskAir, unsigned long long* outBits, cudaStream_t s)
 {
     maxKernel<<<148 * 4, 256, 0, s>>>(in, voxels, n, maskAir, outBits);
 }
-void launchOrganDose(const double* dose, const double* variance, const uint2* voxels, const unsigned char* organ, size_t n,
+void launchOrganDose(const double* dose, const double* variance, const unsigned int* voxels, const unsigned char* organ, size_t n,
     double vol, double* energy, double* mass, unsigned long long* count, double* varEnergy, cudaStream_t s)
 {
     organDoseKernel<<<148 * 4, 256, 0, s>>>(dose, variance, voxels, organ, n, vol, energy, mass, count, varEnergy);

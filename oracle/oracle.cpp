@@ -440,8 +440,15 @@ struct AAVoxelGrid {
         // per-material maximum density (as float, like the packed device voxels)
         std::vector<double> maxDens(materials.size(), 0.0);
         for (size_t i = 0; i < density.size(); ++i) {
-            const double rho = static_cast<double>(static_cast<float>(density[i] > 0 ? density[i] : 0.0));
-            density[i] = rho; // the grid stores f32 densities (voxel layout)
+            // the device grid stores the top 24 bits of the f32 density (round to nearest; DESIGN.md: voxel layout)
+            const float rf = static_cast<float>(density[i] > 0 ? density[i] : 0.0);
+            uint32_t bits;
+            std::memcpy(&bits, &rf, 4);
+            bits = (bits + 0x80u) & 0xFFFFFF00u;
+            float rq;
+            std::memcpy(&rq, &bits, 4);
+            const double rho = static_cast<double>(rq);
+            density[i] = rho;
             maxDens[materialIndex[i]] = std::max(maxDens[materialIndex[i]], rho);
         }
         const uint32_t nE = materials[0].nE;

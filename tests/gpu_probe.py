@@ -32,8 +32,8 @@ if __name__ == "__main__":
         run(dx.workloads.ct_spiral_patient(scale=1, histories=100_000_000))
     if which == "sweep":
         wl = dx.workloads.ct_spiral_patient(scale=1, histories=100_000_000)
-        for td, ti in itertools.product((2, 4, 6, 8, 12), (4, 8, 12, 16, 20)):
-            run(wl, opts={"refill_threshold": td, "interact_threshold": ti}, tag=f"TD={td} TI={ti}")
-        for bps in (2, 3, 4):
+        for td, ti, trr in itertools.product((2, 4, 8), (8, 12, 16), (4, 8)):
+            run(wl, opts={"refill_threshold": td, "interact_threshold": ti, "rayleigh_threshold": trr}, tag=f"TD={td} TI={ti} TR={trr}")
+        for bps in (3, 4):
             for th in (128, 256):
                 run(wl, opts={"blocks_per_sm": bps * (256 // th), "threads_per_block": th}, tag=f"bps={bps * (256 // th)} threads={th}")
