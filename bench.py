@@ -178,19 +178,13 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-class _DevView:
-    """exposes a raw device pointer to torch through __cuda_array_interface__ (int64 words)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
-
-
 def run_ours(args):
     import ctypes as C
     import numpy as np
     import torch
     import opendxmc_b200 as dx
     from opendxmc_b200 import _capi as K
+    from opendxmc_b200 import distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,9 +217,7 @@ def run_ours(args):
     K.load().dxb_set_stream(ctx, C.c_void_p(stream.cuda_stream))
     tr = dx.Transport()
     desc = wl.beam.desc()
-    ptr, nwords = C.c_void_p(), C.c_uint64()
-    lib.dxb_tally_buffer(ctx, C.byref(ptr), C.byref(nwords))
-    tally = torch.as_tensor(_DevView(ptr.value, nwords.value), device=f"cuda:{local_rank}")
+    tally = D.tally_tensor(world, local_rank)
 
     def barrier():
         if dist is not None:
@@ -241,7 +233,7 @@ def run_ours(args):
             timed_stats.append(world.run_stats())
         if dist is not None:
             with torch.cuda.stream(stream):
-                dist.reduce(tally, dst=0, op=dist.ReduceOp.SUM)
+                D.reduce_tallies(tally, 0)
             stream.synchronize()
         if rank == 0:
             rc = lib.dxb_finish_beam(ctx, C.byref(desc), 1, 0, None)

@@ -286,6 +286,12 @@ int dxb_set_grid_center(dxb_ctx*, const double center_cm[3]); /* default origin 
 /* Transport knobs */
 int dxb_set_seed(dxb_ctx*, uint64_t seed);                    /* Philox key; default 0x0DDC0FFEE */
 int dxb_set_history_range(dxb_ctx*, uint64_t rank, uint64_t world); /* this context runs block `rank` of `world` of every exposure (multi-process sharding) */
+/* the sharding rule itself (host arithmetic, no device needed): histories are dealt to shards in blocks of
+ * DXB_SHARD_BLOCK consecutive ids, round-robin.  dxb_shard_local_count = local indices owned by `rank` (padded to
+ * whole blocks); dxb_shard_history_id maps a local index to the global history id (ids >= n_total are skipped). */
+#define DXB_SHARD_BLOCK 65536u
+uint64_t dxb_shard_local_count(uint64_t n_total, uint64_t rank, uint64_t world);
+uint64_t dxb_shard_history_id(uint64_t local_index, uint64_t rank, uint64_t world);
 int dxb_set_calibration_histories(dxb_ctx*, uint64_t n);      /* nested CTDI run size */
 int dxb_set_stream(dxb_ctx*, void* cuda_stream);              /* launch on a caller-owned stream (device 0 of the ctx) */
 int dxb_set_option(dxb_ctx*, const char* key, double value);  /* tuning knobs, see DESIGN.md */

@@ -155,6 +155,8 @@ SIGNATURES = {
     "dxb_set_grid_center": (C.c_int, [VP, c_double_p]),
     "dxb_set_seed": (C.c_int, [VP, C.c_uint64]),
     "dxb_set_history_range": (C.c_int, [VP, C.c_uint64, C.c_uint64]),
+    "dxb_shard_local_count": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),
+    "dxb_shard_history_id": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "dxb_set_calibration_histories": (C.c_int, [VP, C.c_uint64]),
     "dxb_set_stream": (C.c_int, [VP, VP]),
     "dxb_set_option": (C.c_int, [VP, C.c_char_p, C.c_double]),

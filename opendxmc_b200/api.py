@@ -480,14 +480,18 @@ class DXBeam(_TubeBeam):
     rotation centre / source-patient distance / primary + secondary angle drive the pose."""
     TYPE = K.BEAM_DX
 
-    def __init__(self, pos=(0, 0, 0), cosines=((1, 0, 0), (0, -1, 0)), filtration=None):
+    def __init__(self, pos=None, cosines=None, filtration=None):
         super().__init__(filtration if filtration is not None else {13: 2.0, 29: 0.1})
-        self.setPosition(pos)
-        self.setDirectionCosines(cosines)
         self._center = [0.0, 0.0, 0.0]
-        self._spd = 100.0
+        self._spd = 100.0  # R:src/libopendxmc/dxmc_specialization.hpp:72-73
         self._sdd = 100.0
         self._angles = [0.0, 0.0]
+        if pos is None and cosines is None:
+            self._updatePosition()  # the OpenDXMC subclass constructor, R:src/libopendxmc/dxmc_specialization.cpp:22-26
+        else:
+            # dxmc::DXBeam<false>(pos, cosines, filtration) base form
+            self.setPosition(pos if pos is not None else (0, 0, 0))
+            self.setDirectionCosines(cosines if cosines is not None else ((1, 0, 0), (0, -1, 0)))
         self.setCollimation([20.0, 20.0])
 
     def position(self):
@@ -531,16 +535,16 @@ class DXBeam(_TubeBeam):
         return self._sdd
 
     def setSourceDetectorDistance(self, d):
-        col = self.collimation()
-        self._sdd = max(abs(float(d)), 1.0)
+        # R:src/libopendxmc/dxmc_specialization.cpp:40-44: only m_SDD changes; the stored half angles stay
+        self._sdd = abs(float(d))
         self._d.sdd = self._sdd
-        self.setCollimation(col)
+        self._updatePosition()
 
     def sourcePatientDistance(self):
         return self._spd
 
     def setSourcePatientDistance(self, d):
-        self._spd = max(abs(float(d)), 1.0)
+        self._spd = abs(float(d))
         self._updatePosition()
 
     def rotationCenter(self):
@@ -557,11 +561,11 @@ class DXBeam(_TubeBeam):
         return self._angles[1] * RAD_TO_DEG()
 
     def setPrimaryAngleDeg(self, a):
-        self._angles[0] = float(a) * DEG_TO_RAD()
+        self._angles[0] = min(max(float(a), -180.0), 180.0) * DEG_TO_RAD()
         self._updatePosition()
 
     def setSecondaryAngleDeg(self, a):
-        self._angles[1] = float(a) * DEG_TO_RAD()
+        self._angles[1] = min(max(float(a), -90.0), 90.0) * DEG_TO_RAD()
         self._updatePosition()
 
     def _updatePosition(self):

@@ -25,6 +25,7 @@ static_assert(kDevNX == static_cast<int>(kNX), "x grid mismatch");
 static_assert(kDevEPerOctave == static_cast<int>(kENodesPerOctave), "energy grid mismatch");
 static_assert(kDevXPerOctave == static_cast<int>(kXNodesPerOctave), "x grid mismatch");
 static_assert(sizeof(ExposureDev) == 64, "ExposureDev must be 64 bytes");
+static_assert(kShardBlock == DXB_SHARD_BLOCK, "shard block");
 
 struct dxb_progress {
     std::atomic<uint64_t> done { 0 }, total { 0 };
@@ -94,7 +95,9 @@ struct World {
     DevBuf<float> tot, etr, majorant, ffcdf, sf;
     DevBuf<ShellDev> shells;
     DevBuf<int> nshells;
-    DevBuf<unsigned int> maxDensityBits; // [256]
+    DevBuf<unsigned int> maxDensityBits; // [257]: per-material max density bits, [256] = largest material index seen
+    DevBuf<double> stageDensity;         // staging for the caller's f64 density / u8 material (kept between set_grid calls)
+    DevBuf<unsigned char> stageMaterial;
     bool hasGrid = false, hasTables = false;
 
     GridDev gridDev() const
@@ -287,23 +290,27 @@ int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing
         w.spacing[i] = spacing[i];
     }
     w.nvox = n;
+    w.hasGrid = false;
     CUDA_TRY(c, w.voxels.alloc(n, w.device));
     CUDA_TRY(c, w.tally.alloc(n * 4, w.device));
-    CUDA_TRY(c, w.maxDensityBits.alloc(256, w.device));
-    // staging buffers for the caller's f64 density + u8 material; freed after packing
-    DevBuf<double> dDens;
-    DevBuf<unsigned char> dMat;
-    CUDA_TRY(c, dDens.alloc(n, w.device));
-    CUDA_TRY(c, dMat.alloc(n, w.device));
-    CUDA_TRY(c, cudaMemcpyAsync(dDens.p, density, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(dMat.p, material, n, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemsetAsync(w.maxDensityBits.p, 0, 256 * sizeof(unsigned int), s));
-    launchPackVoxels(dDens.p, dMat.p, w.voxels.p, n, w.maxDensityBits.p, s);
+    CUDA_TRY(c, w.maxDensityBits.alloc(257, w.device));
+    CUDA_TRY(c, w.stageDensity.alloc(n, w.device));
+    CUDA_TRY(c, w.stageMaterial.alloc(n, w.device));
+    CUDA_TRY(c, cudaMemcpyAsync(w.stageDensity.p, density, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(w.stageMaterial.p, material, n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemsetAsync(w.maxDensityBits.p, 0, 257 * sizeof(unsigned int), s));
+    launchPackVoxels(w.stageDensity.p, w.stageMaterial.p, w.voxels.p, n, w.maxDensityBits.p, s);
     CUDA_TRY(c, cudaGetLastError());
     launchMajorant(w.tot.p, w.maxDensityBits.p, w.n_mat, w.majorant.p, s);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, n * 4 * sizeof(unsigned long long), s));
+    // the reference checks max(material) < n_materials before running (R:src/libopendxmc/simulationpipeline.cpp:54-57);
+    // here the pack kernel finds the largest index while it reads the array anyway
+    unsigned int mmax = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&mmax, w.maxDensityBits.p + 256, sizeof(mmax), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (mmax >= static_cast<unsigned int>(w.n_mat))
+        return fail(c, DXB_EINVAL, "set_grid: material index out of range");
     w.hasGrid = true;
     return DXB_OK;
 }
@@ -810,12 +817,6 @@ int dxb_set_grid(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], 
     for (int i = 0; i < 3; ++i)
         if (!(spacing_cm[i] > 0))
             return fail(c, DXB_EINVAL, "set_grid: spacing must be positive");
-    // the reference checks max(material) < n_materials before running (R:...simulationpipeline.cpp:54-57)
-    uint8_t mmax = 0;
-    for (uint64_t i = 0; i < n; ++i)
-        mmax = std::max(mmax, material[i]);
-    if (mmax >= c->materials.size())
-        return fail(c, DXB_EINVAL, "set_grid: material index out of range");
     for (auto& d : c->devs) {
         CUDA_TRY(c, cudaSetDevice(d->device));
         int rc = uploadGrid(c, d->world, dim, spacing_cm, density, material, d->stream);
@@ -871,6 +872,17 @@ int dxb_set_history_range(dxb_ctx* c, uint64_t rank, uint64_t world)
     c->rank = rank;
     c->world = world;
     return DXB_OK;
+}
+
+uint64_t dxb_shard_local_count(uint64_t n_total, uint64_t rank, uint64_t world)
+{
+    return world == 0 ? 0 : localCount(n_total, rank, world);
+}
+
+uint64_t dxb_shard_history_id(uint64_t local_index, uint64_t rank, uint64_t world)
+{
+    // the same arithmetic as the refill phase of transportKernel
+    return ((local_index / kShardBlock) * world + rank) * kShardBlock + (local_index % kShardBlock);
 }
 
 int dxb_set_calibration_histories(dxb_ctx* c, uint64_t n)

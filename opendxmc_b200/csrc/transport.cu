@@ -733,12 +733,13 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
 
 // ------------------------------------------------------------------ grid preparation kernels
 __global__ void packVoxelsKernel(const double* __restrict__ density, const unsigned char* __restrict__ material,
-    unsigned int* __restrict__ out, size_t n, unsigned int* __restrict__ maxDensityBits /* [256] */)
+    unsigned int* __restrict__ out, size_t n, unsigned int* __restrict__ maxDensityBits /* [257]: [256] = largest material index */)
 {
     __shared__ unsigned int s_max[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         s_max[i] = 0u;
     __syncthreads();
+    unsigned int mmax = 0u;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         float rho = static_cast<float>(density[i]);
@@ -747,8 +748,13 @@ __global__ void packVoxelsKernel(const double* __restrict__ density, const unsig
         const unsigned int m = material[i];
         const unsigned int q = quantizeDensityBits(__float_as_uint(rho));
         out[i] = q | m;
+        mmax = max(mmax, m);
         atomicMax(&s_max[m], q); // non-negative floats order like their bit patterns
     }
+    for (int o = 16; o > 0; o >>= 1)
+        mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+    if ((threadIdx.x & 31) == 0 && mmax)
+        atomicMax(&maxDensityBits[256], mmax);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         if (s_max[i])

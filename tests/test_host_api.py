@@ -1,0 +1,383 @@
+"""Host-side logic (no GPU): materials, tube, filters, beam -> exposure expansion, the reference-API mirror, the data
+fixtures mined from OpenDXMC, and the oracle's non-transport helpers against numpy restatements of the reference
+formulas (file:line cited at each test)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+
+# ----------------------------------------------------------------------------- materials / NIST / atoms
+def test_material_factories_and_nullopt(dx):
+    # R:src/libopendxmc/simulationpipeline.cpp:136-141: byWeight -> nullopt stops the simulation
+    assert dx.Material.byWeight({}) is None
+    assert dx.Material.byWeight({0: 1.0}) is None
+    assert dx.Material.byWeight({120: 1.0}) is None
+    assert dx.Material.byNistName("no such material") is None
+    m = dx.Material.byWeight({1: 11.1894, 8: 88.8106})  # mass-% like ICRP media: weights are normalised
+    w = dx.Material.byNistName("Water, Liquid")
+    for e in (15.0, 60.0, 140.0):
+        assert m.attenuationValues(e).sum() == pytest.approx(w.attenuationValues(e).sum(), rel=1e-12)
+    f = dx.Material.byChemicalFormula("H2O")
+    assert f.attenuationValues(60.0).sum() == pytest.approx(w.attenuationValues(60.0).sum(), rel=2e-3)
+
+
+def test_attenuation_close_to_nist_xcom(dx):
+    # analytic tables (no EPICS data offline): sanity band against published XCOM totals [cm2/g]
+    ref = {"Water, Liquid": {20: 0.8096, 40: 0.2683, 60: 0.2059, 100: 0.1707, 150: 0.1505},
+           "Bone, Cortical (ICRP)": {40: 0.6655, 60: 0.3148, 100: 0.1855},
+           "Polymethyl Methacralate (Lucite, Perspex)": {40: 0.2350, 60: 0.1924, 100: 0.1641}}
+    for name, tab in ref.items():
+        m = dx.Material.byNistName(name)
+        for e, v in tab.items():
+            assert m.attenuationValues(e).sum() == pytest.approx(v, rel=0.03), (name, e)
+
+
+def test_nist_names_used_by_the_reference(dx):
+    # the seven names OpenDXMC asks for
+    for n in ["Air, Dry (near sea level)", "Water, Liquid", "Adipose Tissue (ICRP)", "Tissue, Soft (ICRP)", "Muscle, Skeletal",
+              "Bone, Cortical (ICRP)", "Polymethyl Methacralate (Lucite, Perspex)"]:
+        assert dx.NISTMaterials.density(n) > 0
+        comp = dx.NISTMaterials.Composition(n)
+        assert sum(comp.values()) == pytest.approx(1.0, abs=2e-3)
+        assert dx.Material.byWeight(comp) is not None
+    assert dx.NISTMaterials.density("nope") < 0
+    assert dx.AtomHandler.toSymbol(1) == "H" and dx.AtomHandler.toSymbol(20) == "Ca" and dx.AtomHandler.toSymbol(82) == "Pb"
+
+
+def test_table_geometry_is_exact_in_float(dx):
+    """semi-log grids: node(i) = vmin 2^(i/P) (1 + (i%P)/P) -> every node is exactly representable in f32, and
+    interpolation at a node returns the node value."""
+    w = dx.Material.byNistName("Water, Liquid")
+    t = w.table_arrays()
+    e = t["energy"]
+    assert e[0] == 1.0 and e[64] == 2.0 and e[65] == 2.0 * (1 + 1 / 64) and e[-1] >= 150.0
+    assert np.all(e.astype(np.float32).astype(np.float64) == e)
+    for i in (0, 17, 64, 200, 463):
+        a = w.attenuationValues(e[i])
+        assert a.photoelectric == pytest.approx(t["photo"][i], rel=1e-14)
+        assert a.incoherent == pytest.approx(t["incoh"][i], rel=1e-14)
+    # midpoint: linear in E inside a cell
+    mid = 0.5 * (e[100] + e[101])
+    assert w.attenuationValues(mid).coherent == pytest.approx(0.5 * (t["coh"][100] + t["coh"][101]), rel=1e-12)
+    x = t["x"]
+    assert x[0] == 1 / 128 and x[32] == 1 / 64 and x[-1] == 16.0
+    assert np.all(np.diff(t["ff_cdf"]) >= 0) and np.all((t["sf"] >= 0) & (t["sf"] <= 1.0))
+
+
+def test_oracle_lookup_equals_host_lookup(dx, orc):
+    b = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    for e in np.geomspace(1.0, 150.0, 97):
+        a = b.attenuationValues(e)
+        o = orc.attenuation(b, e)
+        assert o[0] == pytest.approx(a.photoelectric, rel=1e-13)
+        assert o[1] == pytest.approx(a.incoherent, rel=1e-13)
+        assert o[2] == pytest.approx(a.coherent, rel=1e-13)
+
+
+# ----------------------------------------------------------------------------- tube
+def test_tube_spectrum_basics(dx):
+    # R:src/libopendxmc/ctsegmentationpipeline.cpp:66-71
+    t = dx.Tube(120.0)
+    t.setAlFiltration(9.0)
+    e = t.getEnergy()
+    s = t.getSpecter(e, True)
+    assert e[0] == 1.0 and e[-1] == 120.0 and len(e) == 120
+    assert s.sum() == pytest.approx(1.0, abs=1e-12) and np.all(s >= 0) and s[e > 120.0].sum() == 0
+    mean0 = t.meanSpecterEnergy()
+    assert 55.0 < mean0 < 75.0
+    # characteristic tungsten K lines show up above 69.5 kV
+    assert s[58] > s[56] or s[59] > s[56]
+    # more filtration hardens the beam and raises the HVL
+    hvl0 = t.alHalfValueLayer()
+    t.setSnFiltration(0.4)
+    assert t.meanSpecterEnergy() > mean0 + 5 and t.alHalfValueLayer() > hvl0
+    t80 = dx.Tube(80.0)
+    t80.setAlFiltration(2.0)
+    assert t80.meanSpecterEnergy() < mean0 and t80.getEnergy()[-1] == 80.0
+
+
+# ----------------------------------------------------------------------------- filters
+def test_bowtie_fixture_and_filter(dx, orc):
+    # R:data/bowtiefilters/bowtiefilters.json via tests/golden/make_fixtures.py; reader schema R:src/libopendxmc/bowtiefilterreader.cpp:51-97
+    filters = dx.workloads.read_bowtie_filters()
+    assert len(filters) == 41
+    bt = filters[dx.workloads.DEFAULT_BOWTIE]
+    assert len(bt.angle) >= 7 and bt.angle.max() < 0.4
+    # unsorted input, sign ignored, normalised to mean 1 over [0, max angle]
+    a = np.linspace(0, bt.angle.max(), 4001)
+    w = np.array([bt(v) for v in a])
+    assert np.trapezoid(w, a) / a[-1] == pytest.approx(1.0, abs=2e-3)
+    assert bt(-0.1) == bt(0.1) and bt(10.0) == bt(bt.angle.max())
+    assert w[0] > w[-1]  # central ray least attenuated
+    d = bt._desc()
+    for v in (0.0, 0.05, 0.2, 0.39, 1.0):
+        # the oracle keeps f32 knots like the device
+        assert orc.load().orc_bowtie_weight(C.byref(d), v) == pytest.approx(bt(v), rel=1e-6)
+    assert dx.BowtieFilter([])(0.3) == 1.0
+
+
+def test_aec_filter(dx, orc):
+    # R:src/libopendxmc/datacontainer.cpp:37,59: (start, stop, weights)
+    w = np.array([1.0, 2.0, 4.0, 2.0, 1.0])
+    f = dx.CTAECFilter([0, 0, -10], [0, 0, 10], w)
+    assert not f.isEmpty() and f.size() == 5 and f.length() == 20.0
+    assert f([0, 0, 0]) == pytest.approx(4.0 / w.mean())
+    assert f([5, 5, -10]) == pytest.approx(1.0 / w.mean()) and f([0, 0, -50]) == f([0, 0, -10])
+    assert f([0, 0, 2.5]) == pytest.approx(3.0 / w.mean())
+    d = f._desc()
+    for z in (-12, -3.3, 0, 4.4, 10, 30):
+        p = (C.c_double * 3)(0, 0, z)
+        assert orc.load().orc_aec_weight(C.byref(d), p) == pytest.approx(f([0, 0, z]), rel=1e-13)
+    assert dx.CTAECFilter()([0, 0, 0]) == 1.0  # empty
+
+
+def test_wed_aec_profile_formula(dx):
+    # R:src/libopendxmc/datacontainer.cpp:42-100: Dw = 2 sqrt(sum(rho) dx dy / pi), weight exp(0.2 Dw)
+    dim, sp = (8, 6, 3), (0.5, 0.25, 1.0)
+    rho = np.arange(8 * 6 * 3, dtype=np.float64).reshape(3, 6, 8) / 100
+    w = dx.workloads.wed_aec_profile(rho.reshape(-1), dim, sp)
+    for k in range(3):
+        dw = 2 * math.sqrt(rho[k].sum() * 0.5 * 0.25 / math.pi)
+        assert w[k] == pytest.approx(math.exp(0.2 * dw))
+
+
+def test_organ_aec(dx, orc):
+    o = dx.CTOrganAECFilter()
+    assert o(1.0) == 1.0  # off
+    o.setUseFilter(True)
+    o.setStartAngleDeg(-45)
+    o.setStopAngleDeg(45)
+    o.setRampAngleDeg(20)
+    o.setLowWeight(0.5)
+    assert o(0.0) == pytest.approx(0.5) and o(math.pi) == pytest.approx(1.0)
+    o.setCompensateOutside(True)
+    a = np.linspace(0, 2 * math.pi, 72001)[:-1]
+    w = np.array([o(v) for v in a])
+    assert w.mean() == pytest.approx(1.0, abs=1e-4)  # total tube output preserved
+    assert w.max() == pytest.approx(o.maxWeight())
+    for v in (0.0, 0.9, 1.0, 3.0, 5.6, -0.7):
+        assert orc.load().orc_organ_aec_weight(C.byref(o._d), v) == pytest.approx(o(v), rel=1e-13)
+
+
+# ----------------------------------------------------------------------------- beams
+def _all_beams(dx):
+    bt = dx.workloads.read_bowtie_filters()[dx.workloads.DEFAULT_BOWTIE]
+    beams = []
+    b = dx.DXBeam()
+    b.setRotationCenter([1, 2, 3])
+    b.setPrimaryAngleDeg(30)
+    b.setSecondaryAngleDeg(-15)
+    b.setNumberOfExposures(5)
+    beams.append(b)
+    p = dx.PencilBeam([1, 2, -30], [0.1, 0.2, 1.0], 55.0)
+    p.setNumberOfExposures(3)
+    beams.append(p)
+    c = dx.CBCTBeam([0, 1, 2], [0, 0.2, 1])
+    c.setStartAngleDeg(10)
+    c.setStopAngleDeg(200)
+    c.setStepAngleDeg(7)
+    c.setCollimationHalfAnglesDeg(8, 6)
+    beams.append(c)
+    s = dx.CTSequentialBeam([0, 0, -5], [0, 0, 1])
+    s.setNumberOfSlices(3)
+    s.setSliceSpacing(2.5)
+    s.setStepAngleDeg(10)
+    s.setBowtieFilter(bt)
+    s.organAECFilter().setUseFilter(True)
+    beams.append(s)
+    sp = dx.CTSpiralBeam([0, 0, -10], [0, 0, 10])
+    sp.setStepAngleDeg(5)
+    sp.setPitch(0.8)
+    sp.setStartAngleDeg(33)
+    sp.setBowtieFilter(bt)
+    sp.setAECFilter([0, 0, -10], [0, 0, 10], [1, 3, 2, 1])
+    beams.append(sp)
+    d = dx.CTSpiralDualEnergyBeam([0, 0, -10], [0, 1, 10])
+    d.setTubeAVoltage(140)
+    d.setTubeBVoltage(80)
+    d.addTubeAFiltrationMaterial(50, 0.4)
+    d.setTubeBoffsetAngleDeg(95)
+    d.setScanFieldOfViewB(33)
+    d.setPitch(3.2)
+    d.setStepAngleDeg(5)
+    d.setRelativeMasTubeA(1.0)
+    d.setRelativeMasTubeB(2.5)
+    d.setBowtieFilterA(bt)
+    beams.append(d)
+    return beams
+
+
+def test_exposures_host_equals_oracle(dx, orc):
+    """the product's beam expansion (beams.cpp) and the oracle's independent restatement agree for every beam type."""
+    for beam in _all_beams(dx):
+        n = beam.numberOfExposures()
+        assert n == orc.beam_number_of_exposures(beam) and n > 0
+        for i in sorted({0, 1, n // 2, n - 1}):
+            a, b = beam.exposure(i), orc.beam_exposure(beam, i)
+            assert np.allclose(a.position(), list(b.position), atol=1e-12)
+            assert np.allclose(a.directionCosines(), [list(b.cosines[0]), list(b.cosines[1])], atol=1e-12)
+            assert np.allclose(a.direction(), list(b.direction), atol=1e-12)
+            assert np.allclose(a.collimationHalfAngles(), list(b.half_angles), atol=1e-15)
+            assert a.weight() == pytest.approx(b.weight, rel=1e-12)
+            assert a.tube() == b.tube
+        with pytest.raises(Exception):
+            beam.exposure(n)
+
+
+def test_dxbeam_pose_and_collimation_round_trip(dx):
+    # R:src/libopendxmc/dxmc_specialization.cpp:22-26, 46-60, 78-90
+    b = dx.DXBeam()
+    assert b.collimationHalfAngles() == pytest.approx([math.tan(0.1), math.tan(0.1)])  # tan(x) stored, not atan
+    assert b.collimation() == pytest.approx([2 * 100 * math.atan(math.tan(0.1))] * 2)
+    c0, c1 = [np.array(v) for v in b.directionCosines()]
+    assert np.allclose(c0, [0, 0, 1]) and np.allclose(c1, [-1, 0, 0])
+    assert np.allclose(np.cross(c0, c1), [0, -1, 0])
+    assert b.position() == pytest.approx([0, 100, 0])  # centre - SPD * ({0,0,1} x {-1,0,0})
+    b.setRotationCenter([1, 2, 3])
+    b.setSourcePatientDistance(80)
+    d = np.cross(*[np.array(v) for v in b.directionCosines()])
+    assert np.allclose(b.position(), np.array([1, 2, 3]) - 80 * d)
+    b.setPrimaryAngleDeg(90)
+    c0, c1 = [np.array(v) for v in b.directionCosines()]
+    assert np.allclose(c0, [0, 0, 1], atol=1e-12) and np.allclose(c1, [0, -1, 0], atol=1e-12)
+    b.setPrimaryAngleDeg(400)   # clamped to 180
+    assert b.primaryAngleDeg() == pytest.approx(180.0)
+    b.setSecondaryAngleDeg(-120)  # clamped to -90
+    assert b.secondaryAngleDeg() == pytest.approx(-90.0)
+    b.setCollimation([35, 43])
+    assert b.collimation() == pytest.approx([2 * 100 * math.atan(math.tan(0.5 * 35 / 100)), 2 * 100 * math.atan(math.tan(0.5 * 43 / 100))])
+    assert b.numberOfParticles() == b.numberOfExposures() * b.numberOfParticlesPerExposure()
+
+
+def test_ct_spiral_defaults_and_geometry(dx):
+    # defaults R:src/libopendxmc/beamsettingsmodel.cpp:1152-1171: 9 mm Al, SDD 119, collimation 3.84, step 5 deg, 1e6 / exposure
+    b = dx.CTSpiralBeam([0, 0, -15], [0, 0, 15])
+    assert b.sourceDetectorDistance() == 119.0 and b.collimation() == 3.84 and b.stepAngleDeg() == pytest.approx(5.0)
+    assert b.numberOfParticlesPerExposure() == 1_000_000 and b.tubeFiltration(13) == 9.0 and b.pitch() == 1.0
+    n = b.numberOfExposures()
+    assert n == math.ceil(30 / 3.84 * 360 / 5)
+    e0, e1 = b.exposure(0), b.exposure(72)
+    # source on a circle of radius SDD/2 around the axis, one pitch*collimation of table feed per rotation
+    assert math.hypot(*e0.position()[:2]) == pytest.approx(59.5)
+    assert e1.position()[2] - e0.position()[2] == pytest.approx(3.84)
+    assert np.allclose(e0.position()[:2], e1.position()[:2], atol=1e-9)
+    # beam axis points at the rotation axis
+    p, d = np.array(e0.position()), np.array(e0.direction())
+    assert np.allclose((p + 59.5 * d)[:2], [0, 0], atol=1e-9)
+    assert e0.collimationHalfAngles() == pytest.approx([math.atan(50 / 119), math.atan(3.84 / 119)])
+    # dual source: exposure(2i) = tube A, exposure(2i+1) = tube B (R:src/libopendxmc/beamactorcontainer.cpp:134-146)
+    d2 = dx.CTSpiralDualEnergyBeam([0, 0, -15], [0, 0, 15])
+    assert d2.numberOfExposures() == 2 * n
+    assert [d2.exposure(i).tube() for i in range(4)] == [0, 1, 0, 1]
+    a, bb = np.array(d2.exposure(0).direction()), np.array(d2.exposure(1).direction())
+    assert math.degrees(math.acos(np.clip(a @ bb, -1, 1))) == pytest.approx(d2.tubeBoffsetAngleDeg())
+    wa, wb = d2.tubeRelativeWeightA(), d2.tubeRelativeWeightB()
+    assert wa + wb == pytest.approx(2.0) and d2.exposure(0).weight() == pytest.approx(wa) and d2.exposure(1).weight() == pytest.approx(wb)
+
+
+def test_progress_object(dx):
+    p = dx.TransportProgress()
+    assert p.continueSimulation() and p.progress() == (0, 0)
+    assert "Starting" in p.message()
+    p.setStopSimulation()
+    assert not p.continueSimulation()
+    p.reset()
+    assert p.continueSimulation()
+
+
+def test_voxel_grid_set_data_validation(dx):
+    g = dx.AAVoxelGrid()
+    w = dx.Material.byNistName("Water, Liquid")
+    assert not g.setData([2, 2, 2], np.ones(7), np.zeros(8, dtype=np.uint8), [w])
+    assert not g.setData([2, 2, 2], np.ones(8), np.ones(8, dtype=np.uint8), [w])  # index >= n_materials (R:...simulationpipeline.cpp:54-57)
+    assert g.setData([2, 2, 2], np.ones(8), np.zeros(8, dtype=np.uint8), [w]) and g.size() == 8
+
+
+# ----------------------------------------------------------------------------- fixtures from the reference's data
+def test_icrp_tables_and_import_rules(dx):
+    t = dx.workloads.icrp_tables()
+    assert set(t) == {"00F", "00M", "01F", "01M", "05F", "05M", "10F", "10M", "15F", "15M", "AF", "AM"}
+    am = t["AM"]
+    assert len(am["organs"]) == 140 and len(am["media"]) == 53
+    assert am["organs"][0] == {"id": 1, "name": "Adrenal, left", "medium": 43, "density": 1.03}
+    assert am["media"][0]["name"] == "Teeth" and am["media"][0]["composition"]["20"] == 28.9
+    dens = [o["density"] for o in am["organs"]]
+    assert min(dens) == 0.001 and max(dens) == 2.75
+    shapes = dx.workloads.icrp_shapes()
+    assert shapes["AM"]["dimensions"] == [254, 127, 222] and shapes["10M"]["dimensions"] == [419, 226, 576]
+    # import rules (R:src/libopendxmc/icrpphantomimportpipeline.cpp:209-351) on a toy organ array
+    raw = np.array([0, 0, 5, 5, 9, 140, 140, 9], dtype=np.uint8)
+    organ, names, material, density, media_names, comps = dx.workloads.import_icrp_tables("AM", raw)
+    assert list(organ) == [0, 0, 1, 1, 2, 3, 3, 2] and names[0] == "Air" and len(names) == 4
+    assert material[0] == 0 and density[0] == 0.001 and comps[0] == {7: 0.8, 8: 0.2}
+    assert len(set(material)) == len(media_names) and material.max() == len(media_names) - 1
+    by_id = {o["id"]: o for o in am["organs"]}
+    assert density[2] == by_id[5]["density"] and density[4] == by_id[9]["density"]
+    for c in comps:
+        assert dx.Material.byWeight(c) is not None
+
+
+def test_synthetic_workloads_shapes(dx):
+    c1 = dx.workloads.ctdi_body_phantom(n=32, histories=1000)
+    assert c1.dim == [32, 32, 32] and c1.beam.numberOfExposures() == 360 and set(np.unique(c1.material)) == {0, 1}
+    # cylinder rule of R:src/libopendxmc/otherphantomimportpipeline.cpp:32-50 scaled to r = 16 cm
+    frac = (c1.material == 1).mean()
+    assert frac == pytest.approx(math.pi * 16 ** 2 / 36 ** 2, rel=0.02)
+    c2 = dx.workloads.ct_spiral_patient(scale=8, histories=1000)
+    assert c2.dim == [64, 64, 37] and c2.spacing == pytest.approx([0.64, 0.64, 0.8])
+    assert set(np.unique(c2.material)) == {0, 1, 2, 3} and c2.beam.numberOfExposures() == math.ceil(37 * 0.8 / 3.84 * 360)
+    assert 0.0011 < c2.density.min() < 0.0013 and 1.5 < c2.density.max() < 1.7
+    full = dx.workloads.ct_spiral_patient(scale=64, histories=10 ** 9)  # beam of the full-size config on a toy grid
+    c3 = dx.workloads.icrp_phantom("AM", scale=6, histories=1000)
+    assert len(c3.materials) == len(c3.material_names) and c3.organ.max() < len(c3.organ_names)
+    c5 = dx.workloads.icrp_phantom("10M", scale=8, histories=6400, beam_kind="dx")
+    assert c5.beam.TYPE == 0 and c5.beam.tube().voltage() == 80.0
+
+
+# ----------------------------------------------------------------------------- oracle helpers vs numpy restatements
+def test_organ_dose_formula(orc):
+    # R:src/libopendxmc/dosetablepipeline.cpp:60-84: dose_o = sum(dose rho V) / sum(rho V)
+    rng = np.random.default_rng(0)
+    n = 5000
+    dose, rho = rng.random(n), rng.random(n) + 0.1
+    organ = rng.integers(0, 7, n).astype(np.uint8)
+    vol = 0.123
+    d, m, c = orc.organ_dose(dose, rho, organ, vol, 8)
+    for o in range(8):
+        sel = organ == o
+        assert c[o] == sel.sum()
+        if sel.any():
+            assert m[o] == pytest.approx(vol * rho[sel].sum()) and d[o] == pytest.approx((dose[sel] * rho[sel]).sum() / rho[sel].sum())
+        else:
+            assert d[o] == 0 and m[o] == 0
+
+
+def test_postprocess_rules(orc):
+    # R:src/libopendxmc/simulationpipeline.cpp:180-195, 206-211, 221-229
+    dose = np.array([0.5, 0.2, 0.9, 0.0])
+    var = np.array([0.01, 0.02, 0.03, 0.0])
+    ev = np.array([5.0, 6.0, 7.0, 0.0])
+    mat = np.array([0, 1, 1, 0], dtype=np.uint8)
+    d, v, e, units = orc.postprocess(dose, var, ev, mat, True)
+    assert units == "uGy" and list(d) == [0.0, 200.0, 900.0, 0.0] and list(e) == [0.0, 6.0, 7.0, 0.0]
+    assert v == pytest.approx([0.0, 0.02e6, 0.03e6, 0.0])
+    d, v, e, units = orc.postprocess(dose * 10, var, ev, mat, False)
+    assert units == "mGy" and list(d) == [5.0, 2.0, 9.0, 0.0] and list(v) == list(var)
+
+
+def test_segmentation_rule(orc):
+    # R:src/libopendxmc/ctsegmentationpipeline.cpp:136-156
+    hu = np.array([-1000.0, -200.0, -50.0, 20.0, 60.0, 400.0, 3000.0])
+    sep = np.array([-500.0, -30.0, 30.0, 100.0])
+    att = np.array([0.20, 0.21, 0.22, 0.225, 0.30])
+    wa, aa = 0.22 * 1.0, 0.2 * 1.2e-3
+    mat = np.zeros(len(hu), dtype=np.uint8)
+    dens = np.zeros(len(hu))
+    orc.load().orc_segment(hu.ctypes.data_as(C.POINTER(C.c_double)), len(hu), sep.ctypes.data_as(C.POINTER(C.c_double)), 4,
+                           att.ctypes.data_as(C.POINTER(C.c_double)), wa, aa, mat.ctypes.data_as(C.POINTER(C.c_uint8)),
+                           dens.ctypes.data_as(C.POINTER(C.c_double)))
+    assert list(mat) == [0, 1, 1, 2, 3, 4, 4]
+    expect = np.maximum(((wa - aa) * hu / 1000 + wa) / att[mat], 0.0)
+    assert dens == pytest.approx(expect)
