@@ -10,7 +10,7 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 LIB := $(LIBDIR)/libdxmc_b200.so
 OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/context.o
 
-all: $(LIB) oracle
+all: $(LIB) oracle shim
 
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
@@ -28,7 +28,14 @@ oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -shared -pthread -o $@ oracle/oracle.cpp
 
+# the reference's driver (simulationpipeline.cpp worker<>) retyped against the C++ shim headers in include/dxmc/
+shim: build/opendxmc_worker
+SHIM_HDRS := $(wildcard include/dxmc/*.hpp include/dxmc/*/*.hpp include/dxmc/*/*/*.hpp)
+build/opendxmc_worker: examples/opendxmc_worker.cpp $(SHIM_HDRS) include/dxb.h $(LIB)
+	@mkdir -p build
+	$(CXX) -std=c++20 -O2 -Wall -Iinclude $< -o $@ -L$(LIBDIR) -ldxmc_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
 clean:
 	rm -rf build $(LIB) oracle/liboracle.so
 
-.PHONY: all oracle clean
+.PHONY: all oracle shim clean

@@ -346,6 +346,8 @@ class CTOrganAECFilter:
     def setLowWeight(self, w):
         self._d.low_weight = min(max(float(w), 0.0), 1.0)
 
+    setLowWeightFactor = setLowWeight  # the name the reference calls (R:src/libopendxmc/beamsettingsmodel.cpp:407)
+
     def maxWeight(self):
         return _lib().dxb_organ_aec_max_weight(C.byref(self._d))
 

@@ -151,3 +151,15 @@ def test_full_transport_dose_matches_oracle(dx, orc, c1):
     expect = c1.beam.CTDIw() * c1.beam.collimation() / (c1.dim[2] * c1.spacing[2])
     assert abs(mean_gpu - expect) / expect < 0.25, (mean_gpu, expect)
     world.close()
+
+
+def test_cpp_shim_runs_the_reference_driver():
+    """examples/opendxmc_worker.cpp = R:src/libopendxmc/simulationpipeline.cpp:124-235 compiled against include/dxmc/."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "opendxmc_worker")
+    assert os.path.exists(exe), "run `make` first"
+    out = subprocess.run([exe, "2000000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "finished=1" in out.stdout and "units=" in out.stdout
