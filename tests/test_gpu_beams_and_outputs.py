@@ -1,0 +1,306 @@
+"""GPU parity, part 2: every beam type, the scaled C3/C4/C5 configurations, calibration, post-processing, per-organ
+dose, CT segmentation, progress / cancel, and in-process multi-GPU invariance — CUDA path through the C ABI vs the oracle."""
+import ctypes as C
+import threading
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SEED = 0x0DDC0FFEE
+
+
+def _compare_run(dx, orc, wl, mode=1, rois=None, tol=5e-3):
+    world = wl.build_world(mode, [0])
+    tr = dx.Transport()
+    tr.run_transport(world, wl.beam)
+    e, e2, cnt = world.energy_scored()
+    st = world.run_stats()
+    ow = orc.OracleWorld.from_workload(wl)
+    oe, oe2, ocnt, ost = ow.run(wl.beam, mode, SEED)
+    assert st["histories"] == ost["histories"] == wl.beam.numberOfParticles()
+    assert abs(st["energy_emitted_kev"] - ost["energy_emitted_kev"]) / ost["energy_emitted_kev"] < 1e-5
+    assert abs(e.sum() - oe.sum()) / oe.sum() <= tol, (e.sum(), oe.sum())
+    for k in ("steps", "interactions", "deposits"):
+        assert abs(st[k] - ost[k]) / max(ost[k], 1) < tol, (k, st[k], ost[k])
+    for name, m in (rois or {}).items():
+        a, b = e[m].sum(), oe[m].sum()
+        s = np.sqrt(e2[m].sum() + oe2[m].sum())
+        assert s == 0 or abs(a - b) / s <= 3.0, (name, a, b, s)
+    world.close()
+    return e, oe
+
+
+def _small_block(dx):
+    """24^3 water block with a bone insert and an air gap, 0.5 cm voxels."""
+    n = 24
+    names = ["Air, Dry (near sea level)", "Water, Liquid", "Bone, Cortical (ICRP)"]
+    mats = [dx.Material.byNistName(nm) for nm in names]
+    material = np.ones((n, n, n), dtype=np.uint8)
+    material[:, :, :3] = 0
+    material[8:16, 8:16, 10:14] = 2
+    density = np.choose(material, [1.2e-3, 1.0, 1.85]).astype(np.float64)
+    return [n, n, n], [0.5, 0.5, 0.5], density.reshape(-1), material.reshape(-1), mats, names
+
+
+@pytest.mark.parametrize("kind", ["dx", "pencil", "cbct", "sequential", "spiral_aec_organ", "dual"])
+def test_every_beam_type_matches_the_oracle(dx, orc, kind):
+    dim, sp, density, material, mats, names = _small_block(dx)
+    bt = dx.workloads.read_bowtie_filters()[dx.workloads.DEFAULT_BOWTIE]
+    if kind == "dx":
+        beam = dx.DXBeam()
+        beam.setTubeVoltage(80)
+        beam.setRotationCenter([0, 0, 0])
+        beam.setSourcePatientDistance(60)
+        beam.setPrimaryAngleDeg(20)
+        beam.setSecondaryAngleDeg(10)
+        beam.setCollimation([12, 9])
+        beam.setNumberOfExposures(8)
+        beam.setNumberOfParticlesPerExposure(60_000)
+    elif kind == "pencil":
+        beam = dx.PencilBeam([0.3, -0.2, -20], [0.05, 0.02, 1], 45.0)
+        beam.setNumberOfExposures(4)
+        beam.setNumberOfParticlesPerExposure(100_000)
+    elif kind == "cbct":
+        beam = dx.CBCTBeam([0, 0, 0], [0, 0.1, 1])
+        beam.setTubeVoltage(100)
+        beam.setSourceDetectorDistance(90)
+        beam.setStartAngleDeg(0)
+        beam.setStopAngleDeg(200)
+        beam.setStepAngleDeg(10)
+        beam.setCollimationHalfAnglesDeg(6, 5)
+        beam.setNumberOfParticlesPerExposure(25_000)
+    elif kind == "sequential":
+        beam = dx.CTSequentialBeam([0, 0, -3], [0, 0, 1], {13: 9.0})
+        beam.setNumberOfSlices(3)
+        beam.setSliceSpacing(3.0)
+        beam.setCollimation(2.0)
+        beam.setScanFieldOfView(20)
+        beam.setStepAngleDeg(10)
+        beam.setBowtieFilter(bt)
+        beam.setNumberOfParticlesPerExposure(5_000)
+    elif kind == "spiral_aec_organ":
+        beam = dx.CTSpiralBeam([0, 0, -5], [0, 0, 5], {13: 9.0})
+        beam.setCollimation(2.0)
+        beam.setPitch(0.9)
+        beam.setScanFieldOfView(20)
+        beam.setStepAngleDeg(10)
+        beam.setBowtieFilter(bt)
+        beam.setAECFilter([0, 0, -5], [0, 0, 5], [1.0, 2.5, 0.7, 1.3])
+        o = beam.organAECFilter()
+        o.setUseFilter(True)
+        o.setStartAngleDeg(-40)
+        o.setStopAngleDeg(40)
+        o.setLowWeightFactor(0.4)
+        o.setCompensateOutside(True)
+        beam.setNumberOfParticlesPerExposure(3_000)
+    else:
+        beam = dx.CTSpiralDualEnergyBeam([0, 0, -5], [0, 0, 5], {13: 9.0})
+        beam.setTubeAVoltage(140)
+        beam.setTubeBVoltage(80)
+        beam.addTubeAFiltrationMaterial(50, 0.4)
+        beam.setTubeBoffsetAngleDeg(95)
+        beam.setScanFieldOfViewA(20)
+        beam.setScanFieldOfViewB(13)
+        beam.setCollimation(2.0)
+        beam.setPitch(1.5)
+        beam.setStepAngleDeg(10)
+        beam.setRelativeMasTubeB(2.0)
+        beam.setBowtieFilterA(bt)
+        beam.setBowtieFilterB(bt)
+        beam.setNumberOfParticlesPerExposure(2_500)
+    wl = dx.workloads.Workload(kind, dim, sp, density, material, mats, names, beam)
+    rois = {"bone": material == 2, "water": material == 1, "air": material == 0}
+    for mode in (0, 1):
+        _compare_run(dx, orc, wl, mode, rois)
+
+
+def test_c3_icrp_shape_per_organ_dose(dx, orc):
+    """C3 scaled: ICRP AM shape, 53 media from the real tables, chest spiral CT; per-organ dose within 3 combined sigma."""
+    wl = dx.workloads.icrp_phantom("AM", scale=3, histories=3_000_000)
+    assert len(wl.materials) > 40  # more tables than fit in shared memory at once -> global-memory table path too
+    world = wl.build_world(1, [0])
+    tr = dx.Transport()
+    assert tr(world, wl.beam, None, False)
+    d, v, n = world._item.doseArrays()
+    ow = orc.OracleWorld.from_workload(wl)
+    od, ov, on, ost = ow.transport(wl.beam, 1, False, SEED)
+    vol = wl.spacing[0] * wl.spacing[1] * wl.spacing[2]
+    n_org = len(wl.organ_names)
+    gd, gm, gc, gv = world.organ_dose(wl.organ, n_org)
+    cd, cm, cc = orc.organ_dose(od, wl.density, wl.organ, vol, n_org)
+    # the device reduction reproduces the reference formula on its own dose array
+    rd, rm, rc = orc.organ_dose(d, wl.density, wl.organ, vol, n_org)
+    ok = rm > 0
+    assert np.array_equal(gc, rc)
+    assert np.allclose(gd[ok], rd[ok], rtol=2e-5, atol=0) and np.allclose(gm[ok], rm[ok], rtol=2e-5)
+    # GPU vs oracle per organ: 3 combined standard errors (variance of the organ mean from the voxel variances)
+    var_c = np.zeros(n_org)
+    var_g = np.zeros(n_org)
+    mass = wl.density * vol
+    np.add.at(var_c, wl.organ, ov * mass ** 2)
+    np.add.at(var_g, wl.organ, v * mass ** 2)
+    checked = 0
+    for o in range(n_org):
+        if cm[o] <= 0 or cd[o] <= 0:
+            continue
+        s = np.sqrt(var_c[o] + var_g[o]) / cm[o]
+        assert abs(gd[o] - cd[o]) <= 3.0 * s + 1e-5 * cd[o], (wl.organ_names[o], gd[o], cd[o], s)
+        checked += 1
+    assert checked > 50
+    world.close()
+
+
+def test_c4_dual_source_aec_small(dx, orc):
+    wl = dx.workloads.ct_dual_source_thorax(scale=8, histories=2_000_000, step_deg=5.0)
+    rois = {nm: wl.organ == i for i, nm in enumerate(wl.organ_names)}
+    _compare_run(dx, orc, wl, 1, rois)
+
+
+def test_c5_child_dx_small(dx, orc):
+    wl = dx.workloads.icrp_phantom("10M", scale=6, histories=2_000_000, beam_kind="dx")
+    _compare_run(dx, orc, wl, 1, {"all": np.ones(wl.n_voxels, dtype=bool)})
+
+
+def test_calibrated_dose_dx_and_ct(dx, orc):
+    dim, sp, density, material, mats, names = _small_block(dx)
+    # DX: DAP calibration (analytic)
+    beam = dx.DXBeam()
+    beam.setTubeVoltage(70)
+    beam.setSourcePatientDistance(60)
+    beam.setCollimation([10, 10])
+    beam.setDAPvalue(2.5)
+    beam.setNumberOfExposures(4)
+    beam.setNumberOfParticlesPerExposure(100_000)
+    wl = dx.workloads.Workload("dxcal", dim, sp, density, material, mats, names, beam)
+    world = wl.build_world(1, [0])
+    tr = dx.Transport()
+    assert tr(world, beam, None, True)
+    d, v, n = world._item.doseArrays()
+    ow = orc.OracleWorld.from_workload(wl)
+    od, ov, on, ost = ow.transport(beam, 1, True, SEED)
+    assert world.run_stats()["calibration_factor"] == pytest.approx(ost["calibration_factor"], rel=1e-9)
+    assert d.sum() == pytest.approx(od.sum(), rel=5e-3)
+    sel = n > 20
+    assert np.all(v[sel] > 0)
+    # a second beam accumulates into the same dose score (repeated transport() on one world)
+    assert tr(world, beam, None, True)
+    d2, v2, n2 = world._item.doseArrays()
+    assert d2.sum() == pytest.approx(2 * d.sum(), rel=1e-9) and int(n2.sum()) == 2 * int(n.sum())
+    world.clear_dose()
+    assert world.fetch_dose()[0].sum() == 0
+    # CT: nested CTDI run; the factor of GPU and oracle agree statistically
+    ct = dx.CTSpiralBeam([0, 0, -4], [0, 0, 4], {13: 9.0})
+    ct.setStepAngleDeg(10)
+    ct.setCTDIvol(12.0)
+    ct.setNumberOfParticlesPerExposure(10_000)
+    world.set_calibration_histories(3_600_000)
+    assert tr(world, ct, None, True)
+    f_gpu = world.run_stats()["calibration_factor"]
+    f_cpu = ow.ct_calibration(ct, 1, SEED, 3_600_000)
+    assert f_gpu == pytest.approx(f_cpu, rel=0.02)
+    world.close()
+
+
+def test_postprocess_matches_reference_rules(dx, orc):
+    wl = dx.workloads.ctdi_body_phantom(n=32, histories=400_000, step_deg=5.0)
+    world = wl.build_world(1, [0])
+    tr = dx.Transport()
+    assert tr(world, wl.beam, None, True)
+    d, v, n = world._item.doseArrays()
+    for delete_air in (False, True):
+        gd, gv, gn, units = world.dose_postprocessed(delete_air)
+        od, ov, on, ounits = orc.postprocess(d, v, n.astype(np.float64), wl.material, delete_air)
+        assert units == ounits
+        assert np.array_equal(gd, od) and np.array_equal(gn, on) and np.allclose(gv, ov, rtol=1e-15)
+    world.close()
+
+
+def test_ct_segmentation_matches_oracle(dx, orc):
+    wl = dx.workloads.ctdi_body_phantom(n=16, histories=1000)
+    world = wl.build_world(1, [0])
+    from opendxmc_b200 import _capi as K
+    lib = K.load()
+    rng = np.random.default_rng(3)
+    hu = np.concatenate([rng.uniform(-1100, 2500, 200_000), [-1000.0, 0.0, 55.0, 3000.0]])
+    tube = dx.Tube(120.0)
+    tube.setAlFiltration(9.0)
+    mat = np.zeros(hu.size, dtype=np.uint8)
+    dens = np.zeros(hu.size)
+    handles = (K.VP * 5)()
+    rc = lib.dxb_segment_ct(world.ctx(), hu.ctypes.data_as(K.c_double_p), hu.size, tube._sync(), mat.ctypes.data_as(K.c_u8_p),
+                            dens.ctypes.data_as(K.c_double_p), handles)
+    assert rc == 0
+    # restate R:src/libopendxmc/ctsegmentationpipeline.cpp:61-156 with the library's own materials / tube
+    names = ["Air, Dry (near sea level)", "Adipose Tissue (ICRP)", "Tissue, Soft (ICRP)", "Muscle, Skeletal", "Bone, Cortical (ICRP)"]
+    mats = [dx.Material.byNistName(nm) for nm in names]
+    dn = [dx.NISTMaterials.density(nm) for nm in names]
+    dn[-1] = 1.09
+    e = tube.getEnergy()
+    w = tube.getSpecter(e, True)
+    water, air = dx.Material.byNistName("Water, Liquid"), mats[0]
+    wd, ad = 1.0, dx.NISTMaterials.density(names[0])
+    uw = np.array([water.attenuationValues(x).sum() for x in e])
+    ua = np.array([air.attenuationValues(x).sum() for x in e])
+    um = [np.array([m.attenuationValues(x).sum() for x in e]) for m in mats]
+    HU = [1000 * np.sum(w * (um[i] * dn[i] - uw * wd) / (uw * wd - ua * ad)) for i in range(5)]
+    sep = np.array([(HU[i] + HU[i + 1]) / 2 for i in range(4)])
+    att = np.array([np.sum(w * um[i]) for i in range(5)])
+    omat = np.zeros(hu.size, dtype=np.uint8)
+    odens = np.zeros(hu.size)
+    orc.load().orc_segment(hu.ctypes.data_as(K.c_double_p), hu.size, sep.ctypes.data_as(K.c_double_p), 4, att.ctypes.data_as(K.c_double_p),
+                           float(np.sum(w * uw) * wd), float(np.sum(w * ua) * ad), omat.ctypes.data_as(K.c_u8_p), odens.ctypes.data_as(K.c_double_p))
+    assert np.array_equal(mat, omat)
+    assert np.allclose(dens, odens, rtol=1e-12, atol=1e-15)
+    assert set(np.unique(mat)) == {0, 1, 2, 3, 4}
+    for h in handles:
+        lib.dxb_material_destroy(h)
+    world.close()
+
+
+def test_progress_and_cancel(dx):
+    wl = dx.workloads.ct_spiral_patient(scale=4, histories=400_000_000, step_deg=5.0)
+    world = wl.build_world(1, [0])
+    world.set_option("batch_histories", 1 << 22)  # stop must be observed within one batch
+    prog = dx.TransportProgress()
+    tr = dx.Transport()
+    result = {}
+
+    def run():
+        result["ok"] = tr(world, wl.beam, prog, False)
+    t = threading.Thread(target=run)
+    t0 = time.time()
+    t.start()
+    seen = 0
+    while time.time() - t0 < 20:
+        done, total = prog.progress()
+        if done > 0:
+            seen = done
+            assert total == wl.beam.numberOfParticles()
+            assert "Remaining" in prog.message()
+            break
+        time.sleep(0.001)
+    prog.setStopSimulation()
+    t.join(timeout=60)
+    assert not t.is_alive()
+    assert result["ok"] is False and seen > 0  # cancelled is distinguishable from finished
+    assert not prog.continueSimulation()
+    world.close()
+
+
+def test_in_process_multi_gpu_is_bit_identical(dx):
+    from opendxmc_b200 import _capi as K
+    if K.load().dxb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    wl = dx.workloads.ctdi_body_phantom(n=32, histories=1_000_000, step_deg=5.0)
+    w1 = wl.build_world(1, [0])
+    w2 = wl.build_world(1, [0, 1])
+    tr = dx.Transport()
+    tr.run_transport(w1, wl.beam)
+    tr.run_transport(w2, wl.beam)
+    a, b = w1.energy_scored(), w2.energy_scored()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    w1.close()
+    w2.close()
