@@ -8,7 +8,7 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-f
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
-OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/context.o
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/context.o
 
 all: $(LIB) oracle shim
 
@@ -20,7 +20,7 @@ build/%.o: $(CSRC)/%.cpp $(CSRC)/physics.hpp $(CSRC)/internal.hpp include/dxb.h
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/kernels.hpp include/dxb.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/transport_common.cuh $(CSRC)/kernels.hpp include/dxb.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

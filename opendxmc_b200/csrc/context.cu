@@ -160,9 +160,15 @@ struct Options {
     int threads = 256;
     int blocksPerSm = 0;         // 0: occupancy query
     int tableInSmem = 1;
-    int refillThreshold = 4;     // warp phase machine (transport.cu)
-    int interactThreshold = 12;
-    int rayleighThreshold = 4;
+    int slots = 0;               // 0 = one photon per lane in registers (transport.cu, default: fastest);
+                                 // 2/3/4/6 = lane-multiplexed photons in shared memory (transport_mux.cu)
+    int refillThreshold = -1;    // warp phase machine; -1 = the default of the selected kernel
+    int interactThreshold = -1;
+    int rayleighThreshold = -1;
+    int voxelLoadMode = 1;       // voxel gathers bypass L1 (ld.global.cg): +3 %, leaves L1 to the tables
+    int smemPadKb = 0;           // experiment: extra dynamic shared memory per block (shrinks L1)
+    int stepPairs = 1;           // mux kernel: step pairs per step phase
+    int interactBias = 0;        // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
 };
 
 } // namespace
@@ -454,9 +460,14 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.tally_scale_e = c->scaleE;
     P.tally_scale_e2 = c->scaleE2;
     P.score_material = calib ? scoreMaterial : -1;
-    P.refill_threshold = std::clamp(c->opt.refillThreshold, 1, 32);
-    P.interact_threshold = std::clamp(c->opt.interactThreshold, 1, 32);
-    P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold, 1, 32);
+    const bool mux = c->opt.slots >= 2;
+    // defaults: register kernel 4 / 12 / 4 dead / waiting / Rayleigh lanes; mux kernel 8 / 33 (bias rule only) / 8
+    P.refill_threshold = std::clamp(c->opt.refillThreshold > 0 ? c->opt.refillThreshold : (mux ? 8 : 4), 1, 32);
+    P.interact_threshold = std::clamp(c->opt.interactThreshold > 0 ? c->opt.interactThreshold : (mux ? 33 : 12), 1, 33);
+    P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold > 0 ? c->opt.rayleighThreshold : (mux ? 8 : 4), 1, 32);
+    P.voxel_load_mode = c->opt.voxelLoadMode;
+    P.step_pairs = std::clamp(c->opt.stepPairs, 1, 8);
+    P.interact_bias = std::clamp(c->opt.interactBias, -32, 32);
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -464,10 +475,22 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.threads = c->opt.threads;
     const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
-    cfg.smem = transportSmemBytes(cfg.threads, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
+    cfg.slots = mux ? c->opt.slots : 0;
+    if (mux) {
+        // the table shares the SM's shared memory with the photon slots: keep it only while two blocks still fit
+        cfg.smem = muxSmemBytes(cfg.threads, cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
+        if (cfg.table_in_smem && cfg.smem > 110 * 1024) {
+            cfg.table_in_smem = false;
+            cfg.smem = muxSmemBytes(cfg.threads, cfg.slots, 0);
+        }
+    } else {
+        cfg.smem = transportSmemBytes(cfg.threads, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
+    }
+    cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
+        perSm = mux ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
+                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)
             return fail(c, DXB_ECUDA, "transport kernel cannot be resident (occupancy 0)");
     }
@@ -478,16 +501,23 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     CUDA_TRY(c, cudaEventRecord(d.evStart, d.stream));
     uint64_t launches = 0;
     bool cancelled = false;
-    for (uint64_t begin = 0; begin < nLocal; begin += c->opt.batch) {
+    // the mux kernel keeps 32 bits of the history id per photon: the ids of one launch must span < 2^32
+    uint64_t batch = c->opt.batch;
+    if (mux)
+        batch = std::max<uint64_t>(kShardBlock, std::min<uint64_t>(batch, ((1ull << 31) / world) / kShardBlock * kShardBlock));
+    for (uint64_t begin = 0; begin < nLocal; begin += batch) {
         if (progress && progress->stop.load(std::memory_order_relaxed)) {
             cancelled = true;
             break;
         }
-        const uint64_t end = std::min(nLocal, begin + c->opt.batch);
+        const uint64_t end = std::min(nLocal, begin + batch);
         P.local_begin = begin;
         P.local_end = end;
+        const uint64_t firstId = ((begin / kShardBlock) * world + rank) * kShardBlock + begin % kShardBlock;
+        P.hbase_lo = static_cast<unsigned int>(firstId);
+        P.hbase_hi = static_cast<unsigned int>(firstId >> 32);
         CUDA_TRY(c, cudaMemsetAsync(d.counters.p, 0, sizeof(unsigned long long), d.stream));
-        CUDA_TRY(c, launchTransport(P, mode, calib, cfg, d.stream));
+        CUDA_TRY(c, mux ? launchTransportMux(P, mode, calib, cfg, d.stream) : launchTransport(P, mode, calib, cfg, d.stream));
         ++launches;
         if (progress && !asyncOnly && end < nLocal) {
             // stop must be observed within one batch; progress is published per batch
@@ -931,6 +961,19 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.blocksPerSm = static_cast<int>(value);
     } else if (k == "table_in_smem") {
         c->opt.tableInSmem = value != 0;
+    } else if (k == "slots_per_lane") {
+        const int v = static_cast<int>(value);
+        if (v != 0 && v != 2 && v != 3 && v != 4 && v != 6)
+            return fail(c, DXB_EINVAL, "slots_per_lane must be 0 (register kernel), 2, 3, 4 or 6");
+        c->opt.slots = v;
+    } else if (k == "voxel_load_mode") {
+        c->opt.voxelLoadMode = static_cast<int>(value);
+    } else if (k == "smem_pad_kb") {
+        c->opt.smemPadKb = static_cast<int>(value);
+    } else if (k == "step_pairs") {
+        c->opt.stepPairs = static_cast<int>(value);
+    } else if (k == "interact_bias") {
+        c->opt.interactBias = static_cast<int>(value);
     } else if (k == "refill_threshold") {
         c->opt.refillThreshold = static_cast<int>(value);
     } else if (k == "interact_threshold") {

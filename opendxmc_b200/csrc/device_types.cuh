@@ -96,6 +96,10 @@ struct RunParams {
     int refill_threshold;           // dead lanes per warp that trigger a refill phase
     int interact_threshold;         // waiting lanes per warp that trigger an interaction phase
     int rayleigh_threshold;         // lanes waiting for a Rayleigh try that trigger a Rayleigh phase
+    int voxel_load_mode;            // see loadVoxel (transport_common.cuh)
+    int step_pairs;                 // mux kernel: step pairs per step phase (>= 1)
+    int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes
+    unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
 };
@@ -112,11 +116,21 @@ __host__ __device__ inline size_t transportSmemBytes(int threads, int table_floa
     return warps * 32 + warps * kSourceBufWords * 32 * 4 + static_cast<size_t>(threads) * kLaneCounters * 4 + static_cast<size_t>(table_floats) * 4;
 }
 
-// launch wrappers (transport.cu)
+// the lane-multiplexed kernel (transport_mux.cu): every lane owns `slots` photons in shared memory
+constexpr int kSlotWords = 11;  // px py pz dx dy dz E w remaining hlo meta
+constexpr int kMuxBufWords = 10; // px py pz dx dy dz E w remaining lane-offset
+__host__ __device__ inline size_t muxSmemBytes(int threads, int slots, int table_floats)
+{
+    const size_t warps = static_cast<size_t>(threads) / 32;
+    return (static_cast<size_t>(table_floats) + kDevNE) * 4 + warps * (static_cast<size_t>(kSlotWords) * slots + kMuxBufWords) * 32 * 4;
+}
+
+// launch wrappers (transport.cu, transport_mux.cu)
 struct LaunchConfig {
     int blocks, threads;
     size_t smem;
     bool table_in_smem;
+    int slots; // 0: one photon per lane in registers (transport.cu); >= 2: lane-multiplexed kernel
 };
 
 } // namespace dxb

@@ -24,246 +24,11 @@
 //     Rayleigh try     w0 = form-factor CDF target (Thomson: rejection variable), w1 = rejection test (Thomson:
 //                      polar angle), w2 = azimuth
 //     roulette         w0
-#include "device_types.cuh"
-
-#include <cstdio>
+#include "transport_common.cuh"
 
 namespace dxb {
 
 namespace {
-
-constexpr float kElectronMass = 510.99895f;
-constexpr float kHc = 12.398419843f;
-constexpr float kMinEnergy = 1.0f;           // keV cut-off
-constexpr float kRouletteThreshold = 0.1f;   // weight below which roulette is played
-constexpr float kRouletteKill = 0.9f;        // kill probability
-constexpr float kTwoPi = 6.283185307179586f;
-constexpr float kPiF = 3.14159265358979f;
-constexpr float kU24 = 5.9604644775390625e-8f; // 2^-24
-
-// ------------------------------------------------------------------ Philox4x32-10
-struct PhiloxBlock {
-    unsigned int w[4];
-    // k * 2^-24, k in [0, 2^24): exactly representable, in [0,1)
-    __device__ __forceinline__ float u(int i) const { return static_cast<float>(w[i] >> 8) * kU24; }
-};
-
-// rk = the ten round keys (key + r * Weyl constants), precomputed on the host and read as constant-bank operands
-__device__ __forceinline__ PhiloxBlock philox4x32_10(const unsigned int (&rk)[10][2], unsigned int c0, unsigned int c1, unsigned int c2)
-{
-    unsigned int x0 = c0, x1 = c1, x2 = c2, x3 = 0u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned int hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-        const unsigned int hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-        x0 = hi1 ^ x1 ^ rk[r][0];
-        x1 = lo1;
-        x2 = hi0 ^ x3 ^ rk[r][1];
-        x3 = lo0;
-    }
-    PhiloxBlock b;
-    b.w[0] = x0;
-    b.w[1] = x1;
-    b.w[2] = x2;
-    b.w[3] = x3;
-    return b;
-}
-
-// ------------------------------------------------------------------ table coordinates
-struct TabPos {
-    int i;
-    float f;
-};
-
-// Grid coordinate of v >= 1 on a semi-log grid with PER = 2^LOG2PER nodes per octave (uniform inside the
-// octave, physics.hpp): index = exponent and top mantissa bits, fraction = remaining mantissa bits.  Exact.
-template <int LOG2PER, int N>
-__device__ __forceinline__ TabPos tabPos(float v)
-{
-    TabPos p;
-    const int bits = __float_as_int(fmaxf(v, 1.0f));
-    constexpr int SH = 23 - LOG2PER;
-    int i = (bits >> SH) - (127 << LOG2PER);
-    float f = static_cast<float>(bits & ((1 << SH) - 1)) * (1.0f / static_cast<float>(1 << SH));
-    if (i >= N - 1) {
-        i = N - 2;
-        f = 1.0f;
-    }
-    p.i = i;
-    p.f = f;
-    return p;
-}
-// value of grid node k (relative to the grid minimum)
-template <int LOG2PER>
-__device__ __forceinline__ float tabNode(int k)
-{
-    return __int_as_float(((127 << LOG2PER) + k) << (23 - LOG2PER));
-}
-constexpr int kLog2EPer = 6, kLog2XPer = 5;
-static_assert((1 << kLog2EPer) == kDevEPerOctave && (1 << kLog2XPer) == kDevXPerOctave, "grid geometry");
-
-__device__ __forceinline__ TabPos energyPos(float e) { return tabPos<kLog2EPer, kDevNE>(e); }
-
-__device__ __forceinline__ float lerp(float a, float b, float f) { return fmaf(f, b - a, a); }
-
-// ------------------------------------------------------------------ geometry helpers
-__device__ __forceinline__ float exitDistance(const GridDev& g, float px, float py, float pz, float dx, float dy, float dz)
-{
-    const float tx = __fdividef((dx > 0.0f ? g.x1 : g.x0) - px, dx);
-    const float ty = __fdividef((dy > 0.0f ? g.y1 : g.y0) - py, dy);
-    const float tz = __fdividef((dz > 0.0f ? g.z1 : g.z0) - pz, dz);
-    // a zero direction component gives +-inf or NaN: excluded explicitly
-    float t = 3.0e38f;
-    if (dx != 0.0f)
-        t = fminf(t, tx);
-    if (dy != 0.0f)
-        t = fminf(t, ty);
-    if (dz != 0.0f)
-        t = fminf(t, tz);
-    return fmaxf(t, 0.0f);
-}
-
-__device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float cosT, float phi)
-{
-    // dxmc::vectormath::peturb: rotate the direction by polar angle theta and azimuth phi
-    const float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
-    float sinP, cosP;
-    __sincosf(phi, &sinP, &cosP);
-    float nx, ny, nz;
-    if (fabsf(dz) < 0.99999f) {
-        const float inv = rsqrtf(1.0f - dz * dz);
-        const float tmp = (1.0f - dz * dz) * inv;
-        nx = dx * cosT + sinT * (dx * dz * cosP - dy * sinP) * inv;
-        ny = dy * cosT + sinT * (dy * dz * cosP + dx * sinP) * inv;
-        nz = dz * cosT - tmp * sinT * cosP;
-    } else {
-        nx = sinT * cosP;
-        ny = sinT * sinP;
-        nz = dz > 0.0f ? cosT : -cosT;
-    }
-    const float n = rsqrtf(nx * nx + ny * ny + nz * nz);
-    dx = nx * n;
-    dy = ny * n;
-    dz = nz * n;
-}
-
-// ------------------------------------------------------------------ scoring
-// Warp-aggregated fixed-point tally update.  `mask` = the lanes that score in this phase (all of them call
-// this function together); lanes of the mask that hit the same voxel are merged before the atomics (exact
-// integer sums, so the result does not depend on the merge or on arrival order).
-__device__ __forceinline__ void scoreEnergy(unsigned int mask, unsigned long long* __restrict__ tally, unsigned int voxel, float edep,
-    float scale_e, float scale_e2)
-{
-    unsigned long long e = static_cast<unsigned long long>(__float2ll_rn(edep * scale_e));
-    unsigned long long e2 = static_cast<unsigned long long>(__float2ll_rn(edep * edep * scale_e2));
-    unsigned int n = 1;
-    const unsigned int peers = __match_any_sync(mask, voxel);
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(peers) - 1;
-    if (peers != (1u << lane)) {
-        // rare path: several lanes on one voxel; every peer walks the peer set
-        unsigned long long se = 0, se2 = 0;
-        unsigned int walk = peers;
-        while (walk) {
-            const int src = __ffs(walk) - 1;
-            walk &= walk - 1;
-            se += __shfl_sync(peers, e, src);
-            se2 += __shfl_sync(peers, e2, src);
-        }
-        e = se;
-        e2 = se2;
-        n = __popc(peers);
-    }
-    if (lane == leader) {
-        unsigned long long* t = tally + static_cast<size_t>(voxel) * 4;
-        atomicAdd(t + 0, e);
-        atomicAdd(t + 1, e2);
-        atomicAdd(t + 2, static_cast<unsigned long long>(n));
-    }
-}
-
-// ------------------------------------------------------------------ interaction samplers (one try each)
-// Klein-Nishina candidate e = E'/E uniform in [emin, 1], accepted with g(e)/gmax; MODE >= 1 multiplies the
-// acceptance by the incoherent scatter function S(x)/Z (Livermore).  Returns true if accepted.
-template <int MODE>
-__device__ __forceinline__ bool comptonTry(const TablesDev& tab, int mat, float E, float r1, float ra, float& e, float& cosT)
-{
-    const float k = E * (1.0f / kElectronMass);
-    const float emin = __fdividef(1.0f, 1.0f + 2.0f * k);
-    const float gmaxInv = __fdividef(emin, 1.0f + emin * emin);
-    e = r1 + (1.0f - r1) * emin;
-    const float einv = __fdividef(1.0f, e);
-    const float t = fminf((1.0f - e) * einv * __fdividef(1.0f, k), 2.0f);
-    const float sin2 = t * (2.0f - t);
-    cosT = 1.0f - t;
-    float g = (einv + e - sin2) * gmaxInv;
-    if (MODE >= 1) {
-        const float xs = E * (kDevXMinInv / kHc) * sqrtf(0.5f * t); // momentum transfer in units of the grid minimum
-        float sfv;
-        if (xs <= 1.0f) {
-            sfv = __ldg(tab.sf + mat * kDevNX) * xs * xs;
-        } else {
-            const TabPos p = tabPos<kLog2XPer, kDevNX>(xs);
-            const float* s = tab.sf + mat * kDevNX + p.i;
-            sfv = lerp(__ldg(s), __ldg(s + 1), p.f);
-        }
-        g *= sfv;
-    }
-    return !(ra > g);
-}
-
-// Rayleigh: MODE 0 Thomson (pdf ~ (1 + cos^2) sin(theta), rejection from a box); MODE >= 1 samples
-// q^2 ~ F(q)^2 on [0, qmax^2] from the tabulated cumulative A(x^2) (piecewise linear in x^2) and accepts with
-// (1 + cos^2)/2.  Returns true if accepted.
-template <int MODE>
-__device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float E, float r0, float r1, float& cosT)
-{
-    if (MODE == 0) {
-        const float rr = r0 * 1.0886621079036347f; // 4 sqrt2 / (3 sqrt3)
-        float s, c;
-        __sincosf(kPiF * r1, &s, &c);
-        cosT = c;
-        return !(rr > (2.0f - s * s) * s);
-    }
-    const float xmaxs = E * (kDevXMinInv / kHc); // in units of the grid minimum
-    const float xmax2 = xmaxs * xmaxs;
-    const float* cdf = tab.ffcdf + mat * kDevNX;
-    const float a0 = __ldg(cdf);
-    float amax;
-    int top; // the target lies below node `top`
-    if (xmaxs <= 1.0f) {
-        amax = a0 * xmax2; // F^2 flat below the first node: A = F0^2 x^2
-        top = 0;
-    } else {
-        const TabPos p = tabPos<kLog2XPer, kDevNX>(xmaxs);
-        const float xa = tabNode<kLog2XPer>(p.i), xb = tabNode<kLog2XPer>(p.i + 1);
-        const float fa = __fdividef(xmax2 - xa * xa, xb * xb - xa * xa);
-        amax = lerp(__ldg(cdf + p.i), __ldg(cdf + p.i + 1), fminf(fmaxf(fa, 0.0f), 1.0f));
-        top = p.i + 1;
-    }
-    const float target = r0 * amax;
-    float x2;
-    if (target <= a0) {
-        x2 = __fdividef(target, a0);
-    } else {
-        // binary search: largest i with A[i] <= target (target <= amax <= A[top])
-        int lo = 0, hi = top;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(cdf + mid) <= target)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        const float al = __ldg(cdf + lo), ah = __ldg(cdf + lo + 1);
-        const float xa = tabNode<kLog2XPer>(lo), xb = tabNode<kLog2XPer>(lo + 1);
-        const float f = ah > al ? __fdividef(target - al, ah - al) : 0.0f;
-        x2 = xa * xa + f * (xb * xb - xa * xa);
-    }
-    x2 = fminf(x2, xmax2);
-    cosT = 1.0f - 2.0f * __fdividef(x2, xmax2);
-    return !((1.0f + cosT * cosT) * 0.5f < r1);
-}
 
 // ------------------------------------------------------------------ the history kernel
 //
@@ -331,7 +96,8 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
     unsigned int hlo = 0, hhi = 0, blk = 2; // Philox counter of this lane's history
     int status = kStDead;
     TabPos epos;
-    float muMax = 1.0f, muMaxInv = 1.0f;
+    // majorant of the photon's energy, pre-multiplied: u * mu_max = k * muMaxU24 (k = 2^24 u), step = log2(1 - u) * stepScale
+    float muMaxU24 = kU24, stepScale = -kLn2;
     unsigned int voxel = 0;
     int mat = 0;
     epos.i = 0;
@@ -357,8 +123,9 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
         if (alive) {
             if (energyChanged) {
                 epos = energyPos(ph.E);
-                muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
-                muMaxInv = __fdividef(1.0f, muMax);
+                const float muMax = lerp(__ldg(P.tab.majorant + epos.i), __ldg(P.tab.majorant + epos.i + 1), epos.f);
+                muMaxU24 = muMax * kU24;
+                stepScale = -kLn2 * __fdividef(1.0f, muMax);
             }
             ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
             status = kStStep;
@@ -395,32 +162,20 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
             unsigned int voxA = 0, voxB = 0;
             if (status == kStStep) {
                 const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
-                const float sA = -__logf(1.0f - rb.u(0)) * muMaxInv;
-                const float sB = -__logf(1.0f - rb.u(2)) * muMaxInv;
+                const float sA = __log2f(fmaf(rb.k(0), -kU24, 1.0f)) * stepScale;
+                const float sB = __log2f(fmaf(rb.k(2), -kU24, 1.0f)) * stepScale;
                 const bool inA = sA < ph.remaining;
                 const bool inB = inA && (sA + sB < ph.remaining);
                 const float ax = fmaf(ph.dx, sA, ph.px), ay = fmaf(ph.dy, sA, ph.py), az = fmaf(ph.dz, sA, ph.pz);
                 const float bx = fmaf(ph.dx, sB, ax), by = fmaf(ph.dy, sB, ay), bz = fmaf(ph.dz, sB, az);
-                int ix = static_cast<int>(fmaf(ax, G.inv_dx, G.offx));
-                int iy = static_cast<int>(fmaf(ay, G.inv_dy, G.offy));
-                int iz = static_cast<int>(fmaf(az, G.inv_dz, G.offz));
-                ix = min(max(ix, 0), G.nx - 1);
-                iy = min(max(iy, 0), G.ny - 1);
-                iz = min(max(iz, 0), G.nz - 1);
-                voxA = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
-                ix = static_cast<int>(fmaf(bx, G.inv_dx, G.offx));
-                iy = static_cast<int>(fmaf(by, G.inv_dy, G.offy));
-                iz = static_cast<int>(fmaf(bz, G.inv_dz, G.offz));
-                ix = min(max(ix, 0), G.nx - 1);
-                iy = min(max(iy, 0), G.ny - 1);
-                iz = min(max(iz, 0), G.nz - 1);
-                voxB = (static_cast<unsigned int>(iz) * G.ny + iy) * G.nx + ix;
+                voxA = voxelIndex(G, ax, ay, az);
+                voxB = voxelIndex(G, bx, by, bz);
                 // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                 unsigned int cellA = 0u, cellB = 0u;
                 if (inA)
-                    cellA = __ldg(G.voxels + voxA);
+                    cellA = loadVoxel(G.voxels + voxA, P.voxel_load_mode);
                 if (inB)
-                    cellB = __ldg(G.voxels + voxB);
+                    cellB = loadVoxel(G.voxels + voxB, P.voxel_load_mode);
                 if (!inA) {
                     status = kStDead; // left the grid
                 } else {
@@ -431,9 +186,9 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                     if (CALIB && matA == P.score_material) {
                         // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
                         const float* et = P.tab.etr + matA * kDevNE + epos.i;
-                        kermaA = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
+                        kermaA = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * (stepScale * -kInvLn2);
                     }
-                    if (rb.u(1) * muMax < muA) {
+                    if (rb.k(1) * muMaxU24 < muA) {
                         ph.px = ax;
                         ph.py = ay;
                         ph.pz = az;
@@ -450,13 +205,13 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                         const float muB = voxelDensity(cellB) * lerp(tb[0], tb[1], epos.f);
                         if (CALIB && matB == P.score_material) {
                             const float* et = P.tab.etr + matB * kDevNE + epos.i;
-                            kermaB = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * muMaxInv;
+                            kermaB = ph.w * ph.E * lerp(__ldg(et), __ldg(et + 1), epos.f) * (stepScale * -kInvLn2);
                         }
                         ph.px = bx;
                         ph.py = by;
                         ph.pz = bz;
                         ph.remaining -= sA + sB;
-                        if (rb.u(3) * muMax < muB) {
+                        if (rb.k(3) * muMaxU24 < muB) {
                             voxel = voxB;
                             mat = matB;
                             status = kStWaitNew;
@@ -704,8 +459,9 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                     const unsigned long long h = spool[2] + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
                     epos.i = __float_as_int(sbuf[10 * 32 + k]);
                     epos.f = sbuf[11 * 32 + k];
-                    muMax = sbuf[12 * 32 + k];
-                    muMaxInv = __fdividef(1.0f, muMax);
+                    const float muMax = sbuf[12 * 32 + k];
+                    muMaxU24 = muMax * kU24;
+                    stepScale = -kLn2 * __fdividef(1.0f, muMax);
                     hlo = static_cast<unsigned int>(h);
                     hhi = static_cast<unsigned int>(h >> 32);
                     blk = 2u; // blocks 0-1 belong to the source

@@ -163,3 +163,25 @@ def test_cpp_shim_runs_the_reference_driver():
     out = subprocess.run([exe, "2000000"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "finished=1" in out.stdout and "units=" in out.stdout
+
+
+@pytest.mark.parametrize("slots,pairs", [(4, 1), (4, 2), (2, 1), (3, 2), (6, 3)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_lane_multiplexed_kernel_is_bit_exact(dx, slots, pairs, mode):
+    """transport_mux.cu (photons regrouped per lane in shared memory) follows the same random-number protocol as
+    the register kernel and sums the same fixed-point tallies: every tally word and counter must be identical."""
+    wl = dx.workloads.ct_spiral_patient(scale=8, histories=300_000)
+    out = []
+    for opts in ({"slots_per_lane": 0}, {"slots_per_lane": slots, "step_pairs": pairs}):
+        world = wl.build_world(mode, [0])
+        for k, v in opts.items():
+            world.set_option(k, v)
+        dx.Transport().run_transport(world, wl.beam)
+        e, e2, cnt = world.energy_scored()
+        out.append((np.array(e), np.array(e2), np.array(cnt), world.run_stats()))
+        world.close()
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(a, b)
+    for k in ("histories", "steps", "interactions", "deposits"):
+        assert out[0][3][k] == out[1][3][k]
+    assert out[0][2].sum() > 0
