@@ -120,7 +120,8 @@ typedef struct dxb_material_tables {
     const double* sf;       /* [n_x] S(x_k)/Z */
     uint32_t n_shells;      /* <= DXB_MAX_SHELLS, most tightly bound first */
     dxb_shell shells[DXB_MAX_SHELLS];
-    double   rest_electrons_fraction; /* electrons not covered by `shells` (treated as free, mode 2) */
+    double   rest_electrons_fraction; /* electrons not covered by `shells`: one unbound group (mode 2) */
+    double   rest_compton_j0;         /* J(0) of that group (electron-weighted mean of its orbitals); 0: electrons at rest */
     double   electrons_per_gram;
     double   effective_z;
     uint32_t nodes_per_octave_e, nodes_per_octave_x;

@@ -39,7 +39,7 @@ class dxb_material_tables(C.Structure):
         ("n_x", C.c_uint32), ("x_min", C.c_double), ("x_max", C.c_double),
         ("ff_cdf", c_double_p), ("sf", c_double_p),
         ("n_shells", C.c_uint32), ("shells", dxb_shell * MAX_SHELLS),
-        ("rest_electrons_fraction", C.c_double), ("electrons_per_gram", C.c_double), ("effective_z", C.c_double),
+        ("rest_electrons_fraction", C.c_double), ("rest_compton_j0", C.c_double), ("electrons_per_gram", C.c_double), ("effective_z", C.c_double),
         ("nodes_per_octave_e", C.c_uint32), ("nodes_per_octave_x", C.c_uint32),
     ]
 

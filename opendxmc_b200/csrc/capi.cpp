@@ -100,6 +100,7 @@ int dxb_material_tables_get(const dxb_material* m, dxb_material_tables* t)
     for (uint32_t i = 0; i < M.nShells; ++i)
         t->shells[i] = M.shells[i];
     t->rest_electrons_fraction = M.restElectronsFraction;
+    t->rest_compton_j0 = M.restComptonJ0;
     t->electrons_per_gram = M.electronsPerGram;
     t->effective_z = M.effectiveZ;
     t->nodes_per_octave_e = kENodesPerOctave;

@@ -95,6 +95,7 @@ struct World {
     DevBuf<float> tot, etr, majorant, ffcdf, sf;
     DevBuf<ShellDev> shells;
     DevBuf<int> nshells;
+    DevBuf<float> restJ0;
     DevBuf<unsigned int> maxDensityBits; // [257]: per-material max density bits, [256] = largest material index seen
     DevBuf<double> stageDensity;         // staging for the caller's f64 density / u8 material (kept between set_grid calls)
     DevBuf<unsigned char> stageMaterial;
@@ -135,6 +136,7 @@ struct World {
         t.sf = sf.p;
         t.shells = shells.p;
         t.n_shells = nshells.p;
+        t.rest_j0 = restJ0.p;
         return t;
     }
 };
@@ -246,6 +248,7 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
     std::vector<float> ff(static_cast<size_t>(n) * kDevNX), sf(ff.size());
     std::vector<ShellDev> shells(static_cast<size_t>(n) * kMaxShells);
     std::vector<int> nsh(n);
+    std::vector<float> restJ(n);
     for (int m = 0; m < n; ++m) {
         const Material& M = *mats[m];
         for (int i = 0; i < kDevNE; ++i) {
@@ -261,6 +264,7 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
             sf[static_cast<size_t>(m) * kDevNX + i] = static_cast<float>(M.sf[i]);
         }
         nsh[m] = static_cast<int>(M.nShells);
+        restJ[m] = static_cast<float>(M.restComptonJ0);
         for (uint32_t k = 0; k < M.nShells; ++k) {
             ShellDev& d = shells[static_cast<size_t>(m) * kMaxShells + k];
             const dxb_shell& h = M.shells[k];
@@ -281,6 +285,7 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
     CUDA_TRY(c, w.sf.upload(sf, w.device, s));
     CUDA_TRY(c, w.shells.upload(shells, w.device, s));
     CUDA_TRY(c, w.nshells.upload(nsh, w.device, s));
+    CUDA_TRY(c, w.restJ0.upload(restJ, w.device, s));
     CUDA_TRY(c, w.majorant.alloc(kDevNE, w.device));
     CUDA_TRY(c, cudaStreamSynchronize(s)); // host vectors go out of scope
     w.hasTables = true;
@@ -475,12 +480,14 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.threads = c->opt.threads;
     const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
-    cfg.slots = mux ? c->opt.slots : 0;
+    cfg.slots = 0;
     if (mux) {
         // the table shares the SM's shared memory with the photon slots: keep it only while two blocks still fit
+        cfg.slots = transportMuxSlots(mode, calib, cfg.table_in_smem, c->opt.slots);
         cfg.smem = muxSmemBytes(cfg.threads, cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
         if (cfg.table_in_smem && cfg.smem > 110 * 1024) {
             cfg.table_in_smem = false;
+            cfg.slots = transportMuxSlots(mode, calib, false, c->opt.slots);
             cfg.smem = muxSmemBytes(cfg.threads, cfg.slots, 0);
         }
     } else {

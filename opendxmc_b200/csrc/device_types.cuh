@@ -52,6 +52,7 @@ struct TablesDev {
     const float* __restrict__ sf;     // [n_mat*NX]
     const ShellDev* __restrict__ shells; // [n_mat*kMaxShells]
     const int* __restrict__ n_shells; // [n_mat]
+    const float* __restrict__ rest_j0; // [n_mat] J(0) of the electrons outside the shell table (0: at rest)
 };
 
 struct SpectrumDev {

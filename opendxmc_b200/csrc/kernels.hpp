@@ -7,6 +7,7 @@ cudaError_t launchTransport(const RunParams& p, int mode, bool calib, const Laun
 int transportOccupancy(int mode, bool calib, bool smemTable, int threads, size_t smem);
 // lane-multiplexed kernel (transport_mux.cu), cfg.slots photons per lane
 cudaError_t launchTransportMux(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream);
+int transportMuxSlots(int mode, bool calib, bool smemTable, int slots); // slot count of the variant that will run
 int transportMuxOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem);
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s);
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s);

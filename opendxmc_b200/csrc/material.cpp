@@ -87,14 +87,19 @@ void buildShells(Material& m, const std::vector<std::pair<const Element*, double
     // keep the most tightly bound shells that still hold a noticeable share of electrons
     std::sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.binding > y.binding; });
     m.nShells = 0;
-    double covered = 0;
+    double covered = 0, restElectrons = 0, restJ = 0;
+    bool tableClosed = false;
     for (const auto& c : cands) {
-        if (m.nShells >= DXB_MAX_SHELLS)
-            break;
-        if (c.binding < kEMin) // below the transport cut-off: indistinguishable from free
-            break;
-        if (c.electrons / totalElectrons < 1e-5)
+        // the table keeps the most tightly bound groups above the transport cut-off; everything else forms one
+        // unbound group whose profile height is the electron-weighted mean (per-electron profiles add linearly)
+        const bool keep = !tableClosed && m.nShells < DXB_MAX_SHELLS && c.binding >= kEMin && c.electrons / totalElectrons >= 1e-5;
+        if (!keep) {
+            if (c.binding < kEMin || m.nShells >= DXB_MAX_SHELLS)
+                tableClosed = true;
+            restElectrons += c.electrons;
+            restJ += c.electrons * c.j0;
             continue;
+        }
         dxb_shell& s = m.shells[m.nShells++];
         s.binding_energy_kev = c.binding;
         s.n_electrons = c.electrons;
@@ -105,6 +110,7 @@ void buildShells(Material& m, const std::vector<std::pair<const Element*, double
         s.photo_fraction_above = 0; // filled by the caller (needs cross sections)
         covered += s.n_electrons_fraction;
     }
+    m.restComptonJ0 = restElectrons > 0 ? restJ / restElectrons : 0.0;
     m.restElectronsFraction = std::max(0.0, 1.0 - covered);
 }
 

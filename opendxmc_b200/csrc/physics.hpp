@@ -87,6 +87,7 @@ struct Material {
     uint32_t nShells = 0;
     dxb_shell shells[DXB_MAX_SHELLS] = {};
     double restElectronsFraction = 1.0;
+    double restComptonJ0 = 0.0; // J(0) of the electrons not covered by `shells`
     double electronsPerGram = 0;
     double effectiveZ = 0;
     double sumAZ = 0, sumAZ2 = 0;              // per average atom

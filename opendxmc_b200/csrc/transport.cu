@@ -242,9 +242,19 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                     const float aTot = lerp(a.w, b.w, epos.f);
                     const float r2 = rb.u(0) * aTot;
                     if (r2 < aPhoto) {
-                        edep = ph.E * ph.w;
-                        ph.E = 0.0f;
-                        status = kStDead;
+                        const float ef = MODE >= 2 ? photoFluorescence(P.tab, mat, ph.E, rb.u(1), rb.u(2)) : 0.0f;
+                        if (MODE >= 2 && ef > 0.0f) {
+                            // fluorescence photon: isotropic, one extra block for its direction
+                            const PhiloxBlock rf = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                            isotropic(rf.u(0), rf.u(1), ph.dx, ph.dy, ph.dz);
+                            edep = (ph.E - ef) * ph.w;
+                            ph.E = ef;
+                            finishScatter(edep, true);
+                        } else {
+                            edep = ph.E * ph.w;
+                            ph.E = 0.0f;
+                            status = kStDead;
+                        }
                     } else if (r2 < aPhoto + aIncoh) {
                         compton = true;
                     } else {
@@ -253,7 +263,13 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 }
                 if (compton) {
                     float e, cosT;
-                    if (comptonTry<MODE>(P.tab, mat, ph.E, rb.u(1), rb.u(2), e, cosT)) {
+                    bool ok = comptonTry<MODE>(P.tab, mat, ph.E, rb.u(1), rb.u(2), e, cosT);
+                    if (MODE >= 2 && ok) {
+                        // impulse approximation: shell + Doppler broadening from one extra block
+                        const PhiloxBlock ri = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                        ok = dopplerBroaden(P.tab, mat, ph.E, e, cosT, ri.u(0), ri.u(1), e);
+                    }
+                    if (ok) {
                         deflect(ph.dx, ph.dy, ph.dz, cosT, kTwoPi * rb.u(3));
                         const float E0 = ph.E;
                         ph.E = E0 * e;
@@ -736,14 +752,18 @@ cudaError_t launchTransport(const RunParams& p, int mode, bool calib, const Laun
     if (!calib) {
         if (mode == 0) {
             DXB_DISPATCH(0, false)
-        } else {
+        } else if (mode == 1) {
             DXB_DISPATCH(1, false)
+        } else {
+            DXB_DISPATCH(2, false)
         }
     } else {
         if (mode == 0) {
             DXB_DISPATCH(0, true)
-        } else {
+        } else if (mode == 1) {
             DXB_DISPATCH(1, true)
+        } else {
+            DXB_DISPATCH(2, true)
         }
     }
 #undef DXB_DISPATCH
@@ -763,14 +783,18 @@ int transportOccupancy(int mode, bool calib, bool smemTable, int threads, size_t
     if (!calib) {
         if (mode == 0) {
             if (smemTable) DXB_OCC(0, false, true) else DXB_OCC(0, false, false)
-        } else {
+        } else if (mode == 1) {
             if (smemTable) DXB_OCC(1, false, true) else DXB_OCC(1, false, false)
+        } else {
+            if (smemTable) DXB_OCC(2, false, true) else DXB_OCC(2, false, false)
         }
     } else {
         if (mode == 0) {
             if (smemTable) DXB_OCC(0, true, true) else DXB_OCC(0, true, false)
-        } else {
+        } else if (mode == 1) {
             if (smemTable) DXB_OCC(1, true, true) else DXB_OCC(1, true, false)
+        } else {
+            if (smemTable) DXB_OCC(2, true, true) else DXB_OCC(2, true, false)
         }
     }
 #undef DXB_OCC

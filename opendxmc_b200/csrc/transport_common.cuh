@@ -217,6 +217,90 @@ __device__ __forceinline__ bool comptonTry(const TablesDev& tab, int mat, float 
     return !(ra > g);
 }
 
+// ---- MODE 2 (impulse approximation), one extra Philox block per accepted Klein-Nishina x S(x) candidate ----
+// The struck electron is drawn from the material's shell table by electron share (electrons not covered by the
+// table form one unbound group with a common profile).  A bound electron carries a momentum component pz along the scattering vector, sampled from
+// the one-parameter profile J(pz) = J0 sech^2(2 J0 pz) (normalised, J(0) = J0, inverse CDF
+// pz = ln(u / (1 - u)) / (4 J0), atomic units) [D: profile shape defined by this project, DESIGN.md §6b]; the
+// scattered energy follows from energy-momentum conservation for that pz (Doppler broadening, e.g. PENELOPE
+// eq. 2.39).  The try is rejected if the shell cannot be ionised (binding >= E) or the energy transfer is below
+// the binding energy.  Returns true and the ratio E'/E if accepted.
+constexpr float kFineStructure = 7.2973525693e-3f;
+__device__ __forceinline__ bool dopplerBroaden(const TablesDev& tab, int mat, float E, float e0, float cosT, float rShell, float rPz, float& eOut)
+{
+    const ShellDev* __restrict__ sh = tab.shells + mat * kMaxShells;
+    const int n = __ldg(tab.n_shells + mat);
+    float r = rShell, U = 0.0f, j0 = 0.0f;
+    bool bound = false;
+    for (int i = 0; i < n; ++i) {
+        const float f = __ldg(&sh[i].nel_fraction);
+        if (r < f) {
+            U = __ldg(&sh[i].binding);
+            j0 = __ldg(&sh[i].j0);
+            bound = true;
+            break;
+        }
+        r -= f;
+    }
+    eOut = e0;
+    if (!bound) {
+        // the electrons outside the table: unbound, one common profile (0: at rest)
+        j0 = __ldg(tab.rest_j0 + mat);
+        if (!(j0 > 0.0f))
+            return true;
+    }
+    if (!(U < E))
+        return false;
+    const float u = fminf(fmaxf(rPz, kU24), 1.0f - kU24);
+    float pz = __logf(__fdividef(u, 1.0f - u)) * __fdividef(0.25f, j0) * kFineStructure; // in units of m_e c
+    pz = fminf(fmaxf(pz, -0.5f), 0.5f);
+    const float t = pz * pz;
+    const float a = 1.0f - t * e0 * cosT;
+    const float b = 1.0f - t * e0 * e0;
+    const float disc = fmaxf(a * a - b * (1.0f - t), 0.0f);
+    const float root = sqrtf(disc);
+    const float e = __fdividef(e0, b) * (a + (pz < 0.0f ? -root : root));
+    if (!(e > 0.0f) || !(E - E * e > U))
+        return false;
+    eOut = fminf(e, 1.0f);
+    return true;
+}
+
+// MODE 2 photoelectric absorption: picks the ionised shell by its share of the photoelectric cross section
+// (shells with binding < E only) and decides whether a fluorescence photon is emitted.  Returns the energy of
+// that photon (0: everything is absorbed locally).
+__device__ __forceinline__ float photoFluorescence(const TablesDev& tab, int mat, float E, float rShell, float rYield)
+{
+    const ShellDev* __restrict__ sh = tab.shells + mat * kMaxShells;
+    const int n = __ldg(tab.n_shells + mat);
+    float r = rShell;
+    for (int i = 0; i < n; ++i) {
+        if (!(__ldg(&sh[i].binding) < E))
+            continue;
+        const float f = __ldg(&sh[i].photo_fraction);
+        if (r < f) {
+            const float ef = __ldg(&sh[i].fluor_energy);
+            if (rYield < __ldg(&sh[i].fluor_yield) && ef >= kMinEnergy && ef < E)
+                return ef;
+            return 0.0f;
+        }
+        r -= f;
+    }
+    return 0.0f;
+}
+
+// isotropic direction from two uniforms
+__device__ __forceinline__ void isotropic(float r0, float r1, float& dx, float& dy, float& dz)
+{
+    const float c = 2.0f * r0 - 1.0f;
+    const float s = sqrtf(fmaxf(0.0f, 1.0f - c * c));
+    float sp, cp;
+    __sincosf(kTwoPi * r1, &sp, &cp);
+    dx = s * cp;
+    dy = s * sp;
+    dz = c;
+}
+
 // Rayleigh: MODE 0 Thomson (pdf ~ (1 + cos^2) sin(theta), rejection from a box); MODE >= 1 samples
 // q^2 ~ F(q)^2 on [0, qmax^2] from the tabulated cumulative A(x^2) (piecewise linear in x^2) and accepts with
 // (1 + cos^2)/2.  Returns true if accepted.

@@ -242,9 +242,19 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                         const float aTot = lerp(a.w, b.w, epos.f);
                         const float r2 = rb.u(0) * aTot;
                         if (r2 < aPhoto) {
-                            edep = E * w;
-                            E = 0.0f;
-                            newPhase = kPhDead;
+                            const float ef = MODE >= 2 ? photoFluorescence(P.tab, mat, E, rb.u(1), rb.u(2)) : 0.0f;
+                            if (MODE >= 2 && ef > 0.0f) {
+                                // fluorescence photon: isotropic, one extra block for its direction
+                                const PhiloxBlock rf = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                                isotropic(rf.u(0), rf.u(1), dx, dy, dz);
+                                edep = (E - ef) * w;
+                                E = ef;
+                                scattered = true;
+                            } else {
+                                edep = E * w;
+                                E = 0.0f;
+                                newPhase = kPhDead;
+                            }
                         } else if (r2 < aPhoto + aIncoh) {
                             compton = true;
                         } else {
@@ -253,7 +263,13 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     }
                     if (compton) {
                         float e, cosT;
-                        if (comptonTry<MODE>(P.tab, mat, E, rb.u(1), rb.u(2), e, cosT)) {
+                        bool ok = comptonTry<MODE>(P.tab, mat, E, rb.u(1), rb.u(2), e, cosT);
+                        if (MODE >= 2 && ok) {
+                            // impulse approximation: shell + Doppler broadening from one extra block
+                            const PhiloxBlock ri = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                            ok = dopplerBroaden(P.tab, mat, E, e, cosT, ri.u(0), ri.u(1), e);
+                        }
+                        if (ok) {
                             deflect(dx, dy, dz, cosT, kTwoPi * rb.u(3));
                             const float E0 = E;
                             E = E0 * e;
@@ -517,9 +533,13 @@ int occupancyMux(int threads, size_t smem)
 // applies CALL(MODE, CALIB, SMEM, M) for the run-time (mode, calib, smem, slots).  The slot count is a tuning
 // knob of the production variant only (mode 1, scoring); every other variant is built with 4 slots per lane.
 #define DXB_MUX_DISPATCH(CALL)                                                  \
-    const int md = mode == 0 ? 0 : 1;                                           \
+    const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
     switch (key) {                                                              \
+    case 8: return CALL(2, false, false, 4);                                    \
+    case 9: return CALL(2, false, true, 4);                                     \
+    case 10: return CALL(2, true, false, 4);                                    \
+    case 11: return CALL(2, true, true, 4);                                     \
     case 0: return CALL(0, false, false, 4);                                    \
     case 1: return CALL(0, false, true, 4);                                     \
     case 2: return CALL(0, true, false, 4);                                     \
@@ -545,6 +565,14 @@ cudaError_t launchTransportMux(const RunParams& p, int mode, bool calib, const L
 #define DXB_CALL(MO, CA, SM, MM) launchMux<MO, CA, SM, MM>(p, cfg, stream)
     DXB_MUX_DISPATCH(DXB_CALL)
 #undef DXB_CALL
+}
+
+int transportMuxSlots(int mode, bool calib, bool smemTable, int slots)
+{
+    // must mirror DXB_MUX_DISPATCH: only the production variant is built for several slot counts
+    if (mode == 1 && !calib && smemTable && (slots == 2 || slots == 3 || slots == 6))
+        return slots;
+    return 4;
 }
 
 int transportMuxOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem)

@@ -174,7 +174,7 @@ struct OMaterial {
     std::vector<double> photo, incoh, coh, etr, ffCdf, sf;
     uint32_t nShells = 0;
     dxb_shell shells[DXB_MAX_SHELLS];
-    double restFraction = 1;
+    double restFraction = 1, restJ0 = 0;
 
     void load(const dxb_material_tables& t)
     {
@@ -194,6 +194,7 @@ struct OMaterial {
         for (uint32_t i = 0; i < nShells; ++i)
             shells[i] = t.shells[i];
         restFraction = t.rest_electrons_fraction;
+        restJ0 = t.rest_compton_j0;
     }
     static double lerpAt(const std::vector<double>& tab, double u)
     {
@@ -334,14 +335,86 @@ bool rayleighTry(double energy, const OMaterial& material, int correction, doubl
     return !((1.0 + cosAngle * cosAngle) * 0.5 < r1);
 }
 
+// ---- correction 2 (impulse approximation) [D: profile shape; R: intent] ----
+// Shell by electron share (uncovered electrons: one unbound group with a common profile); pz from J(pz) = J0 sech^2(2 J0 pz), i.e.
+// pz = ln(u/(1-u)) / (4 J0) atomic units; Doppler-broadened energy from energy-momentum conservation.  False: try
+// rejected (shell cannot be ionised, or energy transfer below the binding energy).  The device reads the shell
+// table as f32, so the same rounded values are used here.
+constexpr double FINE_STRUCTURE = 7.2973525693e-3;
+constexpr double U24 = 5.9604644775390625e-8;
+bool dopplerBroaden(const OMaterial& material, double energy, double e0, double cosTheta, double rShell, double rPz, double& eOut)
+{
+    double r = rShell, U = 0, j0 = 0;
+    bool bound = false;
+    for (uint32_t i = 0; i < material.nShells; ++i) {
+        const double f = static_cast<float>(material.shells[i].n_electrons_fraction);
+        if (r < f) {
+            U = static_cast<float>(material.shells[i].binding_energy_kev);
+            j0 = static_cast<float>(material.shells[i].compton_j0);
+            bound = true;
+            break;
+        }
+        r -= f;
+    }
+    eOut = e0;
+    if (!bound) {
+        j0 = static_cast<float>(material.restJ0); // the electrons outside the table: unbound, one common profile
+        if (!(j0 > 0))
+            return true;
+    }
+    if (!(U < energy))
+        return false;
+    const double u = std::min(std::max(rPz, U24), 1.0 - U24);
+    double pz = std::log(u / (1.0 - u)) * (0.25 / j0) * FINE_STRUCTURE;
+    pz = std::min(std::max(pz, -0.5), 0.5);
+    const double t = pz * pz;
+    const double a = 1.0 - t * e0 * cosTheta;
+    const double b = 1.0 - t * e0 * e0;
+    const double disc = std::max(a * a - b * (1.0 - t), 0.0);
+    const double root = std::sqrt(disc);
+    const double e = e0 / b * (a + (pz < 0 ? -root : root));
+    if (!(e > 0) || !(energy - energy * e > U))
+        return false;
+    eOut = std::min(e, 1.0);
+    return true;
+}
+
+// correction 2 photoelectric effect: energy of the emitted fluorescence photon (0: all absorbed locally)
+double photoFluorescence(const OMaterial& material, double energy, double rShell, double rYield)
+{
+    double r = rShell;
+    for (uint32_t i = 0; i < material.nShells; ++i) {
+        const dxb_shell& s = material.shells[i];
+        if (!(static_cast<float>(s.binding_energy_kev) < energy))
+            continue;
+        const double f = static_cast<float>(s.photo_fraction_above);
+        if (r < f) {
+            const double ef = static_cast<float>(s.fluor_energy_kev);
+            if (rYield < static_cast<float>(s.fluor_yield) && ef >= MIN_ENERGY && ef < energy)
+                return ef;
+            return 0;
+        }
+        r -= f;
+    }
+    return 0;
+}
+
 double comptonScatter(Particle& p, const OMaterial& material, int correction, RandomState& state, const std::array<double, 4>* first,
     double* eRatio = nullptr, double* cosOut = nullptr)
 {
     // the first try may share its block with the channel choice (words 1..3 of *first)
     std::array<double, 4> u = first ? *first : state.block();
     double e, cosTheta;
-    while (!comptonTry(p.energy, material, correction, u[1], u[2], e, cosTheta))
+    for (;;) {
+        bool ok = comptonTry(p.energy, material, correction, u[1], u[2], e, cosTheta);
+        if (ok && correction >= 2) {
+            const std::array<double, 4> ia = state.block(); // one extra block per accepted candidate
+            ok = dopplerBroaden(material, p.energy, e, cosTheta, ia[0], ia[1], e);
+        }
+        if (ok)
+            break;
         u = state.block();
+    }
     p.dir = peturb(p.dir, cosTheta, 2.0 * PI * u[3]);
     const double E = p.energy;
     p.energy *= e;
@@ -370,9 +443,20 @@ InteractionResult interact(const OMaterial::AttenuationValues& att, Particle& p,
     const std::array<double, 4> u = state.block();
     const double r2 = u[0] * att.sum();
     if (r2 < att.photoelectric) {
-        res.energyImparted = p.energy * p.weight;
-        p.energy = 0;
-        res.particleAlive = false;
+        const double ef = correction >= 2 ? photoFluorescence(material, p.energy, u[1], u[2]) : 0.0;
+        if (ef > 0) {
+            // isotropic fluorescence photon, one extra block for its direction
+            const std::array<double, 4> f = state.block();
+            const double c = 2.0 * f[0] - 1.0, sn = std::sqrt(std::max(0.0, 1.0 - c * c)), phi = 2.0 * PI * f[1];
+            p.dir = { sn * std::cos(phi), sn * std::sin(phi), c };
+            res.energyImparted = (p.energy - ef) * p.weight;
+            p.energy = ef;
+            res.particleDirectionChanged = true;
+        } else {
+            res.energyImparted = p.energy * p.weight;
+            p.energy = 0;
+            res.particleAlive = false;
+        }
         res.particleEnergyChanged = true;
     } else if (r2 < att.photoelectric + att.incoherent) {
         res.energyImparted = comptonScatter(p, material, correction, state, &u);

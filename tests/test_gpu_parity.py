@@ -51,7 +51,7 @@ def test_lookup_parity_1e6(dx, orc, c1, c1_world):
     assert (np.abs(dev - ref) / ref).max() <= 1e-6
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_c1_energy_and_roi_parity(dx, orc, c1, mode):
     world = c1.build_world(mode, [0])
     tr = dx.Transport()
@@ -166,7 +166,7 @@ def test_cpp_shim_runs_the_reference_driver():
 
 
 @pytest.mark.parametrize("slots,pairs", [(4, 1), (4, 2), (2, 1), (3, 2), (6, 3)])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_lane_multiplexed_kernel_is_bit_exact(dx, slots, pairs, mode):
     """transport_mux.cu (photons regrouped per lane in shared memory) follows the same random-number protocol as
     the register kernel and sums the same fixed-point tallies: every tally word and counter must be identical."""
@@ -185,3 +185,40 @@ def test_lane_multiplexed_kernel_is_bit_exact(dx, slots, pairs, mode):
     for k in ("histories", "steps", "interactions", "deposits"):
         assert out[0][3][k] == out[1][3][k]
     assert out[0][2].sum() > 0
+
+
+def test_mode2_fluorescence_and_doppler_parity(dx, orc):
+    """physics mode 2 on a calcium-rich block at 25 keV (above the Ca K edge): impulse-approximation Compton
+    (shell choice, Doppler broadening, binding rejection) and K fluorescence photons, GPU vs oracle."""
+    bone = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    water = dx.Material.byNistName("Water, Liquid")
+    n = 24
+    dim, spacing = [n, n, n], [0.5, 0.5, 0.5]
+    mat = np.zeros((n, n, n), dtype=np.uint8)
+    mat[:, :, n // 2:] = 1                      # z-layers: water, then bone
+    dens = np.where(mat == 1, 1.85, 1.0).astype(np.float64)
+    beam = dx.PencilBeam([0.1, -0.1, -8.0], [0, 0, 1], 25.0)
+    beam.setNumberOfExposures(4)
+    beam.setNumberOfParticlesPerExposure(250_000)
+    out = {}
+    for mode in (1, 2):
+        world = dx.World([0])
+        grid = world.addItem(dx.AAVoxelGrid(mode))
+        assert grid.setData(dim, dens.reshape(-1), mat.reshape(-1), [water, bone])
+        grid.setSpacing(spacing)
+        world.build()
+        dx.Transport().run_transport(world, beam)
+        e, e2, cnt = world.energy_scored()
+        st = world.run_stats()
+        ow = orc.OracleWorld(dim, spacing, dens.reshape(-1), mat.reshape(-1), [water, bone])
+        oe, oe2, ocnt, ost = ow.run(beam, mode, SEED)
+        assert st["histories"] == ost["histories"]
+        assert abs(e.sum() - oe.sum()) / oe.sum() <= 5e-3
+        for k in ("steps", "interactions", "deposits"):
+            assert abs(st[k] - ost[k]) / ost[k] < 5e-3, (mode, k, st[k], ost[k])
+        rois = {"water": mat.reshape(-1) == 0, "bone": mat.reshape(-1) == 1}
+        _roi_check(np.array(e), np.array(e2), oe, oe2, rois)
+        out[mode] = (st, float(np.array(e).sum()))
+        world.close()
+    # fluorescence photons and re-tried bound-electron collisions change the event statistics between the modes
+    assert out[2][0]["deposits"] > out[1][0]["deposits"]

@@ -199,3 +199,48 @@ def test_sharded_oracle_runs_sum_to_the_whole(dx, orc):
     assert hist == st["histories"]
     assert np.array_equal(acc_c, cnt)
     assert np.allclose(acc, e, rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ physics mode 2 (impulse approximation, fluorescence)
+def test_impulse_approximation_doppler_broadening(dx, orc):
+    """mode 2: the scattered energy at a fixed angle is no longer the single Compton line: it is broadened around it
+    (moving electrons); transfers below a shell's binding energy are rejected, which shifts the tightly bound
+    shells to lower scattered energies."""
+    bone = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    energy = 60.0
+    k = energy / 510.99895
+    c1, r1 = orc.sample_compton(bone, 1, energy, 300_000, seed=11)
+    c2, r2 = orc.sample_compton(bone, 2, energy, 300_000, seed=11)
+    line = 1.0 / (1.0 + k * (1.0 - c2))
+    assert np.allclose(r1, 1.0 / (1.0 + k * (1.0 - c1)), rtol=1e-9)  # mode 1 keeps free-electron kinematics
+    dev = r2 / line - 1.0
+    t = bone.tables()
+    assert t.n_shells >= 1
+    assert t.rest_compton_j0 > 0 and 0.5 < t.rest_electrons_fraction < 1.0
+    assert (np.abs(dev) < 1e-12).mean() < 1e-3         # nobody sits exactly on the line any more
+    assert 2e-3 < dev.std() < 0.1                      # visible Doppler width (a few per cent of E')
+    assert abs(np.median(dev)) < 5e-3                  # the bulk (outer electrons) is centred on the Compton line
+    back = c2 < -0.5                                   # back-scatter: broadest line (largest momentum transfer)
+    fwd = c2 > 0.5
+    assert dev[back].std() > dev[fwd].std()
+    assert (r2 <= 1.0).all() and (r2 > 0).all()
+    # the angular law is still Klein-Nishina x S(x) to first order: mean cosine within 2 %
+    assert c2.mean() == pytest.approx(c1.mean(), abs=0.02)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_energy_conservation_all_modes_with_fluorescence(dx, orc, mode):
+    """thick calcium-rich absorber, 20 keV (above the Ca K edge, fluorescence 3.7 keV > cut-off): whatever the
+    physics mode does with binding, Doppler shifts and fluorescence photons, deposited == emitted."""
+    bone = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    n = 12
+    ow = orc.OracleWorld([n, n, n], [40.0 / n] * 3, np.full(n ** 3, 1.85), np.zeros(n ** 3, dtype=np.uint8), [bone])
+    beam = dx.PencilBeam([0, 0, 0.0], [0, 0, 1], 20.0)
+    beam.setNumberOfExposures(2)
+    beam.setNumberOfParticlesPerExposure(50_000)
+    e, e2, cnt, st = ow.run(beam, mode, seed=9)
+    assert e.sum() == pytest.approx(st["energy_emitted_kev"], rel=1e-3)
+    if mode == 2:
+        # fluorescence photons add scoring events: more deposits per history than in mode 1
+        _, _, _, st1 = ow.run(beam, 1, seed=9)
+        assert st["deposits"] > st1["deposits"]
