@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "multicast", "nccl"],
+                    help="N > 1: fused reduce->dose reading peers over NVLink P2P (default) or through the NVSwitch multicast "
+                         "address, or an NCCL reduce to rank 0 followed by energy->dose there")
     return ap.parse_args()
 
 
@@ -127,13 +130,16 @@ def cpu_oracle_rate(args, wl, target_seconds):
     ow = orc.OracleWorld.from_workload(wl)
     nexp = wl.beam.numberOfExposures()
     full_ppe = wl.beam.numberOfParticlesPerExposure()
-    # probe
-    wl.beam.setNumberOfParticlesPerExposure(max(1, 200_000 // nexp))
-    _, _, _, st = ow.run(wl.beam, 1, SEED0, 0)
-    rate = st["histories"] / max(st["seconds"], 1e-9)
-    ppe = max(1, int(rate * target_seconds / nexp))
-    wl.beam.setNumberOfParticlesPerExposure(ppe)
-    _, _, _, st = ow.run(wl.beam, 1, SEED0 + 1, 0)
+    # size the sample so that it takes about target_seconds: probe, then rescale until the run is long enough
+    ppe = max(1, 200_000 // nexp)
+    st = None
+    for attempt in range(4):
+        wl.beam.setNumberOfParticlesPerExposure(ppe)
+        _, _, _, st = ow.run(wl.beam, 1, SEED0 + attempt, 0)
+        if st["seconds"] >= 0.6 * target_seconds:
+            break
+        rate = st["histories"] / max(st["seconds"], 1e-9)
+        ppe = max(ppe + 1, int(rate * target_seconds / nexp))
     wl.beam.setNumberOfParticlesPerExposure(full_ppe)
     return {"value": st["histories"] / st["seconds"], "unit": "histories/s", "cores": int(st["threads"]), "kind": "port",
             "sample": "%d histories (%d per exposure x %d exposures) of the same beam through the full volume, %.1f s" % (
@@ -150,11 +156,15 @@ def run_reference(args):
     ow = orc.OracleWorld.from_workload(wl)
     nexp = wl.beam.numberOfExposures()
     full = wl.beam.numberOfParticles()
-    wl.beam.setNumberOfParticlesPerExposure(max(1, 200_000 // nexp))
-    _, _, _, st = ow.run(wl.beam, 1, SEED0, 0)
-    rate = st["histories"] / max(st["seconds"], 1e-9)
     per_step_seconds = min(20.0, 180.0 / max(1, args.steps + args.warmup))
-    ppe = max(1, int(rate * per_step_seconds / nexp))
+    ppe = max(1, 200_000 // nexp)
+    for attempt in range(3):
+        wl.beam.setNumberOfParticlesPerExposure(ppe)
+        _, _, _, st = ow.run(wl.beam, 1, SEED0 + attempt, 0)
+        if st["seconds"] >= 0.6 * per_step_seconds:
+            break
+        rate = st["histories"] / max(st["seconds"], 1e-9)
+        ppe = max(ppe + 1, int(rate * per_step_seconds / nexp))
     wl.beam.setNumberOfParticlesPerExposure(ppe)
     for i in range(args.warmup):
         ow.run(wl.beam, 1, SEED0 + i, 0)
@@ -217,7 +227,23 @@ def run_ours(args):
     K.load().dxb_set_stream(ctx, C.c_void_p(stream.cuda_stream))
     tr = dx.Transport()
     desc = wl.beam.desc()
-    tally = D.tally_tensor(world, local_rank)
+    # N > 1: the exchange step.  Preferred: tallies in symmetric memory + the fused reduce->dose kernel (NVSwitch
+    # multicast sum, else P2P pull); fallback: one NCCL reduce of the tally buffer to rank 0 + energy->dose there.
+    exchange, tally = None, None
+    if dist is not None and args.exchange != "nccl":
+        try:
+            exchange = D.FusedExchange(world, local_rank, multicast=(args.exchange == "multicast"))
+        except Exception as exc:  # symmetric memory unavailable on this box
+            if rank == 0:
+                print(f"bench.py: fused exchange unavailable ({exc!r}); using the NCCL reduce", file=sys.stderr, flush=True)
+            exchange = None
+        ok = torch.tensor([1 if exchange is not None else 0], device=f"cuda:{local_rank}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0 and exchange is not None:
+            exchange.close()
+            exchange = None
+    if exchange is None:
+        tally = D.tally_tensor(world, local_rank)
 
     def barrier():
         if dist is not None:
@@ -231,6 +257,10 @@ def run_ours(args):
         assert rc == 0, lib.dxb_last_error(ctx)
         if timed_stats is not None:
             timed_stats.append(world.run_stats())
+        if exchange is not None:
+            with torch.cuda.stream(stream):
+                exchange.finish_beam(wl.beam, 1, False)
+            return
         if dist is not None:
             with torch.cuda.stream(stream):
                 D.reduce_tallies(tally, 0)
@@ -246,6 +276,9 @@ def run_ours(args):
         rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
         assert rc == 0, lib.dxb_last_error(ctx)
         step(1000 + i)
+        if exchange is not None:
+            with torch.cuda.stream(stream):
+                exchange.gather_dose(0)
         if rank == 0:
             rc = lib.dxb_get_dose(ctx, C.cast(out_pin[0].data_ptr(), K.c_double_p), C.cast(out_pin[1].data_ptr(), K.c_double_p),
                                   C.cast(out_pin[2].data_ptr(), K.c_u64_p))
@@ -298,9 +331,12 @@ def run_ours(args):
         e2e = {"value": n_hist * n_e2e / float(te[0]), "unit": "histories/s",
                "h2d_bytes_per_step": int(nvox * 9 * world_size), "d2h_bytes_per_step": int(nvox * 24),
                "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e,
-               "note": "host-clock around dxb_set_grid + dxb_run_transport + NCCL reduce + dxb_finish_beam + dxb_get_dose, pinned host buffers"}
+               "note": "host-clock around dxb_set_grid + dxb_run_transport + exchange/finish + (N>1: slab gather to rank 0) + dxb_get_dose, pinned host buffers"}
 
     if rank != 0:
+        if exchange is not None:
+            exchange.close()
+        world.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -324,14 +360,18 @@ def run_ours(args):
     value = n_hist * args.steps / (ms_total * 1e-3)
     out = {"metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl, {"parallelism": "histories sharded over %d GPU(s), "
-                                                                                 "int64 tally reduce" % world_size}),
-           "clocks": clocks, "gpu_launches": int(launches + args.steps),  # transport kernels (all ranks) + energyToDose on rank 0
+           "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl, {"parallelism": "histories sharded over %d GPU(s)" % world_size,
+                                                                 "exchange": ("none (1 GPU)" if dist is None else
+                                                                              ("fused reduce->dose per slab, " + exchange.kind) if exchange is not None
+                                                                              else "NCCL int64 reduce to rank 0 + energy->dose")}),
+           "clocks": clocks, "gpu_launches": int(launches + args.steps * (world_size if exchange is not None else 1)),  # transport kernels (all ranks) + energy->dose (rank 0, or one fused slab kernel per rank)
            "roofline": roofline}
     if e2e:
         out["e2e"] = e2e
+    if exchange is not None:
+        exchange.close()
+    world.close()
     if not args.no_cpu_baseline:
-        world.close()
         cb, _ = cpu_oracle_rate(args, wl, args.cpu_seconds)
         out["cpu_baseline"] = cb
     print(json.dumps(out), flush=True)

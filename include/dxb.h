@@ -312,6 +312,27 @@ int dxb_finish_beam(dxb_ctx*, const dxb_beam_desc*, int physics_mode, int use_be
 /* device pointer + element count (int64 words) of the raw fixed-point tally buffer of device 0 */
 int dxb_tally_buffer(dxb_ctx*, void** device_ptr, uint64_t* n_words);
 
+/* Fused exchange + finish for one process per GPU inside one NVSwitch domain (replaces "reduce to rank 0, then
+ * dxb_finish_beam"; same arithmetic as the tail of dxmc::Transport::operator(), call site
+ * R:src/libopendxmc/simulationpipeline.cpp:165).
+ *   dxb_set_tally_storage  — make caller-provided device memory (4 x u64 per voxel, 32-byte aligned; e.g. a
+ *                            symmetric allocation that is peer- and multicast-mapped on every rank) the tally
+ *                            buffer of this context; NULL returns to library-owned storage.  The library zeroes it.
+ *   dxb_finish_beam_sharded — this rank converts voxels [voxel_begin, voxel_end) of the SUM over ranks of the
+ *                            tallies into dose/variance/events, reading the sum in ONE kernel either through
+ *                            `multicast_tally` (NVSwitch in-flight add, multimem.ld_reduce) or, when that is NULL,
+ *                            from its own buffer plus the `n_peers` peer-mapped buffers `peer_tallies` (NVLink
+ *                            P2P loads).  The caller separates it from the transport of all ranks, and from the
+ *                            next beam, by a barrier.  The dose score of a slab lives on the rank that owns it
+ *                            until the caller gathers it (dxb_dose_buffers gives the device arrays).
+ *   Every rank computes the beam calibration factor itself (deterministic), so none is exchanged. */
+int dxb_set_tally_storage(dxb_ctx*, void* device_ptr, uint64_t n_words);
+int dxb_finish_beam_sharded(dxb_ctx*, const dxb_beam_desc*, int physics_mode, int use_beam_calibration,
+                            const void* multicast_tally, const void* const* peer_tallies, int n_peers,
+                            uint64_t voxel_begin, uint64_t voxel_end, double* factor_out);
+/* device arrays of the accumulated dose score of device 0: f64 dose [mGy], f64 variance, u64 events, n_voxels each */
+int dxb_dose_buffers(dxb_ctx*, void** dose, void** variance, void** n_events, uint64_t* n_voxels);
+
 /* doseScored(i).dose()/variance()/numberOfEvents() for all i — R:src/libopendxmc/simulationpipeline.cpp:174-219.
  * Any pointer may be NULL. dose [mGy], variance [mGy^2]. */
 int dxb_get_dose(dxb_ctx*, double* dose, double* variance, uint64_t* n_events);

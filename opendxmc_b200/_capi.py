@@ -164,6 +164,10 @@ SIGNATURES = {
     "dxb_run_transport": (C.c_int, [VP, C.POINTER(dxb_beam_desc), C.c_int, VP]),
     "dxb_finish_beam": (C.c_int, [VP, C.POINTER(dxb_beam_desc), C.c_int, C.c_int, c_double_p]),
     "dxb_tally_buffer": (C.c_int, [VP, C.POINTER(VP), c_u64_p]),
+    "dxb_set_tally_storage": (C.c_int, [VP, VP, C.c_uint64]),
+    "dxb_finish_beam_sharded": (C.c_int, [VP, C.POINTER(dxb_beam_desc), C.c_int, C.c_int, VP, C.POINTER(VP), C.c_int, C.c_uint64,
+                                          C.c_uint64, C.POINTER(C.c_double)]),
+    "dxb_dose_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), c_u64_p]),
     "dxb_get_dose": (C.c_int, [VP, c_double_p, c_double_p, c_u64_p]),
     "dxb_get_energy_scored": (C.c_int, [VP, c_double_p, c_double_p, c_u64_p]),
     "dxb_clear_dose": (C.c_int, [VP]),

@@ -40,13 +40,14 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     int device = -1;
+    bool owned = true; // false: caller-provided storage (dxb_set_tally_storage), never freed here
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) {
+        if (p && owned) {
             int cur = 0;
             cudaGetDevice(&cur);
             if (device >= 0)
@@ -56,6 +57,15 @@ struct DevBuf {
         }
         p = nullptr;
         n = 0;
+        owned = true;
+    }
+    void adopt(T* ptr, size_t count, int dev)
+    {
+        release();
+        p = ptr;
+        n = count;
+        device = dev;
+        owned = false;
     }
     cudaError_t alloc(size_t count, int dev)
     {
@@ -1102,6 +1112,98 @@ int dxb_finish_beam(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int
     c->stats.calibration_ms = calibMs;
     if (factor_out)
         *factor_out = factor;
+    return DXB_OK;
+}
+
+int dxb_set_tally_storage(dxb_ctx* c, void* device_ptr, uint64_t n_words)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "set_tally_storage: set the grid first");
+    if (c->devs.size() != 1)
+        return fail(c, DXB_ESTATE, "set_tally_storage: single-device contexts only (one process per GPU)");
+    DeviceState& d0 = *c->devs[0];
+    World& w = d0.world;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    if (!device_ptr) {
+        if (!w.tally.owned) {
+            w.tally.release();
+            CUDA_TRY(c, w.tally.alloc(w.nvox * 4, w.device));
+        }
+    } else {
+        if (n_words != w.nvox * 4)
+            return fail(c, DXB_EINVAL, "set_tally_storage: the buffer must hold 4 x 64-bit words per voxel");
+        if (reinterpret_cast<uintptr_t>(device_ptr) % 32)
+            return fail(c, DXB_EINVAL, "set_tally_storage: the buffer must be 32-byte aligned");
+        w.tally.adopt(static_cast<unsigned long long*>(device_ptr), w.nvox * 4, w.device);
+    }
+    CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, w.nvox * 4 * sizeof(unsigned long long), d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    c->tallyValid = false;
+    return DXB_OK;
+}
+
+int dxb_finish_beam_sharded(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int use_beam_calibration, const void* multicast_tally,
+    const void* const* peer_tallies, int n_peers, uint64_t voxel_begin, uint64_t voxel_end, double* factor_out)
+{
+    if (!c || !beam)
+        return DXB_EINVAL;
+    if (!c->tallyValid)
+        return fail(c, DXB_ESTATE, "finish_beam_sharded: no tallies (call dxb_run_transport first)");
+    if (c->devs.size() != 1)
+        return fail(c, DXB_ESTATE, "finish_beam_sharded: single-device contexts only (one process per GPU)");
+    DeviceState& d0 = *c->devs[0];
+    World& w = d0.world;
+    if (voxel_begin > voxel_end || voxel_end > w.nvox || n_peers < 0 || n_peers > 63 || (n_peers > 0 && !peer_tallies && !multicast_tally))
+        return fail(c, DXB_EINVAL, "finish_beam_sharded: bad slab or peer list");
+    double factor = kKeVperGramToMilliGray;
+    double calibMs = 0;
+    if (use_beam_calibration) {
+        // every rank derives the factor itself: the nested CTDI run is deterministic (Philox + integer tallies), so all
+        // ranks get the same bits without a broadcast
+        if (isCtBeam(beam->type)) {
+            int rc = ctCalibration(c, *beam, physics_mode, &factor, &calibMs);
+            if (rc != DXB_OK)
+                return rc;
+        } else {
+            factor = beamAnalyticCalibration(*beam);
+        }
+    }
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    DevBuf<const unsigned long long*> dPeers;
+    if (!multicast_tally && n_peers > 0) {
+        std::vector<const unsigned long long*> peers(n_peers);
+        for (int i = 0; i < n_peers; ++i)
+            peers[i] = static_cast<const unsigned long long*>(peer_tallies[i]);
+        CUDA_TRY(c, dPeers.upload(peers, d0.device, d0.stream));
+    }
+    const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
+    const unsigned long long* src = multicast_tally ? static_cast<const unsigned long long*>(multicast_tally) : w.tally.p;
+    launchFusedReduceToDose(src, multicast_tally != nullptr, dPeers.p, multicast_tally ? 0 : n_peers, w.voxels.p, d0.dose.p, d0.variance.p,
+        d0.events.p, voxel_begin, voxel_end, 1.0 / c->scaleE, 1.0 / c->scaleE2, factor, vol, d0.stream);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    c->stats.calibration_factor = factor;
+    c->stats.calibration_ms = calibMs;
+    if (factor_out)
+        *factor_out = factor;
+    return DXB_OK;
+}
+
+int dxb_dose_buffers(dxb_ctx* c, void** dose, void** variance, void** n_events, uint64_t* n_voxels)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "dose_buffers: no grid");
+    DeviceState& d0 = *c->devs[0];
+    if (dose)
+        *dose = d0.dose.p;
+    if (variance)
+        *variance = d0.variance.p;
+    if (n_events)
+        *n_events = d0.events.p;
+    if (n_voxels)
+        *n_voxels = d0.world.nvox;
     return DXB_OK;
 }
 

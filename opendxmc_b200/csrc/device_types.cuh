@@ -12,7 +12,7 @@ constexpr int kDevNX = 353;
 constexpr int kDevXPerOctave = 32;
 constexpr float kDevXMinInv = 128.0f;
 constexpr int kMaxShells = 5;
-constexpr int kSourceBufWords = 13; // words per entry of the per-warp source buffer (transport.cu)
+constexpr int kSourceBufWords = 12; // words per entry of the per-warp source buffer (transport.cu)
 
 // HBM layout of the voxel grid (x fastest, like the reference: i + j*nx + k*nx*ny,
 // R:src/libopendxmc/otherphantomimportpipeline.cpp:44).
@@ -118,8 +118,8 @@ __host__ __device__ inline size_t transportSmemBytes(int threads, int table_floa
 }
 
 // the lane-multiplexed kernel (transport_mux.cu): every lane owns `slots` photons in shared memory
-constexpr int kSlotWords = 11;  // px py pz dx dy dz E w remaining hlo meta
-constexpr int kMuxBufWords = 10; // px py pz dx dy dz E w remaining lane-offset
+constexpr int kSlotWords = 10;  // px py pz dx dy dz E w hlo meta
+constexpr int kMuxBufWords = 9; // px py pz dx dy dz E w lane-offset
 __host__ __device__ inline size_t muxSmemBytes(int threads, int slots, int table_floats)
 {
     const size_t warps = static_cast<size_t>(threads) / 32;

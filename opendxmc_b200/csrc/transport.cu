@@ -49,14 +49,13 @@ struct Photon {
     float px, py, pz;
     float dx, dy, dz;
     float E, w;
-    float remaining; // distance to the grid exit along the current direction
 };
 
 // state values double as vote increments: one __reduce_add_sync gives all lane counts (dead: bits 0-7,
 // waiting for an interaction try: bits 8-15, waiting for a Rayleigh try: bits 16-23; bit 30 only tags WAIT_C)
 constexpr int kStStep = 0, kStDead = 1, kStWaitNew = 0x100, kStWaitC = 0x100 | (1 << 30), kStWaitR = 0x10000;
-constexpr int kWarpBufFloats = kSourceBufWords * 32; // px py pz dx dy dz E w remaining histOffset epos.i epos.f muMax
-static_assert(kSourceBufWords == 13, "source buffer layout");
+constexpr int kWarpBufFloats = kSourceBufWords * 32; // px py pz dx dy dz E w histOffset epos.i epos.f muMax
+static_assert(kSourceBufWords == 12, "source buffer layout");
 
 template <int MODE, bool CALIB, bool SMEM_TABLE>
 __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant__ RunParams P)
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
     int mat = 0;
     epos.i = 0;
     epos.f = 0.0f;
-    ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.E = ph.w = ph.remaining = 0.0f;
+    ph.px = ph.py = ph.pz = ph.dx = ph.dy = ph.dz = ph.E = ph.w = 0.0f;
 
     unsigned int nSteps = 0; // the other per-lane counters live in shared memory (scnt)
 
@@ -127,7 +126,6 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 muMaxU24 = muMax * kU24;
                 stepScale = -kLn2 * __fdividef(1.0f, muMax);
             }
-            ph.remaining = exitDistance(G, ph.px, ph.py, ph.pz, ph.dx, ph.dy, ph.dz);
             status = kStStep;
         } else {
             status = kStDead;
@@ -164,12 +162,11 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
                 const float sA = __log2f(fmaf(rb.k(0), -kU24, 1.0f)) * stepScale;
                 const float sB = __log2f(fmaf(rb.k(2), -kU24, 1.0f)) * stepScale;
-                const bool inA = sA < ph.remaining;
-                const bool inB = inA && (sA + sB < ph.remaining);
                 const float ax = fmaf(ph.dx, sA, ph.px), ay = fmaf(ph.dy, sA, ph.py), az = fmaf(ph.dz, sA, ph.pz);
                 const float bx = fmaf(ph.dx, sB, ax), by = fmaf(ph.dy, sB, ay), bz = fmaf(ph.dz, sB, az);
-                voxA = voxelIndex(G, ax, ay, az);
-                voxB = voxelIndex(G, bx, by, bz);
+                // a step whose end point is outside the grid ends the history (B is only reached through A)
+                const bool inA = voxelIndex(G, ax, ay, az, voxA);
+                const bool inB = voxelIndex(G, bx, by, bz, voxB) && inA;
                 // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                 unsigned int cellA = 0u, cellB = 0u;
                 if (inA)
@@ -192,7 +189,6 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                         ph.px = ax;
                         ph.py = ay;
                         ph.pz = az;
-                        ph.remaining -= sA;
                         voxel = voxA;
                         mat = matA;
                         status = kStWaitNew;
@@ -210,7 +206,6 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                         ph.px = bx;
                         ph.py = by;
                         ph.pz = bz;
-                        ph.remaining -= sA + sB;
                         if (rb.k(3) * muMaxU24 < muB) {
                             voxel = voxB;
                             mat = matB;
@@ -333,7 +328,7 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 float qmu = 1.0f;
                 qpos.i = 0;
                 qpos.f = 0.0f;
-                q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = q.remaining = 0.0f;
+                q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = 0.0f;
                 if (lane < nb && h < P.n_total) {
                     const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
                     const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
@@ -425,7 +420,6 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                         q.px = fmaf(q.dx, tmin, q.px);
                         q.py = fmaf(q.dy, tmin, q.py);
                         q.pz = fmaf(q.dz, tmin, q.pz);
-                        q.remaining = tmax - tmin;
                         qpos = energyPos(E);
                         qmu = lerp(__ldg(P.tab.majorant + qpos.i), __ldg(P.tab.majorant + qpos.i + 1), qpos.f);
                         hit = true;
@@ -448,11 +442,10 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                     sbuf[5 * 32 + k] = q.dz;
                     sbuf[6 * 32 + k] = q.E;
                     sbuf[7 * 32 + k] = q.w;
-                    sbuf[8 * 32 + k] = q.remaining;
-                    sbuf[9 * 32 + k] = __int_as_float(lane);
-                    sbuf[10 * 32 + k] = __int_as_float(qpos.i);
-                    sbuf[11 * 32 + k] = qpos.f;
-                    sbuf[12 * 32 + k] = qmu;
+                    sbuf[8 * 32 + k] = __int_as_float(lane);
+                    sbuf[9 * 32 + k] = __int_as_float(qpos.i);
+                    sbuf[10 * 32 + k] = qpos.f;
+                    sbuf[11 * 32 + k] = qmu;
                 }
                 bufCount = __popc(mHit);
                 __syncwarp();
@@ -471,11 +464,10 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                     ph.dz = sbuf[5 * 32 + k];
                     ph.E = sbuf[6 * 32 + k];
                     ph.w = sbuf[7 * 32 + k];
-                    ph.remaining = sbuf[8 * 32 + k];
-                    const unsigned long long h = spool[2] + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
-                    epos.i = __float_as_int(sbuf[10 * 32 + k]);
-                    epos.f = sbuf[11 * 32 + k];
-                    const float muMax = sbuf[12 * 32 + k];
+                    const unsigned long long h = spool[2] + static_cast<unsigned int>(__float_as_int(sbuf[8 * 32 + k]));
+                    epos.i = __float_as_int(sbuf[9 * 32 + k]);
+                    epos.f = sbuf[10 * 32 + k];
+                    const float muMax = sbuf[11 * 32 + k];
                     muMaxU24 = muMax * kU24;
                     stepScale = -kLn2 * __fdividef(1.0f, muMax);
                     hlo = static_cast<unsigned int>(h);
@@ -567,6 +559,55 @@ __global__ void energyToDoseKernel(const unsigned long long* __restrict__ tally,
         dose[i] += e * f;
         variance[i] += varE * f * f;
         events[i] += t.z;
+    }
+}
+
+// Multi-process finish, fused with the exchange step: this rank converts voxels [begin, end) and
+// reads, per voxel, the SUM over all ranks of the fixed-point tallies
+//   MULTICAST  through an NVSwitch multicast address: one multimem.ld_reduce per word, the switch adds the ranks'
+//              words in flight (NVLS), so the slab costs one pass at link speed and no intermediate buffer;
+//   otherwise  by P2P loads from the peer-mapped tally buffers of the other ranks (NVLink) + the local one.
+// Integer sums: identical to the single-GPU tallies whatever the order.
+template <bool MULTICAST>
+__global__ void fusedReduceToDoseKernel(const unsigned long long* __restrict__ tally /* multicast or local */,
+    const unsigned long long* const* __restrict__ peers, int n_peers, const unsigned int* __restrict__ voxels,
+    double* __restrict__ dose, double* __restrict__ variance, unsigned long long* __restrict__ events, size_t begin, size_t end,
+    double inv_scale_e, double inv_scale_e2, double factor, double voxel_volume)
+{
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = begin + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < end; i += stride) {
+        unsigned long long se, se2, sn;
+        if (MULTICAST) {
+            const unsigned long long* p = tally + i * 4;
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(se) : "l"(p) : "memory");
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(se2) : "l"(p + 1) : "memory");
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(sn) : "l"(p + 2) : "memory");
+        } else {
+            const ulonglong4 t = reinterpret_cast<const ulonglong4*>(tally)[i];
+            se = t.x;
+            se2 = t.y;
+            sn = t.z;
+            for (int p = 0; p < n_peers; ++p) {
+                const ulonglong2* q = reinterpret_cast<const ulonglong2*>(peers[p] + i * 4);
+                const ulonglong2 v0 = __ldcg(q), v1 = __ldcg(q + 1);
+                se += v0.x;
+                se2 += v0.y;
+                sn += v1.x;
+            }
+        }
+        if (sn == 0)
+            continue;
+        const double rho = static_cast<double>(voxelDensity(voxels[i]));
+        if (!(rho > 0.0))
+            continue;
+        const double e = static_cast<double>(se) * inv_scale_e;
+        const double e2 = static_cast<double>(se2) * inv_scale_e2;
+        const double nn = static_cast<double>(sn);
+        const double varE = fmax(0.0, e2 - e * e / nn);
+        const double f = factor / (rho * voxel_volume);
+        dose[i] += e * f;
+        variance[i] += varE * f * f;
+        events[i] += sn;
     }
 }
 
@@ -813,6 +854,15 @@ void launchEnergyToDose(const unsigned long long* tally, const unsigned int* vox
     unsigned long long* events, size_t n, double inv_e, double inv_e2, double factor, double vol, cudaStream_t s)
 {
     energyToDoseKernel<<<148 * 8, 256, 0, s>>>(tally, voxels, dose, variance, events, n, inv_e, inv_e2, factor, vol);
+}
+void launchFusedReduceToDose(const unsigned long long* tally, bool multicast, const unsigned long long* const* peers, int n_peers,
+    const unsigned int* voxels, double* dose, double* variance, unsigned long long* events, size_t begin, size_t end, double inv_e,
+    double inv_e2, double factor, double vol, cudaStream_t s)
+{
+    if (multicast)
+        fusedReduceToDoseKernel<true><<<148 * 8, 256, 0, s>>>(tally, peers, n_peers, voxels, dose, variance, events, begin, end, inv_e, inv_e2, factor, vol);
+    else
+        fusedReduceToDoseKernel<false><<<148 * 8, 256, 0, s>>>(tally, peers, n_peers, voxels, dose, variance, events, begin, end, inv_e, inv_e2, factor, vol);
 }
 void launchTallyToEnergy(const unsigned long long* tally, double* e, double* e2, unsigned long long* cnt, size_t n,
     double inv_e, double inv_e2, cudaStream_t s)

@@ -102,30 +102,16 @@ __device__ __forceinline__ unsigned int loadVoxel(const unsigned int* p, int mod
 }
 
 // ------------------------------------------------------------------ geometry helpers
-__device__ __forceinline__ float exitDistance(const GridDev& g, float px, float py, float pz, float dx, float dy, float dz)
+// Voxel of a point: linear index (x fastest) and whether the point lies inside the grid.  floor() of a negative
+// coordinate is a negative integer, i.e. a huge unsigned one, so one unsigned compare per axis tests both faces.
+// This IS the Woodcock exit test: a tentative step ends the history when its end point is outside the AABB.
+__device__ __forceinline__ bool voxelIndex(const GridDev& G, float x, float y, float z, unsigned int& index)
 {
-    const float tx = __fdividef((dx > 0.0f ? g.x1 : g.x0) - px, dx);
-    const float ty = __fdividef((dy > 0.0f ? g.y1 : g.y0) - py, dy);
-    const float tz = __fdividef((dz > 0.0f ? g.z1 : g.z0) - pz, dz);
-    // a zero direction component gives +-inf or NaN: excluded explicitly
-    float t = 3.0e38f;
-    if (dx != 0.0f)
-        t = fminf(t, tx);
-    if (dy != 0.0f)
-        t = fminf(t, ty);
-    if (dz != 0.0f)
-        t = fminf(t, tz);
-    return fmaxf(t, 0.0f);
-}
-
-// linear voxel index of a point inside (or, by rounding, on the surface of) the grid.  The float -> unsigned
-// conversion saturates negative values to 0, the upper side is clamped explicitly.
-__device__ __forceinline__ unsigned int voxelIndex(const GridDev& G, float x, float y, float z)
-{
-    const unsigned int ix = min(__float2uint_rz(fmaf(x, G.inv_dx, G.offx)), static_cast<unsigned int>(G.nx - 1));
-    const unsigned int iy = min(__float2uint_rz(fmaf(y, G.inv_dy, G.offy)), static_cast<unsigned int>(G.ny - 1));
-    const unsigned int iz = min(__float2uint_rz(fmaf(z, G.inv_dz, G.offz)), static_cast<unsigned int>(G.nz - 1));
-    return (iz * G.ny + iy) * G.nx + ix;
+    const unsigned int ix = static_cast<unsigned int>(__float2int_rd(fmaf(x, G.inv_dx, G.offx)));
+    const unsigned int iy = static_cast<unsigned int>(__float2int_rd(fmaf(y, G.inv_dy, G.offy)));
+    const unsigned int iz = static_cast<unsigned int>(__float2int_rd(fmaf(z, G.inv_dz, G.offz)));
+    index = (iz * G.ny + iy) * G.nx + ix;
+    return ix < static_cast<unsigned int>(G.nx) && iy < static_cast<unsigned int>(G.ny) && iz < static_cast<unsigned int>(G.nz);
 }
 
 __device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float cosT, float phi)

@@ -3,7 +3,7 @@
 // Same physics, same random-number protocol (header of transport.cu) and therefore the same results, history
 // for history, as the one-photon-per-lane kernel in transport.cu; what changes is where photons live.
 //
-// Every lane owns M photon *slots* in shared memory (11 words each, lane-private columns: word f of slot j of
+// Every lane owns M photon *slots* in shared memory (10 words each, lane-private columns: word f of slot j of
 // lane l sits at [(f*M + j)*32 + l], so every access of a warp is bank-conflict free) and a status word with
 // one bit per slot and state.  Each iteration the warp votes for ONE phase (step / interaction try / Rayleigh
 // try / refill) and every lane picks, among ITS OWN slots, a photon that is in that phase.  With M = 4 a lane
@@ -24,7 +24,7 @@ constexpr int kMetaMatShift = 20;               // material of the pending inter
 constexpr unsigned int kMetaRetry = 1u << 28;   // Compton already chosen, previous candidate rejected
 
 // slot words
-enum : int { kWPx = 0, kWPy, kWPz, kWDx, kWDy, kWDz, kWE, kWW, kWRem, kWHlo, kWMeta };
+enum : int { kWPx = 0, kWPy, kWPz, kWDx, kWDy, kWDz, kWE, kWW, kWHlo, kWMeta };
 static_assert(kWMeta + 1 == kSlotWords, "slot layout");
 // byte of the status word that holds the slot mask of a state
 enum : int { kPhStep = 0, kPhInt = 1, kPhRay = 2, kPhDead = 3, kPhNone = 4 };
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
             const bool active = m != 0u;
             const int j = active ? __ffs(m) - 1 : 0;
             float* __restrict__ sp = slots + j * 32;
-            float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, E = 0.f, w = 0.f, remaining = 0.f;
+            float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, E = 0.f, w = 0.f;
             unsigned int hlo = 0, hhi = 0, blk = 0;
             TabPos epos;
             epos.i = 0;
@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                 E = sp[kWE * kStride];
                 if (CALIB)
                     w = sp[kWW * kStride];
-                remaining = sp[kWRem * kStride];
                 hlo = __float_as_uint(sp[kWHlo * kStride]);
                 blk = __float_as_uint(sp[kWMeta * kStride]) & kMetaBlkMask;
                 hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
@@ -132,12 +131,11 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
                     const float sA = __log2f(fmaf(rb.k(0), -kU24, 1.0f)) * stepScale;
                     const float sB = __log2f(fmaf(rb.k(2), -kU24, 1.0f)) * stepScale;
-                    const bool inA = sA < remaining;
-                    const bool inB = inA && (sA + sB < remaining);
                     const float ax = fmaf(dx, sA, px), ay = fmaf(dy, sA, py), az = fmaf(dz, sA, pz);
                     const float bx = fmaf(dx, sB, ax), by = fmaf(dy, sB, ay), bz = fmaf(dz, sB, az);
-                    voxA = voxelIndex(G, ax, ay, az);
-                    voxB = voxelIndex(G, bx, by, bz);
+                    // a step whose end point is outside the grid ends the history (B is only reached through A)
+                    const bool inA = voxelIndex(G, ax, ay, az, voxA);
+                    const bool inB = voxelIndex(G, bx, by, bz, voxB) && inA;
                     // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                     unsigned int cellA = 0u, cellB = 0u;
                     if (inA)
@@ -161,7 +159,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                             px = ax;
                             py = ay;
                             pz = az;
-                            remaining -= sA;
                             mat = matA;
                             newPhase = kPhInt;
                             stepping = false;
@@ -180,7 +177,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                             px = bx;
                             py = by;
                             pz = bz;
-                            remaining -= sA + sB;
                             if (rb.k(3) * muMaxU24 < muB) {
                                 mat = matB;
                                 newPhase = kPhInt;
@@ -205,7 +201,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     sp[kWPx * kStride] = px;
                     sp[kWPy * kStride] = py;
                     sp[kWPz * kStride] = pz;
-                    sp[kWRem * kStride] = remaining;
                     sp[kWMeta * kStride] = __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift));
                 }
                 st ^= (1u << j) ^ (1u << (8 * newPhase + j));
@@ -305,7 +300,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                         sp[kWDz * kStride] = dz;
                         sp[kWE * kStride] = E;
                         sp[kWW * kStride] = w;
-                        sp[kWRem * kStride] = exitDistance(G, px, py, pz, dx, dy, dz);
                         meta &= ~kMetaRetry;
                     }
                 }
@@ -314,7 +308,7 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                 if (CALIB)
                     edep = 0.0f;
                 if (edep > 0.0f)
-                    voxel = voxelIndex(G, px, py, pz);
+                    voxelIndex(G, px, py, pz, voxel);
                 st ^= (1u << (8 * phase + j)) ^ (1u << (8 * newPhase + j));
             }
             if (!CALIB && phase == kPhInt) {
@@ -352,7 +346,7 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                 poolNext += nb;
                 const unsigned long long h = bufBase + lane;
                 bool hit = false;
-                float qpx = 0.f, qpy = 0.f, qpz = 0.f, qdx = 0.f, qdy = 0.f, qdz = 0.f, qE = 0.f, qw = 0.f, qrem = 0.f;
+                float qpx = 0.f, qpy = 0.f, qpz = 0.f, qdx = 0.f, qdy = 0.f, qdz = 0.f, qE = 0.f, qw = 0.f;
                 if (lane < nb && h < P.n_total) {
                     const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
                     const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
@@ -439,7 +433,6 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                         qpx = fmaf(qdx, tmin, qpx);
                         qpy = fmaf(qdy, tmin, qpy);
                         qpz = fmaf(qdz, tmin, qpz);
-                        qrem = tmax - tmin;
                         hit = true;
                     }
                 }
@@ -454,8 +447,7 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     sbuf[5 * 32 + k] = qdz;
                     sbuf[6 * 32 + k] = qE;
                     sbuf[7 * 32 + k] = qw;
-                    sbuf[8 * 32 + k] = qrem;
-                    sbuf[9 * 32 + k] = __int_as_float(lane);
+                    sbuf[8 * 32 + k] = __int_as_float(lane);
                 }
                 bufCount = __popc(mHit);
                 __syncwarp();
@@ -478,8 +470,7 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     sp[kWDz * kStride] = sbuf[5 * 32 + k];
                     sp[kWE * kStride] = sbuf[6 * 32 + k];
                     sp[kWW * kStride] = sbuf[7 * 32 + k];
-                    sp[kWRem * kStride] = sbuf[8 * 32 + k];
-                    const unsigned long long h = bufBase + static_cast<unsigned int>(__float_as_int(sbuf[9 * 32 + k]));
+                    const unsigned long long h = bufBase + static_cast<unsigned int>(__float_as_int(sbuf[8 * 32 + k]));
                     sp[kWHlo * kStride] = __uint_as_float(static_cast<unsigned int>(h));
                     sp[kWMeta * kStride] = __uint_as_float(2u); // blocks 0-1 belong to the source
                     st ^= (1u << (8 * kPhDead + j)) ^ (1u << j);

@@ -53,3 +53,113 @@ def run_beam(world, beam, tally, rank, use_beam_calibration=True, progress=None,
     if rank == 0:
         return tr.finish_beam(world, beam, use_beam_calibration)
     return None
+
+
+class FusedExchange:
+    """The exchange step fused with energy->dose over NVLink / NVSwitch (include/dxb.h: dxb_finish_beam_sharded).
+
+    The tally buffer of every rank is re-homed into torch symmetric memory, so that each rank sees its peers' buffers
+    (P2P mappings) and, on NVSwitch systems, one multicast address whose loads return the in-switch SUM of all ranks'
+    words (multimem.ld_reduce).  After the transport kernels, rank r converts ITS slab of voxels reading that sum
+    directly: no reduced copy of the 32 B/voxel tallies is ever written, and the 1/N slabs run in parallel.  The dose
+    score of a slab stays on its rank until `gather_dose` refreshes rank 0's copy (read-out time, not per beam).
+    torch supplies the memory mapping and the barrier; the arithmetic is libdxmc_b200's kernel.
+    """
+
+    def __init__(self, world, local_rank, group=None, multicast=True):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self._torch, self._dist = torch, dist
+        self.world = world
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.size = dist.get_world_size(self.group)
+        self.device = torch.device("cuda", local_rank)
+        lib = K.load()
+        ptr, n = C.c_void_p(), C.c_uint64()
+        rc = lib.dxb_tally_buffer(world.ctx(), C.byref(ptr), C.byref(n))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_tally_buffer")
+        self.n_words = int(n.value)
+        self.n_voxels = self.n_words // 4
+        self.tally = symm.empty(self.n_words, dtype=torch.int64, device=self.device)
+        self.handle = symm.rendezvous(self.tally, self.group)
+        mc = int(self.handle.multicast_ptr or 0) if multicast else 0   # 0: no NVSwitch multicast object on this system
+        self.multicast_ptr = mc
+        self.peer_ptrs = [int(p) for r, p in enumerate(self.handle.buffer_ptrs) if r != self.rank]
+        self.begin = self.n_voxels * self.rank // self.size
+        self.end = self.n_voxels * (self.rank + 1) // self.size
+        self.kind = "nvls-multicast" if mc else "p2p-pull"
+        # adopt last: nothing above may leave the context pointing at memory that is about to be freed
+        rc = lib.dxb_set_tally_storage(world.ctx(), C.c_void_p(self.tally.data_ptr()), self.n_words)
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_set_tally_storage", (lib.dxb_last_error(world.ctx()) or b"").decode())
+
+    def slab(self, rank):
+        return self.n_voxels * rank // self.size, self.n_voxels * (rank + 1) // self.size
+
+    def barrier(self):
+        """all ranks' work enqueued so far is complete (device-side barrier over the symmetric signal pads)."""
+        self.handle.barrier(channel=0)
+        self._torch.cuda.current_stream(self.device).synchronize()
+
+    def finish_beam(self, beam, physics_mode, use_beam_calibration=True):
+        """call after dxb_run_transport on every rank; returns the calibration factor (identical on all ranks)."""
+        lib = K.load()
+        self.barrier()  # every rank's transport kernels have finished: the tallies are final
+        f = C.c_double()
+        peers = (K.VP * max(1, len(self.peer_ptrs)))(*self.peer_ptrs)
+        rc = lib.dxb_finish_beam_sharded(self.world.ctx(), C.byref(beam.desc()), int(physics_mode), 1 if use_beam_calibration else 0,
+                                         C.c_void_p(self.multicast_ptr) if self.multicast_ptr else None, peers, len(self.peer_ptrs),
+                                         self.begin, self.end, C.byref(f))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_finish_beam_sharded", (lib.dxb_last_error(self.world.ctx()) or b"").decode())
+        self.barrier()  # nobody clears its tallies for the next beam while a peer still reads them
+        return f.value
+
+    def _dose_tensors(self):
+        torch = self._torch
+        lib = K.load()
+        d, v, e, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        rc = lib.dxb_dose_buffers(self.world.ctx(), C.byref(d), C.byref(v), C.byref(e), C.byref(n))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_dose_buffers")
+
+        def view(ptr, typestr):
+            iface = {"shape": (int(n.value),), "typestr": typestr, "data": (ptr.value, False), "version": 3, "strides": None}
+            holder = type("_V", (), {"__cuda_array_interface__": iface})()
+            return torch.as_tensor(holder, device=self.device)
+        return view(d, "<f8"), view(v, "<f8"), view(e, "<i8")
+
+    def gather_dose(self, dst=0):
+        """refresh rank `dst`'s copy of the remote slabs of the accumulated dose score (dose, variance, events)."""
+        dist = self._dist
+        ops = []
+        for t in self._dose_tensors():
+            if self.rank == dst:
+                for r in range(self.size):
+                    if r != dst:
+                        b, e = self.slab(r)
+                        if e > b:
+                            ops.append(dist.P2POp(dist.irecv, t[b:e], r, self.group))
+            elif self.end > self.begin:
+                ops.append(dist.P2POp(dist.isend, t[self.begin:self.end], dst, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self._torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        """hand the tally storage back to the library before the symmetric allocation goes away."""
+        K.load().dxb_set_tally_storage(self.world.ctx(), None, 0)
+        self.tally = None
+        self.handle = None
+
+
+def run_beam_fused(world, beam, exchange, use_beam_calibration=True, progress=None):
+    """Transport::operator() across ranks with the fused exchange: shard tallies -> (barrier) -> every rank converts
+    its slab of the multicast-summed tallies.  Returns the calibration factor."""
+    from .api import Transport
+    Transport().run_transport(world, beam, progress)
+    return exchange.finish_beam(beam, world._item.lowEnergyCorrection, use_beam_calibration)

@@ -304,3 +304,20 @@ def test_in_process_multi_gpu_is_bit_identical(dx):
         assert np.array_equal(x, y)
     w1.close()
     w2.close()
+
+
+def test_fused_exchange_matches_single_gpu_bit_for_bit():
+    """one process per GPU: symmetric-memory tallies + dxb_finish_beam_sharded (NVSwitch multicast sum and P2P pull)
+    against the single-GPU dose score — tests/mp_fused_exchange.py under torchrun."""
+    import os
+    import subprocess
+    import sys
+    from opendxmc_b200 import _capi as K
+    n = K.load().dxb_device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "mp_fused_exchange.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
