@@ -46,9 +46,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "multicast", "nccl"],
-                    help="N > 1: fused reduce->dose reading peers over NVLink P2P (default) or through the NVSwitch multicast "
-                         "address, or an NCCL reduce to rank 0 followed by energy->dose there")
+    ap.add_argument("--exchange", default="multicast", choices=["multicast", "p2p", "nccl"],
+                    help="N > 1: fused reduce->dose per voxel slab, reading the sum over ranks through the NVSwitch multicast "
+                         "address (default; falls back to P2P pulls without multicast support) or by NVLink P2P pulls, or an "
+                         "NCCL reduce to rank 0 followed by energy->dose there")
     return ap.parse_args()
 
 

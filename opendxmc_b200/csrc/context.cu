@@ -1179,7 +1179,8 @@ int dxb_finish_beam_sharded(dxb_ctx* c, const dxb_beam_desc* beam, int physics_m
     }
     const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
     const unsigned long long* src = multicast_tally ? static_cast<const unsigned long long*>(multicast_tally) : w.tally.p;
-    launchFusedReduceToDose(src, multicast_tally != nullptr, dPeers.p, multicast_tally ? 0 : n_peers, w.voxels.p, d0.dose.p, d0.variance.p,
+    launchFusedReduceToDose(src, multicast_tally != nullptr, dPeers.p, multicast_tally ? 0 : n_peers,
+        n_peers > 0 ? static_cast<int>(c->rank % static_cast<uint64_t>(n_peers)) : 0, w.voxels.p, d0.dose.p, d0.variance.p,
         d0.events.p, voxel_begin, voxel_end, 1.0 / c->scaleE, 1.0 / c->scaleE2, factor, vol, d0.stream);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));

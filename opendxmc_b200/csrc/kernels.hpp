@@ -14,7 +14,7 @@ void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, fl
 void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,
     unsigned long long* events, size_t n, double inv_e, double inv_e2, double factor, double vol, cudaStream_t s);
 void launchFusedReduceToDose(const unsigned long long* tally, bool multicast, const unsigned long long* const* peers, int n_peers,
-    const unsigned int* voxels, double* dose, double* variance, unsigned long long* events, size_t begin, size_t end, double inv_e,
+    int first_peer, const unsigned int* voxels, double* dose, double* variance, unsigned long long* events, size_t begin, size_t end, double inv_e,
     double inv_e2, double factor, double vol, cudaStream_t s);
 void launchTallyToEnergy(const unsigned long long* tally, double* e, double* e2, unsigned long long* cnt, size_t n,
     double inv_e, double inv_e2, cudaStream_t s);
