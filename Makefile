@@ -8,7 +8,7 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-f
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
-OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/context.o
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o
 
 all: $(LIB) oracle shim
 

@@ -354,7 +354,7 @@ def run_ours(args):
     # per-GPU roofline of the transport kernel: this rank's share of the histories over the slowest rank's kernel time
     achieved = (hist_done / world_size) * a_hist / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "transportKernel<1,false,true>", "peak_source": "measured" if peaks else "fallback",
+                "kernel": "transportKernelPool<1,false,true,16>", "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": D,
                 "sector_bytes_per_history": (S + 3 * D) * 32.0,
                 "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / ms_total}

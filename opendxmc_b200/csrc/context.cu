@@ -177,10 +177,14 @@ struct Options {
     int refillThreshold = -1;    // warp phase machine; -1 = the default of the selected kernel
     int interactThreshold = -1;
     int rayleighThreshold = -1;
+    int poolSlots = 16;          // > 0: block-pooled kernel (transport_pool.cu, default) with this many slots per lane class;
+                                 // 0: `slots` selects the register kernel (0) or the lane-multiplexed one
     int voxelLoadMode = 1;       // voxel gathers bypass L1 (ld.global.cg): +3 %, leaves L1 to the tables
     int smemPadKb = 0;           // experiment: extra dynamic shared memory per block (shrinks L1)
-    int stepPairs = 1;           // mux kernel: step pairs per step phase
-    int interactBias = 0;        // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
+    int stepPairs = 0;           // pool / mux kernels: step pairs per step phase (0: kernel default, pool 2, mux 1)
+    int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
+    int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
+    int interactBias = 8;        // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
 };
 
 } // namespace
@@ -475,14 +479,18 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.tally_scale_e = c->scaleE;
     P.tally_scale_e2 = c->scaleE2;
     P.score_material = calib ? scoreMaterial : -1;
-    const bool mux = c->opt.slots >= 2;
-    // defaults: register kernel 4 / 12 / 4 dead / waiting / Rayleigh lanes; mux kernel 8 / 33 (bias rule only) / 8
-    P.refill_threshold = std::clamp(c->opt.refillThreshold > 0 ? c->opt.refillThreshold : (mux ? 8 : 4), 1, 32);
+    const bool pool = c->opt.poolSlots > 0;
+    const bool mux = pool || c->opt.slots >= 2; // both keep photons in shared memory and share the policy knobs
+    // defaults (dead / waiting / Rayleigh lanes that trigger a phase): register kernel 4 / 12 / 4; mux kernel 8 / 33 (bias rule
+    // only) / 8; pool kernel 28 / - / 8 (profiles/r01_pool_policy_sweep.txt)
+    P.refill_threshold = std::clamp(c->opt.refillThreshold > 0 ? c->opt.refillThreshold : (pool ? 28 : mux ? 8 : 4), 1, 32);
     P.interact_threshold = std::clamp(c->opt.interactThreshold > 0 ? c->opt.interactThreshold : (mux ? 33 : 12), 1, 33);
     P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold > 0 ? c->opt.rayleighThreshold : (mux ? 8 : 4), 1, 32);
     P.voxel_load_mode = c->opt.voxelLoadMode;
-    P.step_pairs = std::clamp(c->opt.stepPairs, 1, 8);
+    P.step_pairs = std::clamp(c->opt.stepPairs > 0 ? c->opt.stepPairs : (pool ? 2 : 1), 1, 8);
     P.interact_bias = std::clamp(c->opt.interactBias, -32, 32);
+    P.service_warps = std::clamp(c->opt.serviceWarps, 0, 32);
+    P.diag = c->opt.diag;
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -491,7 +499,17 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     const size_t tableBytes = static_cast<size_t>(w.n_mat) * kDevNE * sizeof(float);
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
     cfg.slots = 0;
-    if (mux) {
+    cfg.pool = pool;
+    if (pool) {
+        cfg.threads = 256;
+        cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots);
+        cfg.smem = poolSmemBytes(cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
+        if (cfg.table_in_smem && cfg.smem > 56 * 1024) {
+            cfg.table_in_smem = false;
+            cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots);
+            cfg.smem = poolSmemBytes(cfg.slots, 0);
+        }
+    } else if (mux) {
         // the table shares the SM's shared memory with the photon slots: keep it only while two blocks still fit
         cfg.slots = transportMuxSlots(mode, calib, cfg.table_in_smem, c->opt.slots);
         cfg.smem = muxSmemBytes(cfg.threads, cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
@@ -506,15 +524,16 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = mux ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
-                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
+        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
+            : mux  ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
+                   : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)
             return fail(c, DXB_ECUDA, "transport kernel cannot be resident (occupancy 0)");
     }
     cfg.blocks = c->smCount * perSm;
 
     const uint64_t nLocal = localCount(pb.nTotal, rank, world);
-    CUDA_TRY(c, cudaMemsetAsync(d.counters.p + 8, 0, 8 * sizeof(unsigned long long), d.stream));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters.p + 8, 0, 24 * sizeof(unsigned long long), d.stream));
     CUDA_TRY(c, cudaEventRecord(d.evStart, d.stream));
     uint64_t launches = 0;
     bool cancelled = false;
@@ -534,7 +553,9 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
         P.hbase_lo = static_cast<unsigned int>(firstId);
         P.hbase_hi = static_cast<unsigned int>(firstId >> 32);
         CUDA_TRY(c, cudaMemsetAsync(d.counters.p, 0, sizeof(unsigned long long), d.stream));
-        CUDA_TRY(c, mux ? launchTransportMux(P, mode, calib, cfg, d.stream) : launchTransport(P, mode, calib, cfg, d.stream));
+        CUDA_TRY(c, pool ? launchTransportPool(P, mode, calib, cfg, d.stream)
+                : mux ? launchTransportMux(P, mode, calib, cfg, d.stream)
+                      : launchTransport(P, mode, calib, cfg, d.stream));
         ++launches;
         if (progress && !asyncOnly && end < nLocal) {
             // stop must be observed within one batch; progress is published per batch
@@ -558,6 +579,15 @@ int collectStats(dxb_ctx* c, DeviceState& d, TransportResult& res)
     CUDA_TRY(c, cudaMemcpy(h, d.counters.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 5; ++i)
         res.stats[i] = h[i];
+    if (c->opt.diag) {
+        // pool kernel diagnostics: executions and claimed lanes per phase (step, interaction, Rayleigh, refill)
+        unsigned long long g[8];
+        CUDA_TRY(c, cudaMemcpy(g, d.counters.p + 16, sizeof(g), cudaMemcpyDeviceToHost));
+        static const char* names[4] = { "step", "interact", "rayleigh", "refill" };
+        for (int i = 0; i < 4; ++i)
+            std::fprintf(stderr, "dxb diag: phase %-8s executions %12llu  lanes/execution %5.2f\n", names[i], g[i],
+                g[i] ? static_cast<double>(g[4 + i]) / static_cast<double>(g[i]) : 0.0);
+    }
     float ms = 0;
     CUDA_TRY(c, cudaEventElapsedTime(&ms, d.evStart, d.evTransport));
     res.ms = ms;
@@ -740,8 +770,8 @@ int initDevice(dxb_ctx* c, DeviceState& d)
     CUDA_TRY(c, cudaEventCreate(&d.evStart));
     CUDA_TRY(c, cudaEventCreate(&d.evTransport));
     CUDA_TRY(c, cudaEventCreate(&d.evEnd));
-    CUDA_TRY(c, d.counters.alloc(16, d.device));
-    CUDA_TRY(c, cudaMemset(d.counters.p, 0, 16 * sizeof(unsigned long long)));
+    CUDA_TRY(c, d.counters.alloc(32, d.device));
+    CUDA_TRY(c, cudaMemset(d.counters.p, 0, 32 * sizeof(unsigned long long)));
     d.world.device = d.device;
     return DXB_OK;
 }
@@ -987,8 +1017,17 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.voxelLoadMode = static_cast<int>(value);
     } else if (k == "smem_pad_kb") {
         c->opt.smemPadKb = static_cast<int>(value);
+    } else if (k == "pool_slots") {
+        const int v = static_cast<int>(value);
+        if (v != 0 && v != 6 && v != 8 && v != 12 && v != 16)
+            return fail(c, DXB_EINVAL, "pool_slots must be 0 (off), 6, 8, 12 or 16");
+        c->opt.poolSlots = v;
     } else if (k == "step_pairs") {
         c->opt.stepPairs = static_cast<int>(value);
+    } else if (k == "diag") {
+        c->opt.diag = static_cast<int>(value);
+    } else if (k == "service_warps") {
+        c->opt.serviceWarps = static_cast<int>(value);
     } else if (k == "interact_bias") {
         c->opt.interactBias = static_cast<int>(value);
     } else if (k == "refill_threshold") {

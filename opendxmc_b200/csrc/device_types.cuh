@@ -99,6 +99,8 @@ struct RunParams {
     int rayleigh_threshold;         // lanes waiting for a Rayleigh try that trigger a Rayleigh phase
     int voxel_load_mode;            // see loadVoxel (transport_common.cuh)
     int step_pairs;                 // mux kernel: step pairs per step phase (>= 1)
+    int diag;                       // pool kernel: stats[8..15] = executions / claimed lanes per phase
+    int service_warps;              // pool kernel: warps per block that prefer interaction / refill phases
     int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
@@ -126,12 +128,19 @@ __host__ __device__ inline size_t muxSmemBytes(int threads, int slots, int table
     return (static_cast<size_t>(table_floats) + kDevNE) * 4 + warps * (static_cast<size_t>(kSlotWords) * slots + kMuxBufWords) * 32 * 4;
 }
 
-// launch wrappers (transport.cu, transport_mux.cu)
+// the block-pooled kernel (transport_pool.cu): 32 classes x `slots` photons per block + 2 status words per class
+__host__ __device__ inline size_t poolSmemBytes(int slots, int table_floats)
+{
+    return (static_cast<size_t>(table_floats) + kDevNE + 64 + static_cast<size_t>(kSlotWords) * slots * 32) * 4;
+}
+
+// launch wrappers (transport.cu, transport_mux.cu, transport_pool.cu)
 struct LaunchConfig {
     int blocks, threads;
     size_t smem;
     bool table_in_smem;
-    int slots; // 0: one photon per lane in registers (transport.cu); >= 2: lane-multiplexed kernel
+    int slots; // 0: one photon per lane in registers (transport.cu); >= 2: slots per lane (mux) / per class (pool)
+    bool pool; // block-pooled kernel instead of the lane-multiplexed one
 };
 
 } // namespace dxb

@@ -1,0 +1,601 @@
+// transport_pool.cu — block-pooled photon-history kernel for sm_100a (event-based regrouping).
+//
+// Same physics and random-number protocol as transport.cu (results are identical, history for history); photons
+// live in a block-wide pool in shared memory instead of in registers.  The pool has 32 *classes* (one per lane
+// index, so every access is bank-conflict free) of SPC slots; a class is shared by the same-numbered lanes of all
+// warps of the block.  Two status words per class hold one bit per (slot, state).  Each iteration a warp votes
+// for ONE phase, every lane CLAIMS a slot of its class that is in that phase (atomicAnd on the status word),
+// processes it, and publishes it in its new state (fence + atomicOr).  Any warp can continue any photon, so
+// phases run with nearly full warps although only ~1.5 photons per thread are resident (15 KB per block: the
+// L1 carve-out that sank the lane-private variant, transport_mux.cu, stays small).
+//
+// Replaces (recalled DXMClib): Transport::runWorker -> exposure.sampleParticle
+// -> World::transport -> AAVoxelGrid::woodcockTransport -> interactions::interact -> EnergyScore.
+#include "transport_common.cuh"
+
+namespace dxb {
+
+namespace {
+
+constexpr unsigned int kMetaBlkMask = 0xFFFFFu; // Philox block index of the history (20 bits)
+constexpr int kMetaMatShift = 20;               // material of the pending interaction (8 bits)
+constexpr unsigned int kMetaRetry = 1u << 28;   // Compton already chosen, previous candidate rejected
+
+// slot words
+enum : int { kWPx = 0, kWPy, kWPz, kWDx, kWDy, kWDz, kWE, kWW, kWHlo, kWMeta };
+static_assert(kWMeta + 1 == kSlotWords, "slot layout");
+// byte of the status word that holds the slot mask of a state
+enum : int { kPhStep = 0, kPhInt = 1, kPhRay = 2, kPhDead = 3, kPhNone = 4 };
+
+// status words of a class: A = step mask (bits 0-15) | interaction mask (bits 16-31), B = Rayleigh mask | dead mask
+__device__ __forceinline__ int phaseWord(int phase) { return phase >> 1; }          // step,int -> A; ray,dead -> B
+__device__ __forceinline__ int phaseShift(int phase) { return (phase & 1) << 4; }   // int, dead in the upper half
+
+// claims one slot of the lane's class that is in `phase`; returns its index inside the class or -1
+__device__ __forceinline__ int claimSlot(unsigned int* word, int shift, unsigned int seen)
+{
+    unsigned int m = (seen >> shift) & 0xffffu;
+    while (m) {
+        const unsigned int bit = (m & (0u - m)) << shift;
+        const unsigned int old = atomicAnd(word, ~bit);
+        if (old & bit) {
+            __threadfence_block(); // pairs with publishSlot: the slot's words are read after its status bit
+            return __ffs(bit >> shift) - 1;
+        }
+        m = (old >> shift) & 0xffffu; // somebody else took it: look again
+    }
+    return -1;
+}
+__device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the class */, int phase, int j)
+{
+    __threadfence_block(); // the slot's words are visible before its status bit
+    atomicOr(words + phaseWord(phase), 1u << (phaseShift(phase) + j));
+}
+
+template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC>
+__global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_constant__ RunParams P)
+{
+    static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    constexpr unsigned int kFull = 0xffffffffu;
+    constexpr int kStride = SPC * 32; // distance between two words of one slot
+    constexpr unsigned int kAllSlots = (1u << SPC) - 1u;
+    const int lane = threadIdx.x & 31;
+    // layout: poolSmemBytes (device_types.cuh)
+    float* __restrict__ s_f = reinterpret_cast<float*>(s_raw);
+    const int nTab = SMEM_TABLE ? P.tab.n_mat * kDevNE : 0;
+    float* __restrict__ s_tot = s_f;
+    float* __restrict__ s_maj = s_f + nTab;
+    unsigned int* s_status = reinterpret_cast<unsigned int*>(s_maj + kDevNE) + 2 * lane; // the lane's class: words A, B
+    float* __restrict__ slots = s_maj + kDevNE + 64 + lane;
+    for (int i = threadIdx.x; i < nTab; i += blockDim.x)
+        s_tot[i] = P.tab.tot[i];
+    for (int i = threadIdx.x; i < kDevNE; i += blockDim.x)
+        s_maj[i] = P.tab.majorant[i];
+    if (threadIdx.x < 32) {
+        s_status[0] = 0u;
+        s_status[1] = kAllSlots << 16; // every slot dead
+    }
+    __syncthreads();
+    const float* __restrict__ totTable = SMEM_TABLE ? s_tot : P.tab.tot;
+    const GridDev& G = P.grid;
+    volatile unsigned int* vstatus = s_status;
+
+    // warp-uniform bookkeeping: the warp's pool of local history indices (256-history pieces of the global cursor)
+    unsigned long long poolNext = 0, poolEnd = 0;
+    bool drained = false;
+    // per-lane
+    unsigned int nSteps = 0, nInteractions = 0, nDeposits = 0, nHistories = 0;
+    unsigned long long emitted = 0;
+
+    for (;;) {
+        const unsigned int wa = vstatus[0], wb = vstatus[1];
+        const unsigned int flags = ((wa & 0xffffu) ? 1u : 0u) | ((wa >> 16) ? 0x100u : 0u) | ((wb & 0xffffu) ? 0x10000u : 0u)
+            | ((wb >> 16) ? 0x1000000u : 0u);
+        const unsigned int votes = __reduce_add_sync(kFull, flags);
+        const int nStep = votes & 0xff, nInt = (votes >> 8) & 0xff, nRay = (votes >> 16) & 0xff, nDead = votes >> 24;
+        const bool canRefill = !(drained && poolNext == poolEnd);
+        // Phase choice = largest lane count, with a role bonus: the first `service_warps` warps of the block prefer
+        // interaction tries / Rayleigh tries / refills, the others prefer stepping.  All warps watch the same class
+        // words, so without roles they would all jump on the same phase at once and share its lanes.
+        const int bonus = P.interact_bias;
+        const bool service = (threadIdx.x >> 5) < P.service_warps;
+        int best = -1, phase = kPhStep;
+        if (nStep > 0) {
+            best = nStep + (service ? 0 : bonus);
+        }
+        if (nInt > 0 && nInt + (service ? bonus : 0) > best) {
+            best = nInt + (service ? bonus : 0);
+            phase = kPhInt;
+        }
+        if (nRay >= P.rayleigh_threshold && nRay + (service ? bonus : 0) > best) {
+            best = nRay + (service ? bonus : 0);
+            phase = kPhRay;
+        }
+        if (canRefill && nDead >= P.refill_threshold && nDead + (service ? bonus : 0) > best) {
+            best = nDead + (service ? bonus : 0);
+            phase = kPhDead;
+        }
+        if (best < 0) {
+            // below the thresholds: anything that can still make progress
+            if (nRay > 0)
+                phase = kPhRay, best = nRay;
+            else if (canRefill && nDead > 0)
+                phase = kPhDead, best = nDead;
+        }
+        if (best < 0) {
+            // nothing claimable: finished if no history is left anywhere in the block (every slot of every class
+            // is dead, none is in another warp's hands), else wait for the other warps to publish
+            if (!canRefill && __all_sync(kFull, (wb >> 16) == kAllSlots))
+                break;
+            __nanosleep(200);
+            continue;
+        }
+
+        if (phase == kPhStep) {
+            // ------------------------------------------------------------ pairs of tentative Woodcock steps
+            const int j = claimSlot(s_status + 0, 0, wa);
+            const bool active = j >= 0;
+            if (P.diag) {
+                const int n = __popc(__ballot_sync(kFull, active));
+                if (lane == 0) {
+                    atomicAdd(P.stats + 8 + kPhStep, 1ull);
+                    atomicAdd(P.stats + 12 + kPhStep, static_cast<unsigned long long>(n));
+                }
+            }
+            float* __restrict__ sp = slots + (active ? j : 0) * 32;
+            float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, E = 0.f, w = 0.f;
+            unsigned int hlo = 0, hhi = 0, blk = 0;
+            TabPos epos;
+            epos.i = 0;
+            epos.f = 0.f;
+            float muMaxU24 = kU24, stepScale = -kLn2;
+            if (active) {
+                px = sp[kWPx * kStride];
+                py = sp[kWPy * kStride];
+                pz = sp[kWPz * kStride];
+                dx = sp[kWDx * kStride];
+                dy = sp[kWDy * kStride];
+                dz = sp[kWDz * kStride];
+                E = sp[kWE * kStride];
+                if (CALIB)
+                    w = sp[kWW * kStride];
+                hlo = __float_as_uint(sp[kWHlo * kStride]);
+                blk = __float_as_uint(sp[kWMeta * kStride]) & kMetaBlkMask;
+                hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
+                epos = energyPos(E);
+                const float muMax = lerp(s_maj[epos.i], s_maj[epos.i + 1], epos.f);
+                muMaxU24 = muMax * kU24;
+                stepScale = -kLn2 * __fdividef(1.0f, muMax);
+            }
+            bool stepping = active;
+            int newPhase = kPhStep;
+            int mat = 0;
+            for (int it = 0; it < P.step_pairs; ++it) {
+                float kermaA = 0.0f, kermaB = 0.0f;
+                unsigned int voxA = 0, voxB = 0;
+                if (stepping) {
+                    const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                    const float sA = __log2f(fmaf(rb.k(0), -kU24, 1.0f)) * stepScale;
+                    const float sB = __log2f(fmaf(rb.k(2), -kU24, 1.0f)) * stepScale;
+                    const float ax = fmaf(dx, sA, px), ay = fmaf(dy, sA, py), az = fmaf(dz, sA, pz);
+                    const float bx = fmaf(dx, sB, ax), by = fmaf(dy, sB, ay), bz = fmaf(dz, sB, az);
+                    // a step whose end point is outside the grid ends the history (B is only reached through A)
+                    const bool inA = voxelIndex(G, ax, ay, az, voxA);
+                    const bool inB = voxelIndex(G, bx, by, bz, voxB) && inA;
+                    // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
+                    unsigned int cellA = 0u, cellB = 0u;
+                    if (inA)
+                        cellA = loadVoxel(G.voxels + voxA, P.voxel_load_mode);
+                    if (inB)
+                        cellB = loadVoxel(G.voxels + voxB, P.voxel_load_mode);
+                    if (!inA) {
+                        newPhase = kPhDead; // left the grid
+                        stepping = false;
+                    } else {
+                        ++nSteps;
+                        const int matA = voxelMaterial(cellA);
+                        const float* tt = totTable + matA * kDevNE + epos.i;
+                        const float muA = voxelDensity(cellA) * lerp(tt[0], tt[1], epos.f);
+                        if (CALIB && matA == P.score_material) {
+                            // collision estimator of air kerma: every tentative collision carries 1/mu_max of track length
+                            const float* et = P.tab.etr + matA * kDevNE + epos.i;
+                            kermaA = w * E * lerp(__ldg(et), __ldg(et + 1), epos.f) * (stepScale * -kInvLn2);
+                        }
+                        if (rb.k(1) * muMaxU24 < muA) {
+                            px = ax;
+                            py = ay;
+                            pz = az;
+                            mat = matA;
+                            newPhase = kPhInt;
+                            stepping = false;
+                        } else if (!inB) {
+                            newPhase = kPhDead;
+                            stepping = false;
+                        } else {
+                            ++nSteps;
+                            const int matB = voxelMaterial(cellB);
+                            const float* tb = totTable + matB * kDevNE + epos.i;
+                            const float muB = voxelDensity(cellB) * lerp(tb[0], tb[1], epos.f);
+                            if (CALIB && matB == P.score_material) {
+                                const float* et = P.tab.etr + matB * kDevNE + epos.i;
+                                kermaB = w * E * lerp(__ldg(et), __ldg(et + 1), epos.f) * (stepScale * -kInvLn2);
+                            }
+                            px = bx;
+                            py = by;
+                            pz = bz;
+                            if (rb.k(3) * muMaxU24 < muB) {
+                                mat = matB;
+                                newPhase = kPhInt;
+                                stepping = false;
+                            }
+                        }
+                    }
+                }
+                if (CALIB) {
+                    unsigned int mScore = __ballot_sync(kFull, kermaA > 0.0f);
+                    if (kermaA > 0.0f)
+                        scoreEnergy(mScore, G.tally, voxA, kermaA, P.tally_scale_e, P.tally_scale_e2);
+                    mScore = __ballot_sync(kFull, kermaB > 0.0f);
+                    if (kermaB > 0.0f)
+                        scoreEnergy(mScore, G.tally, voxB, kermaB, P.tally_scale_e, P.tally_scale_e2);
+                }
+                if (!__any_sync(kFull, stepping))
+                    break;
+            }
+            if (active) {
+                if (newPhase != kPhDead) {
+                    sp[kWPx * kStride] = px;
+                    sp[kWPy * kStride] = py;
+                    sp[kWPz * kStride] = pz;
+                    sp[kWMeta * kStride] = __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift));
+                }
+                publishSlot(s_status, newPhase, j);
+            }
+        } else if (phase == kPhInt || phase == kPhRay) {
+            // ------------------------------------------------------------ one sampling try per claimed photon
+            const int j = claimSlot(s_status + phaseWord(phase), phaseShift(phase), phase == kPhInt ? wa : wb);
+            const bool active = j >= 0;
+            if (P.diag) {
+                const int n = __popc(__ballot_sync(kFull, active));
+                if (lane == 0) {
+                    atomicAdd(P.stats + 8 + phase, 1ull);
+                    atomicAdd(P.stats + 12 + phase, static_cast<unsigned long long>(n));
+                }
+            }
+            float* __restrict__ sp = slots + (active ? j : 0) * 32;
+            float edep = 0.0f;
+            unsigned int voxel = 0;
+            if (active) {
+                float px = sp[kWPx * kStride], py = sp[kWPy * kStride], pz = sp[kWPz * kStride];
+                float dx = sp[kWDx * kStride], dy = sp[kWDy * kStride], dz = sp[kWDz * kStride];
+                float E = sp[kWE * kStride], w = sp[kWW * kStride];
+                const unsigned int hlo = __float_as_uint(sp[kWHlo * kStride]);
+                unsigned int meta = __float_as_uint(sp[kWMeta * kStride]);
+                const unsigned int hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
+                unsigned int blk = meta & kMetaBlkMask;
+                const int mat = static_cast<int>((meta >> kMetaMatShift) & 0xffu);
+                int newPhase = phase;
+                bool scattered = false; // an accepted scatter: cut-off, roulette
+                const PhiloxBlock rb = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                if (phase == kPhInt) {
+                    bool compton = (meta & kMetaRetry) != 0u;
+                    if (!compton) {
+                        ++nInteractions;
+                        const TabPos epos = energyPos(E);
+                        const float4 a = __ldg(P.tab.att + mat * kDevNE + epos.i);
+                        const float4 b = __ldg(P.tab.att + mat * kDevNE + epos.i + 1);
+                        const float aPhoto = lerp(a.x, b.x, epos.f);
+                        const float aIncoh = lerp(a.y, b.y, epos.f);
+                        const float aTot = lerp(a.w, b.w, epos.f);
+                        const float r2 = rb.u(0) * aTot;
+                        if (r2 < aPhoto) {
+                            const float ef = MODE >= 2 ? photoFluorescence(P.tab, mat, E, rb.u(1), rb.u(2)) : 0.0f;
+                            if (MODE >= 2 && ef > 0.0f) {
+                                // fluorescence photon: isotropic, one extra block for its direction
+                                const PhiloxBlock rf = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                                isotropic(rf.u(0), rf.u(1), dx, dy, dz);
+                                edep = (E - ef) * w;
+                                E = ef;
+                                scattered = true;
+                            } else {
+                                edep = E * w;
+                                E = 0.0f;
+                                newPhase = kPhDead;
+                            }
+                        } else if (r2 < aPhoto + aIncoh) {
+                            compton = true;
+                        } else {
+                            newPhase = kPhRay;
+                        }
+                    }
+                    if (compton) {
+                        float e, cosT;
+                        bool ok = comptonTry<MODE>(P.tab, mat, E, rb.u(1), rb.u(2), e, cosT);
+                        if (MODE >= 2 && ok) {
+                            // impulse approximation: shell + Doppler broadening from one extra block
+                            const PhiloxBlock ri = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                            ok = dopplerBroaden(P.tab, mat, E, e, cosT, ri.u(0), ri.u(1), e);
+                        }
+                        if (ok) {
+                            deflect(dx, dy, dz, cosT, kTwoPi * rb.u(3));
+                            const float E0 = E;
+                            E = E0 * e;
+                            edep = (E0 - E) * w;
+                            scattered = true;
+                        } else {
+                            meta |= kMetaRetry;
+                        }
+                    }
+                } else {
+                    float cosT;
+                    if (rayleighTry<MODE>(P.tab, mat, E, rb.u(0), rb.u(1), cosT)) {
+                        deflect(dx, dy, dz, cosT, kTwoPi * rb.u(2));
+                        scattered = true;
+                    }
+                }
+                if (scattered) {
+                    newPhase = kPhStep;
+                    if (E < kMinEnergy) {
+                        edep += E * w;
+                        E = 0.0f;
+                        newPhase = kPhDead;
+                    } else if (w < kRouletteThreshold) {
+                        const PhiloxBlock rr = philox4x32_10(P.round_key, hlo, hhi, blk++);
+                        if (rr.u(0) < kRouletteKill)
+                            newPhase = kPhDead;
+                        else
+                            w *= 1.0f / (1.0f - kRouletteKill);
+                    }
+                    if (newPhase == kPhStep) {
+                        sp[kWDx * kStride] = dx;
+                        sp[kWDy * kStride] = dy;
+                        sp[kWDz * kStride] = dz;
+                        sp[kWE * kStride] = E;
+                        sp[kWW * kStride] = w;
+                        meta &= ~kMetaRetry;
+                    }
+                }
+                if (newPhase != kPhDead)
+                    sp[kWMeta * kStride] = __uint_as_float((meta & ~kMetaBlkMask) | blk);
+                if (CALIB)
+                    edep = 0.0f;
+                if (edep > 0.0f)
+                    voxelIndex(G, px, py, pz, voxel);
+                publishSlot(s_status, newPhase, j);
+            }
+            if (!CALIB && phase == kPhInt) {
+                const unsigned int mScore = __ballot_sync(kFull, edep > 0.0f);
+                if (edep > 0.0f) {
+                    ++nDeposits;
+                    scoreEnergy(mScore, G.tally, voxel, edep, P.tally_scale_e, P.tally_scale_e2);
+                }
+            }
+        } else {
+            // ------------------------------------------------------------ refill: lanes that claim a dead slot sample a history into it
+            const unsigned int laneLt = (1u << lane) - 1u;
+            const int j = claimSlot(s_status + 1, 16, wb);
+            const unsigned int mGot = __ballot_sync(kFull, j >= 0);
+            const int want = __popc(mGot);
+            if (P.diag && lane == 0) {
+                atomicAdd(P.stats + 8 + kPhDead, 1ull);
+                atomicAdd(P.stats + 12 + kPhDead, static_cast<unsigned long long>(want));
+            }
+            if (poolNext == poolEnd && !drained && want > 0) {
+                constexpr unsigned long long kPiece = 256;
+                unsigned long long base = 0;
+                if (lane == 0)
+                    base = atomicAdd(P.work_counter, kPiece);
+                base = __shfl_sync(kFull, base, 0);
+                const unsigned long long start = P.local_begin + base;
+                if (start >= P.local_end) {
+                    drained = true;
+                } else {
+                    poolNext = start;
+                    poolEnd = min(start + kPiece, P.local_end);
+                }
+            }
+            const unsigned long long avail = poolEnd - poolNext;
+            const int nb = static_cast<int>(min(avail, static_cast<unsigned long long>(want)));
+            // local index -> global history id (65536-history blocks dealt round-robin over ranks); a piece never
+            // straddles a shard block (256 divides 65536), so the ids of one refill are consecutive
+            const unsigned long long sblk = poolNext / kShardBlock;
+            const unsigned long long idBase = (sblk * P.world + P.rank) * kShardBlock + (poolNext % kShardBlock);
+            poolNext += nb;
+            if (j >= 0) {
+                const int r = __popc(mGot & laneLt);
+                const unsigned long long h = idBase + r;
+                bool hit = false;
+                float* __restrict__ sp = slots + j * 32;
+                if (r < nb && h < P.n_total) {
+                    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
+                    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
+                    const unsigned long long ei = h / P.ppe;
+                    const ExposureDev* ex = P.exposures + ei;
+                    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
+                    const float angx = (2.0f * s0.u(0) - 1.0f) * hx;
+                    const float angy = (2.0f * s0.u(1) - 1.0f) * hy;
+                    const int tube = __ldg(&ex->tube);
+                    const SpectrumDev& spc = P.spec[tube];
+                    float E;
+                    if (spc.n <= 1) {
+                        E = spc.e0;
+                    } else {
+                        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(spc.n)), spc.n - 1);
+                        if (!(s0.u(3) < __ldg(spc.prob + idx)))
+                            idx = __ldg(spc.alias + idx);
+                        E = spc.e0 + static_cast<float>(idx) * spc.step;
+                        if (idx < spc.n - 1) {
+                            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
+                            E += s1.u(0) * spc.step;
+                        }
+                    }
+                    float w = __ldg(&ex->weight);
+                    const BowtieDev& bt = P.bow[tube];
+                    if (bt.n > 0) {
+                        const float a = fabsf(angx);
+                        float bw;
+                        if (a <= __ldg(bt.angle)) {
+                            bw = __ldg(bt.weight);
+                        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
+                            bw = __ldg(bt.weight + bt.n - 1);
+                        } else {
+                            int i = 1;
+                            while (__ldg(bt.angle + i) < a)
+                                ++i;
+                            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
+                            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
+                        }
+                        w *= bw;
+                    }
+                    const float sx = __sinf(angx), sy = __sinf(angy);
+                    const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
+                    float qdx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
+                    float qdy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
+                    float qdz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
+                    float qpx = __ldg(&ex->pos[0]);
+                    float qpy = __ldg(&ex->pos[1]);
+                    float qpz = __ldg(&ex->pos[2]);
+                    ++nHistories;
+                    emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
+                    // move to the grid AABB (World::transport)
+                    const float ix = 1.0f / qdx, iy = 1.0f / qdy, iz = 1.0f / qdz;
+                    float tmin = 0.0f, tmax = 3.0e38f;
+                    float t0 = (G.x0 - qpx) * ix, t1 = (G.x1 - qpx) * ix;
+                    if (qdx == 0.0f) {
+                        if (qpx < G.x0 || qpx > G.x1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    t0 = (G.y0 - qpy) * iy;
+                    t1 = (G.y1 - qpy) * iy;
+                    if (qdy == 0.0f) {
+                        if (qpy < G.y0 || qpy > G.y1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    t0 = (G.z0 - qpz) * iz;
+                    t1 = (G.z1 - qpz) * iz;
+                    if (qdz == 0.0f) {
+                        if (qpz < G.z0 || qpz > G.z1)
+                            tmax = -1.0f;
+                    } else {
+                        tmin = fmaxf(tmin, fminf(t0, t1));
+                        tmax = fminf(tmax, fmaxf(t0, t1));
+                    }
+                    if (tmax > tmin && E >= kMinEnergy) {
+                        sp[kWPx * kStride] = fmaf(qdx, tmin, qpx);
+                        sp[kWPy * kStride] = fmaf(qdy, tmin, qpy);
+                        sp[kWPz * kStride] = fmaf(qdz, tmin, qpz);
+                        sp[kWDx * kStride] = qdx;
+                        sp[kWDy * kStride] = qdy;
+                        sp[kWDz * kStride] = qdz;
+                        sp[kWE * kStride] = E;
+                        sp[kWW * kStride] = w;
+                        sp[kWHlo * kStride] = __uint_as_float(qlo);
+                        sp[kWMeta * kStride] = __uint_as_float(2u); // blocks 0-1 belong to the source
+                        hit = true;
+                    }
+                }
+                publishSlot(s_status, hit ? kPhStep : kPhDead, j);
+            }
+        }
+    }
+
+    // ---------------- statistics
+    unsigned long long v[5] = { nSteps, nInteractions, nDeposits, emitted, nHistories };
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            x += __shfl_xor_sync(kFull, x, o);
+        if (lane == 0 && x)
+            atomicAdd(P.stats + k, x);
+    }
+}
+
+template <int MODE, bool CALIB, bool SMEM, int M>
+cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t stream)
+{
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
+    if (e != cudaSuccess)
+        return e;
+    kern<<<cfg.blocks, cfg.threads, cfg.smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int MODE, bool CALIB, bool SMEM, int M>
+int occupancyPool(int threads, size_t smem)
+{
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+
+// applies CALL(MODE, CALIB, SMEM, M) for the run-time (mode, calib, smem, slots).  The slot count is a tuning
+// knob of the production variant only (mode 1, scoring); every other variant is built with 12 slots per class.
+#define DXB_POOL_DISPATCH(CALL)                                                  \
+    const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
+    const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
+    switch (key) {                                                              \
+    case 8: return CALL(2, false, false, 12);                                    \
+    case 9: return CALL(2, false, true, 12);                                     \
+    case 10: return CALL(2, true, false, 12);                                    \
+    case 11: return CALL(2, true, true, 12);                                     \
+    case 0: return CALL(0, false, false, 12);                                    \
+    case 1: return CALL(0, false, true, 12);                                     \
+    case 2: return CALL(0, true, false, 12);                                     \
+    case 3: return CALL(0, true, true, 12);                                      \
+    case 4: return CALL(1, false, false, 12);                                    \
+    case 6: return CALL(1, true, false, 12);                                     \
+    case 7: return CALL(1, true, true, 12);                                      \
+    default: break;                                                             \
+    }                                                                           \
+    switch (slots) {                                                            \
+    case 6: return CALL(1, false, true, 6);                                     \
+    case 8: return CALL(1, false, true, 8);                                     \
+    case 16: return CALL(1, false, true, 16);                                   \
+    default: return CALL(1, false, true, 12);                                   \
+    }
+
+} // namespace
+
+cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream)
+{
+    const bool smemTable = cfg.table_in_smem;
+    const int slots = cfg.slots;
+#define DXB_CALL(MO, CA, SM, MM) launchPool<MO, CA, SM, MM>(p, cfg, stream)
+    DXB_POOL_DISPATCH(DXB_CALL)
+#undef DXB_CALL
+}
+
+int transportPoolSlots(int mode, bool calib, bool smemTable, int slots)
+{
+    // must mirror DXB_POOL_DISPATCH: only the production variant is built for several slot counts
+    if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 16))
+        return slots;
+    return 12;
+}
+
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem)
+{
+#define DXB_CALL(MO, CA, SM, MM) occupancyPool<MO, CA, SM, MM>(threads, smem)
+    DXB_POOL_DISPATCH(DXB_CALL)
+#undef DXB_CALL
+}
+
+} // namespace dxb

@@ -29,6 +29,14 @@ MARKERS = {
         ("            // ------------------------------------------------------------ refill", "refill: source sampling"),
         ("            // lanes with a dead slot pop", "refill: pop"),
         ("    // ---------------- statistics", "stats")],
+    "transport_pool.cu": [
+        ("__device__ __forceinline__ int phaseWord", "claim/publish"), ("__global__ void __launch_bounds__", "kernel prologue"),
+        ("    for (;;) {", "vote/policy"),
+        ("        if (phase == kPhStep) {", "step: claim+load"), ("            bool stepping = active;", "step: pairs"),
+        ("            if (active) {\n                if (newPhase != kPhDead) {\n                    sp[kWPx", "step: store"),
+        ("        } else if (phase == kPhInt || phase == kPhRay) {", "interact"),
+        ("            // ------------------------------------------------------------ refill", "refill/source"),
+        ("    // ---------------- statistics", "stats")],
     "device_types.cuh": [("__host__ __device__ inline unsigned int quantizeDensityBits", "voxel unpack")],
 }
 

@@ -27,9 +27,9 @@ def tallies(wl, opts, mode=1):
 def check_exact():
     for name, wl in (("c2/4", dx.workloads.ct_spiral_patient(scale=4, histories=2_000_000)),
                      ("c1", dx.workloads.ctdi_body_phantom(n=32, histories=1_000_000, step_deg=5.0))):
-        ref = tallies(wl, {"slots_per_lane": 0})
+        ref = tallies(wl, {"pool_slots": 0, "slots_per_lane": 0})
         for slots, pairs in ((4, 1), (4, 2), (3, 1), (2, 1), (6, 2)):
-            got = tallies(wl, {"slots_per_lane": slots, "step_pairs": pairs})
+            got = tallies(wl, {"pool_slots": 0, "slots_per_lane": slots, "step_pairs": pairs})
             same = all(np.array_equal(a, b) for a, b in zip(ref[:3], got[:3]))
             keys = ("histories", "steps", "interactions", "deposits")
             print(f"exact {name} slots={slots} pairs={pairs}: tallies identical={same} "
@@ -58,19 +58,48 @@ if __name__ == "__main__":
         check_exact()
     wl = dx.workloads.ct_spiral_patient(scale=1, histories=nh)
     if "base" in which:
-        timing(wl, {"slots_per_lane": 0}, "register kernel (v4)")
+        timing(wl, {"pool_slots": 0, "slots_per_lane": 0}, "register kernel (v4)")
         for slots in (2, 3, 4, 6):
             for pairs in (1, 2, 3):
-                timing(wl, {"slots_per_lane": slots, "step_pairs": pairs}, f"mux slots={slots} pairs={pairs}")
-    if which.startswith("single"):
-        # single:<slots>:<pairs>[:key=value...] — one configuration, one repetition (for ncu captures)
+                timing(wl, {"pool_slots": 0, "slots_per_lane": slots, "step_pairs": pairs}, f"mux slots={slots} pairs={pairs}")
+    if "poolexact" in which:
+        for name, w2 in (("c2/4", dx.workloads.ct_spiral_patient(scale=4, histories=2_000_000)),
+                         ("c1", dx.workloads.ctdi_body_phantom(n=32, histories=1_000_000, step_deg=5.0))):
+            ref = tallies(w2, {"pool_slots": 0, "slots_per_lane": 0})
+            for slots, pairs in ((12, 1), (12, 2), (8, 1), (16, 2), (6, 1)):
+                got = tallies(w2, {"pool_slots": slots, "step_pairs": pairs})
+                same = all(np.array_equal(a, b) for a, b in zip(ref[:3], got[:3]))
+                keys = ("histories", "steps", "interactions", "deposits")
+                print(f"pool exact {name} slots={slots} pairs={pairs}: tallies identical={same} "
+                      f"counters identical={all(ref[3][k] == got[3][k] for k in keys)}", flush=True)
+    if "pooltime" in which:
+        timing(wl, {"pool_slots": 0, "slots_per_lane": 0}, "register kernel (v4)")
+        for slots in (6, 8, 12, 16):
+            for pairs in (1, 2):
+                timing(wl, {"pool_slots": slots, "step_pairs": pairs}, f"pool slots={slots} pairs={pairs}")
+    if "poolpolicy" in which:
+        for sw in (0, 2, 3, 4):
+            for bias in (4, 8, 16, 32):
+                for rf in (24, 28):
+                    for rt in (8, 16):
+                        timing(wl, {"pool_slots": 16, "step_pairs": 2, "interact_bias": bias, "refill_threshold": rf, "service_warps": sw,
+                                    "rayleigh_threshold": rt}, f"pool16 pairs=2 service={sw} bias={bias} refill={rf} ray={rt}", reps=1)
+    if which.startswith("psingle"):
         f = which.split(":")
-        opts = {"slots_per_lane": int(f[1]), "step_pairs": int(f[2])}
+        opts = {"pool_slots": int(f[1]), "step_pairs": int(f[2])}
         for kv in f[3:]:
             k, v = kv.split("=")
             opts[k] = float(v)
         timing(wl, opts, which, reps=1)
-    if "policy" in which:
+    if which.startswith("single"):
+        # single:<slots>:<pairs>[:key=value...] — one configuration, one repetition (for ncu captures)
+        f = which.split(":")
+        opts = {"pool_slots": 0, "slots_per_lane": int(f[1]), "step_pairs": int(f[2])}
+        for kv in f[3:]:
+            k, v = kv.split("=")
+            opts[k] = float(v)
+        timing(wl, opts, which, reps=1)
+    if "muxpolicy" in which:
         for bias in (-8, -4, 0, 4, 8):
             for rf in (4, 8, 16):
                 timing(wl, {"slots_per_lane": 4, "step_pairs": 2, "interact_bias": bias, "refill_threshold": rf},

@@ -165,16 +165,23 @@ def test_cpp_shim_runs_the_reference_driver():
     assert "finished=1" in out.stdout and "units=" in out.stdout
 
 
-@pytest.mark.parametrize("slots,pairs", [(4, 1), (4, 2), (2, 1), (3, 2), (6, 3)])
+KERNELS = [{"pool_slots": 16}, {"pool_slots": 12, "step_pairs": 1}, {"pool_slots": 8, "step_pairs": 3, "service_warps": 0},
+           {"pool_slots": 6, "refill_threshold": 4, "service_warps": 8},
+           {"pool_slots": 0, "slots_per_lane": 4, "step_pairs": 1}, {"pool_slots": 0, "slots_per_lane": 2, "step_pairs": 2},
+           {"pool_slots": 0, "slots_per_lane": 6, "step_pairs": 3}]
+
+
+@pytest.mark.parametrize("opts", KERNELS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_lane_multiplexed_kernel_is_bit_exact(dx, slots, pairs, mode):
-    """transport_mux.cu (photons regrouped per lane in shared memory) follows the same random-number protocol as
-    the register kernel and sums the same fixed-point tallies: every tally word and counter must be identical."""
+def test_shared_memory_kernels_are_bit_exact(dx, opts, mode):
+    """transport_pool.cu (block-pooled photons, the default) and transport_mux.cu (lane-private slots) follow the same
+    random-number protocol as the register kernel (transport.cu) and sum the same fixed-point tallies: every tally
+    word and every counter must be identical, whatever the regrouping policy."""
     wl = dx.workloads.ct_spiral_patient(scale=8, histories=300_000)
     out = []
-    for opts in ({"slots_per_lane": 0}, {"slots_per_lane": slots, "step_pairs": pairs}):
+    for o in ({"pool_slots": 0, "slots_per_lane": 0}, opts):
         world = wl.build_world(mode, [0])
-        for k, v in opts.items():
+        for k, v in o.items():
             world.set_option(k, v)
         dx.Transport().run_transport(world, wl.beam)
         e, e2, cnt = world.energy_scored()
@@ -185,6 +192,27 @@ def test_lane_multiplexed_kernel_is_bit_exact(dx, slots, pairs, mode):
     for k in ("histories", "steps", "interactions", "deposits"):
         assert out[0][3][k] == out[1][3][k]
     assert out[0][2].sum() > 0
+
+
+def test_kernels_agree_on_calibration_run_and_many_materials(dx):
+    """the kerma-scoring (calibration) variant and a 54-material world (table too large for shared memory):
+    pool kernel == register kernel, bit for bit."""
+    cases = [dx.workloads.ctdi_body_phantom(n=32, histories=300_000, step_deg=10.0),
+             dx.workloads.icrp_phantom("AM", scale=4, histories=400_000)]
+    for w in cases:
+        res = []
+        for o in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 16}):
+            world = w.build_world(1, [0])
+            world.set_calibration_histories(360_000)
+            for k, v in o.items():
+                world.set_option(k, v)
+            assert dx.Transport()(world, w.beam, None, True)
+            d, v, n = world.fetch_dose()
+            res.append((np.array(d), np.array(v), np.array(n), world.run_stats()["calibration_factor"]))
+            world.close()
+        assert res[0][3] == res[1][3]
+        for a, b in zip(res[0][:3], res[1][:3]):
+            assert np.array_equal(a, b)
 
 
 def test_mode2_fluorescence_and_doppler_parity(dx, orc):
