@@ -179,12 +179,13 @@ struct Options {
     int rayleighThreshold = -1;
     int poolSlots = 16;          // > 0: block-pooled kernel (transport_pool.cu, default) with this many slots per lane class;
                                  // 0: `slots` selects the register kernel (0) or the lane-multiplexed one
-    int voxelLoadMode = 1;       // voxel gathers bypass L1 (ld.global.cg): +3 %, leaves L1 to the tables
     int smemPadKb = 0;           // experiment: extra dynamic shared memory per block (shrinks L1)
     int stepPairs = 0;           // pool / mux kernels: step pairs per step phase (0: kernel default, pool 2, mux 1)
+    int poolThreads = 256;       // pool kernel: threads per block (the block shares one photon pool)
+    int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
-    int interactBias = 8;        // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
+    int interactBias = 16;       // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
 };
 
 } // namespace
@@ -482,15 +483,15 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     const bool pool = c->opt.poolSlots > 0;
     const bool mux = pool || c->opt.slots >= 2; // both keep photons in shared memory and share the policy knobs
     // defaults (dead / waiting / Rayleigh lanes that trigger a phase): register kernel 4 / 12 / 4; mux kernel 8 / 33 (bias rule
-    // only) / 8; pool kernel 28 / - / 8 (profiles/r01_pool_policy_sweep.txt)
+    // only) / 8; pool kernel 28 / 28 / 20 (profiles/r01_pool_policy_sweep.txt)
     P.refill_threshold = std::clamp(c->opt.refillThreshold > 0 ? c->opt.refillThreshold : (pool ? 28 : mux ? 8 : 4), 1, 32);
-    P.interact_threshold = std::clamp(c->opt.interactThreshold > 0 ? c->opt.interactThreshold : (mux ? 33 : 12), 1, 33);
-    P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold > 0 ? c->opt.rayleighThreshold : (mux ? 8 : 4), 1, 32);
-    P.voxel_load_mode = c->opt.voxelLoadMode;
+    P.interact_threshold = std::clamp(c->opt.interactThreshold > 0 ? c->opt.interactThreshold : (pool ? 28 : mux ? 33 : 12), 1, 33);
+    P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold > 0 ? c->opt.rayleighThreshold : (pool ? 20 : mux ? 8 : 4), 1, 32);
     P.step_pairs = std::clamp(c->opt.stepPairs > 0 ? c->opt.stepPairs : (pool ? 2 : 1), 1, 8);
     P.interact_bias = std::clamp(c->opt.interactBias, -32, 32);
     P.service_warps = std::clamp(c->opt.serviceWarps, 0, 32);
     P.diag = c->opt.diag;
+    P.step_quad = pool && c->opt.stepQuad && P.step_pairs == 2;
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -501,7 +502,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.slots = 0;
     cfg.pool = pool;
     if (pool) {
-        cfg.threads = 256;
+        cfg.threads = std::clamp(c->opt.poolThreads, 64, 512) / 32 * 32;
         cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots);
         cfg.smem = poolSmemBytes(cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
         if (cfg.table_in_smem && cfg.smem > 56 * 1024) {
@@ -1013,8 +1014,6 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         if (v != 0 && v != 2 && v != 3 && v != 4 && v != 6)
             return fail(c, DXB_EINVAL, "slots_per_lane must be 0 (register kernel), 2, 3, 4 or 6");
         c->opt.slots = v;
-    } else if (k == "voxel_load_mode") {
-        c->opt.voxelLoadMode = static_cast<int>(value);
     } else if (k == "smem_pad_kb") {
         c->opt.smemPadKb = static_cast<int>(value);
     } else if (k == "pool_slots") {
@@ -1024,6 +1023,10 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.poolSlots = v;
     } else if (k == "step_pairs") {
         c->opt.stepPairs = static_cast<int>(value);
+    } else if (k == "pool_threads") {
+        c->opt.poolThreads = static_cast<int>(value);
+    } else if (k == "step_quad") {
+        c->opt.stepQuad = static_cast<int>(value);
     } else if (k == "diag") {
         c->opt.diag = static_cast<int>(value);
     } else if (k == "service_warps") {

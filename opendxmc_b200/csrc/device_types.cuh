@@ -97,11 +97,12 @@ struct RunParams {
     int refill_threshold;           // dead lanes per warp that trigger a refill phase
     int interact_threshold;         // waiting lanes per warp that trigger an interaction phase
     int rayleigh_threshold;         // lanes waiting for a Rayleigh try that trigger a Rayleigh phase
-    int voxel_load_mode;            // see loadVoxel (transport_common.cuh)
     int step_pairs;                 // mux kernel: step pairs per step phase (>= 1)
+    int step_quad;                  // pool kernel: two step pairs per phase with all four gathers in flight
     int diag;                       // pool kernel: stats[8..15] = executions / claimed lanes per phase
     int service_warps;              // pool kernel: warps per block that prefer interaction / refill phases
-    int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes
+    int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes;
+                                    // pool kernel: stepper warps keep stepping while at least this many lanes can
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories

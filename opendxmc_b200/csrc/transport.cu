@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                 unsigned int cellA = 0u, cellB = 0u;
                 if (inA)
-                    cellA = loadVoxel(G.voxels + voxA, P.voxel_load_mode);
+                    cellA = loadVoxel(G.voxels + voxA);
                 if (inB)
-                    cellB = loadVoxel(G.voxels + voxB, P.voxel_load_mode);
+                    cellB = loadVoxel(G.voxels + voxB);
                 if (!inA) {
                     status = kStDead; // left the grid
                 } else {

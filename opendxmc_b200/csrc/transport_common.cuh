@@ -87,19 +87,9 @@ __device__ __forceinline__ TabPos energyPos(float e) { return tabPos<kLog2EPer, 
 
 __device__ __forceinline__ float lerp(float a, float b, float f) { return fmaf(f, b - a, a); }
 
-// voxel gather: mode 0 = read-only path with L1 allocation (ld.global.nc), 1 = L2 only (ld.global.cg),
-// 2 = read-only path without L1 allocation (experiment knob `voxel_load_mode`)
-__device__ __forceinline__ unsigned int loadVoxel(const unsigned int* p, int mode)
-{
-    if (mode == 1)
-        return __ldcg(p);
-    if (mode == 2) {
-        unsigned int v;
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-        return v;
-    }
-    return __ldg(p);
-}
+// voxel gather: L2 only (ld.global.cg).  The gathers are random over a 315 MB array, L1 cannot hold them; bypassing it
+// leaves L1 to the interaction tables (+3 % measured against ld.global.nc, profiles/r01_tuning_log.txt).
+__device__ __forceinline__ unsigned int loadVoxel(const unsigned int* p) { return __ldcg(p); }
 
 // ------------------------------------------------------------------ geometry helpers
 // Voxel of a point: linear index (x fastest) and whether the point lies inside the grid.  floor() of a negative

@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                     // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                     unsigned int cellA = 0u, cellB = 0u;
                     if (inA)
-                        cellA = loadVoxel(G.voxels + voxA, P.voxel_load_mode);
+                        cellA = loadVoxel(G.voxels + voxA);
                     if (inB)
-                        cellB = loadVoxel(G.voxels + voxB, P.voxel_load_mode);
+                        cellB = loadVoxel(G.voxels + voxB);
                     if (!inA) {
                         newPhase = kPhDead; // left the grid
                         stepping = false;

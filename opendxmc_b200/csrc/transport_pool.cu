@@ -53,7 +53,7 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
 }
 
 template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC>
-__global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_constant__ RunParams P)
+__global__ void __launch_bounds__(512, 2) transportKernelPool(const __grid_constant__ RunParams P)
 {
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -95,35 +95,28 @@ __global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_const
         const unsigned int votes = __reduce_add_sync(kFull, flags);
         const int nStep = votes & 0xff, nInt = (votes >> 8) & 0xff, nRay = (votes >> 16) & 0xff, nDead = votes >> 24;
         const bool canRefill = !(drained && poolNext == poolEnd);
-        // Phase choice = largest lane count, with a role bonus: the first `service_warps` warps of the block prefer
-        // interaction tries / Rayleigh tries / refills, the others prefer stepping.  All warps watch the same class
-        // words, so without roles they would all jump on the same phase at once and share its lanes.
-        const int bonus = P.interact_bias;
+        // Phase choice by thresholds on the lane counts, with roles: the first `service_warps` warps of the block
+        // prefer interaction tries / refills / Rayleigh tries, the others keep stepping while enough lanes can.
+        // (All warps watch the same class words; without roles they jump on the same phase at once and share it.)
         const bool service = (threadIdx.x >> 5) < P.service_warps;
-        int best = -1, phase = kPhStep;
-        if (nStep > 0) {
-            best = nStep + (service ? 0 : bonus);
-        }
-        if (nInt > 0 && nInt + (service ? bonus : 0) > best) {
-            best = nInt + (service ? bonus : 0);
+        int phase = kPhNone;
+        if (!service && nStep >= P.interact_bias)
+            phase = kPhStep;
+        else if (nInt >= P.interact_threshold)
             phase = kPhInt;
-        }
-        if (nRay >= P.rayleigh_threshold && nRay + (service ? bonus : 0) > best) {
-            best = nRay + (service ? bonus : 0);
-            phase = kPhRay;
-        }
-        if (canRefill && nDead >= P.refill_threshold && nDead + (service ? bonus : 0) > best) {
-            best = nDead + (service ? bonus : 0);
+        else if (canRefill && nDead >= P.refill_threshold)
             phase = kPhDead;
-        }
-        if (best < 0) {
-            // below the thresholds: anything that can still make progress
-            if (nRay > 0)
-                phase = kPhRay, best = nRay;
-            else if (canRefill && nDead > 0)
-                phase = kPhDead, best = nDead;
-        }
-        if (best < 0) {
+        else if (nRay >= P.rayleigh_threshold)
+            phase = kPhRay;
+        else if (nStep > 0)
+            phase = kPhStep;
+        else if (nInt > 0)
+            phase = kPhInt;
+        else if (nRay > 0)
+            phase = kPhRay;
+        else if (canRefill && nDead > 0)
+            phase = kPhDead;
+        if (phase == kPhNone) {
             // nothing claimable: finished if no history is left anywhere in the block (every slot of every class
             // is dead, none is in another warp's hands), else wait for the other warps to publish
             if (!canRefill && __all_sync(kFull, (wb >> 16) == kAllSlots))
@@ -171,6 +164,75 @@ __global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_const
             bool stepping = active;
             int newPhase = kPhStep;
             int mat = 0;
+            if (!CALIB && P.step_quad) {
+                // Two step pairs with all four voxel gathers in flight at once: the second pair (block blk + 1) is
+                // speculative and is simply not consumed if the first pair ends in a real collision or outside the grid
+                // (counter-based generator: the same block is regenerated when the history gets there).
+                if (stepping) {
+                    const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
+                    const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
+                    const float s0 = __log2f(fmaf(r1.k(0), -kU24, 1.0f)) * stepScale;
+                    const float s1 = __log2f(fmaf(r1.k(2), -kU24, 1.0f)) * stepScale;
+                    const float s2 = __log2f(fmaf(r2.k(0), -kU24, 1.0f)) * stepScale;
+                    const float s3 = __log2f(fmaf(r2.k(2), -kU24, 1.0f)) * stepScale;
+                    const float x0 = fmaf(dx, s0, px), y0 = fmaf(dy, s0, py), z0 = fmaf(dz, s0, pz);
+                    const float x1 = fmaf(dx, s1, x0), y1 = fmaf(dy, s1, y0), z1 = fmaf(dz, s1, z0);
+                    const float x2 = fmaf(dx, s2, x1), y2 = fmaf(dy, s2, y1), z2 = fmaf(dz, s2, z1);
+                    const float x3 = fmaf(dx, s3, x2), y3 = fmaf(dy, s3, y2), z3 = fmaf(dz, s3, z2);
+                    unsigned int v0, v1, v2, v3;
+                    const bool in0 = voxelIndex(G, x0, y0, z0, v0);
+                    const bool in1 = voxelIndex(G, x1, y1, z1, v1) && in0;
+                    const bool in2 = voxelIndex(G, x2, y2, z2, v2) && in1;
+                    const bool in3 = voxelIndex(G, x3, y3, z3, v3) && in2;
+                    unsigned int c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+                    if (in0)
+                        c0 = loadVoxel(G.voxels + v0);
+                    if (in1)
+                        c1 = loadVoxel(G.voxels + v1);
+                    if (in2)
+                        c2 = loadVoxel(G.voxels + v2);
+                    if (in3)
+                        c3 = loadVoxel(G.voxels + v3);
+                    // walk the four tentative collisions in order; stop at the first real one or at the exit
+                    const float* tt = totTable + epos.i;
+                    newPhase = kPhDead;
+                    blk += 1u;
+                    if (in0) {
+                        ++nSteps;
+                        mat = voxelMaterial(c0);
+                        const float mu0 = voxelDensity(c0) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                        px = x0, py = y0, pz = z0;
+                        if (r1.k(1) * muMaxU24 < mu0) {
+                            newPhase = kPhInt;
+                        } else if (in1) {
+                            ++nSteps;
+                            mat = voxelMaterial(c1);
+                            const float mu1 = voxelDensity(c1) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                            px = x1, py = y1, pz = z1;
+                            if (r1.k(3) * muMaxU24 < mu1) {
+                                newPhase = kPhInt;
+                            } else {
+                                blk += 1u; // the second pair is now consumed
+                                if (in2) {
+                                    ++nSteps;
+                                    mat = voxelMaterial(c2);
+                                    const float mu2 = voxelDensity(c2) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                    px = x2, py = y2, pz = z2;
+                                    if (r2.k(1) * muMaxU24 < mu2) {
+                                        newPhase = kPhInt;
+                                    } else if (in3) {
+                                        ++nSteps;
+                                        mat = voxelMaterial(c3);
+                                        const float mu3 = voxelDensity(c3) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                        px = x3, py = y3, pz = z3;
+                                        newPhase = (r2.k(3) * muMaxU24 < mu3) ? kPhInt : kPhStep;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            } else
             for (int it = 0; it < P.step_pairs; ++it) {
                 float kermaA = 0.0f, kermaB = 0.0f;
                 unsigned int voxA = 0, voxB = 0;
@@ -186,9 +248,9 @@ __global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_const
                     // both gathers are issued before either is used: B is speculative (wasted if A turns out real)
                     unsigned int cellA = 0u, cellB = 0u;
                     if (inA)
-                        cellA = loadVoxel(G.voxels + voxA, P.voxel_load_mode);
+                        cellA = loadVoxel(G.voxels + voxA);
                     if (inB)
-                        cellB = loadVoxel(G.voxels + voxB, P.voxel_load_mode);
+                        cellB = loadVoxel(G.voxels + voxB);
                     if (!inA) {
                         newPhase = kPhDead; // left the grid
                         stepping = false;
@@ -240,7 +302,7 @@ __global__ void __launch_bounds__(256, 4) transportKernelPool(const __grid_const
                     if (kermaB > 0.0f)
                         scoreEnergy(mScore, G.tally, voxB, kermaB, P.tally_scale_e, P.tally_scale_e2);
                 }
-                if (!__any_sync(kFull, stepping))
+                if (CALIB && !__any_sync(kFull, stepping))
                     break;
             }
             if (active) {

@@ -78,12 +78,10 @@ if __name__ == "__main__":
             for pairs in (1, 2):
                 timing(wl, {"pool_slots": slots, "step_pairs": pairs}, f"pool slots={slots} pairs={pairs}")
     if "poolpolicy" in which:
-        for sw in (0, 2, 3, 4):
-            for bias in (4, 8, 16, 32):
-                for rf in (24, 28):
-                    for rt in (8, 16):
-                        timing(wl, {"pool_slots": 16, "step_pairs": 2, "interact_bias": bias, "refill_threshold": rf, "service_warps": sw,
-                                    "rayleigh_threshold": rt}, f"pool16 pairs=2 service={sw} bias={bias} refill={rf} ray={rt}", reps=1)
+        for th, sw in ((128, 2), (192, 3), (256, 4), (384, 6), (512, 8), (512, 7)):
+            for slots in (12, 16):
+                timing(wl, {"pool_slots": slots, "pool_threads": th, "service_warps": sw},
+                       f"pool{slots} threads={th} service={sw}", reps=2)
     if which.startswith("psingle"):
         f = which.split(":")
         opts = {"pool_slots": int(f[1]), "step_pairs": int(f[2])}
@@ -106,14 +104,6 @@ if __name__ == "__main__":
                        f"mux slots=4 pairs=2 bias={bias} refill={rf}")
         for rt in (4, 8, 16):
             timing(wl, {"slots_per_lane": 4, "step_pairs": 2, "rayleigh_threshold": rt}, f"mux slots=4 pairs=2 ray={rt}")
-    if "l1" in which:
-        for pad in (0, 8, 16, 24, 32):
-            timing(wl, {"slots_per_lane": 0, "smem_pad_kb": pad}, f"register kernel, smem pad {pad} KB/block")
-        for mode in (0, 1, 2):
-            timing(wl, {"slots_per_lane": 0, "voxel_load_mode": mode}, f"register kernel, voxel load mode {mode}")
-            timing(wl, {"slots_per_lane": 0, "voxel_load_mode": mode, "smem_pad_kb": 32}, f"register kernel, voxel load mode {mode}, pad 32 KB")
-            timing(wl, {"slots_per_lane": 4, "step_pairs": 2, "voxel_load_mode": mode}, f"mux slots=4 pairs=2 voxel load mode {mode}")
-            timing(wl, {"slots_per_lane": 3, "step_pairs": 2, "voxel_load_mode": mode}, f"mux slots=3 pairs=2 voxel load mode {mode}")
     if "blocks" in which:
         for slots, th, bps in ((4, 128, 6), (4, 128, 5), (4, 256, 2), (3, 128, 8), (3, 256, 3), (6, 128, 4), (6, 128, 3), (2, 256, 5)):
             timing(wl, {"slots_per_lane": slots, "step_pairs": 2, "threads_per_block": th, "blocks_per_sm": bps},
