@@ -353,7 +353,17 @@ def run_ours(args):
     a_hist = S * 5.0 + D * 48.0
     # per-GPU roofline of the transport kernel: this rank's share of the histories over the slowest rank's kernel time
     achieved = (hist_done / world_size) * a_hist / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # measured DRAM traffic of the kernel (one `ncu --set full` capture, profiles/r01_pool_traffic.json), per launch
+    traffic, traffic_per_hist = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pool_traffic.json")))
+        traffic_per_hist = float(tj["dram_bytes_per_history"])
+        traffic = traffic_per_hist * hist_done / max(launches, 1.0)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per history x histories per launch)",
+                "traffic_bytes_per_history": traffic_per_hist, "algorithmic_bytes_per_launch": a_hist * hist_done / max(launches, 1.0),
                 "kernel": "transportKernelPool<1,false,true,16>", "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": D,
                 "sector_bytes_per_history": (S + 3 * D) * 32.0,
