@@ -182,6 +182,7 @@ struct Options {
     int smemPadKb = 0;           // experiment: extra dynamic shared memory per block (shrinks L1)
     int stepPairs = 0;           // pool / mux kernels: step pairs per step phase (0: kernel default, pool 2, mux 1)
     int poolThreads = 256;       // pool kernel: threads per block (the block shares one photon pool)
+    int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
@@ -501,6 +502,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.table_in_smem = c->opt.tableInSmem && tableBytes <= 200 * 1024;
     cfg.slots = 0;
     cfg.pool = pool;
+    cfg.min_blocks = c->opt.poolMinBlocks;
     if (pool) {
         cfg.threads = std::clamp(c->opt.poolThreads, 64, 512) / 32 * 32;
         cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots);
@@ -525,7 +527,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
+        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks)
             : mux  ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)
@@ -1025,6 +1027,8 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.stepPairs = static_cast<int>(value);
     } else if (k == "pool_threads") {
         c->opt.poolThreads = static_cast<int>(value);
+    } else if (k == "pool_min_blocks") {
+        c->opt.poolMinBlocks = static_cast<int>(value);
     } else if (k == "step_quad") {
         c->opt.stepQuad = static_cast<int>(value);
     } else if (k == "diag") {

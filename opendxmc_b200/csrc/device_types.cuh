@@ -142,6 +142,7 @@ struct LaunchConfig {
     bool table_in_smem;
     int slots; // 0: one photon per lane in registers (transport.cu); >= 2: slots per lane (mux) / per class (pool)
     bool pool; // block-pooled kernel instead of the lane-multiplexed one
+    int min_blocks; // pool kernel: 5 / 6 = the 48 / 40-register builds (5 / 6 blocks of <= 256 threads per SM), else 64 registers
 };
 
 } // namespace dxb

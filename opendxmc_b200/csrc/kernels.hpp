@@ -12,7 +12,7 @@ int transportMuxOccupancy(int mode, bool calib, bool smemTable, int slots, int t
 // block-pooled kernel (transport_pool.cu), cfg.slots photon slots per lane class
 cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream);
 int transportPoolSlots(int mode, bool calib, bool smemTable, int slots);
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem);
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks);
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s);
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s);
 void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,

@@ -52,8 +52,10 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
     atomicOr(words + phaseWord(phase), 1u << (phaseShift(phase) + j));
 }
 
-template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC>
-__global__ void __launch_bounds__(512, 2) transportKernelPool(const __grid_constant__ RunParams P)
+// LB: register budget through the launch bounds.  0: 64 registers (<= 512 threads per block, 1024 resident threads per SM);
+// 5 / 6: <= 256 threads per block with 5 / 6 resident blocks per SM (48 / 40 registers, a few spilled words).
+template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB>
+__global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transportKernelPool(const __grid_constant__ RunParams P)
 {
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -581,10 +583,10 @@ __global__ void __launch_bounds__(512, 2) transportKernelPool(const __grid_const
     }
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB>
 cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t stream)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
     if (e != cudaSuccess)
         return e;
@@ -592,10 +594,10 @@ cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t
     return cudaGetLastError();
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB>
 int occupancyPool(int threads, size_t smem)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -614,24 +616,30 @@ int occupancyPool(int threads, size_t smem)
     const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
     switch (key) {                                                              \
-    case 8: return CALL(2, false, false, 12);                                    \
-    case 9: return CALL(2, false, true, 12);                                     \
-    case 10: return CALL(2, true, false, 12);                                    \
-    case 11: return CALL(2, true, true, 12);                                     \
-    case 0: return CALL(0, false, false, 12);                                    \
-    case 1: return CALL(0, false, true, 12);                                     \
-    case 2: return CALL(0, true, false, 12);                                     \
-    case 3: return CALL(0, true, true, 12);                                      \
-    case 4: return CALL(1, false, false, 12);                                    \
-    case 6: return CALL(1, true, false, 12);                                     \
-    case 7: return CALL(1, true, true, 12);                                      \
+    case 8: return CALL(2, false, false, 12, 0);                                    \
+    case 9: return CALL(2, false, true, 12, 0);                                     \
+    case 10: return CALL(2, true, false, 12, 0);                                    \
+    case 11: return CALL(2, true, true, 12, 0);                                     \
+    case 0: return CALL(0, false, false, 12, 0);                                    \
+    case 1: return CALL(0, false, true, 12, 0);                                     \
+    case 2: return CALL(0, true, false, 12, 0);                                     \
+    case 3: return CALL(0, true, true, 12, 0);                                      \
+    case 4: return CALL(1, false, false, 12, 0);                                    \
+    case 6: return CALL(1, true, false, 12, 0);                                     \
+    case 7: return CALL(1, true, true, 12, 0);                                      \
     default: break;                                                             \
     }                                                                           \
-    switch (slots) {                                                            \
-    case 6: return CALL(1, false, true, 6);                                     \
-    case 8: return CALL(1, false, true, 8);                                     \
-    case 16: return CALL(1, false, true, 16);                                   \
-    default: return CALL(1, false, true, 12);                                   \
+    switch (slots + 100 * lb) {                                                 \
+    case 6: return CALL(1, false, true, 6, 0);                                  \
+    case 8: return CALL(1, false, true, 8, 0);                                  \
+    case 16: return CALL(1, false, true, 16, 0);                                \
+    case 508: return CALL(1, false, true, 8, 5);                                \
+    case 512: return CALL(1, false, true, 12, 5);                               \
+    case 516: return CALL(1, false, true, 16, 5);                               \
+    case 608: return CALL(1, false, true, 8, 6);                                \
+    case 612: return CALL(1, false, true, 12, 6);                               \
+    case 616: return CALL(1, false, true, 16, 6);                               \
+    default: return CALL(1, false, true, 12, 0);                                \
     }
 
 } // namespace
@@ -640,7 +648,8 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
 {
     const bool smemTable = cfg.table_in_smem;
     const int slots = cfg.slots;
-#define DXB_CALL(MO, CA, SM, MM) launchPool<MO, CA, SM, MM>(p, cfg, stream)
+    const int lb = (cfg.threads <= 256 && (cfg.min_blocks == 5 || cfg.min_blocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? cfg.min_blocks : 0;
+#define DXB_CALL(MO, CA, SM, MM, LB) launchPool<MO, CA, SM, MM, LB>(p, cfg, stream)
     DXB_POOL_DISPATCH(DXB_CALL)
 #undef DXB_CALL
 }
@@ -653,9 +662,10 @@ int transportPoolSlots(int mode, bool calib, bool smemTable, int slots)
     return 12;
 }
 
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem)
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks)
 {
-#define DXB_CALL(MO, CA, SM, MM) occupancyPool<MO, CA, SM, MM>(threads, smem)
+    const int lb = (threads <= 256 && (minBlocks == 5 || minBlocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? minBlocks : 0;
+#define DXB_CALL(MO, CA, SM, MM, LB) occupancyPool<MO, CA, SM, MM, LB>(threads, smem)
     DXB_POOL_DISPATCH(DXB_CALL)
 #undef DXB_CALL
 }

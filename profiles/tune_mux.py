@@ -82,6 +82,18 @@ if __name__ == "__main__":
             for slots in (12, 16):
                 timing(wl, {"pool_slots": slots, "pool_threads": th, "service_warps": sw},
                        f"pool{slots} threads={th} service={sw}", reps=2)
+    if "poolocc" in which:
+        # register budget / residency: 64 registers x 4 blocks vs 48 x 5 vs 40 x 6 (256 threads per block)
+        w2 = dx.workloads.ct_spiral_patient(scale=4, histories=2_000_000)
+        ref = tallies(w2, {"pool_slots": 0, "slots_per_lane": 0})
+        for mb in (5, 6):
+            got = tallies(w2, {"pool_slots": 12, "pool_min_blocks": mb})
+            print(f"pool exact c2/4 min_blocks={mb}: tallies identical={all(np.array_equal(a, b) for a, b in zip(ref[:3], got[:3]))}", flush=True)
+        for mb in (0, 5, 6):
+            for slots in (8, 12, 16):
+                for sw in (3, 4):
+                    timing(wl, {"pool_slots": slots, "pool_min_blocks": mb, "service_warps": sw},
+                           f"pool{slots} min_blocks={mb} service={sw}", reps=2)
     if which.startswith("psingle"):
         f = which.split(":")
         opts = {"pool_slots": int(f[1]), "step_pairs": int(f[2])}
