@@ -186,7 +186,8 @@ struct Options {
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
-    int interactBias = 16;       // mux kernel: interaction phase when waiting lanes + bias >= stepping lanes
+    int interactBias = -999;     // -999: kernel default (mux 16: interaction phase when waiting lanes + bias >= stepping lanes;
+                                 // pool 24: stepper warps keep stepping while at least this many lanes can claim a photon)
 };
 
 } // namespace
@@ -489,7 +490,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.interact_threshold = std::clamp(c->opt.interactThreshold > 0 ? c->opt.interactThreshold : (pool ? 28 : mux ? 33 : 12), 1, 33);
     P.rayleigh_threshold = std::clamp(c->opt.rayleighThreshold > 0 ? c->opt.rayleighThreshold : (pool ? 20 : mux ? 8 : 4), 1, 32);
     P.step_pairs = std::clamp(c->opt.stepPairs > 0 ? c->opt.stepPairs : (pool ? 2 : 1), 1, 8);
-    P.interact_bias = std::clamp(c->opt.interactBias, -32, 32);
+    P.interact_bias = std::clamp(c->opt.interactBias == -999 ? (pool ? 24 : 16) : c->opt.interactBias, -32, 32);
     P.service_warps = std::clamp(c->opt.serviceWarps, 0, 32);
     P.diag = c->opt.diag;
     P.step_quad = pool && c->opt.stepQuad && P.step_pairs == 2;

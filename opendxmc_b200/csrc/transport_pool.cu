@@ -21,9 +21,16 @@ constexpr unsigned int kMetaBlkMask = 0xFFFFFu; // Philox block index of the his
 constexpr int kMetaMatShift = 20;               // material of the pending interaction (8 bits)
 constexpr unsigned int kMetaRetry = 1u << 28;   // Compton already chosen, previous candidate rejected
 
-// slot words
-enum : int { kWPx = 0, kWPy, kWPz, kWDx, kWDy, kWDz, kWE, kWW, kWHlo, kWMeta };
-static_assert(kWMeta + 1 == kSlotWords, "slot layout");
+// A photon slot is three vectors, each stored lane-contiguously so that a warp moves it with one 128-bit (64-bit)
+// shared-memory access per vector, bank-conflict free:
+//   A = {px, py, pz, meta}   rewritten by the step phase (one STS.128)
+//   B = {dx, dy, dz, E}      rewritten by an accepted scatter
+//   C = {w, history id lo}
+struct SlotC {
+    float w;
+    unsigned int hlo;
+};
+static_assert(kSlotWords == 10, "slot layout: float4 + float4 + 2 words");
 // byte of the status word that holds the slot mask of a state
 enum : int { kPhStep = 0, kPhInt = 1, kPhRay = 2, kPhDead = 3, kPhNone = 4 };
 
@@ -31,16 +38,19 @@ enum : int { kPhStep = 0, kPhInt = 1, kPhRay = 2, kPhDead = 3, kPhNone = 4 };
 __device__ __forceinline__ int phaseWord(int phase) { return phase >> 1; }          // step,int -> A; ray,dead -> B
 __device__ __forceinline__ int phaseShift(int phase) { return (phase & 1) << 4; }   // int, dead in the upper half
 
-// claims one slot of the lane's class that is in `phase`; returns its index inside the class or -1
-__device__ __forceinline__ int claimSlot(unsigned int* word, int shift, unsigned int seen)
+// claims one slot of the lane's class that is in `phase`; returns its index inside the class or -1.  The search
+// starts at a warp-specific slot (`rot`) and wraps around: warps that run the same phase at the same time would
+// otherwise all go for the lowest set bit of a class and retry.
+__device__ __forceinline__ int claimSlot(unsigned int* word, int shift, unsigned int seen, int rot)
 {
     unsigned int m = (seen >> shift) & 0xffffu;
     while (m) {
-        const unsigned int bit = (m & (0u - m)) << shift;
+        const int k = (__ffs(((m | (m << 16)) >> rot) & 0xffffu) - 1 + rot) & 15; // first set bit at or after `rot`, cyclic
+        const unsigned int bit = 1u << (k + shift);
         const unsigned int old = atomicAnd(word, ~bit);
         if (old & bit) {
             __threadfence_block(); // pairs with publishSlot: the slot's words are read after its status bit
-            return __ffs(bit >> shift) - 1;
+            return k;
         }
         m = (old >> shift) & 0xffffu; // somebody else took it: look again
     }
@@ -60,16 +70,19 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
     extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr unsigned int kFull = 0xffffffffu;
-    constexpr int kStride = SPC * 32; // distance between two words of one slot
+    constexpr int kStride = SPC * 32; // slots per block
     constexpr unsigned int kAllSlots = (1u << SPC) - 1u;
     const int lane = threadIdx.x & 31;
-    // layout: poolSmemBytes (device_types.cuh)
-    float* __restrict__ s_f = reinterpret_cast<float*>(s_raw);
+    // layout (poolSmemBytes, device_types.cuh): [A: SPC x 32 float4][B: SPC x 32 float4][C: SPC x 32 x 2 words]
+    //                                             [status: 32 x 2 words][majorant: kDevNE][total attenuation: n_mat x kDevNE]
+    float4* __restrict__ slotA = reinterpret_cast<float4*>(s_raw) + lane;
+    float4* __restrict__ slotB = slotA + kStride;
+    SlotC* __restrict__ slotC = reinterpret_cast<SlotC*>(reinterpret_cast<float4*>(s_raw) + 2 * kStride) + lane;
+    unsigned int* s_status = reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(s_raw) + kSlotWords * kStride) + 2 * lane; // the lane's class: words A, B
     const int nTab = SMEM_TABLE ? P.tab.n_mat * kDevNE : 0;
-    float* __restrict__ s_tot = s_f;
-    float* __restrict__ s_maj = s_f + nTab;
-    unsigned int* s_status = reinterpret_cast<unsigned int*>(s_maj + kDevNE) + 2 * lane; // the lane's class: words A, B
-    float* __restrict__ slots = s_maj + kDevNE + 64 + lane;
+    float* __restrict__ s_maj = reinterpret_cast<float*>(s_raw) + kSlotWords * kStride + 64;
+    float* __restrict__ s_tot = s_maj + kDevNE;
+    const int rot = static_cast<int>(((threadIdx.x >> 5) * SPC) / (blockDim.x >> 5)); // first slot this warp tries to claim
     for (int i = threadIdx.x; i < nTab; i += blockDim.x)
         s_tot[i] = P.tab.tot[i];
     for (int i = threadIdx.x; i < kDevNE; i += blockDim.x)
@@ -92,32 +105,44 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
 
     for (;;) {
         const unsigned int wa = vstatus[0], wb = vstatus[1];
-        const unsigned int flags = ((wa & 0xffffu) ? 1u : 0u) | ((wa >> 16) ? 0x100u : 0u) | ((wb & 0xffffu) ? 0x10000u : 0u)
-            | ((wb >> 16) ? 0x1000000u : 0u);
-        const unsigned int votes = __reduce_add_sync(kFull, flags);
-        const int nStep = votes & 0xff, nInt = (votes >> 8) & 0xff, nRay = (votes >> 16) & 0xff, nDead = votes >> 24;
         const bool canRefill = !(drained && poolNext == poolEnd);
-        // Phase choice by thresholds on the lane counts, with roles: the first `service_warps` warps of the block
-        // prefer interaction tries / refills / Rayleigh tries, the others keep stepping while enough lanes can.
-        // (All warps watch the same class words; without roles they jump on the same phase at once and share it.)
+        // Phase choice by thresholds on the number of lanes that could claim a slot in each state, with roles: the
+        // first `service_warps` warps of the block prefer interaction tries / refills / Rayleigh tries, the others keep
+        // stepping while enough lanes can.  (All warps watch the same class words; without roles they jump on the same
+        // phase at once and share it.)  The counts are ballots, taken lazily in the order the policy asks for them.
         const bool service = (threadIdx.x >> 5) < P.service_warps;
         int phase = kPhNone;
-        if (!service && nStep >= P.interact_bias)
-            phase = kPhStep;
-        else if (nInt >= P.interact_threshold)
-            phase = kPhInt;
-        else if (canRefill && nDead >= P.refill_threshold)
-            phase = kPhDead;
-        else if (nRay >= P.rayleigh_threshold)
-            phase = kPhRay;
-        else if (nStep > 0)
-            phase = kPhStep;
-        else if (nInt > 0)
-            phase = kPhInt;
-        else if (nRay > 0)
-            phase = kPhRay;
-        else if (canRefill && nDead > 0)
-            phase = kPhDead;
+        unsigned int bStep = 0u;
+        if (!service) {
+            bStep = __ballot_sync(kFull, (wa & 0xffffu) != 0u);
+            if (__popc(bStep) >= max(P.interact_bias, 1))
+                phase = kPhStep;
+        }
+        if (phase == kPhNone) {
+            const unsigned int bInt = __ballot_sync(kFull, (wa >> 16) != 0u);
+            if (__popc(bInt) >= P.interact_threshold) {
+                phase = kPhInt;
+            } else {
+                const unsigned int bDead = canRefill ? __ballot_sync(kFull, (wb >> 16) != 0u) : 0u;
+                if (__popc(bDead) >= P.refill_threshold) {
+                    phase = kPhDead;
+                } else {
+                    const unsigned int bRay = __ballot_sync(kFull, (wb & 0xffffu) != 0u);
+                    if (service)
+                        bStep = __ballot_sync(kFull, (wa & 0xffffu) != 0u);
+                    if (__popc(bRay) >= P.rayleigh_threshold)
+                        phase = kPhRay;
+                    else if (bStep)
+                        phase = kPhStep;
+                    else if (bInt)
+                        phase = kPhInt;
+                    else if (bRay)
+                        phase = kPhRay;
+                    else if (bDead)
+                        phase = kPhDead;
+                }
+            }
+        }
         if (phase == kPhNone) {
             // nothing claimable: finished if no history is left anywhere in the block (every slot of every class
             // is dead, none is in another warp's hands), else wait for the other warps to publish
@@ -129,7 +154,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
 
         if (phase == kPhStep) {
             // ------------------------------------------------------------ pairs of tentative Woodcock steps
-            const int j = claimSlot(s_status + 0, 0, wa);
+            const int j = claimSlot(s_status + 0, 0, wa, rot);
             const bool active = j >= 0;
             if (P.diag) {
                 const int n = __popc(__ballot_sync(kFull, active));
@@ -138,7 +163,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     atomicAdd(P.stats + 12 + kPhStep, static_cast<unsigned long long>(n));
                 }
             }
-            float* __restrict__ sp = slots + (active ? j : 0) * 32;
+            const int so = (active ? j : 0) * 32;
             float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, E = 0.f, w = 0.f;
             unsigned int hlo = 0, hhi = 0, blk = 0;
             TabPos epos;
@@ -146,17 +171,14 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             epos.f = 0.f;
             float muMaxU24 = kU24, stepScale = -kLn2;
             if (active) {
-                px = sp[kWPx * kStride];
-                py = sp[kWPy * kStride];
-                pz = sp[kWPz * kStride];
-                dx = sp[kWDx * kStride];
-                dy = sp[kWDy * kStride];
-                dz = sp[kWDz * kStride];
-                E = sp[kWE * kStride];
+                const float4 a = slotA[so], b = slotB[so];
+                px = a.x, py = a.y, pz = a.z;
+                dx = b.x, dy = b.y, dz = b.z;
+                E = b.w;
                 if (CALIB)
-                    w = sp[kWW * kStride];
-                hlo = __float_as_uint(sp[kWHlo * kStride]);
-                blk = __float_as_uint(sp[kWMeta * kStride]) & kMetaBlkMask;
+                    w = slotC[so].w;
+                hlo = slotC[so].hlo;
+                blk = __float_as_uint(a.w) & kMetaBlkMask;
                 hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
                 epos = energyPos(E);
                 const float muMax = lerp(s_maj[epos.i], s_maj[epos.i + 1], epos.f);
@@ -308,17 +330,13 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     break;
             }
             if (active) {
-                if (newPhase != kPhDead) {
-                    sp[kWPx * kStride] = px;
-                    sp[kWPy * kStride] = py;
-                    sp[kWPz * kStride] = pz;
-                    sp[kWMeta * kStride] = __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift));
-                }
+                if (newPhase != kPhDead)
+                    slotA[so] = make_float4(px, py, pz, __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift)));
                 publishSlot(s_status, newPhase, j);
             }
         } else if (phase == kPhInt || phase == kPhRay) {
             // ------------------------------------------------------------ one sampling try per claimed photon
-            const int j = claimSlot(s_status + phaseWord(phase), phaseShift(phase), phase == kPhInt ? wa : wb);
+            const int j = claimSlot(s_status + phaseWord(phase), phaseShift(phase), phase == kPhInt ? wa : wb, rot);
             const bool active = j >= 0;
             if (P.diag) {
                 const int n = __popc(__ballot_sync(kFull, active));
@@ -327,15 +345,17 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     atomicAdd(P.stats + 12 + phase, static_cast<unsigned long long>(n));
                 }
             }
-            float* __restrict__ sp = slots + (active ? j : 0) * 32;
+            const int so = (active ? j : 0) * 32;
             float edep = 0.0f;
             unsigned int voxel = 0;
             if (active) {
-                float px = sp[kWPx * kStride], py = sp[kWPy * kStride], pz = sp[kWPz * kStride];
-                float dx = sp[kWDx * kStride], dy = sp[kWDy * kStride], dz = sp[kWDz * kStride];
-                float E = sp[kWE * kStride], w = sp[kWW * kStride];
-                const unsigned int hlo = __float_as_uint(sp[kWHlo * kStride]);
-                unsigned int meta = __float_as_uint(sp[kWMeta * kStride]);
+                const float4 va = slotA[so], vb = slotB[so];
+                const SlotC vc = slotC[so];
+                const float px = va.x, py = va.y, pz = va.z;
+                float dx = vb.x, dy = vb.y, dz = vb.z;
+                float E = vb.w, w = vc.w;
+                const unsigned int hlo = vc.hlo;
+                unsigned int meta = __float_as_uint(va.w);
                 const unsigned int hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
                 unsigned int blk = meta & kMetaBlkMask;
                 const int mat = static_cast<int>((meta >> kMetaMatShift) & 0xffu);
@@ -412,16 +432,13 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                             w *= 1.0f / (1.0f - kRouletteKill);
                     }
                     if (newPhase == kPhStep) {
-                        sp[kWDx * kStride] = dx;
-                        sp[kWDy * kStride] = dy;
-                        sp[kWDz * kStride] = dz;
-                        sp[kWE * kStride] = E;
-                        sp[kWW * kStride] = w;
+                        slotB[so] = make_float4(dx, dy, dz, E);
+                        slotC[so].w = w;
                         meta &= ~kMetaRetry;
                     }
                 }
                 if (newPhase != kPhDead)
-                    sp[kWMeta * kStride] = __uint_as_float((meta & ~kMetaBlkMask) | blk);
+                    slotA[so].w = __uint_as_float((meta & ~kMetaBlkMask) | blk);
                 if (CALIB)
                     edep = 0.0f;
                 if (edep > 0.0f)
@@ -438,7 +455,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
         } else {
             // ------------------------------------------------------------ refill: lanes that claim a dead slot sample a history into it
             const unsigned int laneLt = (1u << lane) - 1u;
-            const int j = claimSlot(s_status + 1, 16, wb);
+            const int j = claimSlot(s_status + 1, 16, wb, rot);
             const unsigned int mGot = __ballot_sync(kFull, j >= 0);
             const int want = __popc(mGot);
             if (P.diag && lane == 0) {
@@ -470,7 +487,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 const int r = __popc(mGot & laneLt);
                 const unsigned long long h = idBase + r;
                 bool hit = false;
-                float* __restrict__ sp = slots + j * 32;
+                const int so = j * 32;
                 if (r < nb && h < P.n_total) {
                     const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
                     const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
@@ -552,16 +569,13 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         tmax = fminf(tmax, fmaxf(t0, t1));
                     }
                     if (tmax > tmin && E >= kMinEnergy) {
-                        sp[kWPx * kStride] = fmaf(qdx, tmin, qpx);
-                        sp[kWPy * kStride] = fmaf(qdy, tmin, qpy);
-                        sp[kWPz * kStride] = fmaf(qdz, tmin, qpz);
-                        sp[kWDx * kStride] = qdx;
-                        sp[kWDy * kStride] = qdy;
-                        sp[kWDz * kStride] = qdz;
-                        sp[kWE * kStride] = E;
-                        sp[kWW * kStride] = w;
-                        sp[kWHlo * kStride] = __uint_as_float(qlo);
-                        sp[kWMeta * kStride] = __uint_as_float(2u); // blocks 0-1 belong to the source
+                        // blocks 0-1 belong to the source: the history continues with block 2
+                        slotA[so] = make_float4(fmaf(qdx, tmin, qpx), fmaf(qdy, tmin, qpy), fmaf(qdz, tmin, qpz), __uint_as_float(2u));
+                        slotB[so] = make_float4(qdx, qdy, qdz, E);
+                        SlotC c;
+                        c.w = w;
+                        c.hlo = qlo;
+                        slotC[so] = c;
                         hit = true;
                     }
                 }
