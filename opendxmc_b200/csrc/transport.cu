@@ -330,99 +330,22 @@ __global__ void __launch_bounds__(256, 4) transportKernel(const __grid_constant_
                 qpos.f = 0.0f;
                 q.px = q.py = q.pz = q.dx = q.dy = q.dz = q.E = q.w = 0.0f;
                 if (lane < nb && h < P.n_total) {
-                    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
-                    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
-                    const unsigned long long ei = h / P.ppe;
-                    const ExposureDev* ex = P.exposures + ei;
-                    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
-                    const float angx = (2.0f * s0.u(0) - 1.0f) * hx;
-                    const float angy = (2.0f * s0.u(1) - 1.0f) * hy;
-                    const int tube = __ldg(&ex->tube);
-                    const SpectrumDev& sp = P.spec[tube];
-                    float E;
-                    if (sp.n <= 1) {
-                        E = sp.e0;
-                    } else {
-                        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(sp.n)), sp.n - 1);
-                        if (!(s0.u(3) < __ldg(sp.prob + idx)))
-                            idx = __ldg(sp.alias + idx);
-                        E = sp.e0 + static_cast<float>(idx) * sp.step;
-                        if (idx < sp.n - 1) {
-                            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
-                            E += s1.u(0) * sp.step;
-                        }
-                    }
-                    float w = __ldg(&ex->weight);
-                    const BowtieDev& bt = P.bow[tube];
-                    if (bt.n > 0) {
-                        const float a = fabsf(angx);
-                        float bw;
-                        if (a <= __ldg(bt.angle)) {
-                            bw = __ldg(bt.weight);
-                        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
-                            bw = __ldg(bt.weight + bt.n - 1);
-                        } else {
-                            int i = 1;
-                            while (__ldg(bt.angle + i) < a)
-                                ++i;
-                            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
-                            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
-                        }
-                        w *= bw;
-                    }
-                    const float sx = __sinf(angx), sy = __sinf(angy);
-                    const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
-                    q.dx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
-                    q.dy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
-                    q.dz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
-                    q.px = __ldg(&ex->pos[0]);
-                    q.py = __ldg(&ex->pos[1]);
-                    q.pz = __ldg(&ex->pos[2]);
-                    q.E = E;
-                    q.w = w;
+                    SourceSample ss;
+                    hit = sampleSource(P, h, ss);
+                    q.px = ss.px, q.py = ss.py, q.pz = ss.pz;
+                    q.dx = ss.dx, q.dy = ss.dy, q.dz = ss.dz;
+                    q.E = ss.E;
+                    q.w = ss.w;
                     scnt[2 * blockDim.x] += 1u;
                     {
                         const unsigned long long em = (static_cast<unsigned long long>(scnt[4 * blockDim.x]) << 32 | scnt[3 * blockDim.x])
-                            + static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
+                            + static_cast<unsigned long long>(__float2ll_rn(ss.E * ss.w * 65536.0f));
                         scnt[3 * blockDim.x] = static_cast<unsigned int>(em);
                         scnt[4 * blockDim.x] = static_cast<unsigned int>(em >> 32);
                     }
-                    // move to the grid AABB (World::transport)
-                    const float ix = 1.0f / q.dx, iy = 1.0f / q.dy, iz = 1.0f / q.dz;
-                    float tmin = 0.0f, tmax = 3.0e38f;
-                    float t0 = (G.x0 - q.px) * ix, t1 = (G.x1 - q.px) * ix;
-                    if (q.dx == 0.0f) {
-                        if (q.px < G.x0 || q.px > G.x1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.y0 - q.py) * iy;
-                    t1 = (G.y1 - q.py) * iy;
-                    if (q.dy == 0.0f) {
-                        if (q.py < G.y0 || q.py > G.y1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.z0 - q.pz) * iz;
-                    t1 = (G.z1 - q.pz) * iz;
-                    if (q.dz == 0.0f) {
-                        if (q.pz < G.z0 || q.pz > G.z1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    if (tmax > tmin && E >= kMinEnergy) {
-                        q.px = fmaf(q.dx, tmin, q.px);
-                        q.py = fmaf(q.dy, tmin, q.py);
-                        q.pz = fmaf(q.dz, tmin, q.pz);
-                        qpos = energyPos(E);
+                    if (hit) {
+                        qpos = energyPos(ss.E);
                         qmu = lerp(__ldg(P.tab.majorant + qpos.i), __ldg(P.tab.majorant + qpos.i + 1), qpos.f);
-                        hit = true;
                     }
                 }
                 __syncwarp();

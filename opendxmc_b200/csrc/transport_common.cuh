@@ -106,23 +106,27 @@ __device__ __forceinline__ bool voxelIndex(const GridDev& G, float x, float y, f
 
 __device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float cosT, float phi)
 {
-    // dxmc::vectormath::peturb: rotate the direction by polar angle theta and azimuth phi
-    const float sinT = sqrtf(fmaxf(0.0f, 1.0f - cosT * cosT));
+    // dxmc::vectormath::peturb: rotate the direction by polar angle theta and azimuth phi.
+    // (The library is built with -fmad=false: every fused multiply-add is written out, so that all kernel builds
+    // round identically whatever the compiler's contraction heuristics.)
+    const float sinT = sqrtf(fmaxf(0.0f, fmaf(-cosT, cosT, 1.0f)));
     float sinP, cosP;
     __sincosf(phi, &sinP, &cosP);
     float nx, ny, nz;
     if (fabsf(dz) < 0.99999f) {
-        const float inv = rsqrtf(1.0f - dz * dz);
-        const float tmp = (1.0f - dz * dz) * inv;
-        nx = dx * cosT + sinT * (dx * dz * cosP - dy * sinP) * inv;
-        ny = dy * cosT + sinT * (dy * dz * cosP + dx * sinP) * inv;
-        nz = dz * cosT - tmp * sinT * cosP;
+        const float s2 = fmaf(-dz, dz, 1.0f);
+        const float inv = rsqrtf(s2);
+        const float tmp = s2 * inv;
+        const float sti = sinT * inv;
+        nx = fmaf(sti, fmaf(dx * dz, cosP, -(dy * sinP)), dx * cosT);
+        ny = fmaf(sti, fmaf(dy * dz, cosP, dx * sinP), dy * cosT);
+        nz = fmaf(-(tmp * sinT), cosP, dz * cosT);
     } else {
         nx = sinT * cosP;
         ny = sinT * sinP;
         nz = dz > 0.0f ? cosT : -cosT;
     }
-    const float n = rsqrtf(nx * nx + ny * ny + nz * nz);
+    const float n = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
     dx = nx * n;
     dy = ny * n;
     dz = nz * n;
@@ -170,9 +174,9 @@ template <int MODE>
 __device__ __forceinline__ bool comptonTry(const TablesDev& tab, int mat, float E, float r1, float ra, float& e, float& cosT)
 {
     const float k = E * (1.0f / kElectronMass);
-    const float emin = __fdividef(1.0f, 1.0f + 2.0f * k);
-    const float gmaxInv = __fdividef(emin, 1.0f + emin * emin);
-    e = r1 + (1.0f - r1) * emin;
+    const float emin = __fdividef(1.0f, fmaf(2.0f, k, 1.0f));
+    const float gmaxInv = __fdividef(emin, fmaf(emin, emin, 1.0f));
+    e = fmaf(1.0f - r1, emin, r1);
     const float einv = __fdividef(1.0f, e);
     const float t = fminf((1.0f - e) * einv * __fdividef(1.0f, k), 2.0f);
     const float sin2 = t * (2.0f - t);
@@ -231,12 +235,13 @@ __device__ __forceinline__ bool dopplerBroaden(const TablesDev& tab, int mat, fl
     float pz = __logf(__fdividef(u, 1.0f - u)) * __fdividef(0.25f, j0) * kFineStructure; // in units of m_e c
     pz = fminf(fmaxf(pz, -0.5f), 0.5f);
     const float t = pz * pz;
-    const float a = 1.0f - t * e0 * cosT;
-    const float b = 1.0f - t * e0 * e0;
-    const float disc = fmaxf(a * a - b * (1.0f - t), 0.0f);
+    const float te0 = t * e0;
+    const float a = fmaf(-te0, cosT, 1.0f);
+    const float b = fmaf(-te0, e0, 1.0f);
+    const float disc = fmaxf(fmaf(a, a, -(b * (1.0f - t))), 0.0f);
     const float root = sqrtf(disc);
     const float e = __fdividef(e0, b) * (a + (pz < 0.0f ? -root : root));
-    if (!(e > 0.0f) || !(E - E * e > U))
+    if (!(e > 0.0f) || !(fmaf(-E, e, E) > U))
         return false;
     eOut = fminf(e, 1.0f);
     return true;
@@ -268,8 +273,8 @@ __device__ __forceinline__ float photoFluorescence(const TablesDev& tab, int mat
 // isotropic direction from two uniforms
 __device__ __forceinline__ void isotropic(float r0, float r1, float& dx, float& dy, float& dz)
 {
-    const float c = 2.0f * r0 - 1.0f;
-    const float s = sqrtf(fmaxf(0.0f, 1.0f - c * c));
+    const float c = fmaf(2.0f, r0, -1.0f);
+    const float s = sqrtf(fmaxf(0.0f, fmaf(-c, c, 1.0f)));
     float sp, cp;
     __sincosf(kTwoPi * r1, &sp, &cp);
     dx = s * cp;
@@ -288,7 +293,7 @@ __device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float
         float s, c;
         __sincosf(kPiF * r1, &s, &c);
         cosT = c;
-        return !(rr > (2.0f - s * s) * s);
+        return !(rr > fmaf(-s, s, 2.0f) * s);
     }
     const float xmaxs = E * (kDevXMinInv / kHc); // in units of the grid minimum
     const float xmax2 = xmaxs * xmaxs;
@@ -302,7 +307,8 @@ __device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float
     } else {
         const TabPos p = tabPos<kLog2XPer, kDevNX>(xmaxs);
         const float xa = tabNode<kLog2XPer>(p.i), xb = tabNode<kLog2XPer>(p.i + 1);
-        const float fa = __fdividef(xmax2 - xa * xa, xb * xb - xa * xa);
+        const float xa2 = xa * xa;
+        const float fa = __fdividef(xmax2 - xa2, fmaf(xb, xb, -xa2));
         amax = lerp(__ldg(cdf + p.i), __ldg(cdf + p.i + 1), fminf(fmaxf(fa, 0.0f), 1.0f));
         top = p.i + 1;
     }
@@ -323,11 +329,110 @@ __device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float
         const float al = __ldg(cdf + lo), ah = __ldg(cdf + lo + 1);
         const float xa = tabNode<kLog2XPer>(lo), xb = tabNode<kLog2XPer>(lo + 1);
         const float f = ah > al ? __fdividef(target - al, ah - al) : 0.0f;
-        x2 = xa * xa + f * (xb * xb - xa * xa);
+        const float xa2 = xa * xa;
+        x2 = fmaf(f, fmaf(xb, xb, -xa2), xa2);
     }
     x2 = fminf(x2, xmax2);
-    cosT = 1.0f - 2.0f * __fdividef(x2, xmax2);
-    return !((1.0f + cosT * cosT) * 0.5f < r1);
+    cosT = fmaf(-2.0f, __fdividef(x2, xmax2), 1.0f);
+    return !(fmaf(cosT, cosT, 1.0f) * 0.5f < r1);
+}
+
+// ------------------------------------------------------------------ source sampling
+// One history of the beam: exposure = h / ppe, fan / cone angles uniform in the collimation, energy from the tube's
+// alias table (+ uniform inside the bin), weight = exposure weight x bowtie(|fan angle|), then the ray is moved to the
+// grid's bounding box (World::transport).  Philox blocks 0 and 1 of the history.  Returns false if the ray misses the
+// grid; E and w are valid either way (the caller counts the emitted energy E * w).
+struct SourceSample {
+    float px, py, pz, dx, dy, dz, E, w;
+};
+__device__ __forceinline__ bool sampleSource(const RunParams& P, unsigned long long h, SourceSample& q)
+{
+    const GridDev& G = P.grid;
+    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
+    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
+    const unsigned long long ei = h / P.ppe;
+    const ExposureDev* ex = P.exposures + ei;
+    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
+    const float angx = fmaf(2.0f, s0.u(0), -1.0f) * hx;
+    const float angy = fmaf(2.0f, s0.u(1), -1.0f) * hy;
+    const int tube = __ldg(&ex->tube);
+    const SpectrumDev& spc = P.spec[tube];
+    float E;
+    if (spc.n <= 1) {
+        E = spc.e0;
+    } else {
+        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(spc.n)), spc.n - 1);
+        if (!(s0.u(3) < __ldg(spc.prob + idx)))
+            idx = __ldg(spc.alias + idx);
+        E = fmaf(static_cast<float>(idx), spc.step, spc.e0);
+        if (idx < spc.n - 1) {
+            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
+            E = fmaf(s1.u(0), spc.step, E);
+        }
+    }
+    float w = __ldg(&ex->weight);
+    const BowtieDev& bt = P.bow[tube];
+    if (bt.n > 0) {
+        const float a = fabsf(angx);
+        float bw;
+        if (a <= __ldg(bt.angle)) {
+            bw = __ldg(bt.weight);
+        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
+            bw = __ldg(bt.weight + bt.n - 1);
+        } else {
+            int i = 1;
+            while (__ldg(bt.angle + i) < a)
+                ++i;
+            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
+            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
+        }
+        w *= bw;
+    }
+    const float sx = __sinf(angx), sy = __sinf(angy);
+    const float sz = sqrtf(fmaxf(0.0f, fmaf(-sy, sy, fmaf(-sx, sx, 1.0f))));
+    q.dx = fmaf(__ldg(&ex->dir[0]), sz, fmaf(__ldg(&ex->c1[0]), sy, __ldg(&ex->c0[0]) * sx));
+    q.dy = fmaf(__ldg(&ex->dir[1]), sz, fmaf(__ldg(&ex->c1[1]), sy, __ldg(&ex->c0[1]) * sx));
+    q.dz = fmaf(__ldg(&ex->dir[2]), sz, fmaf(__ldg(&ex->c1[2]), sy, __ldg(&ex->c0[2]) * sx));
+    q.px = __ldg(&ex->pos[0]);
+    q.py = __ldg(&ex->pos[1]);
+    q.pz = __ldg(&ex->pos[2]);
+    q.E = E;
+    q.w = w;
+    // slab test against the grid's bounding box
+    const float ix = 1.0f / q.dx, iy = 1.0f / q.dy, iz = 1.0f / q.dz;
+    float tmin = 0.0f, tmax = 3.0e38f;
+    float t0 = (G.x0 - q.px) * ix, t1 = (G.x1 - q.px) * ix;
+    if (q.dx == 0.0f) {
+        if (q.px < G.x0 || q.px > G.x1)
+            tmax = -1.0f;
+    } else {
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    t0 = (G.y0 - q.py) * iy;
+    t1 = (G.y1 - q.py) * iy;
+    if (q.dy == 0.0f) {
+        if (q.py < G.y0 || q.py > G.y1)
+            tmax = -1.0f;
+    } else {
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    t0 = (G.z0 - q.pz) * iz;
+    t1 = (G.z1 - q.pz) * iz;
+    if (q.dz == 0.0f) {
+        if (q.pz < G.z0 || q.pz > G.z1)
+            tmax = -1.0f;
+    } else {
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    if (!(tmax > tmin && E >= kMinEnergy))
+        return false;
+    q.px = fmaf(q.dx, tmin, q.px);
+    q.py = fmaf(q.dy, tmin, q.py);
+    q.pz = fmaf(q.dz, tmin, q.pz);
+    return true;
 }
 
 } // namespace

@@ -348,93 +348,14 @@ __global__ void __launch_bounds__(256, MuxBounds<M>::kMinBlocks) transportKernel
                 bool hit = false;
                 float qpx = 0.f, qpy = 0.f, qpz = 0.f, qdx = 0.f, qdy = 0.f, qdz = 0.f, qE = 0.f, qw = 0.f;
                 if (lane < nb && h < P.n_total) {
-                    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
-                    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
-                    const unsigned long long ei = h / P.ppe;
-                    const ExposureDev* ex = P.exposures + ei;
-                    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
-                    const float angx = (2.0f * s0.u(0) - 1.0f) * hx;
-                    const float angy = (2.0f * s0.u(1) - 1.0f) * hy;
-                    const int tube = __ldg(&ex->tube);
-                    const SpectrumDev& sp = P.spec[tube];
-                    float E;
-                    if (sp.n <= 1) {
-                        E = sp.e0;
-                    } else {
-                        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(sp.n)), sp.n - 1);
-                        if (!(s0.u(3) < __ldg(sp.prob + idx)))
-                            idx = __ldg(sp.alias + idx);
-                        E = sp.e0 + static_cast<float>(idx) * sp.step;
-                        if (idx < sp.n - 1) {
-                            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
-                            E += s1.u(0) * sp.step;
-                        }
-                    }
-                    float w = __ldg(&ex->weight);
-                    const BowtieDev& bt = P.bow[tube];
-                    if (bt.n > 0) {
-                        const float a = fabsf(angx);
-                        float bw;
-                        if (a <= __ldg(bt.angle)) {
-                            bw = __ldg(bt.weight);
-                        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
-                            bw = __ldg(bt.weight + bt.n - 1);
-                        } else {
-                            int i = 1;
-                            while (__ldg(bt.angle + i) < a)
-                                ++i;
-                            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
-                            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
-                        }
-                        w *= bw;
-                    }
-                    const float sx = __sinf(angx), sy = __sinf(angy);
-                    const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
-                    qdx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
-                    qdy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
-                    qdz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
-                    qpx = __ldg(&ex->pos[0]);
-                    qpy = __ldg(&ex->pos[1]);
-                    qpz = __ldg(&ex->pos[2]);
-                    qE = E;
-                    qw = w;
+                    SourceSample q;
+                    hit = sampleSource(P, h, q);
+                    qpx = q.px, qpy = q.py, qpz = q.pz;
+                    qdx = q.dx, qdy = q.dy, qdz = q.dz;
+                    qE = q.E;
+                    qw = q.w;
                     ++nHistories;
-                    emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
-                    // move to the grid AABB (World::transport)
-                    const float ix = 1.0f / qdx, iy = 1.0f / qdy, iz = 1.0f / qdz;
-                    float tmin = 0.0f, tmax = 3.0e38f;
-                    float t0 = (G.x0 - qpx) * ix, t1 = (G.x1 - qpx) * ix;
-                    if (qdx == 0.0f) {
-                        if (qpx < G.x0 || qpx > G.x1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.y0 - qpy) * iy;
-                    t1 = (G.y1 - qpy) * iy;
-                    if (qdy == 0.0f) {
-                        if (qpy < G.y0 || qpy > G.y1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.z0 - qpz) * iz;
-                    t1 = (G.z1 - qpz) * iz;
-                    if (qdz == 0.0f) {
-                        if (qpz < G.z0 || qpz > G.z1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    if (tmax > tmin && E >= kMinEnergy) {
-                        qpx = fmaf(qdx, tmin, qpx);
-                        qpy = fmaf(qdy, tmin, qpy);
-                        qpz = fmaf(qdz, tmin, qpz);
-                        hit = true;
-                    }
+                    emitted += static_cast<unsigned long long>(__float2ll_rn(q.E * q.w * 65536.0f));
                 }
                 const unsigned int mHit = __ballot_sync(kFull, hit);
                 if (hit) {

@@ -489,94 +489,18 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 bool hit = false;
                 const int so = j * 32;
                 if (r < nb && h < P.n_total) {
-                    const unsigned int qlo = static_cast<unsigned int>(h), qhi = static_cast<unsigned int>(h >> 32);
-                    const PhiloxBlock s0 = philox4x32_10(P.round_key, qlo, qhi, 0u);
-                    const unsigned long long ei = h / P.ppe;
-                    const ExposureDev* ex = P.exposures + ei;
-                    const float hx = __ldg(&ex->hx), hy = __ldg(&ex->hy);
-                    const float angx = (2.0f * s0.u(0) - 1.0f) * hx;
-                    const float angy = (2.0f * s0.u(1) - 1.0f) * hy;
-                    const int tube = __ldg(&ex->tube);
-                    const SpectrumDev& spc = P.spec[tube];
-                    float E;
-                    if (spc.n <= 1) {
-                        E = spc.e0;
-                    } else {
-                        int idx = min(static_cast<int>(s0.u(2) * static_cast<float>(spc.n)), spc.n - 1);
-                        if (!(s0.u(3) < __ldg(spc.prob + idx)))
-                            idx = __ldg(spc.alias + idx);
-                        E = spc.e0 + static_cast<float>(idx) * spc.step;
-                        if (idx < spc.n - 1) {
-                            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
-                            E += s1.u(0) * spc.step;
-                        }
-                    }
-                    float w = __ldg(&ex->weight);
-                    const BowtieDev& bt = P.bow[tube];
-                    if (bt.n > 0) {
-                        const float a = fabsf(angx);
-                        float bw;
-                        if (a <= __ldg(bt.angle)) {
-                            bw = __ldg(bt.weight);
-                        } else if (a >= __ldg(bt.angle + bt.n - 1)) {
-                            bw = __ldg(bt.weight + bt.n - 1);
-                        } else {
-                            int i = 1;
-                            while (__ldg(bt.angle + i) < a)
-                                ++i;
-                            const float a0 = __ldg(bt.angle + i - 1), a1 = __ldg(bt.angle + i);
-                            bw = lerp(__ldg(bt.weight + i - 1), __ldg(bt.weight + i), (a - a0) / (a1 - a0));
-                        }
-                        w *= bw;
-                    }
-                    const float sx = __sinf(angx), sy = __sinf(angy);
-                    const float sz = sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy));
-                    float qdx = __ldg(&ex->c0[0]) * sx + __ldg(&ex->c1[0]) * sy + __ldg(&ex->dir[0]) * sz;
-                    float qdy = __ldg(&ex->c0[1]) * sx + __ldg(&ex->c1[1]) * sy + __ldg(&ex->dir[1]) * sz;
-                    float qdz = __ldg(&ex->c0[2]) * sx + __ldg(&ex->c1[2]) * sy + __ldg(&ex->dir[2]) * sz;
-                    float qpx = __ldg(&ex->pos[0]);
-                    float qpy = __ldg(&ex->pos[1]);
-                    float qpz = __ldg(&ex->pos[2]);
+                    SourceSample q;
+                    hit = sampleSource(P, h, q);
                     ++nHistories;
-                    emitted += static_cast<unsigned long long>(__float2ll_rn(E * w * 65536.0f));
-                    // move to the grid AABB (World::transport)
-                    const float ix = 1.0f / qdx, iy = 1.0f / qdy, iz = 1.0f / qdz;
-                    float tmin = 0.0f, tmax = 3.0e38f;
-                    float t0 = (G.x0 - qpx) * ix, t1 = (G.x1 - qpx) * ix;
-                    if (qdx == 0.0f) {
-                        if (qpx < G.x0 || qpx > G.x1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.y0 - qpy) * iy;
-                    t1 = (G.y1 - qpy) * iy;
-                    if (qdy == 0.0f) {
-                        if (qpy < G.y0 || qpy > G.y1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    t0 = (G.z0 - qpz) * iz;
-                    t1 = (G.z1 - qpz) * iz;
-                    if (qdz == 0.0f) {
-                        if (qpz < G.z0 || qpz > G.z1)
-                            tmax = -1.0f;
-                    } else {
-                        tmin = fmaxf(tmin, fminf(t0, t1));
-                        tmax = fminf(tmax, fmaxf(t0, t1));
-                    }
-                    if (tmax > tmin && E >= kMinEnergy) {
+                    emitted += static_cast<unsigned long long>(__float2ll_rn(q.E * q.w * 65536.0f));
+                    if (hit) {
                         // blocks 0-1 belong to the source: the history continues with block 2
-                        slotA[so] = make_float4(fmaf(qdx, tmin, qpx), fmaf(qdy, tmin, qpy), fmaf(qdz, tmin, qpz), __uint_as_float(2u));
-                        slotB[so] = make_float4(qdx, qdy, qdz, E);
+                        slotA[so] = make_float4(q.px, q.py, q.pz, __uint_as_float(2u));
+                        slotB[so] = make_float4(q.dx, q.dy, q.dz, q.E);
                         SlotC c;
-                        c.w = w;
-                        c.hlo = qlo;
+                        c.w = q.w;
+                        c.hlo = static_cast<unsigned int>(h);
                         slotC[so] = c;
-                        hit = true;
                     }
                 }
                 publishSlot(s_status, hit ? kPhStep : kPhDead, j);
