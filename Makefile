@@ -4,7 +4,7 @@ CXX  ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 CSRC := opendxmc_b200/csrc
 LIBDIR := opendxmc_b200/lib
-NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function
+NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -ftz=true -prec-div=false -prec-sqrt=false -Xcompiler -fPIC,-Wall,-Wno-unused-function
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
