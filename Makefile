@@ -16,16 +16,16 @@ $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
-build/%.o: $(CSRC)/%.cpp $(CSRC)/physics.hpp $(CSRC)/internal.hpp include/dxb.h
+build/%.o: $(CSRC)/%.cpp $(CSRC)/physics.hpp $(CSRC)/internal.hpp include/dxb.h Makefile
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/transport_common.cuh $(CSRC)/kernels.hpp include/dxb.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/transport_common.cuh $(CSRC)/kernels.hpp include/dxb.h Makefile
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 oracle: oracle/liboracle.so
-oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h
+oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h Makefile
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -shared -pthread -o $@ oracle/oracle.cpp
 
 # the reference's driver (simulationpipeline.cpp worker<>) retyped against the C++ shim headers in include/dxmc/

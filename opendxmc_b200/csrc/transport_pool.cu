@@ -548,36 +548,37 @@ int occupancyPool(int threads, size_t smem)
     return nb;
 }
 
-// applies CALL(MODE, CALIB, SMEM, M) for the run-time (mode, calib, smem, slots).  The slot count is a tuning
-// knob of the production variant only (mode 1, scoring); every other variant is built with 12 slots per class.
+// applies CALL(MODE, CALIB, SMEM, M, LB) for the run-time (mode, calib, smem, slots).  The slot count and the register
+// budget are tuning knobs of the production variant only (mode 1, scoring, table in shared memory); every other
+// variant is built with 16 slots per class and 64 registers.
 #define DXB_POOL_DISPATCH(CALL)                                                  \
     const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
     switch (key) {                                                              \
-    case 8: return CALL(2, false, false, 12, 0);                                    \
-    case 9: return CALL(2, false, true, 12, 0);                                     \
-    case 10: return CALL(2, true, false, 12, 0);                                    \
-    case 11: return CALL(2, true, true, 12, 0);                                     \
-    case 0: return CALL(0, false, false, 12, 0);                                    \
-    case 1: return CALL(0, false, true, 12, 0);                                     \
-    case 2: return CALL(0, true, false, 12, 0);                                     \
-    case 3: return CALL(0, true, true, 12, 0);                                      \
-    case 4: return CALL(1, false, false, 12, 0);                                    \
-    case 6: return CALL(1, true, false, 12, 0);                                     \
-    case 7: return CALL(1, true, true, 12, 0);                                      \
+    case 8: return CALL(2, false, false, 16, 0);                                    \
+    case 9: return CALL(2, false, true, 16, 0);                                     \
+    case 10: return CALL(2, true, false, 16, 0);                                    \
+    case 11: return CALL(2, true, true, 16, 0);                                     \
+    case 0: return CALL(0, false, false, 16, 0);                                    \
+    case 1: return CALL(0, false, true, 16, 0);                                     \
+    case 2: return CALL(0, true, false, 16, 0);                                     \
+    case 3: return CALL(0, true, true, 16, 0);                                      \
+    case 4: return CALL(1, false, false, 16, 0);                                    \
+    case 6: return CALL(1, true, false, 16, 0);                                     \
+    case 7: return CALL(1, true, true, 16, 0);                                      \
     default: break;                                                             \
     }                                                                           \
     switch (slots + 100 * lb) {                                                 \
     case 6: return CALL(1, false, true, 6, 0);                                  \
     case 8: return CALL(1, false, true, 8, 0);                                  \
-    case 16: return CALL(1, false, true, 16, 0);                                \
+    case 12: return CALL(1, false, true, 12, 0);                                \
     case 508: return CALL(1, false, true, 8, 5);                                \
     case 512: return CALL(1, false, true, 12, 5);                               \
     case 516: return CALL(1, false, true, 16, 5);                               \
     case 608: return CALL(1, false, true, 8, 6);                                \
     case 612: return CALL(1, false, true, 12, 6);                               \
     case 616: return CALL(1, false, true, 16, 6);                               \
-    default: return CALL(1, false, true, 12, 0);                                \
+    default: return CALL(1, false, true, 16, 0);                                \
     }
 
 } // namespace
@@ -595,9 +596,9 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
 int transportPoolSlots(int mode, bool calib, bool smemTable, int slots)
 {
     // must mirror DXB_POOL_DISPATCH: only the production variant is built for several slot counts
-    if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 16))
+    if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 12))
         return slots;
-    return 12;
+    return 16;
 }
 
 int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks)
