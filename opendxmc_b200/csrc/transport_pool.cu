@@ -38,6 +38,24 @@ enum : int { kPhStep = 0, kPhInt = 1, kPhRay = 2, kPhDead = 3, kPhNone = 4 };
 __device__ __forceinline__ int phaseWord(int phase) { return phase >> 1; }          // step,int -> A; ray,dead -> B
 __device__ __forceinline__ int phaseShift(int phase) { return (phase & 1) << 4; }   // int, dead in the upper half
 
+// Slot hand-over between warps.  A slot's words are written, then its status bit is set with RELEASE semantics
+// (publishSlot); a claim clears the bit with ACQUIRE semantics and reads the words afterwards (claimSlot).
+//   acquire: atom.acquire.cta.shared - ptxas emits a plain ATOMS (the loads that follow depend on its result).
+//   release: a block-scope fence before the atomic (MEMBAR.ALL.CTA; that is also what ptxas emits for
+//            atom.release.cta).  With tally atomics in flight on the SM the fences cost 10 % of the kernel although
+//            each takes < 100 cycles (profiles/r01_fence_cost.txt).  `relaxed` = 1 (option pool_relaxed_publish, off
+//            by default) drops the fence and relies on shared-memory operations of one thread being performed in
+//            program order - true on this hardware (bit-exact over 10^9 histories), not promised by the PTX memory model.
+__device__ __forceinline__ unsigned int atomAndAcquire(unsigned int* word, unsigned int mask)
+{
+    unsigned int old;
+    asm volatile("atom.acquire.cta.shared::cta.and.b32 %0, [%1], %2;"
+                 : "=r"(old)
+                 : "r"(static_cast<unsigned int>(__cvta_generic_to_shared(word))), "r"(mask)
+                 : "memory");
+    return old;
+}
+
 // claims one slot of the lane's class that is in `phase`; returns its index inside the class or -1.  The search
 // starts at a warp-specific slot (`rot`) and wraps around: warps that run the same phase at the same time would
 // otherwise all go for the lowest set bit of a class and retry.
@@ -47,18 +65,19 @@ __device__ __forceinline__ int claimSlot(unsigned int* word, int shift, unsigned
     while (m) {
         const int k = (__ffs(((m | (m << 16)) >> rot) & 0xffffu) - 1 + rot) & 15; // first set bit at or after `rot`, cyclic
         const unsigned int bit = 1u << (k + shift);
-        const unsigned int old = atomicAnd(word, ~bit);
-        if (old & bit) {
-            __threadfence_block(); // pairs with publishSlot: the slot's words are read after its status bit
+        const unsigned int old = atomAndAcquire(word, ~bit);
+        if (old & bit)
             return k;
-        }
         m = (old >> shift) & 0xffffu; // somebody else took it: look again
     }
     return -1;
 }
-__device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the class */, int phase, int j)
+__device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the class */, int phase, int j, int relaxed)
 {
-    __threadfence_block(); // the slot's words are visible before its status bit
+    if (!relaxed)
+        __threadfence_block(); // release: the slot's words are visible before its status bit
+    else
+        asm volatile("" ::: "memory");
     atomicOr(words + phaseWord(phase), 1u << (phaseShift(phase) + j));
 }
 
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             if (active) {
                 if (newPhase != kPhDead)
                     slotA[so] = make_float4(px, py, pz, __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift)));
-                publishSlot(s_status, newPhase, j);
+                publishSlot(s_status, newPhase, j, P.relaxed_publish);
             }
         } else if (phase == kPhInt || phase == kPhRay) {
             // ------------------------------------------------------------ one sampling try per claimed photon
@@ -443,7 +462,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     edep = 0.0f;
                 if (edep > 0.0f)
                     voxelIndex(G, px, py, pz, voxel);
-                publishSlot(s_status, newPhase, j);
+                publishSlot(s_status, newPhase, j, P.relaxed_publish);
             }
             if (!CALIB && phase == kPhInt) {
                 const unsigned int mScore = __ballot_sync(kFull, edep > 0.0f);
@@ -503,7 +522,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         slotC[so] = c;
                     }
                 }
-                publishSlot(s_status, hit ? kPhStep : kPhDead, j);
+                publishSlot(s_status, hit ? kPhStep : kPhDead, j, P.relaxed_publish);
             }
         }
     }
