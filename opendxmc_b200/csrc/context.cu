@@ -184,7 +184,6 @@ struct Options {
     int poolThreads = 256;       // pool kernel: threads per block (the block shares one photon pool)
     int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
-    int relaxedPublish = 0;      // pool kernel: 1 drops the release fence of a slot publish (+11 %, outside the PTX memory model)
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
     int interactBias = -999;     // -999: kernel default (mux 16: interaction phase when waiting lanes + bias >= stepping lanes;
@@ -494,7 +493,6 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.interact_bias = std::clamp(c->opt.interactBias == -999 ? (pool ? 24 : 16) : c->opt.interactBias, -32, 32);
     P.service_warps = std::clamp(c->opt.serviceWarps, 0, 32);
     P.diag = c->opt.diag;
-    P.relaxed_publish = c->opt.relaxedPublish;
     P.step_quad = pool && c->opt.stepQuad && P.step_pairs == 2;
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
@@ -1034,8 +1032,6 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.poolMinBlocks = static_cast<int>(value);
     } else if (k == "step_quad") {
         c->opt.stepQuad = static_cast<int>(value);
-    } else if (k == "pool_relaxed_publish") {
-        c->opt.relaxedPublish = value != 0.0 ? 1 : 0;
     } else if (k == "diag") {
         c->opt.diag = static_cast<int>(value);
     } else if (k == "service_warps") {

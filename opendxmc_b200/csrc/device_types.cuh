@@ -101,7 +101,6 @@ struct RunParams {
     int step_quad;                  // pool kernel: two step pairs per phase with all four gathers in flight
     int diag;                       // pool kernel: stats[8..15] = executions / claimed lanes per phase
     int service_warps;              // pool kernel: warps per block that prefer interaction / refill phases
-    int relaxed_publish;            // pool kernel: 1 = no release fence before a slot's status bit (see publishSlot)
     int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes;
                                     // pool kernel: stepper warps keep stepping while at least this many lanes can
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)

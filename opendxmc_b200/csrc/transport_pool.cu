@@ -42,10 +42,10 @@ __device__ __forceinline__ int phaseShift(int phase) { return (phase & 1) << 4; 
 // (publishSlot); a claim clears the bit with ACQUIRE semantics and reads the words afterwards (claimSlot).
 //   acquire: atom.acquire.cta.shared - ptxas emits a plain ATOMS (the loads that follow depend on its result).
 //   release: a block-scope fence before the atomic (MEMBAR.ALL.CTA; that is also what ptxas emits for
-//            atom.release.cta).  With tally atomics in flight on the SM the fences cost 10 % of the kernel although
-//            each takes < 100 cycles (profiles/r01_fence_cost.txt).  `relaxed` = 1 (option pool_relaxed_publish, off
-//            by default) drops the fence and relies on shared-memory operations of one thread being performed in
-//            program order - true on this hardware (bit-exact over 10^9 histories), not promised by the PTX memory model.
+//            atom.release.cta).  The fence makes the warp wait for every load it has in flight, including the
+//            speculative voxel gathers the walk did not consume: 10 % of the kernel (profiles/r01_fence_cost.txt).
+//            Dropping it (relying on the in-order shared-memory pipeline) is bit-exact over 10^9 histories but
+//            outside the PTX memory model, so it is not done; an mbarrier-based release was 2.5x slower.
 __device__ __forceinline__ unsigned int atomAndAcquire(unsigned int* word, unsigned int mask)
 {
     unsigned int old;
@@ -72,12 +72,9 @@ __device__ __forceinline__ int claimSlot(unsigned int* word, int shift, unsigned
     }
     return -1;
 }
-__device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the class */, int phase, int j, int relaxed)
+__device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the class */, int phase, int j)
 {
-    if (!relaxed)
-        __threadfence_block(); // release: the slot's words are visible before its status bit
-    else
-        asm volatile("" ::: "memory");
+    __threadfence_block(); // release: the slot's words are visible before its status bit
     atomicOr(words + phaseWord(phase), 1u << (phaseShift(phase) + j));
 }
 
@@ -351,7 +348,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             if (active) {
                 if (newPhase != kPhDead)
                     slotA[so] = make_float4(px, py, pz, __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift)));
-                publishSlot(s_status, newPhase, j, P.relaxed_publish);
+                publishSlot(s_status, newPhase, j);
             }
         } else if (phase == kPhInt || phase == kPhRay) {
             // ------------------------------------------------------------ one sampling try per claimed photon
@@ -462,7 +459,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     edep = 0.0f;
                 if (edep > 0.0f)
                     voxelIndex(G, px, py, pz, voxel);
-                publishSlot(s_status, newPhase, j, P.relaxed_publish);
+                publishSlot(s_status, newPhase, j);
             }
             if (!CALIB && phase == kPhInt) {
                 const unsigned int mScore = __ballot_sync(kFull, edep > 0.0f);
@@ -522,7 +519,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         slotC[so] = c;
                     }
                 }
-                publishSlot(s_status, hit ? kPhStep : kPhDead, j, P.relaxed_publish);
+                publishSlot(s_status, hit ? kPhStep : kPhDead, j);
             }
         }
     }

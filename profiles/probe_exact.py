@@ -19,7 +19,7 @@ def run(opts):
 
 
 ref, rst = run({"pool_slots": 0, "slots_per_lane": 0})
-for opts in () if (len(sys.argv) > 2 and sys.argv[2] == "relaxed") else ({"pool_slots": 16}, {"pool_slots": 12}, {"pool_slots": 12, "pool_min_blocks": 5}, {"pool_slots": 12, "pool_min_blocks": 5},
+for opts in ({"pool_slots": 16}, {"pool_slots": 12}, {"pool_slots": 12, "pool_min_blocks": 5}, {"pool_slots": 12, "pool_min_blocks": 5},
              {"pool_slots": 16, "pool_min_blocks": 5}, {"pool_slots": 12, "pool_min_blocks": 6}, {"pool_slots": 8, "pool_min_blocks": 5}):
     got, st = run(opts)
     same = [bool(np.array_equal(a, b)) for a, b in zip(ref, got)]
@@ -29,9 +29,3 @@ for opts in () if (len(sys.argv) > 2 and sys.argv[2] == "relaxed") else ({"pool_
           "counters", {k: int(st[k]) - int(rst[k]) for k in ("histories", "steps", "interactions", "deposits")},
           "sumE rel", float((got[0].sum() - ref[0].sum()) / ref[0].sum()), flush=True)
 
-if len(sys.argv) > 2 and sys.argv[2] == "relaxed":
-    # the relaxed-publish build of the hand-over protocol against the fenced one, on many histories
-    a, sa = run({"pool_slots": 16})
-    b, sb = run({"pool_slots": 16, "pool_relaxed_publish": 1})
-    print("relaxed publish vs fenced:", [bool(np.array_equal(x, y)) for x, y in zip(a, b)], "histories", sa["histories"],
-          "ms fenced %.2f relaxed %.2f" % (sa["transport_ms"], sb["transport_ms"]), flush=True)
