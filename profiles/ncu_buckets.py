@@ -11,7 +11,8 @@ MARKERS = {
     "transport_common.cuh": [
         ("struct PhiloxBlock", "philox"), ("struct TabPos", "tabpos/lerp"), ("float exitDistance(", "exitDistance"),
         ("void deflect(", "deflect"), ("void scoreEnergy(", "score"), ("bool comptonTry(", "comptonTry"),
-        ("bool rayleighTry(", "rayleighTry"), ("unsigned int voxelIndex(", "voxelIndex")],
+        ("bool rayleighTry(", "rayleighTry"), ("unsigned int voxelIndex(", "voxelIndex"),
+        ("bool dopplerBroaden(", "mode-2 samplers"), ("void isotropic(", "isotropic"), ("bool sampleSource(", "source sampling")],
     "transport.cu": [
         ("// ------------------------------------------------------------------ the history kernel", "kernel prologue"),
         ("auto finishScatter", "finishScatter"), ("    for (;;) {", "vote/policy"), ("        if (phase == 0) {", "step phase"),
