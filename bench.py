@@ -107,6 +107,60 @@ class ClockSampler:
                 "power_w_max": pmax}
 
 
+class SharedHostArrays:
+    """dose f64, variance f64, events u64 (n voxels each) in /dev/shm, mapped and page-locked by every rank."""
+
+    def __init__(self, rank, dist, n, torch):
+        import numpy as np
+        self.ok, self.arrays, self.paths, self._torch = False, [], [], torch
+        names = [None]
+        if rank == 0:
+            names = ["/dev/shm/dxb_bench_%d_%d" % (os.getpid(), k) for k in range(3)]
+            try:
+                for nm in names:
+                    with open(nm, "wb") as f:
+                        f.truncate(n * 8)
+            except OSError:
+                names = [None]
+        box = [names]
+        dist.broadcast_object_list(box, src=0)
+        names = box[0]
+        if not names or names[0] is None:
+            return
+        self.paths = names
+        good = 1
+        try:
+            for nm, dt in zip(names, (np.float64, np.float64, np.uint64)):
+                a = np.memmap(nm, dtype=dt, mode="r+", shape=(n,))
+                self.arrays.append(a)
+                rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+                if int(rc) != 0:
+                    good = 0
+        except Exception:
+            good = 0
+        t = torch.tensor([good], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        self.ok = bool(int(t))
+
+    def ptr(self, k, ctype):
+        import ctypes as C
+        return C.cast(self.arrays[k].ctypes.data, ctype)
+
+    def close(self, rank):
+        for a in self.arrays:
+            try:
+                self._torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
+            except Exception:
+                pass
+        self.arrays = []
+        if rank == 0:
+            for nm in self.paths:
+                try:
+                    os.unlink(nm)
+                except OSError:
+                    pass
+
+
 def make_workload(args):
     import opendxmc_b200 as dx
     return dx.workloads.ct_spiral_patient(scale=args.scale, histories=int(args.histories))
@@ -251,6 +305,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1 with the fused exchange: the dose score stays distributed (rank r holds its slab), so the e2e read-out is
+    # sharded too - every rank copies ITS slab over its own PCIe link into result arrays that rank 0 (the caller) placed
+    # in host memory shared by the processes (dxb_get_dose_range), instead of gathering everything through rank 0.
+    shared_out = None
+    if exchange is not None and not args.no_e2e:
+        shared_out = SharedHostArrays(rank, dist, nvox, torch)
+        if not shared_out.ok:
+            shared_out = None
+
     def step(i, timed_stats=None):
         """one beam with everything resident: tallies -> (reduce) -> dose."""
         lib.dxb_set_seed(ctx, SEED0 + 7919 * (i + 1))
@@ -272,11 +335,20 @@ def run_ours(args):
 
     def e2e_step(i):
         """the reference-facing call sequence with host buffers: setData/build -> transport -> read dose."""
-        dim = (C.c_uint64 * 3)(*wl.dim)
-        sp = (C.c_double * 3)(*wl.spacing)
-        rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
-        assert rc == 0, lib.dxb_last_error(ctx)
+        if exchange is not None:
+            # one process per GPU: every rank uploads its slab, the packed slabs travel over NVLink
+            D.set_grid_sharded(world, wl.dim, wl.spacing, wl.density, wl.material, local_rank, stream=stream)
+        else:
+            dim = (C.c_uint64 * 3)(*wl.dim)
+            sp = (C.c_double * 3)(*wl.spacing)
+            rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
+            assert rc == 0, lib.dxb_last_error(ctx)
         step(1000 + i)
+        if shared_out is not None:
+            rc = lib.dxb_get_dose_range(ctx, exchange.begin, exchange.end, shared_out.ptr(0, K.c_double_p), shared_out.ptr(1, K.c_double_p),
+                                        shared_out.ptr(2, K.c_u64_p))
+            assert rc == 0, lib.dxb_last_error(ctx)
+            return
         if exchange is not None:
             with torch.cuda.stream(stream):
                 exchange.gather_dose(0)
@@ -330,10 +402,18 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_hist * n_e2e / float(te[0]), "unit": "histories/s",
-               "h2d_bytes_per_step": int(nvox * 9 * world_size), "d2h_bytes_per_step": int(nvox * 24),
+               "h2d_bytes_per_step": int(nvox * 9 * (1 if exchange is not None else world_size)), "d2h_bytes_per_step": int(nvox * 24),
                "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e,
-               "note": "host-clock around dxb_set_grid + dxb_run_transport + exchange/finish + (N>1: slab gather to rank 0) + dxb_get_dose, pinned host buffers"}
+               "note": ("host-clock around dxb_set_grid_sharded (every rank uploads its slab, packed slabs all-gathered over NVLink) + "
+                        "dxb_run_transport + fused exchange/finish + dxb_get_dose_range of every rank's slab into "
+                        "pinned host arrays shared by the processes" if shared_out is not None else
+                        "host-clock around dxb_set_grid + dxb_run_transport + exchange/finish + (N>1: slab gather to rank 0) + dxb_get_dose, pinned host buffers")}
+        if shared_out is not None and rank == 0:
+            # the caller's view: every voxel of the three arrays was written by exactly one rank
+            e2e["events_read_back"] = int(shared_out.arrays[2].sum())
 
+    if shared_out is not None:
+        shared_out.close(rank)
     if rank != 0:
         if exchange is not None:
             exchange.close()

@@ -274,6 +274,17 @@ int  dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices);
 void dxb_destroy(dxb_ctx*);
 const char* dxb_last_error(const dxb_ctx*); /* text of the last failure on this context */
 
+/* setData for one process per GPU (every rank needs the full replica).  Instead of N full uploads,
+ * rank r uploads and packs only voxels [voxel_begin, voxel_end) of the caller's FULL-size arrays; the ranks then
+ * exchange the packed 4-byte slabs (dxb_grid_buffers: `voxels`, u32 x n_voxels) and take the element-wise maximum of
+ * `max_density_bits` (u32 x 257: per-material density maxima, [256] = largest material index) over NVLink - one
+ * broadcast per slab + one all-reduce(MAX), opendxmc_b200/distributed.py: set_grid_sharded - and call dxb_finish_grid
+ * (majorant, material-index check).  Same result as dxb_set_grid on every rank, 1/N of the host-to-device bytes each. */
+int dxb_set_grid_sharded(dxb_ctx*, const uint64_t dim[3], const double spacing_cm[3], const double* density, const uint8_t* material,
+                         uint64_t voxel_begin, uint64_t voxel_end);
+int dxb_grid_buffers(dxb_ctx*, void** voxels, void** max_density_bits, uint64_t* n_voxels);
+int dxb_finish_grid(dxb_ctx*);
+
 /* AAVoxelGrid::setData(materials part) — R:src/libopendxmc/simulationpipeline.cpp:134-149 */
 int dxb_set_materials(dxb_ctx*, uint32_t n, const dxb_material* const* materials);
 /* AAVoxelGrid::setData(dims, density, material) + setSpacing + World::build():
@@ -336,6 +347,12 @@ int dxb_dose_buffers(dxb_ctx*, void** dose, void** variance, void** n_events, ui
 /* doseScored(i).dose()/variance()/numberOfEvents() for all i — R:src/libopendxmc/simulationpipeline.cpp:174-219.
  * Any pointer may be NULL. dose [mGy], variance [mGy^2]. */
 int dxb_get_dose(dxb_ctx*, double* dose, double* variance, uint64_t* n_events);
+/* The same read-out for voxels [voxel_begin, voxel_end) only: element i of the FULL-size caller arrays is written for
+ * voxel_begin <= i < voxel_end, nothing else is touched.  With one process per GPU and the fused exchange every rank
+ * holds the dose score of its own slab (dxb_finish_beam_sharded); the ranks then read their slabs out in parallel,
+ * each over its own PCIe link, into arrays the caller placed in host memory shared by the processes - instead of
+ * gathering 24 B/voxel to rank 0 and pushing all of it through one link. */
+int dxb_get_dose_range(dxb_ctx*, uint64_t voxel_begin, uint64_t voxel_end, double* dose, double* variance, uint64_t* n_events);
 /* the per-beam energy tallies of the LAST beam (keV, keV^2, count) */
 int dxb_get_energy_scored(dxb_ctx*, double* energy, double* energy_sq, uint64_t* n_events);
 int dxb_clear_dose(dxb_ctx*);

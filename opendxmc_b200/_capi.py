@@ -169,6 +169,10 @@ SIGNATURES = {
                                           C.c_uint64, C.POINTER(C.c_double)]),
     "dxb_dose_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), c_u64_p]),
     "dxb_get_dose": (C.c_int, [VP, c_double_p, c_double_p, c_u64_p]),
+    "dxb_set_grid_sharded": (C.c_int, [VP, C.POINTER(C.c_uint64), c_double_p, c_double_p, c_u8_p, C.c_uint64, C.c_uint64]),
+    "dxb_grid_buffers": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), c_u64_p]),
+    "dxb_finish_grid": (C.c_int, [VP]),
+    "dxb_get_dose_range": (C.c_int, [VP, C.c_uint64, C.c_uint64, c_double_p, c_double_p, c_u64_p]),
     "dxb_get_energy_scored": (C.c_int, [VP, c_double_p, c_double_p, c_u64_p]),
     "dxb_clear_dose": (C.c_int, [VP]),
     "dxb_get_dose_postprocessed": (C.c_int, [VP, C.c_int, c_double_p, c_double_p, c_double_p, C.c_char_p]),

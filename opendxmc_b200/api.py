@@ -1177,6 +1177,14 @@ class World:
         self._item._dose = (d, v, cnt)
         return self._item._dose
 
+    def fetch_dose_range(self, begin, end, out=None):
+        """sharded read-out (dxb_get_dose_range): voxels [begin, end) of dose, variance, events into full-size arrays."""
+        n = self._item.size()
+        d, v, cnt = out if out is not None else (np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint64))
+        _check(_lib().dxb_get_dose_range(self._ctx, int(begin), int(end), _dp(d), _dp(v), cnt.ctypes.data_as(K.c_u64_p)),
+               "dxb_get_dose_range", self._ctx)
+        return d, v, cnt
+
     def clear_dose(self):
         _check(_lib().dxb_clear_dose(self._ctx), "dxb_clear_dose", self._ctx)
 

@@ -309,8 +309,26 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
     return DXB_OK;
 }
 
+// majorant from the per-material density maxima + the reference's material-index check; the grid becomes usable
+int finishGrid(dxb_ctx* c, World& w, cudaStream_t s)
+{
+    launchMajorant(w.tot.p, w.maxDensityBits.p, w.n_mat, w.majorant.p, s);
+    CUDA_TRY(c, cudaGetLastError());
+    // the reference checks max(material) < n_materials before running (R:src/libopendxmc/simulationpipeline.cpp:54-57);
+    // here the pack kernel finds the largest index while it reads the array anyway
+    unsigned int mmax = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&mmax, w.maxDensityBits.p + 256, sizeof(mmax), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (mmax >= static_cast<unsigned int>(w.n_mat))
+        return fail(c, DXB_EINVAL, "set_grid: material index out of range");
+    w.hasGrid = true;
+    return DXB_OK;
+}
+
+// Uploads and packs voxels [begin, end) of the caller's arrays (the whole grid for dxb_set_grid; one slab per rank for
+// dxb_set_grid_sharded, where the ranks then exchange their packed slabs and density maxima over NVLink).
 int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing[3], const double* density,
-    const uint8_t* material, cudaStream_t s)
+    const uint8_t* material, cudaStream_t s, size_t begin, size_t end, bool finish)
 {
     const size_t n = static_cast<size_t>(dim[0]) * dim[1] * dim[2];
     for (int i = 0; i < 3; ++i) {
@@ -324,23 +342,16 @@ int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing
     CUDA_TRY(c, w.maxDensityBits.alloc(257, w.device));
     CUDA_TRY(c, w.stageDensity.alloc(n, w.device));
     CUDA_TRY(c, w.stageMaterial.alloc(n, w.device));
-    CUDA_TRY(c, cudaMemcpyAsync(w.stageDensity.p, density, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(w.stageMaterial.p, material, n, cudaMemcpyHostToDevice, s));
+    const size_t m = end - begin;
     CUDA_TRY(c, cudaMemsetAsync(w.maxDensityBits.p, 0, 257 * sizeof(unsigned int), s));
-    launchPackVoxels(w.stageDensity.p, w.stageMaterial.p, w.voxels.p, n, w.maxDensityBits.p, s);
-    CUDA_TRY(c, cudaGetLastError());
-    launchMajorant(w.tot.p, w.maxDensityBits.p, w.n_mat, w.majorant.p, s);
-    CUDA_TRY(c, cudaGetLastError());
+    if (m > 0) {
+        CUDA_TRY(c, cudaMemcpyAsync(w.stageDensity.p + begin, density + begin, m * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(w.stageMaterial.p + begin, material + begin, m, cudaMemcpyHostToDevice, s));
+        launchPackVoxels(w.stageDensity.p + begin, w.stageMaterial.p + begin, w.voxels.p + begin, m, w.maxDensityBits.p, s);
+        CUDA_TRY(c, cudaGetLastError());
+    }
     CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, n * 4 * sizeof(unsigned long long), s));
-    // the reference checks max(material) < n_materials before running (R:src/libopendxmc/simulationpipeline.cpp:54-57);
-    // here the pack kernel finds the largest index while it reads the array anyway
-    unsigned int mmax = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(&mmax, w.maxDensityBits.p + 256, sizeof(mmax), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(c, cudaStreamSynchronize(s));
-    if (mmax >= static_cast<unsigned int>(w.n_mat))
-        return fail(c, DXB_EINVAL, "set_grid: material index out of range");
-    w.hasGrid = true;
-    return DXB_OK;
+    return finish ? finishGrid(c, w, s) : DXB_OK;
 }
 
 struct PreparedBeam {
@@ -691,7 +702,8 @@ int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOu
         int rc = uploadTables(c, *d.ctdi, ph.mats, d.stream);
         if (rc != DXB_OK)
             return rc;
-        rc = uploadGrid(c, *d.ctdi, ph.dim, ph.spacing, ph.density.data(), ph.material.data(), d.stream);
+        rc = uploadGrid(c, *d.ctdi, ph.dim, ph.spacing, ph.density.data(), ph.material.data(), d.stream, 0,
+            static_cast<size_t>(ph.dim[0]) * ph.dim[1] * ph.dim[2], true);
         if (rc != DXB_OK)
             return rc;
         d.ctdiDiameter = diameter;
@@ -900,7 +912,7 @@ int dxb_set_grid(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], 
             return fail(c, DXB_EINVAL, "set_grid: spacing must be positive");
     for (auto& d : c->devs) {
         CUDA_TRY(c, cudaSetDevice(d->device));
-        int rc = uploadGrid(c, d->world, dim, spacing_cm, density, material, d->stream);
+        int rc = uploadGrid(c, d->world, dim, spacing_cm, density, material, d->stream, 0, n, true);
         if (rc != DXB_OK)
             return rc;
     }
@@ -912,6 +924,62 @@ int dxb_set_grid(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], 
     CUDA_TRY(c, d0.events.alloc(n, d0.device));
     c->tallyValid = false;
     return dxb_clear_dose(c);
+}
+
+int dxb_set_grid_sharded(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], const double* density, const uint8_t* material,
+    uint64_t voxel_begin, uint64_t voxel_end)
+{
+    if (!c || !dim || !spacing_cm || !density || !material)
+        return fail(c, DXB_EINVAL, "set_grid_sharded: null argument");
+    if (c->materials.empty())
+        return fail(c, DXB_ESTATE, "set_grid_sharded: call dxb_set_materials first");
+    if (c->devs.size() != 1)
+        return fail(c, DXB_ESTATE, "set_grid_sharded: one device per context (one process per GPU)");
+    const uint64_t n = dim[0] * dim[1] * dim[2];
+    if (n == 0 || n >= (1ull << 32) || dim[0] >= (1u << 20) || dim[1] >= (1u << 20) || dim[2] >= (1u << 20))
+        return fail(c, DXB_EINVAL, "set_grid_sharded: bad dimensions");
+    for (int i = 0; i < 3; ++i)
+        if (!(spacing_cm[i] > 0))
+            return fail(c, DXB_EINVAL, "set_grid_sharded: spacing must be positive");
+    if (voxel_begin > voxel_end || voxel_end > n)
+        return fail(c, DXB_EINVAL, "set_grid_sharded: voxel range outside the grid");
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    int rc = uploadGrid(c, d0.world, dim, spacing_cm, density, material, d0.stream, voxel_begin, voxel_end, false);
+    if (rc != DXB_OK)
+        return rc;
+    CUDA_TRY(c, d0.dose.alloc(n, d0.device));
+    CUDA_TRY(c, d0.variance.alloc(n, d0.device));
+    CUDA_TRY(c, d0.events.alloc(n, d0.device));
+    c->tallyValid = false;
+    const size_t nn = n;
+    CUDA_TRY(c, cudaMemsetAsync(d0.dose.p, 0, nn * sizeof(double), d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(d0.variance.p, 0, nn * sizeof(double), d0.stream));
+    CUDA_TRY(c, cudaMemsetAsync(d0.events.p, 0, nn * sizeof(unsigned long long), d0.stream));
+    return DXB_OK;
+}
+
+int dxb_grid_buffers(dxb_ctx* c, void** voxels, void** max_density_bits, uint64_t* n_voxels)
+{
+    if (!c || c->devs.empty() || c->devs[0]->world.nvox == 0 || !c->devs[0]->world.voxels.p)
+        return fail(c, DXB_ESTATE, "grid_buffers: no grid");
+    World& w = c->devs[0]->world;
+    if (voxels)
+        *voxels = w.voxels.p;
+    if (max_density_bits)
+        *max_density_bits = w.maxDensityBits.p;
+    if (n_voxels)
+        *n_voxels = w.nvox;
+    return DXB_OK;
+}
+
+int dxb_finish_grid(dxb_ctx* c)
+{
+    if (!c || c->devs.size() != 1 || c->devs[0]->world.nvox == 0 || !c->devs[0]->world.voxels.p)
+        return fail(c, DXB_ESTATE, "finish_grid: call dxb_set_grid_sharded first");
+    DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    return finishGrid(c, d0.world, d0.stream);
 }
 
 int dxb_set_grid_center(dxb_ctx* c, const double center_cm[3])
@@ -1294,6 +1362,28 @@ int dxb_get_dose(dxb_ctx* c, double* dose, double* variance, uint64_t* n_events)
         CUDA_TRY(c, cudaMemcpyAsync(variance, d0.variance.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
     if (n_events)
         CUDA_TRY(c, cudaMemcpyAsync(n_events, d0.events.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d0.stream));
+    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_get_dose_range(dxb_ctx* c, uint64_t voxel_begin, uint64_t voxel_end, double* dose, double* variance, uint64_t* n_events)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_dose_range: no grid");
+    DeviceState& d0 = *c->devs[0];
+    const size_t n = d0.world.nvox;
+    if (voxel_begin > voxel_end || voxel_end > n)
+        return fail(c, DXB_EINVAL, "get_dose_range: voxel range outside the grid");
+    const size_t b = voxel_begin, m = voxel_end - voxel_begin;
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    if (m > 0) {
+        if (dose)
+            CUDA_TRY(c, cudaMemcpyAsync(dose + b, d0.dose.p + b, m * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+        if (variance)
+            CUDA_TRY(c, cudaMemcpyAsync(variance + b, d0.variance.p + b, m * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
+        if (n_events)
+            CUDA_TRY(c, cudaMemcpyAsync(n_events + b, d0.events.p + b, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, d0.stream));
+    }
     CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
     return DXB_OK;
 }

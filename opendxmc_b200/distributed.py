@@ -55,6 +55,69 @@ def run_beam(world, beam, tally, rank, use_beam_calibration=True, progress=None,
     return None
 
 
+def slab(n_voxels, rank, size):
+    """voxel slab [begin, end) of `rank`: the partition used by the fused exchange and the sharded upload / read-out."""
+    return n_voxels * rank // size, n_voxels * (rank + 1) // size
+
+
+def set_grid_sharded(world, dim, spacing, density, material, device_index, group=None, stream=None):
+    """AAVoxelGrid::setData + World::build for one process per GPU (include/dxb.h: dxb_set_grid_sharded): every rank
+    uploads and packs only ITS slab of the caller's arrays, then the packed 4-byte slabs are broadcast and the
+    per-material density maxima max-reduced over NVLink, and every rank finishes with the majorant.  The result is the
+    grid dxb_set_grid builds, for 1/N of the host-to-device bytes per rank.  torch is plumbing (NCCL calls on views of
+    the library's buffers); `density` / `material` are the full host arrays (pinned for an asynchronous copy)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    lib = K.load()
+    group = group if group is not None else dist.group.WORLD
+    rank, size = dist.get_rank(group), dist.get_world_size(group)
+    n = int(dim[0]) * int(dim[1]) * int(dim[2])
+    b, e = slab(n, rank, size)
+    ctx = world.ctx()
+    cdim = (C.c_uint64 * 3)(*[int(v) for v in dim])
+    csp = (C.c_double * 3)(*[float(v) for v in spacing])
+    density = np.ascontiguousarray(density, dtype=np.float64)
+    material = np.ascontiguousarray(material, dtype=np.uint8)
+    rc = lib.dxb_set_grid_sharded(ctx, cdim, csp, density.ctypes.data_as(K.c_double_p), material.ctypes.data_as(K.c_u8_p), b, e)
+    if rc != K.DXB_OK:
+        raise K.DxbError(rc, "dxb_set_grid_sharded", (lib.dxb_last_error(ctx) or b"").decode())
+    vox, mx, nv = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    rc = lib.dxb_grid_buffers(ctx, C.byref(vox), C.byref(mx), C.byref(nv))
+    if rc != K.DXB_OK:
+        raise K.DxbError(rc, "dxb_grid_buffers")
+
+    def view(ptr, count):
+        iface = {"shape": (count,), "typestr": "<i4", "data": (ptr, False), "version": 3, "strides": None}
+        return torch.as_tensor(type("_V", (), {"__cuda_array_interface__": iface})(), device=f"cuda:{device_index}")
+    voxels, maxbits = view(vox.value, n), view(mx.value, 257)
+    torch.cuda.synchronize(device_index)  # the slab is packed (the library's stream need not be torch's)
+    ctxmgr = torch.cuda.stream(stream) if stream is not None else _nullcontext()
+    with ctxmgr:
+        if size > 1:
+            if n % size == 0:
+                dist.all_gather_into_tensor(voxels, voxels[b:e].clone(), group=group)
+            else:
+                for r in range(size):
+                    rb, re = slab(n, r, size)
+                    if re > rb:
+                        dist.broadcast(voxels[rb:re], src=dist.get_global_rank(group, r), group=group)
+            # non-negative floats and material indices order like their bit patterns read as int32
+            dist.all_reduce(maxbits, op=dist.ReduceOp.MAX, group=group)
+        (stream if stream is not None else torch.cuda.current_stream(device_index)).synchronize()
+    rc = lib.dxb_finish_grid(ctx)
+    if rc != K.DXB_OK:
+        raise K.DxbError(rc, "dxb_finish_grid", (lib.dxb_last_error(ctx) or b"").decode())
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class FusedExchange:
     """The exchange step fused with energy->dose over NVLink / NVSwitch (include/dxb.h: dxb_finish_beam_sharded).
 

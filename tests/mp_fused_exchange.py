@@ -21,6 +21,8 @@ def main():
     kinds = []
     for multicast in (True, False):
         world = wl.build_world(1, [local_rank])
+        # rebuild the grid through the sharded upload (slab per rank + NVLink exchange): must give the same voxels
+        D.set_grid_sharded(world, wl.dim, wl.spacing, wl.density, wl.material, local_rank)
         world.set_history_range(rank, world_size)
         world.set_calibration_histories(720_000)
         ex = D.FusedExchange(world, local_rank, multicast=multicast)
@@ -28,8 +30,16 @@ def main():
         f1 = D.run_beam_fused(world, wl.beam, ex, use_beam_calibration=True)
         world.set_seed(1234)
         f2 = D.run_beam_fused(world, wl.beam, ex, use_beam_calibration=False)   # a second beam accumulates
+        # sharded read-out: every rank reads its own slab; together they must tile the gathered dose score
+        mine = world.fetch_dose_range(ex.begin, ex.end)
         ex.gather_dose(0)
         got = world.fetch_dose() if rank == 0 else None
+        parts = [None] * world_size if rank == 0 else None
+        dist.gather_object([a[ex.begin:ex.end] for a in mine], parts, dst=0)
+        if rank == 0:
+            for k in range(3):
+                tiled = np.concatenate([p[k] for p in parts])
+                assert np.array_equal(tiled, got[k]), "sharded read-out differs from the gathered dose score"
         ex.close()
         world.close()
         if rank == 0:

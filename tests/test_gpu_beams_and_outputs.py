@@ -259,6 +259,25 @@ def test_ct_segmentation_matches_oracle(dx, orc):
     world.close()
 
 
+def test_sharded_dose_read_out(dx):
+    """dxb_get_dose_range writes exactly the voxels of the range and agrees with the full read-out."""
+    wl = dx.workloads.ctdi_body_phantom(n=32, histories=300_000, step_deg=10.0)
+    world = wl.build_world(1, [0])
+    assert dx.Transport()(world, wl.beam, None, False)
+    d, v, c = world.fetch_dose()
+    n = d.size
+    out = (np.full(n, -1.0), np.full(n, -1.0), np.full(n, 7, dtype=np.uint64))
+    cuts = [0, n // 3, n // 3, (2 * n) // 3 + 5]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        world.fetch_dose_range(b, e, out)
+    last = cuts[-1]
+    assert np.array_equal(out[0][:last], d[:last]) and np.array_equal(out[1][:last], v[:last]) and np.array_equal(out[2][:last], c[:last])
+    assert np.all(out[0][last:] == -1.0) and np.all(out[2][last:] == 7)
+    with pytest.raises(Exception):
+        world.fetch_dose_range(5, n + 1, out)
+    world.close()
+
+
 def test_progress_and_cancel(dx):
     wl = dx.workloads.ct_spiral_patient(scale=4, histories=400_000_000, step_deg=5.0)
     world = wl.build_world(1, [0])
