@@ -54,57 +54,113 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    NVML is used in-process (nvidia_ml_py) from a thread that is started BEFORE the warm-up steps: spawning
+    `nvidia-smi -lms` at the start of the timed region attaches to every GPU of the box and stalled the 8-GPU run by
+    several milliseconds per step.  Only samples taken between mark_begin() and mark_end() are reported.  Falls back
+    to an `nvidia-smi` subprocess (also started early) when the NVML bindings are missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index):
-        self.dev = device_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, device_index, period_s=0.02):
+        self.dev, self.period = device_index, period_s
+        self.samples = []  # (t, sm_mhz, sm_max_mhz, power_w, reasons:set)
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self.thread = self.proc = self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.dev])
+            except (ValueError, IndexError):
+                pass
+        return self.dev
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         try:
-            self.proc.wait(timeout=5)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            mx = 0.0
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.perf_counter(), sm, mx, pw, {k for k, b in bits.items() if r & b}))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                sm, mx, pw = float(f[1]), float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # median of the samples taken under load (power above the idle floor)
-        pmax = max(power)
-        load = sorted(s for s, p in zip(sm, power) if p >= 0.5 * pmax) or sorted(sm)
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": pmax}
+            reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                       if v.lower().startswith("active")}
+            self.samples.append((time.perf_counter(), sm, mx, pw, reasons))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.nvml:
+            try:
+                self.nvml[0].nvmlShutdown()
+            except Exception:
+                pass
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi samples"]}
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        used = inside or self.samples[-3:]
+        sm = sorted(x[1] for x in used)
+        reasons = set()
+        for x in used:
+            reasons |= x[4]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(x[2] for x in used), "reasons": sorted(reasons), "samples": len(inside),
+                "power_w_max": max(x[3] for x in used), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 class SharedHostArrays:
@@ -357,13 +413,14 @@ def run_ours(args):
                                   C.cast(out_pin[2].data_ptr(), K.c_u64_p))
             assert rc == 0, lib.dxb_last_error(ctx)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # before the warm-up: attaching to the GPUs is not free
     for i in range(args.warmup):
         step(i)
-    sampler = ClockSampler(local_rank)
     stats = []
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(stream)
@@ -372,6 +429,7 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     tms = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")

@@ -51,7 +51,10 @@ def main():
         t.append(time.perf_counter())
         st = world.run_stats()
         rows.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])] + [st["transport_ms"]])
+    allrows = [None] * world_size
+    dist.all_gather_object(allrows, rows[-1])
     if rank == 0:
+        print("last iteration, per rank: " + " | ".join("r%d run %.2f b1 %.2f fin %.2f b2 %.2f kern %.2f" % (i, *r) for i, r in enumerate(allrows)))
         print(f"{kind} ranks={world_size}: ms  run_transport(host)  barrier1  finish_sharded  barrier2 | transport kernel(events)")
         for r in rows:
             print("   " + "  ".join(f"{v:9.3f}" for v in r), flush=True)
