@@ -11,6 +11,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_voxel_slabs_tile_the_grid():
+    """the slab rule of the fused exchange, the sharded upload and the sharded read-out: disjoint, ordered, complete."""
+    from opendxmc_b200 import distributed as D
+    for n, size in [(78_643_200, 8), (78_643_200, 2), (7_161_276, 4), (17, 8), (5, 8), (1, 1)]:
+        edges = [D.slab(n, r, size) for r in range(size)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (b0, e0), (b1, e1) in zip(edges[:-1], edges[1:]):
+            assert b0 <= e0 == b1 <= e1
+        assert max(e - b for b, e in edges) - min(e - b for b, e in edges) <= 1
+
+
 def test_shard_rule_partitions_all_histories():
     from opendxmc_b200 import distributed as D
     for n_total, world in [(1, 1), (65536, 2), (65537, 2), (1_000_003, 3), (10 * 65536 + 17, 8), (200_000, 4)]:
