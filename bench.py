@@ -166,7 +166,7 @@ class ClockSampler:
 class SharedHostArrays:
     """dose f64, variance f64, events u64 (n voxels each) in /dev/shm, mapped and page-locked by every rank."""
 
-    def __init__(self, rank, dist, n, torch):
+    def __init__(self, rank, dist, n, torch, begin, end):
         import numpy as np
         self.ok, self.arrays, self.paths, self._torch = False, [], [], torch
         names = [None]
@@ -188,7 +188,13 @@ class SharedHostArrays:
         try:
             for nm, dt in zip(names, (np.float64, np.float64, np.uint64)):
                 a = np.memmap(nm, dtype=dt, mode="r+", shape=(n,))
+                a[begin:end] = 0  # first touch by the rank that will write the slab: its pages land on its socket
                 self.arrays.append(a)
+        except Exception:
+            good = 0
+        dist.barrier()  # every slab is placed before anybody pins the whole array
+        try:
+            for a in self.arrays:
                 rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
                 if int(rc) != 0:
                     good = 0
@@ -317,6 +323,14 @@ def run_ours(args):
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one process per GPU: run on the CPUs next to this GPU, so that the pinned host buffers it allocates and the
+        # slab of the shared result arrays it touches first live in the memory of that socket (PCIe DMA stays local)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(ClockSampler(local_rank)._physical_index()))
+        except Exception:
+            pass
     lib = K.load()
 
     wl = make_workload(args)
@@ -366,7 +380,7 @@ def run_ours(args):
     # in host memory shared by the processes (dxb_get_dose_range), instead of gathering everything through rank 0.
     shared_out = None
     if exchange is not None and not args.no_e2e:
-        shared_out = SharedHostArrays(rank, dist, nvox, torch)
+        shared_out = SharedHostArrays(rank, dist, nvox, torch, exchange.begin, exchange.end)
         if not shared_out.ok:
             shared_out = None
 
@@ -520,7 +534,7 @@ def run_ours(args):
     if exchange is not None:
         exchange.close()
     world.close()
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world_size == 1:  # the CPU baseline is reported at N = 1 only
         cb, _ = cpu_oracle_rate(args, wl, args.cpu_seconds)
         out["cpu_baseline"] = cb
     print(json.dumps(out), flush=True)
