@@ -322,6 +322,8 @@ def run_ours(args):
     dist = None
     if world_size > 1:
         import torch.distributed as dist
+        # stdout carries the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # one process per GPU: run on the CPUs next to this GPU, so that the pinned host buffers it allocates and the
         # slab of the shared result arrays it touches first live in the memory of that socket (PCIe DMA stays local)
