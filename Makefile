@@ -10,7 +10,7 @@ CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 LIB := $(LIBDIR)/libdxmc_b200.so
 OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o
 
-all: $(LIB) oracle shim
+all: $(LIB) oracle shim ref
 
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
@@ -35,7 +35,11 @@ build/opendxmc_worker: examples/opendxmc_worker.cpp $(SHIM_HDRS) include/dxb.h $
 	@mkdir -p build
 	$(CXX) -std=c++20 -O2 -Wall -Iinclude $< -o $@ -L$(LIBDIR) -ldxmc_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
-clean:
-	rm -rf build $(LIB) oracle/liboracle.so
+# OpenDXMC's own translation units for this boundary, compiled where they lie (only where the reference tree is mounted)
+ref: $(LIB)
+	@if [ -f /root/reference/src/libopendxmc/dxmc_specialization.cpp ]; then $(MAKE) --no-print-directory -f oracle/Makefile.ref; fi
 
-.PHONY: all oracle shim clean
+clean:
+	rm -rf build $(LIB) oracle/liboracle.so oracle/_ref
+
+.PHONY: all oracle shim ref clean

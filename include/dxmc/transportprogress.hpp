@@ -22,7 +22,8 @@ public:
     {
         std::uint64_t d = 0, t = 0;
         dxb_progress_read(m_h, &d, &t);
-        return { d, t };
+        // the driver computes (n * 100) / total from its timer (R:src/libopendxmc/simulationpipeline.cpp:114-115): never 0
+        return { d, t > 0 ? t : 1 };
     }
     std::string message() const
     {

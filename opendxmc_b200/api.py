@@ -1019,7 +1019,8 @@ class TransportProgress:
     def progress(self):
         d, t = C.c_uint64(), C.c_uint64()
         _lib().dxb_progress_read(self._h, C.byref(d), C.byref(t))
-        return d.value, t.value
+        # never 0: the reference's timer divides by the total (R:src/libopendxmc/simulationpipeline.cpp:114-115)
+        return d.value, max(t.value, 1)
 
     def message(self):
         buf = C.create_string_buffer(128)

@@ -1,12 +1,15 @@
 """GPU parity, part 2: every beam type, the scaled C3/C4/C5 configurations, calibration, post-processing, per-organ
 dose, CT segmentation, progress / cancel, and in-process multi-GPU invariance — CUDA path through the C ABI vs the oracle."""
 import ctypes as C
+import os
+import sys
 import threading
 import time
 
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 SEED = 0x0DDC0FFEE
 
@@ -340,3 +343,15 @@ def test_fused_exchange_matches_single_gpu_bit_for_bit():
            "--master-port", "29533", os.path.join(root, "tests", "mp_fused_exchange.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("DXB_RUN_REF_PIPELINE") != "1" or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref")),
+                    reason="opt-in (DXB_RUN_REF_PIPELINE=1): needs oracle/_ref/opendxmc_ref built where the reference tree is mounted")
+def test_reference_pipeline_binary_matches_python_mirror():
+    """OpenDXMC's own SimulationPipeline (compiled unmodified, oracle/ref_driver.cpp) against the Python mirror."""
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import run_reference_pipeline as rp
+    same, units, ref_units, mine, ref = rp.run(1, 1, 20000)
+    assert units == ref_units
+    assert np.array_equal(mine[2], ref[2])
+    assert np.allclose(mine[0], ref[0], rtol=1e-12, atol=0) and np.allclose(mine[1], ref[1], rtol=1e-12, atol=0)

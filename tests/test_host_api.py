@@ -279,7 +279,7 @@ def test_ct_spiral_defaults_and_geometry(dx):
 
 def test_progress_object(dx):
     p = dx.TransportProgress()
-    assert p.continueSimulation() and p.progress() == (0, 0)
+    assert p.continueSimulation() and p.progress() == (0, 1)  # total is never 0: the reference divides by it
     assert "Starting" in p.message()
     p.setStopSimulation()
     assert not p.continueSimulation()
