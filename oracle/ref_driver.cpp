@@ -2,19 +2,21 @@
 // TEST INFRASTRUCTURE (oracle/): built by oracle/Makefile.ref into oracle/_ref/opendxmc_ref from the reference's
 // translation units WHERE THEY LIE under /root/reference/src/libopendxmc (nothing is copied):
 //     dxmc_specialization.cpp  beamactorcontainer.cpp  datacontainer.cpp  basepipeline.cpp
-//     otherphantomimportpipeline.cpp  simulationpipeline.cpp
+//     otherphantomimportpipeline.cpp  ctsegmentationpipeline.cpp  simulationpipeline.cpp
 // with the tests-only Qt / VTK stand-ins of tests/stubs/ (Qt's moc is replaced by the signal bodies below).
 //
 //   opendxmc_ref host
 //       CPU only.  JSON lines: the app's DXBeam pose / collimation (R:dxmc_specialization.cpp:22-90), the beam outline
 //       geometry BeamActorContainer::update builds from exposure(i) for all six beam types
 //       (R:beamactorcontainer.cpp:104-203), the water-equivalent-diameter AEC profile of DataContainer
-//       (R:datacontainer.cpp:42-100) on the reference's own PMMA cylinder (R:otherphantomimportpipeline.cpp:32-128).
+//       (R:datacontainer.cpp:42-100) on the reference's own PMMA cylinder (R:otherphantomimportpipeline.cpp:32-128), the
+//       HU -> (material, density) segmentation of CTSegmentationPipeline (R:ctsegmentationpipeline.cpp:61-169) on a HU ramp.
 //   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix>
 //       Needs a GPU.  The reference's SimulationPipeline (worker<CORRECTION>, R:simulationpipeline.cpp:124-235) runs a
 //       CT sequential beam on that cylinder; writes <prefix>.json (geometry, units) and raw little-endian arrays
 //       <prefix>.{density,material,dose,variance,count}.bin for the Python side to rebuild the same world and compare.
 #include <beamactorcontainer.hpp>
+#include <ctsegmentationpipeline.hpp>
 #include <datacontainer.hpp>
 #include <dxmc_specialization.hpp>
 #include <otherphantomimportpipeline.hpp>
@@ -35,10 +37,13 @@
 // ---- what moc would generate: the signals.  They record what the test wants to see.
 static std::shared_ptr<DataContainer> g_imported, g_simulated;
 static std::atomic<int> g_running { -1 };
+static std::shared_ptr<DataContainer> g_segmented;
 void BasePipeline::imageDataChanged(std::shared_ptr<DataContainer> d)
 {
     if (dynamic_cast<SimulationPipeline*>(this))
         g_simulated = d;
+    else if (dynamic_cast<CTSegmentationPipeline*>(this))
+        g_segmented = d;
     else
         g_imported = d;
 }
@@ -147,6 +152,33 @@ static int hostMode()
     for (std::size_t i = 0; i < w.size(); ++i)
         std::printf("%s%.17g", i ? ", " : "", w[i]);
     std::printf("], \"aec_start_z\": %.17g, \"aec_stop_z\": %.17g, \"aec_empty\": %s}\n", aec.start()[2], aec.stop()[2], aec.isEmpty() ? "true" : "false");
+
+    // CT segmentation of a HU ramp, 120 kV with 9 mm Al (R:src/libopendxmc/ctsegmentationpipeline.cpp:114-169)
+    auto ct = std::make_shared<DataContainer>();
+    const std::size_t nhu = 1800;
+    ct->setDimensions({ 30, 30, 2 });
+    ct->setSpacing({ 0.1, 0.1, 0.1 });
+    std::vector<double> hu(nhu);
+    for (std::size_t i = 0; i < nhu; ++i)
+        hu[i] = -1100.0 + 2.0 * static_cast<double>(i) + 0.37;
+    ct->setImageArray(DataContainer::ImageType::CT, hu);
+    CTSegmentationPipeline seg;
+    seg.setAqusitionVoltage(120.0);
+    seg.setAlFiltration(9.0);
+    seg.updateImageData(ct);
+    if (!g_segmented)
+        return 4;
+    std::printf("{\"kind\": \"segmentation\", \"hu0\": -1100.0, \"hu_step\": 2.0, \"hu_offset\": 0.37, \"n\": %zu, \"material\": \"", nhu);
+    for (auto m : g_segmented->getMaterialArray())
+        std::printf("%d", static_cast<int>(m));
+    std::printf("\", \"density\": [");
+    const auto& dd = g_segmented->getDensityArray();
+    for (std::size_t i = 0; i < dd.size(); ++i)
+        std::printf("%s%.17g", i ? ", " : "", dd[i]);
+    std::printf("], \"materials\": [");
+    for (std::size_t i = 0; i < g_segmented->getMaterials().size(); ++i)
+        std::printf("%s\"%s\"", i ? ", " : "", g_segmented->getMaterials()[i].name.c_str());
+    std::printf("]}\n");
     return 0;
 }
 

@@ -6,9 +6,10 @@ oracle/_ref/opendxmc_ref, driver oracle/ref_driver.cpp; Qt / VTK replaced by tes
     beamactorcontainer.cpp    exposure(i).position()/directionCosines()/collimationHalfAngles() of every beam type
     datacontainer.cpp         CTAECFilter, the water-equivalent-diameter AEC profile
     otherphantomimportpipeline.cpp  NISTMaterials::Composition / density, the PMMA cylinder
+    ctsegmentationpipeline.cpp  Tube, Material::byNistName / attenuationValues: HU -> (material, density)
     simulationpipeline.cpp    worker<CORRECTION>(): World / AAVoxelGrid / Material / Transport / TransportProgress / doseScored
     basepipeline.cpp
-  + syntax-only: ctsegmentationpipeline.cpp (Tube, Material::attenuationValues), icrpphantomimportpipeline.cpp.
+  + syntax-only: icrpphantomimportpipeline.cpp.
 
 The host-side parts are then RUN here (no GPU) and their numbers compared with the Python mirror (opendxmc_b200/api.py)
 that the GPU tests and bench.py use.  Reads /root/reference, so it only runs where the reference tree is mounted."""
@@ -34,7 +35,7 @@ def ref_rows():
     return [json.loads(ln) for ln in r.stdout.strip().splitlines()]
 
 
-@pytest.mark.parametrize("unit", ["ctsegmentationpipeline.cpp", "icrpphantomimportpipeline.cpp"])
+@pytest.mark.parametrize("unit", ["icrpphantomimportpipeline.cpp"])
 def test_reference_unit_compiles_unmodified(unit):
     r = subprocess.run(["g++", "-std=c++20", "-fsyntax-only", f"-I{ROOT}/tests/stubs", f"-I{ROOT}/include", f"-I{REF}", os.path.join(REF, unit)],
                        capture_output=True, text=True)
@@ -149,3 +150,38 @@ def test_reference_wed_aec_profile_matches_the_python_mirror(dx, ref_rows):
     f = dx.CTAECFilter((0, 0, -half), (0, 0, half), list(w))
     assert np.allclose(f.weights(), d["aec_weights"], rtol=1e-12)
     assert f.start()[2] == pytest.approx(d["aec_start_z"]) and f.stop()[2] == pytest.approx(d["aec_stop_z"]) and f.isEmpty() == d["aec_empty"]
+
+
+def test_reference_ct_segmentation_matches_the_restatement_and_the_oracle(dx, orc, ref_rows):
+    """CTSegmentationPipeline::updateImageData (the reference's code, R:src/libopendxmc/ctsegmentationpipeline.cpp:61-169)
+    on a HU ramp against the numpy restatement the GPU test uses for dxb_segment_ct and against the oracle's rule."""
+    import ctypes as C
+    d = [r for r in ref_rows if r["kind"] == "segmentation"][0]
+    hu = d["hu0"] + d["hu_step"] * np.arange(d["n"]) + d["hu_offset"]
+    ref_mat = np.array([int(ch) for ch in d["material"]], dtype=np.uint8)
+    ref_dens = np.array(d["density"])
+    names = ["Air, Dry (near sea level)", "Adipose Tissue (ICRP)", "Tissue, Soft (ICRP)", "Muscle, Skeletal", "Bone, Cortical (ICRP)"]
+    assert d["materials"] == names
+    tube = dx.Tube(120.0)
+    tube.setAlFiltration(9.0)
+    mats = [dx.Material.byNistName(nm) for nm in names]
+    dn = [dx.NISTMaterials.density(nm) for nm in names]
+    dn[-1] = 1.09
+    e = tube.getEnergy()
+    w = tube.getSpecter(e, True)
+    water, air = dx.Material.byNistName("Water, Liquid"), mats[0]
+    wd, ad = dx.NISTMaterials.density("Water, Liquid"), dx.NISTMaterials.density(names[0])
+    uw = np.array([water.attenuationValues(x).sum() for x in e])
+    ua = np.array([air.attenuationValues(x).sum() for x in e])
+    um = [np.array([m.attenuationValues(x).sum() for x in e]) for m in mats]
+    HU = [1000 * np.sum(w * (um[i] * dn[i] - uw * wd) / (uw * wd - ua * ad)) for i in range(5)]
+    sep = np.array([(HU[i] + HU[i + 1]) / 2 for i in range(4)])
+    att = np.array([np.sum(w * um[i]) for i in range(5)])
+    omat = np.zeros(hu.size, dtype=np.uint8)
+    odens = np.zeros(hu.size)
+    dp = C.POINTER(C.c_double)
+    orc.load().orc_segment(hu.ctypes.data_as(dp), hu.size, sep.ctypes.data_as(dp), 4, att.ctypes.data_as(dp),
+                           float(np.sum(w * uw) * wd), float(np.sum(w * ua) * ad), omat.ctypes.data_as(C.POINTER(C.c_uint8)), odens.ctypes.data_as(dp))
+    assert set(np.unique(ref_mat)) == {0, 1, 2, 3, 4}
+    assert np.array_equal(ref_mat, omat)
+    assert np.allclose(ref_dens, odens, rtol=1e-11, atol=1e-14)
