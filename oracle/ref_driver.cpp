@@ -2,7 +2,9 @@
 // TEST INFRASTRUCTURE (oracle/): built by oracle/Makefile.ref into oracle/_ref/opendxmc_ref from the reference's
 // translation units WHERE THEY LIE under /root/reference/src/libopendxmc (nothing is copied):
 //     dxmc_specialization.cpp  beamactorcontainer.cpp  datacontainer.cpp  basepipeline.cpp
-//     otherphantomimportpipeline.cpp  ctsegmentationpipeline.cpp  simulationpipeline.cpp
+//     otherphantomimportpipeline.cpp  icrpphantomimportpipeline.cpp  ctsegmentationpipeline.cpp  dosetablepipeline.cpp
+//     beamsettingsmodel.cpp  simulationpipeline.cpp
+// (bowtiefilterreader.cpp is Qt-JSON code: its two read() functions are replaced below by a fixed two-filter table.)
 // with the tests-only Qt / VTK stand-ins of tests/stubs/ (Qt's moc is replaced by the signal bodies below).
 //
 //   opendxmc_ref host
@@ -11,14 +13,28 @@
 //       (R:beamactorcontainer.cpp:104-203), the water-equivalent-diameter AEC profile of DataContainer
 //       (R:datacontainer.cpp:42-100) on the reference's own PMMA cylinder (R:otherphantomimportpipeline.cpp:32-128), the
 //       HU -> (material, density) segmentation of CTSegmentationPipeline (R:ctsegmentationpipeline.cpp:61-169) on a HU ramp.
+//   opendxmc_ref icrp <organ array file> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms 0|1>
+//       CPU only.  ICRPPhantomImportPipeline::importPhantom (R:icrpphantomimportpipeline.cpp:258-351) on a caller-made
+//       organ array with the reference's real organ / media tables: organ, material and density arrays, names, compositions.
+//   opendxmc_ref beammodel
+//       CPU only.  BeamSettingsModel (R:beamsettingsmodel.cpp, 1800 lines: every getter / setter of the six beam types, tube,
+//       bowtie, AEC and organ-AEC the GUI offers) creates its six default beams; every (label, value) row of the settings
+//       tree is printed, then a few values are edited through the model's setters and printed again.
+//   opendxmc_ref dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs>
+//       CPU only.  DoseTablePipeline::updateImageData (R:dosetablepipeline.cpp:36-95) on <prefix>.{organ,dose,density}.bin:
+//       per organ the voxel count, volume, mass and dose the app's table shows.
 //   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix>
 //       Needs a GPU.  The reference's SimulationPipeline (worker<CORRECTION>, R:simulationpipeline.cpp:124-235) runs a
 //       CT sequential beam on that cylinder; writes <prefix>.json (geometry, units) and raw little-endian arrays
 //       <prefix>.{density,material,dose,variance,count}.bin for the Python side to rebuild the same world and compare.
 #include <beamactorcontainer.hpp>
+#include <beamsettingsmodel.hpp>
+#include <bowtiefilterreader.hpp>
 #include <ctsegmentationpipeline.hpp>
 #include <datacontainer.hpp>
+#include <dosetablepipeline.hpp>
 #include <dxmc_specialization.hpp>
+#include <icrpphantomimportpipeline.hpp>
 #include <otherphantomimportpipeline.hpp>
 #include <simulationpipeline.hpp>
 
@@ -53,6 +69,56 @@ void SimulationPipeline::simulationReady(bool) { }
 void SimulationPipeline::simulationRunning(bool on) { g_running = on ? 1 : 0; }
 void SimulationPipeline::simulationProgress(QString, int) { }
 void OtherPhantomImportPipeline::errorMessage(QString) { }
+void ICRPPhantomImportPipeline::errorMessage(QString) { }
+static std::vector<std::shared_ptr<BeamActorContainer>> g_actors;
+void BeamSettingsModel::beamActorAdded(std::shared_ptr<BeamActorContainer> a) { g_actors.push_back(a); }
+void BeamSettingsModel::beamActorRemoved(std::shared_ptr<BeamActorContainer>) { }
+void BeamSettingsModel::requestRender() { }
+BowtieFilterReader::BowtieFilterReader(QObject* parent)
+    : QObject(parent)
+{
+}
+QMap<QString, BowtieFilter> BowtieFilterReader::read(const QString&)
+{
+    // stand-in for the JSON reader: the GUI's default key plus one more (angles in radians, R:bowtiefilterreader.cpp:74-93)
+    QMap<QString, BowtieFilter> m;
+    m.insert("Siemens Definition Flash W1 120kV", BowtieFilter({ { 0.0, 1.0 }, { 0.1, 0.8 }, { 0.2, 0.5 }, { 0.3, 0.25 }, { 0.39, 0.1 } }));
+    m.insert("flat", BowtieFilter({ { 0.0, 1.0 }, { 0.39, 1.0 } }));
+    return m;
+}
+QMap<QString, BowtieFilter> BowtieFilterReader::read(const QStringList&) { return read(QString()); }
+
+struct DoseRow {
+    std::string name;
+    int voxels = -1;
+    double volume = 0, mass = 0, dose = 0;
+};
+static std::vector<DoseRow> g_table;
+static std::vector<std::string> g_header;
+void DoseTablePipeline::clearTable() { g_table.clear(); }
+void DoseTablePipeline::enableSorting(bool) { }
+void DoseTablePipeline::doseDataHeader(QStringList h)
+{
+    g_header.clear();
+    for (const auto& q : h)
+        g_header.push_back(q.toStdString());
+}
+void DoseTablePipeline::doseData(int col, int row, QVariant v)
+{
+    if (static_cast<std::size_t>(row) >= g_table.size())
+        g_table.resize(static_cast<std::size_t>(row) + 1);
+    auto& r = g_table[static_cast<std::size_t>(row)];
+    if (col == 0)
+        r.name = v.s.toStdString();
+    else if (col == 1)
+        r.voxels = v.i;
+    else if (col == 2)
+        r.volume = v.d;
+    else if (col == 3)
+        r.mass = v.d;
+    else if (col == 4)
+        r.dose = v.d;
+}
 
 static void printVec(const char* key, const std::array<double, 3>& v, bool comma = true)
 {
@@ -182,6 +248,186 @@ static int hostMode()
     return 0;
 }
 
+static int icrpMode(char** a)
+{
+    ICRPPhantomImportPipeline imp;
+    imp.setRemoveArms(std::atoi(a[8]) != 0);
+    g_imported = nullptr;
+    imp.importPhantom(QString(a[2]), QString(a[3]), QString(a[4]), 1.0, 1.0, 1.0, std::atoi(a[5]), std::atoi(a[6]), std::atoi(a[7]));
+    if (!g_imported)
+        return 5;
+    const auto& d = *g_imported;
+    std::printf("{\"kind\": \"icrp\", \"organ\": [");
+    for (std::size_t i = 0; i < d.getOrganArray().size(); ++i)
+        std::printf("%s%d", i ? ", " : "", static_cast<int>(d.getOrganArray()[i]));
+    std::printf("], \"material\": [");
+    for (std::size_t i = 0; i < d.getMaterialArray().size(); ++i)
+        std::printf("%s%d", i ? ", " : "", static_cast<int>(d.getMaterialArray()[i]));
+    std::printf("], \"density\": [");
+    for (std::size_t i = 0; i < d.getDensityArray().size(); ++i)
+        std::printf("%s%.17g", i ? ", " : "", d.getDensityArray()[i]);
+    std::printf("], \"organ_names\": [");
+    for (std::size_t i = 0; i < d.getOrganNames().size(); ++i)
+        std::printf("%s\"%s\"", i ? ", " : "", d.getOrganNames()[i].c_str());
+    std::printf("], \"materials\": [");
+    for (std::size_t i = 0; i < d.getMaterials().size(); ++i) {
+        std::printf("%s{\"name\": \"%s\", \"Z\": {", i ? ", " : "", d.getMaterials()[i].name.c_str());
+        bool first = true;
+        for (const auto& [z, w] : d.getMaterials()[i].Z) {
+            std::printf("%s\"%llu\": %.17g", first ? "" : ", ", static_cast<unsigned long long>(z), w);
+            first = false;
+        }
+        std::printf("}}");
+    }
+    std::printf("], \"spacing\": [%.17g, %.17g, %.17g]}\n", d.spacing()[0], d.spacing()[1], d.spacing()[2]);
+    return 0;
+}
+
+static std::string jsonEscape(const std::string& in)
+{
+    std::string o;
+    for (char ch : in) {
+        if (ch == '"' || ch == '\\')
+            o.push_back('\\');
+        o.push_back(ch);
+    }
+    return o;
+}
+
+static void dumpItem(const QStandardItem* it, const std::string& path, bool& first)
+{
+    for (int r = 0; r < it->rowCount(); ++r) {
+        const QStandardItem* label = it->child(r, 0);
+        const QStandardItem* value = it->child(r, 1);
+        const std::string p = path + "/" + label->data(Qt::DisplayRole).toString().toStdString();
+        if (value) {
+            const QVariant v = value->data(Qt::DisplayRole);
+            const QVariant c = value->data(Qt::CheckStateRole);
+            std::printf("%s\n  [\"%s\", ", first ? "" : ",", jsonEscape(p).c_str());
+            first = false;
+            if (v.kind == QVariant::Double || v.kind == QVariant::Int || v.kind == QVariant::ULongLong)
+                std::printf("%.17g]", v.d);
+            else if (v.kind == QVariant::String)
+                std::printf("\"%s\"]", jsonEscape(v.s.toStdString()).c_str());
+            else if (c.isValid())
+                std::printf("%s]", c.i == Qt::Checked ? "true" : "false");
+            else
+                std::printf("null]");
+        }
+        dumpItem(label, p, first);
+    }
+}
+
+// value item of the row addressed by a '/'-separated label path below `it` ("Tube B/Tube potential [kV]")
+static QStandardItem* findValueItem(QStandardItem* it, const std::string& path)
+{
+    const auto cut = path.find('/');
+    const std::string head = path.substr(0, cut);
+    for (int r = 0; r < it->rowCount(); ++r) {
+        QStandardItem* l = it->child(r, 0);
+        if (l->data(Qt::DisplayRole).toString().toStdString() != head)
+            continue;
+        if (cut == std::string::npos)
+            return it->child(r, 1);
+        return findValueItem(l, path.substr(cut + 1));
+    }
+    return nullptr;
+}
+
+static int beamModelMode()
+{
+    BeamSettingsModel model;
+    model.addDXBeam();
+    model.addCBCTBeam();
+    model.addPencilBeam();
+    model.addCTSpiralBeam();
+    model.addCTSequentialBeam();
+    model.addCTSpiralDualEnergyBeam();
+    auto dumpAll = [&](const char* tag) {
+        std::printf("{\"kind\": \"beammodel\", \"tag\": \"%s\", \"beams\": %zu, \"rows\": [", tag, g_actors.size());
+        bool first = true;
+        for (int b = 0; b < model.rowCount(); ++b) {
+            const QStandardItem* root = model.item(b);
+            dumpItem(root, root->data(Qt::DisplayRole).toString().toStdString(), first);
+        }
+        std::printf("\n]}\n");
+    };
+    dumpAll("defaults");
+    // edit through the model, the way the GUI's delegate does (EditableItem::setData -> the setter lambdas)
+    struct Edit {
+        int beam;
+        const char* label;
+        QVariant value;
+    };
+    const Edit edits[] = {
+        { 0, "Tube/Tube potential [kV]", QVariant(80.0) }, { 0, "Tube/Tube Al filtration [mm]", QVariant(3.5) },
+        { 0, "Collimation [cm x cm]", QVariant("30, 25") }, { 0, "Primary angle [deg]", QVariant(40.0) },
+        { 0, "Source rotation center distance [cm]", QVariant(75.0) },
+        { 1, "Set angle step [deg]", QVariant(2.0) }, { 1, "Set stop angle [deg]", QVariant(200.0) },
+        { 2, "Photon energy [keV]", QVariant(75.0) }, { 2, "Direction normal (x, y, z)", QVariant("0, 1, 0") },
+        { 3, "Pitch", QVariant(1.4) }, { 3, "Set angle step [deg]", QVariant(10.0) }, { 3, "Total collimation [cm]", QVariant(2.0) },
+        { 3, "CTDIvol [mGy]", QVariant(7.5) }, { 3, "Stop position [cm]", QVariant("0, 0, 10") }, { 3, "Tube/Tube Sn filtration [mm]", QVariant(0.4) },
+        { 3, "Organ AEC/Low weight [0-1]", QVariant(0.3) }, { 3, "Organ AEC/Stop angle [deg]", QVariant(120.0) },
+        { 4, "Number of slices", QVariant(qulonglong { 7 }) }, { 4, "Slice spacing [cm]", QVariant(1.5) }, { 4, "CTDIw [mGy]", QVariant(3.0) },
+        { 5, "Tube B/Tube potential [kV]", QVariant(140.0) }, { 5, "Tube B/Relative tube current", QVariant(2.5) }, { 5, "Pitch", QVariant(3.0) },
+        { 5, "Tube B offset angle [deg]", QVariant(95.0) }, { 5, "Scan FOV Tube B [cm]", QVariant(30.0) },
+    };
+    int applied = 0;
+    for (const auto& e : edits) {
+        if (QStandardItem* it = findValueItem(model.item(e.beam), e.label)) {
+            it->setData(e.value, Qt::EditRole);
+            ++applied;
+        } else {
+            std::fprintf(stderr, "ref_driver: no row '%s' in beam %d\n", e.label, e.beam);
+        }
+    }
+    std::fprintf(stderr, "ref_driver: %d of %zu edits applied\n", applied, sizeof(edits) / sizeof(edits[0]));
+    dumpAll("edited");
+    return 0;
+}
+
+template <typename T>
+static std::vector<T> readRaw(const std::string& path)
+{
+    std::ifstream f(path, std::ios::binary);
+    std::vector<char> raw((std::istreambuf_iterator<char>(f)), {});
+    std::vector<T> v(raw.size() / sizeof(T));
+    std::copy(raw.begin(), raw.begin() + static_cast<std::ptrdiff_t>(v.size() * sizeof(T)), reinterpret_cast<char*>(v.data()));
+    return v;
+}
+
+static int doseTableMode(char** a)
+{
+    const std::string prefix = a[2];
+    auto d = std::make_shared<DataContainer>();
+    d->setDimensions({ static_cast<std::size_t>(std::atoi(a[3])), static_cast<std::size_t>(std::atoi(a[4])), static_cast<std::size_t>(std::atoi(a[5])) });
+    d->setSpacing({ std::atof(a[6]), std::atof(a[7]), std::atof(a[8]) });
+    std::vector<std::string> names;
+    for (int i = 0; i < std::atoi(a[9]); ++i)
+        names.push_back("organ " + std::to_string(i));
+    d->setOrganNames(names);
+    if (!d->setImageArray(DataContainer::ImageType::Organ, readRaw<std::uint8_t>(prefix + ".organ.bin"))
+        || !d->setImageArray(DataContainer::ImageType::Density, readRaw<double>(prefix + ".density.bin"))
+        || !d->setImageArray(DataContainer::ImageType::Dose, readRaw<double>(prefix + ".dose.bin")))
+        return 6;
+    DoseTablePipeline table;
+    table.updateImageData(d);
+    std::printf("{\"kind\": \"dosetable\", \"header\": [");
+    for (std::size_t i = 0; i < g_header.size(); ++i)
+        std::printf("%s\"%s\"", i ? ", " : "", g_header[i].c_str());
+    std::printf("], \"rows\": [");
+    bool first = true;
+    for (std::size_t i = 0; i < g_table.size(); ++i) {
+        if (g_table[i].voxels < 0)
+            continue; // organs without voxels get no row
+        std::printf("%s{\"organ\": %zu, \"name\": \"%s\", \"voxels\": %d, \"volume\": %.17g, \"mass\": %.17g, \"dose\": %.17g}", first ? "" : ", ", i,
+            g_table[i].name.c_str(), g_table[i].voxels, g_table[i].volume, g_table[i].mass, g_table[i].dose);
+        first = false;
+    }
+    std::printf("]}\n");
+    return 0;
+}
+
 template <typename T>
 static void writeRaw(const std::string& path, const std::vector<T>& v)
 {
@@ -237,8 +483,14 @@ int main(int argc, char** argv)
     const std::string what = argc > 1 ? argv[1] : "host";
     if (what == "host")
         return hostMode();
+    if (what == "beammodel")
+        return beamModelMode();
+    if (what == "dosetable" && argc >= 10)
+        return doseTableMode(argv);
+    if (what == "icrp" && argc >= 9)
+        return icrpMode(argv);
     if (what == "run" && argc >= 6)
         return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5]);
-    std::fprintf(stderr, "usage: opendxmc_ref host | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
+    std::fprintf(stderr, "usage: opendxmc_ref host | beammodel | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
     return 1;
 }

@@ -6,10 +6,12 @@ oracle/_ref/opendxmc_ref, driver oracle/ref_driver.cpp; Qt / VTK replaced by tes
     beamactorcontainer.cpp    exposure(i).position()/directionCosines()/collimationHalfAngles() of every beam type
     datacontainer.cpp         CTAECFilter, the water-equivalent-diameter AEC profile
     otherphantomimportpipeline.cpp  NISTMaterials::Composition / density, the PMMA cylinder
+    icrpphantomimportpipeline.cpp   organ / media tables -> organ, material, density arrays
     ctsegmentationpipeline.cpp  Tube, Material::byNistName / attenuationValues: HU -> (material, density)
+    dosetablepipeline.cpp     per-organ voxels / volume / mass / dose
+    beamsettingsmodel.cpp     EVERY getter and setter of the six beam types, tube, bowtie, AEC, organ AEC (1800 lines)
     simulationpipeline.cpp    worker<CORRECTION>(): World / AAVoxelGrid / Material / Transport / TransportProgress / doseScored
     basepipeline.cpp
-  + syntax-only: icrpphantomimportpipeline.cpp.
 
 The host-side parts are then RUN here (no GPU) and their numbers compared with the Python mirror (opendxmc_b200/api.py)
 that the GPU tests and bench.py use.  Reads /root/reference, so it only runs where the reference tree is mounted."""
@@ -185,3 +187,267 @@ def test_reference_ct_segmentation_matches_the_restatement_and_the_oracle(dx, or
     assert set(np.unique(ref_mat)) == {0, 1, 2, 3, 4}
     assert np.array_equal(ref_mat, omat)
     assert np.allclose(ref_dens, odens, rtol=1e-11, atol=1e-14)
+
+
+@pytest.mark.parametrize("case", ["all_organs", "sparse", "remove_arms"])
+def test_reference_icrp_import_matches_the_python_mirror(dx, ref_rows, tmp_path, case):
+    """ICRPPhantomImportPipeline::importPhantom (the reference's code, R:src/libopendxmc/icrpphantomimportpipeline.cpp:258-351)
+    with the reference's real AM organ / media tables on a small organ array, against workloads.import_icrp_tables."""
+    data = "/root/reference/data/phantoms/icrp/AM"
+    if case == "all_organs":
+        raw = np.concatenate([np.arange(141, dtype=np.uint8), np.arange(141, dtype=np.uint8)[::-1], np.zeros(18, dtype=np.uint8)])
+    else:
+        rng = np.random.default_rng(11)
+        raw = rng.choice(np.array([0, 3, 9, 17, 29, 30, 61, 88, 95, 96, 97, 120, 139, 140], dtype=np.uint8), 300).astype(np.uint8)
+    path = tmp_path / "organs.bin"
+    raw.tofile(path)
+    remove = case == "remove_arms"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "icrp", str(path), f"{data}/AM_organs.dat", f"{data}/AM_media.dat",
+                        "30", "5", "2", "1" if remove else "0"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[:200], r.stderr)
+    ref = json.loads(r.stdout)
+    mine_raw = raw.copy()
+    if remove:
+        # the reference blanks organs whose name contains arm / hand / Humeri / Ulnae (:274-295)
+        t = dx.workloads.icrp_tables()["AM"]
+        for o in t["organs"]:
+            if any(k in o["name"] for k in ("arm", "hand", "Humeri", "Ulnae")):
+                mine_raw[mine_raw == o["id"]] = 0
+    organ, names, material, density, media_names, comps = dx.workloads.import_icrp_tables("AM", mine_raw)
+    assert np.array_equal(organ, ref["organ"])
+    assert names == ref["organ_names"]
+    assert np.array_equal(material, ref["material"])
+    assert np.array_equal(density, np.array(ref["density"]))
+    assert media_names == [m["name"] for m in ref["materials"]]
+    for c, m in zip(comps, ref["materials"]):
+        rz = {int(z): w for z, w in m["Z"].items() if w > 0}
+        assert set(c) == set(rz) and all(c[z] == pytest.approx(rz[z], rel=1e-12) for z in c), m["name"]
+    assert ref["spacing"] == pytest.approx([0.1, 0.1, 0.1])  # mm -> cm (setSpacingInmm)
+
+
+def test_reference_dose_table_matches_the_oracle(orc, ref_rows, tmp_path):
+    """DoseTablePipeline::updateImageData (the reference's code, R:src/libopendxmc/dosetablepipeline.cpp:36-95) against the
+    oracle's per-organ dose (the GPU test compares dxb_organ_dose with the same oracle function)."""
+    rng = np.random.default_rng(5)
+    dim, sp = (12, 10, 8), (0.11, 0.07, 0.2)
+    n = dim[0] * dim[1] * dim[2]
+    organ = rng.integers(0, 9, n).astype(np.uint8)
+    organ[organ == 4] = 3                                   # organ 4 has no voxels: no table row
+    dose = rng.random(n) * 3.0
+    dens = rng.random(n) + 0.05
+    prefix = str(tmp_path / "t")
+    organ.tofile(prefix + ".organ.bin")
+    dose.tofile(prefix + ".dose.bin")
+    dens.tofile(prefix + ".density.bin")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "dosetable", prefix, *map(str, dim), *map(repr, sp), "10"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[:200], r.stderr)
+    t = json.loads(r.stdout)
+    assert t["header"][:4] == ["Name", "# Voxels", "Volume cm3", "Mass g"] and t["header"][4].startswith("Dose ")
+    vol = sp[0] * sp[1] * sp[2]
+    d, m, c = orc.organ_dose(dose, dens, organ, vol, 10)
+    rows = {row["organ"]: row for row in t["rows"]}
+    assert sorted(rows) == [o for o in range(10) if c[o] > 0] and 4 not in rows and 9 not in rows
+    for o, row in rows.items():
+        assert row["name"] == f"organ {o}" and row["voxels"] == c[o]
+        assert row["volume"] == pytest.approx(c[o] * vol, rel=1e-13)
+        assert row["mass"] == pytest.approx(m[o], rel=1e-12) and row["dose"] == pytest.approx(d[o], rel=1e-12)
+
+
+def _beam_rows(dx, edited):
+    """the Python mirror of what BeamSettingsModel shows: {row path: value}; the same defaults the model applies to a new
+    beam (R:src/libopendxmc/beamsettingsmodel.cpp:470-474, 729-735, 929-933, 1166-1170, 1412-1416) and, if `edited`, the
+    same edits oracle/ref_driver.cpp makes through the model's setters."""
+    rows = {}
+
+    def tube_rows(prefix, b, names=("Al", "Cu", "Sn", "Ag")):
+        t = b.tube()
+        rows[f"{prefix}/Tube potential [kV]"] = t.voltage()
+        rows[f"{prefix}/Tube anode angle [deg]"] = t.anodeAngleDeg()
+        for nm, z in (("Al", 13), ("Cu", 29), ("Sn", 50), ("Ag", 47)):
+            if nm in names:
+                rows[f"{prefix}/Tube {nm} filtration [mm]"] = t.filtration(z)
+        rows[f"{prefix}/Tube half value layer [mmAl]"] = b.tubeAlHalfValueLayer()
+        rows[f"{prefix}/Tube mean energy [keV]"] = b.tubeMeanSpecterEnergy()
+
+    def organ_rows(prefix, b):
+        o = b.organAECFilter()
+        rows[f"{prefix}/Organ AEC/Use Organ AEC"] = o.useFilter()
+        rows[f"{prefix}/Organ AEC/Start angle [deg]"] = o.startAngleDeg()
+        rows[f"{prefix}/Organ AEC/Stop angle [deg]"] = o.stopAngleDeg()
+        rows[f"{prefix}/Organ AEC/Ramp angle [deg]"] = o.rampAngleDeg()
+        rows[f"{prefix}/Organ AEC/Low weight [0-1]"] = o.lowWeight()
+        rows[f"{prefix}/Organ AEC/High weight"] = o.maxWeight()
+        rows[f"{prefix}/Organ AEC/Compensate outside beam"] = o.compensateOutside()
+
+    def count_rows(prefix, b, jobs=False):
+        rows[f"{prefix}/Number of {'jobs' if jobs else 'exposures'}"] = b.numberOfExposures()
+        rows[f"{prefix}/Particles per {'job' if jobs else 'exposure'}"] = b.numberOfParticlesPerExposure()
+        rows[f"{prefix}/Total number of particles"] = b.numberOfParticles()
+
+    b = dx.DXBeam(filtration={13: 2.0, 29: 0.1})
+    b.setNumberOfParticlesPerExposure(1_000_000)
+    if edited:
+        b.setTubeVoltage(80.0)
+        b.addTubeFiltrationMaterial(13, 3.5)
+        b.setCollimation([30.0, 25.0])
+        b.setPrimaryAngleDeg(40.0)
+        b.setSourcePatientDistance(75.0)
+    p = "DX Beam"
+    rows[f"{p}/Source rotation center distance [cm]"] = b.sourcePatientDistance()
+    rows[f"{p}/Primary angle [deg]"] = b.primaryAngleDeg()
+    rows[f"{p}/Secondary angle [deg]"] = b.secondaryAngleDeg()
+    rows[f"{p}/Source detector distance [cm]"] = b.sourceDetectorDistance()
+    rows[f"{p}/Collimation [cm x cm]"] = list(b.collimation())
+    rows[f"{p}/Collimation angles [deg]"] = [2 * a for a in b.collimationHalfAnglesDeg()]
+    tube_rows(f"{p}/Tube", b)
+    rows[f"{p}/Dose area product [mGycm^2]"] = b.DAPvalue()
+    count_rows(p, b, jobs=True)
+
+    b = dx.CBCTBeam((0, 0, 0), (0, 0, 1), {13: 2.0, 29: 0.1})
+    b.setCollimationHalfAnglesDeg(10, 10)
+    b.setNumberOfParticlesPerExposure(1_000_000)
+    if edited:
+        b.setStepAngleDeg(2.0)
+        b.setStopAngleDeg(200.0)
+    p = "CBCT Beam"
+    rows[f"{p}/Isocenter [cm]"] = list(b.isocenter())
+    rows[f"{p}/Rotation axis"] = list(b.rotationAxis())
+    rows[f"{p}/Source detector distance [cm]"] = b.sourceDetectorDistance()
+    rows[f"{p}/Set start angle [deg]"] = b.startAngleDeg()
+    rows[f"{p}/Set stop angle [deg]"] = b.stopAngleDeg()
+    rows[f"{p}/Set angle step [deg]"] = b.stepAngleDeg()
+    rows[f"{p}/Collimation angles [deg]"] = [2 * a for a in b.collimationHalfAnglesDeg()]
+    rows[f"{p}/Collimation [cm x cm]"] = [2 * b.sourceDetectorDistance() * math.tan(a) for a in b.collimationHalfAngles()]  # :842-851
+    tube_rows(f"{p}/Tube", b)
+    rows[f"{p}/Dose area product [mGycm^2]"] = b.DAPvalue()
+    count_rows(p, b)
+
+    b = dx.PencilBeam()
+    if edited:
+        b.setEnergy(75.0)
+        b.setDirection([0, 1, 0])
+    p = "Pencil Beam"
+    rows[f"{p}/Position (x, y, z) [cm]"] = list(b.position())
+    rows[f"{p}/Direction normal (x, y, z)"] = list(b.direction())
+    rows[f"{p}/Photon energy [keV]"] = b.energy()
+    rows[f"{p}/Air KERMA [mGy]"] = b.airKerma()
+    count_rows(p, b, jobs=True)
+
+    def ct_common(b):
+        b.setSourceDetectorDistance(119)
+        b.setCollimation(3.84)
+        b.setStepAngleDeg(5)
+        b.setNumberOfParticlesPerExposure(1_000_000)
+
+    b = dx.CTSpiralBeam((0, 0, -20), (0, 0, 20), {13: 9.0})
+    ct_common(b)
+    if edited:
+        b.setPitch(1.4)
+        b.setStepAngleDeg(10.0)
+        b.setCollimation(2.0)
+        b.setCTDIvol(7.5)
+        b.setStopPosition([0, 0, 10])
+        b.addTubeFiltrationMaterial(50, 0.4)
+        b.organAECFilter().setLowWeight(0.3)
+        b.organAECFilter().setStopAngleDeg(120.0)
+    p = "CT Spiral Beam"
+    rows[f"{p}/Start position [cm]"] = list(b.startPosition())
+    rows[f"{p}/Stop position [cm]"] = list(b.stopPosition())
+    rows[f"{p}/Scan FOV [cm]"] = b.scanFieldOfView()
+    rows[f"{p}/Source detector distance [cm]"] = b.sourceDetectorDistance()
+    rows[f"{p}/Total collimation [cm]"] = b.collimation()
+    rows[f"{p}/Set start angle [deg]"] = b.startAngleDeg()
+    rows[f"{p}/Set angle step [deg]"] = b.stepAngleDeg()
+    rows[f"{p}/Pitch"] = b.pitch()
+    rows[f"{p}/CTDIvol [mGy]"] = b.CTDIvol()
+    rows[f"{p}/CTDI phantom diameter [cm]"] = b.CTDIdiameter()
+    tube_rows(f"{p}/Tube", b)
+    organ_rows(p, b)
+    count_rows(p, b)
+
+    b = dx.CTSequentialBeam((0, 0, 0), (0, 0, 1), {13: 9.0})
+    ct_common(b)
+    if edited:
+        b.setNumberOfSlices(7)
+        b.setSliceSpacing(1.5)
+        b.setCTDIw(3.0)
+    p = "CT Sequential Beam"
+    rows[f"{p}/Start position [cm]"] = list(b.position())
+    rows[f"{p}/Direction vector"] = list(b.scanNormal())
+    rows[f"{p}/Number of slices"] = b.numberOfSlices()
+    rows[f"{p}/Slice spacing [cm]"] = b.sliceSpacing()
+    rows[f"{p}/Scan FOV [cm]"] = b.scanFieldOfView()
+    rows[f"{p}/Source detector distance [cm]"] = b.sourceDetectorDistance()
+    rows[f"{p}/Total collimation [cm]"] = b.collimation()
+    rows[f"{p}/Set start angle [deg]"] = b.startAngleDeg()
+    rows[f"{p}/Set angle step [deg]"] = b.stepAngleDeg()
+    rows[f"{p}/CTDIw [mGy]"] = b.CTDIw()
+    rows[f"{p}/CTDI phantom diameter [cm]"] = b.CTDIdiameter()
+    tube_rows(f"{p}/Tube", b)
+    organ_rows(p, b)
+    count_rows(p, b)
+
+    b = dx.CTSpiralDualEnergyBeam((0, 0, -20), (0, 0, 20), {13: 9.0})
+    ct_common(b)
+    if edited:
+        b.setTubeBVoltage(140.0)
+        b.setRelativeMasTubeB(2.5)
+        b.setPitch(3.0)
+        b.setTubeBoffsetAngleDeg(95.0)
+        b.setScanFieldOfViewB(30.0)
+    p = "CT Spiral Dual Energy Beam"
+    rows[f"{p}/Start position [cm]"] = list(b.startPosition())
+    rows[f"{p}/Stop position [cm]"] = list(b.stopPosition())
+    rows[f"{p}/Scan FOV Tube A [cm]"] = b.scanFieldOfViewA()
+    rows[f"{p}/Scan FOV Tube B [cm]"] = b.scanFieldOfViewB()
+    rows[f"{p}/Source detector distance [cm]"] = b.sourceDetectorDistance()
+    rows[f"{p}/Total collimation [cm]"] = b.collimation()
+    rows[f"{p}/Set start angle [deg]"] = b.startAngleDeg()
+    rows[f"{p}/Set angle step [deg]"] = b.stepAngleDeg()
+    rows[f"{p}/Tube B offset angle [deg]"] = b.tubeBoffsetAngleDeg()
+    rows[f"{p}/Pitch"] = b.pitch()
+    rows[f"{p}/CTDIvol [mGy]"] = b.CTDIvol()
+    rows[f"{p}/CTDI phantom diameter [cm]"] = b.CTDIdiameter()
+    for ab, tube, mas, hvl, wgt, mean in (("A", b.tubeA(), b.relativeMasTubeA(), b.tubeAAlHalfValueLayer(), b.tubeRelativeWeightA(), b.tubeAMeanSpecterEnergy()),
+                                          ("B", b.tubeB(), b.relativeMasTubeB(), b.tubeBAlHalfValueLayer(), b.tubeRelativeWeightB(), b.tubeBMeanSpecterEnergy())):
+        q = f"{p}/Tube {ab}"
+        rows[f"{q}/Tube potential [kV]"] = tube.voltage()
+        rows[f"{q}/Relative tube current"] = mas
+        rows[f"{q}/Tubes anode angle [deg]"] = tube.anodeAngleDeg()
+        for nm, z in (("Al", 13), ("Cu", 29), ("Sn", 50)):
+            rows[f"{q}/Tube {nm} filtration [mm]"] = tube.filtration(z)
+        rows[f"{q}/Tube half value layer [mmAl]"] = hvl
+        rows[f"{q}/Relative photon count weight"] = wgt
+        rows[f"{q}/Tube mean energy [keV]"] = mean
+    organ_rows(p, b)
+    count_rows(p, b)
+    return rows
+
+
+@pytest.mark.parametrize("tag", ["defaults", "edited"])
+def test_reference_beam_settings_model_matches_the_python_mirror(dx, ref_rows, tag):
+    """BeamSettingsModel (the reference's code, R:src/libopendxmc/beamsettingsmodel.cpp, all 1800 lines of getters and
+    setters over the six beam types) runs on the C++ shims; every row it shows must equal the Python mirror."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "beammodel"], capture_output=True, text=True)
+    assert r.returncode == 0 and "25 of 25 edits applied" in r.stderr, r.stderr
+    dumps = {}
+    for block in r.stdout.split("{\"kind\": \"beammodel\"")[1:]:
+        d = json.loads("{\"kind\": \"beammodel\"" + block)
+        dumps[d["tag"]] = d
+    ref = dict(map(tuple, dumps[tag]["rows"]))
+    assert dumps[tag]["beams"] == 6 and len(ref) >= 140
+    mine = _beam_rows(dx, tag == "edited")
+    missing = [k for k in mine if k not in ref]
+    assert not missing, missing
+    for k, v in mine.items():
+        rv = ref[k]
+        if isinstance(v, (list, tuple)):
+            assert [float(x) for x in rv.split(",")] == pytest.approx([float(x) for x in v], abs=2e-6), k   # QString::number: 6 decimals
+        elif isinstance(v, bool):
+            assert rv is v, k
+        else:
+            assert rv == pytest.approx(float(v), rel=1e-12, abs=1e-12), (k, rv, v)
+    # rows the mirror does not model are only the bowtie / AEC selectors
+    extra = sorted(k for k in ref if k not in mine)
+    assert all(("Bowtie filter" in k) or ("Use current AEC profile" in k) or k.endswith("Rotation center (x, y, z) [cm]") for k in extra), extra
