@@ -3,6 +3,7 @@
 // parseCompoundStr (R:src/libopendxmc/hdf5wrapper.cpp:1100).
 #pragma once
 #include "../../dxb.h"
+#include "atomhandler.hpp" // the reference uses dxmc::AtomHandler after including only material.hpp (R:src/libopendxmc/hdf5wrapper.cpp:429)
 #include "nistmaterials.hpp"
 #include <cctype>
 #include <map>

@@ -3,7 +3,7 @@
 // translation units WHERE THEY LIE under /root/reference/src/libopendxmc (nothing is copied):
 //     dxmc_specialization.cpp  beamactorcontainer.cpp  datacontainer.cpp  basepipeline.cpp
 //     otherphantomimportpipeline.cpp  icrpphantomimportpipeline.cpp  ctsegmentationpipeline.cpp  dosetablepipeline.cpp
-//     beamsettingsmodel.cpp  simulationpipeline.cpp
+//     beamsettingsmodel.cpp  hdf5wrapper.cpp  simulationpipeline.cpp
 // (bowtiefilterreader.cpp is Qt-JSON code: its two read() functions are replaced below by a fixed two-filter table.)
 // with the tests-only Qt / VTK stand-ins of tests/stubs/ (Qt's moc is replaced by the signal bodies below).
 //
@@ -20,6 +20,11 @@
 //       CPU only.  BeamSettingsModel (R:beamsettingsmodel.cpp, 1800 lines: every getter / setter of the six beam types, tube,
 //       bowtie, AEC and organ-AEC the GUI offers) creates its six default beams; every (label, value) row of the settings
 //       tree is printed, then a few values are edited through the model's setters and printed again.
+//   opendxmc_ref h5roundtrip
+//       CPU only.  HDF5Wrapper (R:hdf5wrapper.cpp, 1150 lines) saves the PMMA cylinder + its AEC profile and the five
+//       savable beam types (after the edits of `beammodel`) and loads them back - against the in-memory stand-in for the
+//       HDF5 C++ API in tests/stubs/H5Cpp.h, so this checks the wrapper's use of the dxmc:: accessors (radian forms,
+//       filters, parseCompoundStr / AtomHandler), not the file format.  Prints the settings rows before and after.
 //   opendxmc_ref dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs>
 //       CPU only.  DoseTablePipeline::updateImageData (R:dosetablepipeline.cpp:36-95) on <prefix>.{organ,dose,density}.bin:
 //       per organ the voxel count, volume, mass and dose the app's table shows.
@@ -34,6 +39,7 @@
 #include <datacontainer.hpp>
 #include <dosetablepipeline.hpp>
 #include <dxmc_specialization.hpp>
+#include <hdf5wrapper.hpp>
 #include <icrpphantomimportpipeline.hpp>
 #include <otherphantomimportpipeline.hpp>
 #include <simulationpipeline.hpp>
@@ -334,26 +340,20 @@ static QStandardItem* findValueItem(QStandardItem* it, const std::string& path)
     return nullptr;
 }
 
-static int beamModelMode()
+static void dumpModel(BeamSettingsModel& model, const char* tag, std::size_t nBeams)
 {
-    BeamSettingsModel model;
-    model.addDXBeam();
-    model.addCBCTBeam();
-    model.addPencilBeam();
-    model.addCTSpiralBeam();
-    model.addCTSequentialBeam();
-    model.addCTSpiralDualEnergyBeam();
-    auto dumpAll = [&](const char* tag) {
-        std::printf("{\"kind\": \"beammodel\", \"tag\": \"%s\", \"beams\": %zu, \"rows\": [", tag, g_actors.size());
-        bool first = true;
-        for (int b = 0; b < model.rowCount(); ++b) {
-            const QStandardItem* root = model.item(b);
-            dumpItem(root, root->data(Qt::DisplayRole).toString().toStdString(), first);
-        }
-        std::printf("\n]}\n");
-    };
-    dumpAll("defaults");
-    // edit through the model, the way the GUI's delegate does (EditableItem::setData -> the setter lambdas)
+    std::printf("{\"kind\": \"beammodel\", \"tag\": \"%s\", \"beams\": %zu, \"rows\": [", tag, nBeams);
+    bool first = true;
+    for (int b = 0; b < model.rowCount(); ++b) {
+        const QStandardItem* root = model.item(b);
+        dumpItem(root, root->data(Qt::DisplayRole).toString().toStdString(), first);
+    }
+    std::printf("\n]}\n");
+}
+
+// edit through the model, the way the GUI's delegate does (EditableItem::setData -> the setter lambdas)
+static int applyEdits(BeamSettingsModel& model)
+{
     struct Edit {
         int beam;
         const char* label;
@@ -382,7 +382,77 @@ static int beamModelMode()
         }
     }
     std::fprintf(stderr, "ref_driver: %d of %zu edits applied\n", applied, sizeof(edits) / sizeof(edits[0]));
-    dumpAll("edited");
+    return applied;
+}
+
+static void addDefaultBeams(BeamSettingsModel& model)
+{
+    model.addDXBeam();
+    model.addCBCTBeam();
+    model.addPencilBeam();
+    model.addCTSpiralBeam();
+    model.addCTSequentialBeam();
+    model.addCTSpiralDualEnergyBeam();
+}
+
+static int beamModelMode()
+{
+    BeamSettingsModel model;
+    addDefaultBeams(model);
+    dumpModel(model, "defaults", g_actors.size());
+    applyEdits(model);
+    dumpModel(model, "edited", g_actors.size());
+    return 0;
+}
+
+static int h5RoundTripMode()
+{
+    BeamSettingsModel model;
+    addDefaultBeams(model);
+    applyEdits(model);
+    const auto saved = g_actors; // the six actors the model announced
+    auto vol = makeCylinder(0.5, 24, 5);
+    vol->setAecData(vol->calculateAECfilterFromWaterEquivalentDiameter(true));
+    int nSaved = 0;
+    {
+        HDF5Wrapper out("memory.h5", HDF5Wrapper::FileOpenMode::WriteOver);
+        if (!out.save(vol))
+            return 7;
+        for (const auto& a : saved)
+            nSaved += out.save(a) ? 1 : 0; // the pencil beam has no save() overload (R:hdf5wrapper.cpp:1050-1068)
+    }
+    HDF5Wrapper in("memory.h5", HDF5Wrapper::FileOpenMode::ReadOnly);
+    auto back = in.load();
+    auto beams = in.loadBeams();
+    if (!back)
+        return 8;
+    const bool sameGrid = back->dimensions() == vol->dimensions() && back->spacing() == vol->spacing() && back->getDensityArray() == vol->getDensityArray()
+        && back->getMaterialArray() == vol->getMaterialArray() && back->getOrganArray() == vol->getOrganArray() && back->getOrganNames() == vol->getOrganNames();
+    bool sameMaterials = back->getMaterials().size() == vol->getMaterials().size();
+    double worstZ = 0;
+    for (std::size_t i = 0; sameMaterials && i < vol->getMaterials().size(); ++i) {
+        const auto& a = vol->getMaterials()[i];
+        const auto& b = back->getMaterials()[i];
+        sameMaterials = a.name == b.name && a.Z.size() == b.Z.size();
+        for (const auto& [z, w] : a.Z) {
+            if (!b.Z.contains(z)) {
+                sameMaterials = false;
+                break;
+            }
+            worstZ = std::max(worstZ, std::abs(b.Z.at(z) - w) / w);
+        }
+    }
+    const bool sameAec = back->aecData().weights() == vol->aecData().weights() && back->aecData().start() == vol->aecData().start()
+        && back->aecData().stop() == vol->aecData().stop();
+    std::printf("{\"kind\": \"h5\", \"beams_saved\": %d, \"beams_loaded\": %zu, \"same_grid\": %s, \"same_materials\": %s, "
+                "\"worst_composition_rel\": %.3g, \"same_aec\": %s}\n",
+        nSaved, beams.size(), sameGrid ? "true" : "false", sameMaterials ? "true" : "false", worstZ, sameAec ? "true" : "false");
+    dumpModel(model, "saved", saved.size());
+    g_actors.clear();
+    BeamSettingsModel model2;
+    for (const auto& a : beams)
+        model2.addBeam(a);
+    dumpModel(model2, "loaded", beams.size());
     return 0;
 }
 
@@ -485,12 +555,14 @@ int main(int argc, char** argv)
         return hostMode();
     if (what == "beammodel")
         return beamModelMode();
+    if (what == "h5roundtrip")
+        return h5RoundTripMode();
     if (what == "dosetable" && argc >= 10)
         return doseTableMode(argv);
     if (what == "icrp" && argc >= 9)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
         return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5]);
-    std::fprintf(stderr, "usage: opendxmc_ref host | beammodel | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
+    std::fprintf(stderr, "usage: opendxmc_ref host | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
     return 1;
 }
