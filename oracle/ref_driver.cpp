@@ -4,7 +4,7 @@
 //     dxmc_specialization.cpp  beamactorcontainer.cpp  datacontainer.cpp  basepipeline.cpp
 //     otherphantomimportpipeline.cpp  icrpphantomimportpipeline.cpp  ctsegmentationpipeline.cpp  dosetablepipeline.cpp
 //     beamsettingsmodel.cpp  hdf5wrapper.cpp  simulationpipeline.cpp
-// (bowtiefilterreader.cpp is Qt-JSON code: its two read() functions are replaced below by a fixed two-filter table.)
+//     bowtiefilterreader.cpp (over the small JSON parser in tests/stubs/QJsonDocument)
 // with the tests-only Qt / VTK stand-ins of tests/stubs/ (Qt's moc is replaced by the signal bodies below).
 //
 //   opendxmc_ref host
@@ -16,6 +16,9 @@
 //   opendxmc_ref icrp <organ array file> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms 0|1>
 //       CPU only.  ICRPPhantomImportPipeline::importPhantom (R:icrpphantomimportpipeline.cpp:258-351) on a caller-made
 //       organ array with the reference's real organ / media tables: organ, material and density arrays, names, compositions.
+//   opendxmc_ref bowtie
+//       CPU only, run with the reference tree as working directory.  BowtieFilterReader::read on the reference's
+//       data/bowtiefilters/bowtiefilters.json (R:bowtiefilterreader.cpp:34-110): names, points, weights at sample angles.
 //   opendxmc_ref beammodel
 //       CPU only.  BeamSettingsModel (R:beamsettingsmodel.cpp, 1800 lines: every getter / setter of the six beam types, tube,
 //       bowtie, AEC and organ-AEC the GUI offers) creates its six default beams; every (label, value) row of the settings
@@ -80,20 +83,6 @@ static std::vector<std::shared_ptr<BeamActorContainer>> g_actors;
 void BeamSettingsModel::beamActorAdded(std::shared_ptr<BeamActorContainer> a) { g_actors.push_back(a); }
 void BeamSettingsModel::beamActorRemoved(std::shared_ptr<BeamActorContainer>) { }
 void BeamSettingsModel::requestRender() { }
-BowtieFilterReader::BowtieFilterReader(QObject* parent)
-    : QObject(parent)
-{
-}
-QMap<QString, BowtieFilter> BowtieFilterReader::read(const QString&)
-{
-    // stand-in for the JSON reader: the GUI's default key plus one more (angles in radians, R:bowtiefilterreader.cpp:74-93)
-    QMap<QString, BowtieFilter> m;
-    m.insert("Siemens Definition Flash W1 120kV", BowtieFilter({ { 0.0, 1.0 }, { 0.1, 0.8 }, { 0.2, 0.5 }, { 0.3, 0.25 }, { 0.39, 0.1 } }));
-    m.insert("flat", BowtieFilter({ { 0.0, 1.0 }, { 0.39, 1.0 } }));
-    return m;
-}
-QMap<QString, BowtieFilter> BowtieFilterReader::read(const QStringList&) { return read(QString()); }
-
 struct DoseRow {
     std::string name;
     int voxels = -1;
@@ -395,6 +384,26 @@ static void addDefaultBeams(BeamSettingsModel& model)
     model.addCTSpiralDualEnergyBeam();
 }
 
+static int bowtieMode()
+{
+    const auto filters = BowtieFilterReader::read(QString("data/bowtiefilters/bowtiefilters.json"));
+    std::printf("{\"kind\": \"bowtie\", \"filters\": [");
+    bool first = true;
+    for (auto it = filters.cbegin(); it != filters.cend(); ++it) {
+        std::printf("%s\n  {\"name\": \"%s\", \"data\": [", first ? "" : ",", jsonEscape(it->first.toStdString()).c_str());
+        first = false;
+        const auto data = it->second.data();
+        for (std::size_t i = 0; i < data.size(); ++i)
+            std::printf("%s[%.17g, %.17g]", i ? ", " : "", data[i].first, data[i].second);
+        std::printf("], \"weights\": [");
+        for (int k = 0; k <= 9; ++k)
+            std::printf("%s%.17g", k ? ", " : "", it->second(0.05 * k));
+        std::printf("]}");
+    }
+    std::printf("\n]}\n");
+    return 0;
+}
+
 static int beamModelMode()
 {
     BeamSettingsModel model;
@@ -553,6 +562,8 @@ int main(int argc, char** argv)
     const std::string what = argc > 1 ? argv[1] : "host";
     if (what == "host")
         return hostMode();
+    if (what == "bowtie")
+        return bowtieMode();
     if (what == "beammodel")
         return beamModelMode();
     if (what == "h5roundtrip")
@@ -563,6 +574,6 @@ int main(int argc, char** argv)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
         return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5]);
-    std::fprintf(stderr, "usage: opendxmc_ref host | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
+    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
     return 1;
 }

@@ -10,6 +10,7 @@ oracle/_ref/opendxmc_ref, driver oracle/ref_driver.cpp; Qt / VTK replaced by tes
     ctsegmentationpipeline.cpp  Tube, Material::byNistName / attenuationValues: HU -> (material, density)
     dosetablepipeline.cpp     per-organ voxels / volume / mass / dose
     beamsettingsmodel.cpp     EVERY getter and setter of the six beam types, tube, bowtie, AEC, organ AEC (1800 lines)
+    bowtiefilterreader.cpp    the 41 bowtie filters of data/bowtiefilters/bowtiefilters.json (over a small JSON parser)
     hdf5wrapper.cpp           save / load of the scene (radian accessors, filters, parseCompoundStr) over an in-memory HDF5 stand-in
     simulationpipeline.cpp    worker<CORRECTION>(): World / AAVoxelGrid / Material / Transport / TransportProgress / doseScored
     basepipeline.cpp
@@ -430,7 +431,7 @@ def _beam_rows(dx, edited):
 def test_reference_beam_settings_model_matches_the_python_mirror(dx, ref_rows, tag):
     """BeamSettingsModel (the reference's code, R:src/libopendxmc/beamsettingsmodel.cpp, all 1800 lines of getters and
     setters over the six beam types) runs on the C++ shims; every row it shows must equal the Python mirror."""
-    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "beammodel"], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "beammodel"], capture_output=True, text=True, cwd="/root/reference")
     assert r.returncode == 0 and "25 of 25 edits applied" in r.stderr, r.stderr
     dumps = {}
     for block in r.stdout.split("{\"kind\": \"beammodel\"")[1:]:
@@ -458,7 +459,7 @@ def test_reference_hdf5_wrapper_round_trip_over_the_shims(ref_rows):
     """HDF5Wrapper (the reference's code, R:src/libopendxmc/hdf5wrapper.cpp) saves the scene and loads it back against the
     in-memory stand-in for the HDF5 C++ API: every setting of the loadable beam types survives (radian accessors, tube
     filtration, organ AEC ...), and so do the grid and the materials (AtomHandler::toSymbol -> parseCompoundStr)."""
-    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "h5roundtrip"], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "h5roundtrip"], capture_output=True, text=True, cwd="/root/reference")
     assert r.returncode == 0, r.stderr
     head = json.loads(r.stdout.splitlines()[0])
     assert head["same_grid"] and head["same_materials"] and head["worst_composition_rel"] < 1e-12
@@ -477,3 +478,21 @@ def test_reference_hdf5_wrapper_round_trip_over_the_shims(ref_rows):
     assert len(loaded) >= 95
     for k, v in loaded.items():
         assert saved[k] == v, (k, saved[k], v)
+
+
+def test_reference_bowtie_reader_matches_the_python_reader(dx, ref_rows):
+    """BowtieFilterReader::read (the reference's code, R:src/libopendxmc/bowtiefilterreader.cpp:34-110) on the reference's
+    data/bowtiefilters/bowtiefilters.json - 41 filters with unsorted points - against workloads.read_bowtie_filters, and
+    the shim's BowtieFilter::operator() against the Python mirror at sample fan angles."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "bowtie"], capture_output=True, text=True, cwd="/root/reference")
+    assert r.returncode == 0, r.stderr
+    ref = {f["name"]: f for f in json.loads(r.stdout)["filters"]}
+    mine = dx.workloads.read_bowtie_filters("/root/reference/data/bowtiefilters/bowtiefilters.json")
+    assert len(ref) == 41 and set(ref) == set(mine) and "Siemens Definition Flash W1 120kV" in ref
+    packaged = dx.workloads.read_bowtie_filters()          # the copy shipped with the package must be the same table
+    assert set(packaged) == set(mine)
+    for name, f in ref.items():
+        b = mine[name]
+        assert np.array_equal(np.array(f["data"]), np.stack([b.angle, b.weight], axis=1)), name
+        assert np.array_equal(packaged[name].angle, b.angle) and np.array_equal(packaged[name].weight, b.weight), name
+        assert [b(0.05 * k) for k in range(10)] == pytest.approx(f["weights"], rel=1e-13), name
