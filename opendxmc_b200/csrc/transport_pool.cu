@@ -6,8 +6,8 @@
 // warps of the block.  Two status words per class hold one bit per (slot, state).  Each iteration a warp votes
 // for ONE phase, every lane CLAIMS a slot of its class that is in that phase (atomicAnd on the status word),
 // processes it, and publishes it in its new state (fence + atomicOr).  Any warp can continue any photon, so
-// phases run with nearly full warps although only ~1.5 photons per thread are resident (15 KB per block: the
-// L1 carve-out that sank the lane-private variant, transport_mux.cu, stays small).
+// phases run with nearly full warps although only 2 photons per thread are resident (SPC = 16: 20 KB per
+// 256-thread block; the L1 carve-out that sank the lane-private variant, transport_mux.cu, stays small).
 //
 // Replaces (recalled DXMClib): Transport::runWorker -> exposure.sampleParticle
 // -> World::transport -> AAVoxelGrid::woodcockTransport -> interactions::interact -> EnergyScore.
