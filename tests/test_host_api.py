@@ -32,6 +32,17 @@ def test_attenuation_close_to_nist_xcom(dx):
         m = dx.Material.byNistName(name)
         for e, v in tab.items():
             assert m.attenuationValues(e).sum() == pytest.approx(v, rel=0.03), (name, e)
+    # compositions that leave no room for interpretation (dry air, water, PMMA, elemental aluminium): within 0.6 % from 20 to 150 keV
+    tight = {"Water, Liquid": {20: 0.8096, 30: 0.3756, 40: 0.2683, 50: 0.2269, 60: 0.2059, 80: 0.1837, 100: 0.1707, 150: 0.1505},
+             "Air, Dry (near sea level)": {20: 0.7779, 30: 0.3538, 40: 0.2485, 50: 0.2080, 60: 0.1875, 80: 0.1662, 100: 0.1541, 150: 0.1356},
+             "Polymethyl Methacralate (Lucite, Perspex)": {20: 0.5714, 30: 0.3032, 40: 0.2350, 50: 0.2074, 60: 0.1924, 80: 0.1751, 100: 0.1641, 150: 0.1456}}
+    for name, tab in tight.items():
+        m = dx.Material.byNistName(name)
+        for e, v in tab.items():
+            assert m.attenuationValues(e).sum() == pytest.approx(v, rel=6e-3), (name, e)
+    al = dx.Material.byWeight({13: 1.0})
+    for e, v in {20: 3.441, 30: 1.128, 40: 0.5685, 50: 0.3681, 60: 0.2778, 80: 0.2018, 100: 0.1704, 150: 0.1378}.items():
+        assert al.attenuationValues(e).sum() == pytest.approx(v, rel=4e-3), ("Al", e)
 
 
 def test_nist_names_used_by_the_reference(dx):
