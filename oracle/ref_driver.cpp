@@ -31,8 +31,9 @@
 //   opendxmc_ref dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs>
 //       CPU only.  DoseTablePipeline::updateImageData (R:dosetablepipeline.cpp:36-95) on <prefix>.{organ,dose,density}.bin:
 //       per organ the voxel count, volume, mass and dose the app's table shows.
-//   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix>
-//       Needs a GPU.  The reference's SimulationPipeline (worker<CORRECTION>, R:simulationpipeline.cpp:124-235) runs a
+//   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix> [CTDIw mGy]
+//       Needs a GPU - or the build oracle/_ref/opendxmc_ref_cpu, which links the CPU test double of the context-level
+//       C ABI (oracle/cpu_double.cpp, backed by the oracle) ahead of the library and runs anywhere.  The reference's SimulationPipeline (worker<CORRECTION>, R:simulationpipeline.cpp:124-235) runs a
 //       CT sequential beam on that cylinder; writes <prefix>.json (geometry, units) and raw little-endian arrays
 //       <prefix>.{density,material,dose,variance,count}.bin for the Python side to rebuild the same world and compare.
 #include <beamactorcontainer.hpp>
@@ -514,12 +515,13 @@ static void writeRaw(const std::string& path, const std::vector<T>& v)
     f.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
 }
 
-static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix)
+static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix, double ctdiw)
 {
     auto vol = makeCylinder(0.5, 64, 32);
     CTSequentialBeam seq({ 0, 0, 0 }, { 0, 0, 1 }, { { 13, 9.0 } });
     seq.setStepAngleDeg(10.0);
     seq.setNumberOfParticlesPerExposure(perExposure);
+    seq.setCTDIw(ctdiw);
     auto beam = std::make_shared<Beam>(seq);
     auto actor = std::make_shared<BeamActorContainer>(beam);
 
@@ -552,7 +554,7 @@ static int runMode(int mode, bool deleteAir, unsigned long long perExposure, con
     std::ofstream j(prefix + ".json");
     j << "{\"dim\": [" << d.dimensions()[0] << ", " << d.dimensions()[1] << ", " << d.dimensions()[2] << "], \"spacing\": [" << d.spacing()[0] << ", "
       << d.spacing()[1] << ", " << d.spacing()[2] << "], \"mode\": " << mode << ", \"delete_air\": " << (deleteAir ? 1 : 0)
-      << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << seq.numberOfExposures() << ", \"dose_units\": \""
+      << ", \"ctdiw\": " << ctdiw << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << seq.numberOfExposures() << ", \"dose_units\": \""
       << d.units(DataContainer::ImageType::Dose) << "\"}\n";
     return 0;
 }
@@ -573,7 +575,7 @@ int main(int argc, char** argv)
     if (what == "icrp" && argc >= 9)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
-        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5]);
-    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix>\n");
+        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0);
+    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [CTDIw]\n");
     return 1;
 }

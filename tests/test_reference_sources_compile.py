@@ -16,7 +16,8 @@ oracle/_ref/opendxmc_ref, driver oracle/ref_driver.cpp; Qt / VTK replaced by tes
     basepipeline.cpp
 
 The host-side parts are then RUN here (no GPU) and their numbers compared with the Python mirror (opendxmc_b200/api.py)
-that the GPU tests and bench.py use.  Reads /root/reference, so it only runs where the reference tree is mounted."""
+that the GPU tests and bench.py use; the simulation pipeline itself runs end to end over a CPU test double of the
+context-level C ABI (oracle/cpu_double.cpp).  Reads /root/reference, so it only runs where the reference tree is mounted."""
 import json
 import math
 import os
@@ -496,3 +497,43 @@ def test_reference_bowtie_reader_matches_the_python_reader(dx, ref_rows):
         assert np.array_equal(np.array(f["data"]), np.stack([b.angle, b.weight], axis=1)), name
         assert np.array_equal(packaged[name].angle, b.angle) and np.array_equal(packaged[name].weight, b.weight), name
         assert [b(0.05 * k) for k in range(10)] == pytest.approx(f["weights"], rel=1e-13), name
+
+
+@pytest.mark.parametrize("mode,delete_air,ctdiw", [(1, 1, 1.0), (1, 0, 1.0), (0, 1, 0.004), (2, 1, 1.0)])
+def test_reference_simulation_pipeline_end_to_end_on_the_cpu_double(dx, orc, ref_rows, tmp_path, mode, delete_air, ctdiw):
+    """OpenDXMC's own SimulationPipeline - worker<CORRECTION>() with its World / AAVoxelGrid / Material / Transport calls and
+    its post-processing (air mask, uGy rule; R:src/libopendxmc/simulationpipeline.cpp:124-235) - compiled unmodified, runs
+    end to end on a CT sequential beam over the reference's own PMMA cylinder.  oracle/_ref/opendxmc_ref_cpu links a CPU
+    test double of the nine context-level dxb_* calls (oracle/cpu_double.cpp -> the oracle) ahead of the library, so no
+    GPU is needed; the Python mirror + oracle + orc_postprocess on the same inputs must give the same result, which
+    pins the C++ shims' plumbing (materials, grid, beam descriptor) and the post-processing the GPU path is tested against."""
+    import ctypes as C
+    from opendxmc_b200 import _capi as K
+    prefix = str(tmp_path / "ref")
+    env = dict(os.environ, DXB_DOUBLE_CALIB="360000")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref_cpu"), "run", str(mode), str(delete_air), "1500", prefix, repr(ctdiw)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    meta = json.load(open(prefix + ".json"))
+    n = int(np.prod(meta["dim"]))
+    dens = np.fromfile(prefix + ".density.bin", dtype=np.float64)
+    mat = np.fromfile(prefix + ".material.bin", dtype=np.uint8)
+    ref = [np.fromfile(prefix + f".{k}.bin", dtype=np.float64) for k in ("dose", "variance", "count")]
+    assert dens.size == mat.size == n and meta["exposures"] == 36
+    names = ("Air, Dry (near sea level)", "Polymethyl Methacralate (Lucite, Perspex)")
+    mats = [dx.Material.byWeight(dx.NISTMaterials.Composition(nm)) for nm in names]
+    ow = orc.OracleWorld(meta["dim"], meta["spacing"], dens, mat, mats)
+    beam = dx.CTSequentialBeam((0, 0, 0), (0, 0, 1), {13: 9.0})
+    beam.setStepAngleDeg(10.0)
+    beam.setNumberOfParticlesPerExposure(1500)
+    beam.setCTDIw(ctdiw)
+    d, v, c = ow.transport(beam, mode, True, 0x0DDC0FFEE, 360000)[:3]
+    dd, vv, cc = d.copy(), v.copy(), c.astype(np.float64)
+    micro = orc.load().orc_postprocess(dd.ctypes.data_as(K.c_double_p), vv.ctypes.data_as(K.c_double_p), cc.ctypes.data_as(K.c_double_p),
+                                       mat.ctypes.data_as(K.c_u8_p), n, delete_air)
+    assert meta["dose_units"] == ("uGy" if micro else "mGy")
+    assert (meta["dose_units"] == "uGy") == (ctdiw < 0.1)          # the uGy rule fires for the weak beam
+    assert np.array_equal(cc, ref[2]) and cc.sum() > 10000
+    assert np.allclose(dd, ref[0], rtol=1e-12, atol=0) and np.allclose(vv, ref[1], rtol=1e-12, atol=0)   # thread order: last bits only
+    air = mat == 0
+    assert (ref[0][air].sum() == 0) == bool(delete_air) and ref[0][~air].sum() > 0
