@@ -31,7 +31,7 @@
 //   opendxmc_ref dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs>
 //       CPU only.  DoseTablePipeline::updateImageData (R:dosetablepipeline.cpp:36-95) on <prefix>.{organ,dose,density}.bin:
 //       per organ the voxel count, volume, mass and dose the app's table shows.
-//   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix> [CTDIw mGy]
+//   opendxmc_ref run <mode 0|1|2> <delete_air 0|1> <histories per exposure> <out prefix> [level] [sequential|spiral|dual|dx|cbct|pencil]
 //       Needs a GPU - or the build oracle/_ref/opendxmc_ref_cpu, which links the CPU test double of the context-level
 //       C ABI (oracle/cpu_double.cpp, backed by the oracle) ahead of the library and runs anywhere.  The reference's SimulationPipeline (worker<CORRECTION>, R:simulationpipeline.cpp:124-235) runs a
 //       CT sequential beam on that cylinder; writes <prefix>.json (geometry, units) and raw little-endian arrays
@@ -515,14 +515,101 @@ static void writeRaw(const std::string& path, const std::vector<T>& v)
     f.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
 }
 
-static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix, double ctdiw)
+// the beam of `run`: one of six kinds with non-default settings (mirrored in tests/test_reference_sources_compile.py)
+static std::shared_ptr<Beam> makeRunBeam(const std::string& kind, unsigned long long perExposure, double level, const std::shared_ptr<DataContainer>& vol,
+    unsigned long long& exposures)
+{
+    std::shared_ptr<Beam> beam;
+    if (kind == "sequential") {
+        CTSequentialBeam b({ 0, 0, 0 }, { 0, 0, 1 }, { { 13, 9.0 } });
+        b.setStepAngleDeg(10.0);
+        b.setCTDIw(level);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    } else if (kind == "spiral") {
+        CTSpiralBeam b({ 0, 0, -6 }, { 0, 0, 6 }, { { 13, 7.0 }, { 29, 0.05 } });
+        b.setStepAngleDeg(15.0);
+        b.setPitch(1.2);
+        b.setCollimation(2.4);
+        b.setScanFieldOfView(40.0);
+        b.setStartAngleDeg(30.0);
+        b.setTubeVoltage(100.0);
+        b.setCTDIvol(level);
+        b.setBowtieFilter(BowtieFilter({ { 0.0, 1.0 }, { 0.1, 0.8 }, { 0.2, 0.5 }, { 0.3, 0.25 }, { 0.39, 0.1 } }));
+        b.setAECFilter(vol->calculateAECfilterFromWaterEquivalentDiameter(true));
+        auto& o = b.organAECFilter();
+        o.setUseFilter(true);
+        o.setStartAngleDeg(300.0);
+        o.setStopAngleDeg(60.0);
+        o.setRampAngleDeg(25.0);
+        o.setLowWeightFactor(0.4);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    } else if (kind == "dual") {
+        CTSpiralDualEnergyBeam b({ 0, 0, -5 }, { 0, 0, 5 }, { { 13, 9.0 } });
+        b.setStepAngleDeg(20.0);
+        b.setPitch(2.0);
+        b.setCollimation(3.0);
+        b.setTubeAVoltage(80.0);
+        b.setTubeBVoltage(140.0);
+        b.addTubeBFiltrationMaterial(50, 0.4);
+        b.setRelativeMasTubeB(0.6);
+        b.setTubeBoffsetAngleDeg(95.0);
+        b.setScanFieldOfViewB(33.0);
+        b.setCTDIvol(level);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    } else if (kind == "dx") {
+        DXBeam b({ { 13, 2.0 }, { 29, 0.1 } });
+        b.setRotationCenter({ 0, 0, 1 });
+        b.setSourcePatientDistance(60.0);
+        b.setSourceDetectorDistance(110.0);
+        b.setCollimation({ 20.0, 12.0 });
+        b.setPrimaryAngleDeg(25.0);
+        b.setSecondaryAngleDeg(-10.0);
+        b.setTubeVoltage(80.0);
+        b.setDAPvalue(level);
+        b.setNumberOfExposures(12);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    } else if (kind == "cbct") {
+        CBCTBeam b({ 0, 0, 0.5 }, { 0, 0, 1 }, { { 13, 2.5 } });
+        b.setSourceDetectorDistance(90.0);
+        b.setStartAngleDeg(10.0);
+        b.setStopAngleDeg(250.0);
+        b.setStepAngleDeg(12.0);
+        b.setCollimationHalfAnglesDeg(8.0, 5.0);
+        b.setDAPvalue(level);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    } else if (kind == "pencil") {
+        PencilBeam b;
+        b.setPosition({ 0.3, -30.0, 0.2 });
+        b.setDirection({ 0, 1, 0 });
+        b.setEnergy(70.0);
+        b.setAirKerma(level);
+        b.setNumberOfExposures(10);
+        b.setNumberOfParticlesPerExposure(perExposure);
+        exposures = b.numberOfExposures();
+        beam = std::make_shared<Beam>(b);
+    }
+    return beam;
+}
+
+static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix, double ctdiw, const std::string& kind)
 {
     auto vol = makeCylinder(0.5, 64, 32);
-    CTSequentialBeam seq({ 0, 0, 0 }, { 0, 0, 1 }, { { 13, 9.0 } });
-    seq.setStepAngleDeg(10.0);
-    seq.setNumberOfParticlesPerExposure(perExposure);
-    seq.setCTDIw(ctdiw);
-    auto beam = std::make_shared<Beam>(seq);
+    unsigned long long nExposures = 0;
+    auto beam = makeRunBeam(kind, perExposure, ctdiw, vol, nExposures);
+    if (!beam) {
+        std::fprintf(stderr, "ref_driver: unknown beam kind %s\n", kind.c_str());
+        return 9;
+    }
     auto actor = std::make_shared<BeamActorContainer>(beam);
 
     SimulationPipeline sim;
@@ -554,7 +641,7 @@ static int runMode(int mode, bool deleteAir, unsigned long long perExposure, con
     std::ofstream j(prefix + ".json");
     j << "{\"dim\": [" << d.dimensions()[0] << ", " << d.dimensions()[1] << ", " << d.dimensions()[2] << "], \"spacing\": [" << d.spacing()[0] << ", "
       << d.spacing()[1] << ", " << d.spacing()[2] << "], \"mode\": " << mode << ", \"delete_air\": " << (deleteAir ? 1 : 0)
-      << ", \"ctdiw\": " << ctdiw << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << seq.numberOfExposures() << ", \"dose_units\": \""
+      << ", \"ctdiw\": " << ctdiw << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << nExposures << ", \"beam\": \"" << kind << "\", \"dose_units\": \""
       << d.units(DataContainer::ImageType::Dose) << "\"}\n";
     return 0;
 }
@@ -575,7 +662,7 @@ int main(int argc, char** argv)
     if (what == "icrp" && argc >= 9)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
-        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0);
-    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [CTDIw]\n");
+        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0, argc > 7 ? argv[7] : "sequential");
+    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [level] [beam kind]\n");
     return 1;
 }
