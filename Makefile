@@ -8,32 +8,27 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -ftz=true -prec-div=fals
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
-OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o build/exchange.o
 
-all: $(LIB) oracle shim ref
+all: $(LIB) oracle ref
 
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
-build/%.o: $(CSRC)/%.cpp $(CSRC)/physics.hpp $(CSRC)/internal.hpp include/dxb.h Makefile
+CSRC_HDRS := $(wildcard $(CSRC)/*.hpp $(CSRC)/*.cuh)
+
+build/%.o: $(CSRC)/%.cpp $(CSRC_HDRS) include/dxb.h Makefile
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/physics.hpp $(CSRC)/internal.hpp $(CSRC)/device_types.cuh $(CSRC)/transport_common.cuh $(CSRC)/kernels.hpp include/dxb.h Makefile
+build/%.o: $(CSRC)/%.cu $(CSRC_HDRS) include/dxb.h Makefile
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h Makefile
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -shared -pthread -o $@ oracle/oracle.cpp
-
-# the reference's driver (simulationpipeline.cpp worker<>) retyped against the C++ shim headers in include/dxmc/
-shim: build/opendxmc_worker
-SHIM_HDRS := $(wildcard include/dxmc/*.hpp include/dxmc/*/*.hpp include/dxmc/*/*/*.hpp)
-build/opendxmc_worker: examples/opendxmc_worker.cpp $(SHIM_HDRS) include/dxb.h $(LIB)
-	@mkdir -p build
-	$(CXX) -std=c++20 -O2 -Wall -Iinclude $< -o $@ -L$(LIBDIR) -ldxmc_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 # OpenDXMC's own translation units for this boundary, compiled where they lie (only where the reference tree is mounted)
 ref: $(LIB)
@@ -42,4 +37,4 @@ ref: $(LIB)
 clean:
 	rm -rf build $(LIB) oracle/liboracle.so oracle/_ref
 
-.PHONY: all oracle shim ref clean
+.PHONY: all oracle ref clean

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DXB_ABI_VERSION 1
+#define DXB_ABI_VERSION 2
 
 typedef enum dxb_status {
     DXB_OK = 0,
@@ -127,6 +127,12 @@ typedef struct dxb_material_tables {
     uint32_t nodes_per_octave_e, nodes_per_octave_x;
 } dxb_material_tables;
 int dxb_material_tables_get(const dxb_material*, dxb_material_tables* out);
+/* The reverse direction - the drop-in route for externally built physics data (DXMClib ships EPICS2014-derived tables,
+ * R:src/app/CMakeLists.txt:38 `dxmclib_add_physics_list`): a material made of caller-supplied tables on the library's
+ * grids (geometry as returned by dxb_material_tables_get; DXB_EINVAL otherwise, DXB_EMATERIAL for negative / non-finite
+ * values or a non-monotone ff_cdf).  The arrays are copied; host lookups, the device tables and the majorant follow
+ * them, nothing is recomputed from the built-in atom model.  incoh_kn may be NULL (then = incoh). */
+int dxb_material_from_tables(dxb_material** out, const dxb_material_tables* tables);
 /* library-wide table geometry */
 uint32_t dxb_table_n_energy(void);
 double   dxb_table_e_min(void);
@@ -269,7 +275,14 @@ int  dxb_progress_message(const dxb_progress*, char* buf, int cap);
 /* ====================================================================== */
 typedef struct dxb_ctx dxb_ctx;
 
-/* cuda_devices == NULL && n_devices == 0: use the current device. */
+/* cuda_devices == NULL && n_devices == 0: use the current device.
+ * Several devices (one process drives them all, like the reference's single worker,
+ * R:src/libopendxmc/simulationpipeline.cpp:161-167): the histories of every beam are sharded over the devices and the
+ * library exchanges the tallies itself - dxb_set_grid uploads one slab of the caller's arrays per device and
+ * all-gathers the packed voxels over NVLink, the per-beam tallies are double-buffered, every device pulls its voxel slab
+ * of the peers' tallies with the copy engines underneath the NEXT beam's transport kernels and converts it to dose, the
+ * dose score stays distributed and is read out by all devices concurrently (opendxmc_b200/csrc/exchange.cu).  Same
+ * C ABI, same results (integer tallies: bitwise identical for any device count). */
 int  dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices);
 void dxb_destroy(dxb_ctx*);
 const char* dxb_last_error(const dxb_ctx*); /* text of the last failure on this context */
@@ -296,7 +309,16 @@ int dxb_set_grid(dxb_ctx*, const uint64_t dim[3], const double spacing_cm[3],
 int dxb_set_grid_center(dxb_ctx*, const double center_cm[3]); /* default origin */
 
 /* Transport knobs */
-int dxb_set_seed(dxb_ctx*, uint64_t seed);                    /* Philox key; default 0x0DDC0FFEE */
+/* Philox keys.  dxb_set_seed sets the BASE key (default 0x0DDC0FFEE) and restarts the context's beam counter; the
+ * k-th dxb_run / dxb_run_transport after it runs on key  base + k * DXB_BEAM_KEY_STRIDE  (k = 0: the base key itself), so
+ * that the beams of one job (R:src/libopendxmc/simulationpipeline.cpp:161-167 calls transport() once per beam) draw
+ * independent streams; the nested CTDI calibration run of a beam uses  beam key ^ DXB_CALIBRATION_KEY_XOR.  Every rank
+ * of a sharded job counts the same beams, so results stay independent of the GPU count.  dxb_last_beam_key returns
+ * the key of the last beam (what a test hands to the CPU oracle). */
+#define DXB_BEAM_KEY_STRIDE 0x9E3779B97F4A7C15ull
+#define DXB_CALIBRATION_KEY_XOR 0x4354444900000000ull /* "CTDI" in the high word */
+int dxb_set_seed(dxb_ctx*, uint64_t seed);
+uint64_t dxb_last_beam_key(const dxb_ctx*);
 int dxb_set_history_range(dxb_ctx*, uint64_t rank, uint64_t world); /* this context runs block `rank` of `world` of every exposure (multi-process sharding) */
 /* the sharding rule itself (host arithmetic, no device needed): histories are dealt to shards in blocks of
  * DXB_SHARD_BLOCK consecutive ids, round-robin.  dxb_shard_local_count = local indices owned by `rank` (padded to
@@ -341,6 +363,29 @@ int dxb_set_tally_storage(dxb_ctx*, void* device_ptr, uint64_t n_words);
 int dxb_finish_beam_sharded(dxb_ctx*, const dxb_beam_desc*, int physics_mode, int use_beam_calibration,
                             const void* multicast_tally, const void* const* peer_tallies, int n_peers,
                             uint64_t voxel_begin, uint64_t voxel_end, double* factor_out);
+/* The library-managed exchange for ONE PROCESS PER GPU (torchrun): the same pipelined exchange a multi-device context
+ * runs, with the peers' tally buffers mapped through CUDA IPC instead of living in the same process.
+ *   dxb_exchange_export  - after dxb_set_grid*: allocates the second tally buffer and writes DXB_EXCHANGE_HANDLE_BYTES of
+ *                          opaque handle data; the caller all-gathers them over the ranks (any transport: they are bytes);
+ *   dxb_exchange_import  - maps every peer's buffers, sets the history shard (rank, world) and turns the context into an
+ *                          exchanging one: dxb_finish_beam then enqueues (a) the clear of the previous beam's buffer,
+ *                          (b) the copy-engine pulls of this rank's voxel slab from every peer, (c) slab reduce -> dose,
+ *                          and returns; dxb_get_dose_range / dxb_flush wait for it.  Per beam the caller runs
+ *                              dxb_run_transport;  barrier over the ranks;  dxb_finish_beam
+ *                          (the barrier is the only synchronisation the library cannot do itself across processes).
+ *   dxb_flush            - waits until every enqueued transport / exchange of the context has completed.
+ *   dxb_exchange_times   - device time of the last flushed exchange on device 0: {pulls, slab reduce -> dose, clear} [ms]. */
+#define DXB_EXCHANGE_HANDLE_BYTES 128
+int dxb_exchange_export(dxb_ctx*, void* handles);
+int dxb_exchange_import(dxb_ctx*, uint64_t rank, uint64_t world, const void* all_handles /* world x DXB_EXCHANGE_HANDLE_BYTES */);
+int dxb_exchange_close(dxb_ctx*); /* unmaps the peers' buffers (after a flush and a barrier, before any rank destroys its context) */
+int dxb_flush(dxb_ctx*);
+int dxb_exchange_times(const dxb_ctx*, double out_ms[3]);
+/* Device-side stopwatch over ALL devices and streams of the context (bench.py): begin flushes and records a CUDA event
+ * on every device, end records after everything enqueued since and returns the largest elapsed time. */
+int dxb_timer_begin(dxb_ctx*);
+int dxb_timer_end(dxb_ctx*, double* ms_max);
+
 /* device arrays of the accumulated dose score of device 0: f64 dose [mGy], f64 variance, u64 events, n_voxels each */
 int dxb_dose_buffers(dxb_ctx*, void** dose, void** variance, void** n_events, uint64_t* n_voxels);
 

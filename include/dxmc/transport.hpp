@@ -20,6 +20,11 @@ public:
     template <typename Item, BeamType B>
     bool operator()(World<Item>& world, const B& beam, TransportProgress* progress = nullptr, bool useBeamCalibration = true) const
     {
+        // DXMClib's Transport starts the progress object itself (progress->start(beam.numberOfParticles())):
+        // the driver raises the stop flag at the end of every worker run (R:src/libopendxmc/simulationpipeline.cpp:234) and
+        // reuses its single m_progress for the next startSimulation(), so nothing else ever clears it.
+        if (progress)
+            progress->start(dxb_beam_number_of_particles(&beam.desc()));
         const int rc = dxb_run(world.ctx(), &beam.desc(), Item::lowEnergyCorrection(), useBeamCalibration ? 1 : 0,
             progress ? progress->handle() : nullptr);
         world.item().invalidateDose();

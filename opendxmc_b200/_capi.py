@@ -10,6 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdxmc_b200.so")
 
+DXB_EXCHANGE_HANDLE_BYTES = 128
 DXB_OK, DXB_EINVAL, DXB_EMATERIAL, DXB_ECUDA, DXB_ESTATE, DXB_ECANCELLED, DXB_ENOMEM = range(7)
 STATUS_NAMES = ["DXB_OK", "DXB_EINVAL", "DXB_EMATERIAL", "DXB_ECUDA", "DXB_ESTATE", "DXB_ECANCELLED", "DXB_ENOMEM"]
 
@@ -117,6 +118,7 @@ SIGNATURES = {
     "dxb_material_form_factor": (C.c_double, [VP, C.c_double]),
     "dxb_material_scatter_factor": (C.c_double, [VP, C.c_double]),
     "dxb_material_tables_get": (C.c_int, [VP, C.POINTER(dxb_material_tables)]),
+    "dxb_material_from_tables": (C.c_int, [C.POINTER(VP), C.POINTER(dxb_material_tables)]),
     "dxb_table_n_energy": (C.c_uint32, []),
     "dxb_table_e_min": (C.c_double, []),
     "dxb_table_e_max": (C.c_double, []),
@@ -154,6 +156,14 @@ SIGNATURES = {
     "dxb_set_grid": (C.c_int, [VP, c_u64_p, c_double_p, c_double_p, c_u8_p]),
     "dxb_set_grid_center": (C.c_int, [VP, c_double_p]),
     "dxb_set_seed": (C.c_int, [VP, C.c_uint64]),
+    "dxb_last_beam_key": (C.c_uint64, [VP]),
+    "dxb_exchange_export": (C.c_int, [VP, VP]),
+    "dxb_exchange_import": (C.c_int, [VP, C.c_uint64, C.c_uint64, VP]),
+    "dxb_exchange_close": (C.c_int, [VP]),
+    "dxb_flush": (C.c_int, [VP]),
+    "dxb_exchange_times": (C.c_int, [VP, c_double_p]),
+    "dxb_timer_begin": (C.c_int, [VP]),
+    "dxb_timer_end": (C.c_int, [VP, c_double_p]),
     "dxb_set_history_range": (C.c_int, [VP, C.c_uint64, C.c_uint64]),
     "dxb_shard_local_count": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "dxb_shard_history_id": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),

@@ -85,6 +85,22 @@ class Material:
         rc = _lib().dxb_material_by_chemical_formula(C.byref(h), formula.encode())
         return Material(h) if rc == K.DXB_OK else None
 
+    @staticmethod
+    def fromTables(arrays, like):
+        """a material made of EXTERNALLY supplied tables (include/dxb.h: dxb_material_from_tables - the drop-in route for
+        EPICS-derived data).  `arrays`: dict with photo / incoh / coh / etr [n_energy] and ff_cdf / sf [n_x] on the
+        library grids (see table_arrays()); shells and scalar fields are taken from the material `like`."""
+        t = like.tables()
+        keep = {}
+        for name in ("photo", "incoh", "coh", "etr", "ff_cdf", "sf"):
+            keep[name] = np.ascontiguousarray(arrays[name], dtype=np.float64)
+            setattr(t, name, keep[name].ctypes.data_as(K.c_double_p))
+        t.incoh_kn = t.incoh
+        t.coh_thomson = t.coh
+        h = K.VP()
+        rc = _lib().dxb_material_from_tables(C.byref(h), C.byref(t))
+        return Material(h) if rc == K.DXB_OK else None
+
     def attenuationValues(self, energy):
         out = (C.c_double * 3)()
         _check(_lib().dxb_material_attenuation(self._h, float(energy), out), "attenuationValues")
@@ -1152,7 +1168,15 @@ class World:
         _check(_lib().dxb_set_option(self._ctx, key.encode(), float(value)), "dxb_set_option", self._ctx)
 
     def set_seed(self, seed):
+        """base Philox key; restarts the beam counter (beam k after this call runs on key seed + k * stride, dxb.h)."""
         _check(_lib().dxb_set_seed(self._ctx, int(seed)), "dxb_set_seed", self._ctx)
+
+    def last_beam_key(self):
+        """Philox key of the last beam (what a test hands to the CPU oracle as its seed)."""
+        return int(_lib().dxb_last_beam_key(self._ctx))
+
+    def flush(self):
+        _check(_lib().dxb_flush(self._ctx), "dxb_flush", self._ctx)
 
     def set_history_range(self, rank, world):
         _check(_lib().dxb_set_history_range(self._ctx, int(rank), int(world)), "dxb_set_history_range", self._ctx)
@@ -1235,6 +1259,10 @@ class Transport:
 
     def __call__(self, world, beam, progress=None, useBeamCalibration=True):
         g = world._item
+        if progress is not None:
+            # DXMClib's Transport starts the progress object itself; the reference's driver leaves its stop flag raised
+            # after every run (R:src/libopendxmc/simulationpipeline.cpp:234) and reuses the object
+            progress.reset()
         rc = _lib().dxb_run(world._ctx, C.byref(beam.desc()), g.lowEnergyCorrection, 1 if useBeamCalibration else 0,
                             progress._h if progress is not None else None)
         if rc == K.DXB_ECANCELLED:

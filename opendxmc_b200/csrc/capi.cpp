@@ -107,6 +107,55 @@ int dxb_material_tables_get(const dxb_material* m, dxb_material_tables* t)
     t->nodes_per_octave_x = kXNodesPerOctave;
     return DXB_OK;
 }
+// The drop-in route for externally built physics data (e.g. EPICS2014-derived arrays resampled on the library's grids):
+// the tables are taken as they are, nothing is recomputed from the analytic atom model.
+int dxb_material_from_tables(dxb_material** out, const dxb_material_tables* t)
+{
+    if (!out || !t)
+        return DXB_EINVAL;
+    *out = nullptr;
+    if (t->n_energy != kNEnergy || t->n_x != kNX || t->nodes_per_octave_e != kENodesPerOctave || t->nodes_per_octave_x != kXNodesPerOctave
+        || std::fabs(t->e_min_kev - kEMin) > 1e-12 * kEMin || std::fabs(t->x_min - kXMin) > 1e-12 * kXMin)
+        return DXB_EINVAL; // wrong grid geometry: resample on node(i) = min * 2^(i/P) * (1 + (i%P)/P), see dxb_material_tables
+    if (!t->photo || !t->incoh || !t->coh || !t->etr || !t->ff_cdf || !t->sf || t->n_shells > DXB_MAX_SHELLS)
+        return DXB_EINVAL;
+    auto ok = [](const double* a, uint32_t n) {
+        for (uint32_t i = 0; i < n; ++i)
+            if (!(a[i] >= 0.0) || !std::isfinite(a[i]))
+                return false;
+        return true;
+    };
+    if (!ok(t->photo, kNEnergy) || !ok(t->incoh, kNEnergy) || !ok(t->coh, kNEnergy) || !ok(t->etr, kNEnergy) || !ok(t->ff_cdf, kNX) || !ok(t->sf, kNX))
+        return DXB_EMATERIAL;
+    for (uint32_t i = 1; i < kNX; ++i)
+        if (t->ff_cdf[i] < t->ff_cdf[i - 1])
+            return DXB_EMATERIAL; // a cumulative distribution
+    auto m = std::make_shared<Material>();
+    m->photo.assign(t->photo, t->photo + kNEnergy);
+    m->incoh.assign(t->incoh, t->incoh + kNEnergy);
+    m->coh.assign(t->coh, t->coh + kNEnergy);
+    m->incoh_kn.assign(t->incoh_kn ? t->incoh_kn : t->incoh, (t->incoh_kn ? t->incoh_kn : t->incoh) + kNEnergy);
+    m->etr.assign(t->etr, t->etr + kNEnergy);
+    m->ffCdf.assign(t->ff_cdf, t->ff_cdf + kNX);
+    m->sf.assign(t->sf, t->sf + kNX);
+    // F^2 / Z^2 on the x grid from the slope of the cumulative A(x^2) (only the F(x) getter uses it)
+    m->ff2.assign(kNX, 0.0);
+    for (uint32_t i = 0; i < kNX; ++i) {
+        const uint32_t a = i == 0 ? 0 : i - 1, b = i + 1 < kNX ? i + 1 : i;
+        const double ta = xNode(a) * xNode(a), tb = xNode(b) * xNode(b);
+        m->ff2[i] = tb > ta ? std::max(0.0, (t->ff_cdf[b] - t->ff_cdf[a]) / (tb - ta)) : 0.0;
+    }
+    m->nShells = t->n_shells;
+    for (uint32_t i = 0; i < t->n_shells; ++i)
+        m->shells[i] = t->shells[i];
+    m->restElectronsFraction = t->rest_electrons_fraction;
+    m->restComptonJ0 = t->rest_compton_j0;
+    m->electronsPerGram = t->electrons_per_gram;
+    m->effectiveZ = t->effective_z;
+    m->sumAZ = m->sumAZ2 = 1.0;
+    *out = new dxb_material { m };
+    return DXB_OK;
+}
 uint32_t dxb_table_n_energy(void) { return kNEnergy; }
 double dxb_table_e_min(void) { return kEMin; }
 double dxb_table_e_max(void) { return kEMax; }

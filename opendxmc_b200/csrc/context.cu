@@ -4,9 +4,7 @@
 //   setData/setSpacing/build  -> dxb_set_materials + dxb_set_grid (pack voxels, per-energy majorant)
 //   transport(world, beam, progress, true) -> dxb_run (tallies -> reduce -> calibration -> dose)
 //   doseScored(i).dose()/variance()/numberOfEvents() -> dxb_get_dose
-#include "kernels.hpp"
-#include "physics.hpp"
-#include "internal.hpp"
+#include "context_types.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -27,202 +25,7 @@ static_assert(kDevXPerOctave == static_cast<int>(kXNodesPerOctave), "x grid mism
 static_assert(sizeof(ExposureDev) == 64, "ExposureDev must be 64 bytes");
 static_assert(kShardBlock == DXB_SHARD_BLOCK, "shard block");
 
-struct dxb_progress {
-    std::atomic<uint64_t> done { 0 }, total { 0 };
-    std::atomic<int> stop { 0 };
-    std::atomic<int64_t> start_ns { 0 };
-};
-
-namespace {
-
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    int device = -1;
-    bool owned = true; // false: caller-provided storage (dxb_set_tally_storage), never freed here
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }
-    void release()
-    {
-        if (p && owned) {
-            int cur = 0;
-            cudaGetDevice(&cur);
-            if (device >= 0)
-                cudaSetDevice(device);
-            cudaFree(p);
-            cudaSetDevice(cur);
-        }
-        p = nullptr;
-        n = 0;
-        owned = true;
-    }
-    void adopt(T* ptr, size_t count, int dev)
-    {
-        release();
-        p = ptr;
-        n = count;
-        device = dev;
-        owned = false;
-    }
-    cudaError_t alloc(size_t count, int dev)
-    {
-        if (p && n == count && device == dev)
-            return cudaSuccess;
-        release();
-        device = dev;
-        if (count == 0)
-            return cudaSuccess;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
-        if (e == cudaSuccess)
-            n = count;
-        return e;
-    }
-    template <typename H>
-    cudaError_t upload(const std::vector<H>& h, int dev, cudaStream_t s)
-    {
-        static_assert(sizeof(H) == sizeof(T), "size mismatch");
-        cudaError_t e = alloc(h.size(), dev);
-        if (e != cudaSuccess || h.empty())
-            return e;
-        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    }
-};
-
-// One voxel world resident on one device: grid + the tables of its materials.
-struct World {
-    int device = 0;
-    uint64_t dim[3] = { 0, 0, 0 };
-    double spacing[3] = { 1, 1, 1 };
-    double center[3] = { 0, 0, 0 };
-    size_t nvox = 0;
-    int n_mat = 0;
-    DevBuf<unsigned int> voxels;
-    DevBuf<unsigned long long> tally; // 4 words / voxel
-    DevBuf<float4> att;
-    DevBuf<float> tot, etr, majorant, ffcdf, sf;
-    DevBuf<ShellDev> shells;
-    DevBuf<int> nshells;
-    DevBuf<float> restJ0;
-    DevBuf<unsigned int> maxDensityBits; // [257]: per-material max density bits, [256] = largest material index seen
-    DevBuf<double> stageDensity;         // staging for the caller's f64 density / u8 material (kept between set_grid calls)
-    DevBuf<unsigned char> stageMaterial;
-    bool hasGrid = false, hasTables = false;
-
-    GridDev gridDev() const
-    {
-        GridDev g;
-        g.nx = static_cast<int>(dim[0]);
-        g.ny = static_cast<int>(dim[1]);
-        g.nz = static_cast<int>(dim[2]);
-        const double hx = 0.5 * dim[0] * spacing[0], hy = 0.5 * dim[1] * spacing[1], hz = 0.5 * dim[2] * spacing[2];
-        g.x0 = static_cast<float>(center[0] - hx);
-        g.y0 = static_cast<float>(center[1] - hy);
-        g.z0 = static_cast<float>(center[2] - hz);
-        g.x1 = static_cast<float>(center[0] + hx);
-        g.y1 = static_cast<float>(center[1] + hy);
-        g.z1 = static_cast<float>(center[2] + hz);
-        g.inv_dx = static_cast<float>(1.0 / spacing[0]);
-        g.inv_dy = static_cast<float>(1.0 / spacing[1]);
-        g.inv_dz = static_cast<float>(1.0 / spacing[2]);
-        g.offx = -g.x0 * g.inv_dx;
-        g.offy = -g.y0 * g.inv_dy;
-        g.offz = -g.z0 * g.inv_dz;
-        g.voxels = voxels.p;
-        g.tally = tally.p;
-        return g;
-    }
-    TablesDev tablesDev() const
-    {
-        TablesDev t;
-        t.n_mat = n_mat;
-        t.att = att.p;
-        t.tot = tot.p;
-        t.etr = etr.p;
-        t.majorant = majorant.p;
-        t.ffcdf = ffcdf.p;
-        t.sf = sf.p;
-        t.shells = shells.p;
-        t.n_shells = nshells.p;
-        t.rest_j0 = restJ0.p;
-        return t;
-    }
-};
-
-struct DeviceState {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool ownStream = true;
-    World world;                 // the patient grid
-    std::unique_ptr<World> ctdi; // nested calibration phantom (device 0 only)
-    double ctdiDiameter = 0;
-    DevBuf<double> dose, variance;
-    DevBuf<unsigned long long> events;
-    DevBuf<ExposureDev> exposures;
-    DevBuf<float> specProb[2], bowAngle[2], bowWeight[2];
-    DevBuf<unsigned short> specAlias[2];
-    DevBuf<unsigned long long> counters; // [0] work cursor, [8..12] stats
-    cudaEvent_t evStart = nullptr, evTransport = nullptr, evEnd = nullptr;
-};
-
-struct Options {
-    uint64_t batch = 1ull << 27; // local histories per launch
-    int threads = 256;
-    int blocksPerSm = 0;         // 0: occupancy query
-    int tableInSmem = 1;
-    int slots = 0;               // 0 = one photon per lane in registers (transport.cu, default: fastest);
-                                 // 2/3/4/6 = lane-multiplexed photons in shared memory (transport_mux.cu)
-    int refillThreshold = -1;    // warp phase machine; -1 = the default of the selected kernel
-    int interactThreshold = -1;
-    int rayleighThreshold = -1;
-    int poolSlots = 16;          // > 0: block-pooled kernel (transport_pool.cu, default) with this many slots per lane class;
-                                 // 0: `slots` selects the register kernel (0) or the lane-multiplexed one
-    int smemPadKb = 0;           // experiment: extra dynamic shared memory per block (shrinks L1)
-    int stepPairs = 0;           // pool / mux kernels: step pairs per step phase (0: kernel default, pool 2, mux 1)
-    int poolThreads = 256;       // pool kernel: threads per block (the block shares one photon pool)
-    int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
-    int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
-    int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
-    int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
-    int interactBias = -999;     // -999: kernel default (mux 16: interaction phase when waiting lanes + bias >= stepping lanes;
-                                 // pool 24: stepper warps keep stepping while at least this many lanes can claim a photon)
-};
-
-} // namespace
-
-struct dxb_ctx {
-    std::vector<std::unique_ptr<DeviceState>> devs;
-    std::vector<std::shared_ptr<Material>> materials;
-    uint64_t seed = 0x0DDC0FFEEull;
-    uint64_t rank = 0, world = 1;
-    uint64_t calibHistories = 36000000ull;
-    Options opt;
-    std::string error;
-    dxb_run_stats stats {};
-    float scaleE = 16777216.0f, scaleE2 = 65536.0f; // 2^24, 2^16 fixed-point quanta per keV, keV^2
-    int smCount = 148;
-    bool tallyValid = false;
-};
-
-namespace {
-
-int fail(dxb_ctx* c, int code, const std::string& msg)
-{
-    if (c)
-        c->error = msg;
-    return code;
-}
-
-#define CUDA_TRY(ctx, expr)                                                                        \
-    do {                                                                                           \
-        cudaError_t _e = (expr);                                                                   \
-        if (_e != cudaSuccess) {                                                                   \
-            cudaGetLastError();                                                                    \
-            return fail(ctx, DXB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
-        }                                                                                          \
-    } while (0)
+namespace dxb {
 
 // Vose's alias method (DXMClib RandomDistribution; restated independently in oracle/oracle.cpp)
 void buildAlias(const std::vector<double>& w, std::vector<float>& prob, std::vector<unsigned short>& alias)
@@ -337,19 +140,23 @@ int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing
     }
     w.nvox = n;
     w.hasGrid = false;
+    if (c->ipc && w.tally.p && w.tally.n != n * 4)
+        return fail(c, DXB_ESTATE, "set_grid: the grid size changed while peers map the tally buffers (dxb_exchange_export / _import again)");
     CUDA_TRY(c, w.voxels.alloc(n, w.device));
     CUDA_TRY(c, w.tally.alloc(n * 4, w.device));
     CUDA_TRY(c, w.maxDensityBits.alloc(257, w.device));
-    CUDA_TRY(c, w.stageDensity.alloc(n, w.device));
-    CUDA_TRY(c, w.stageMaterial.alloc(n, w.device));
     const size_t m = end - begin;
+    // staging for the slab of the caller's f64 density / u8 material this device packs (kept between set_grid calls)
+    CUDA_TRY(c, w.stageDensity.alloc(m, w.device));
+    CUDA_TRY(c, w.stageMaterial.alloc(m, w.device));
     CUDA_TRY(c, cudaMemsetAsync(w.maxDensityBits.p, 0, 257 * sizeof(unsigned int), s));
     if (m > 0) {
-        CUDA_TRY(c, cudaMemcpyAsync(w.stageDensity.p + begin, density + begin, m * sizeof(double), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(w.stageMaterial.p + begin, material + begin, m, cudaMemcpyHostToDevice, s));
-        launchPackVoxels(w.stageDensity.p + begin, w.stageMaterial.p + begin, w.voxels.p + begin, m, w.maxDensityBits.p, s);
+        CUDA_TRY(c, cudaMemcpyAsync(w.stageDensity.p, density + begin, m * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(w.stageMaterial.p, material + begin, m, cudaMemcpyHostToDevice, s));
+        launchPackVoxels(w.stageDensity.p, w.stageMaterial.p, w.voxels.p + begin, m, w.maxDensityBits.p, s);
         CUDA_TRY(c, cudaGetLastError());
     }
+    w.cur = 0;
     CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, n * 4 * sizeof(unsigned long long), s));
     return finish ? finishGrid(c, w, s) : DXB_OK;
 }
@@ -408,6 +215,16 @@ int prepareBeam(dxb_ctx* c, const dxb_beam_desc& b, PreparedBeam& out)
                 return fail(c, DXB_EINVAL, "beam spectrum missing");
             if (s.n > 60000)
                 return fail(c, DXB_EINVAL, "spectrum too long");
+            // the device samples E = e0 + (bin + u) * step: the grid must be uniform and ascending (what dxmc::Tube::getEnergy()
+            // produces); an arbitrary energy array would silently be sampled at the wrong energies
+            if (s.n > 1) {
+                const double step = s.energy_kev[1] - s.energy_kev[0];
+                if (!(step > 0))
+                    return fail(c, DXB_EINVAL, "beam spectrum: energies must ascend");
+                for (uint32_t i = 2; i < s.n; ++i)
+                    if (std::fabs((s.energy_kev[i] - s.energy_kev[i - 1]) - step) > 1e-6 * step)
+                        return fail(c, DXB_EINVAL, "beam spectrum: the energy grid must be uniform");
+            }
             out.specN[t] = static_cast<int>(s.n);
             out.specE0[t] = static_cast<float>(s.energy_kev[0]);
             out.specStep[t] = s.n > 1 ? static_cast<float>(s.energy_kev[1] - s.energy_kev[0]) : 0.0f;
@@ -484,8 +301,8 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.n_total = pb.nTotal;
     P.world = static_cast<unsigned int>(world);
     P.rank = static_cast<unsigned int>(rank);
-    P.seed_lo = static_cast<unsigned int>(c->seed);
-    P.seed_hi = static_cast<unsigned int>(c->seed >> 32);
+    P.seed_lo = static_cast<unsigned int>(c->runKey);
+    P.seed_hi = static_cast<unsigned int>(c->runKey >> 32);
     for (unsigned int r = 0; r < 10; ++r) {
         P.round_key[r][0] = P.seed_lo + r * 0x9E3779B9u;
         P.round_key[r][1] = P.seed_hi + r * 0xBB67AE85u;
@@ -628,20 +445,12 @@ void chooseScales(dxb_ctx* c, const PreparedBeam& pb, bool kerma)
 // A PMMA cylinder (diameter = beam.ctdi_diameter, length 15 cm) with five 1.31 cm air holes, voxelised at
 // 0.2 x 0.2 x 0.5 cm; one axial rotation of the same tube/bowtie/collimation; air kerma in the central 10 cm
 // of the holes from a collision estimator; CTDIw = 1/3 centre + 2/3 periphery.
-struct CtdiPhantom {
-    uint64_t dim[3];
-    double spacing[3];
-    std::vector<double> density;
-    std::vector<uint8_t> material; // 0 air, 1 PMMA, 2 measurement air
-    std::vector<int> hole;         // per voxel: -1 or hole id 0..4 (central 10 cm only)
-    std::vector<std::shared_ptr<Material>> mats;
-};
-
 void buildCtdiPhantom(double diameter, CtdiPhantom& ph)
 {
     const double sxy = 0.2, sz = 0.5;
     const int nxy = static_cast<int>(std::ceil((diameter + 4.0) / sxy / 2.0)) * 2;
     const int nz = 30; // 15 cm
+    ph.diameter = diameter;
     ph.dim[0] = ph.dim[1] = nxy;
     ph.dim[2] = nz;
     ph.spacing[0] = ph.spacing[1] = sxy;
@@ -650,6 +459,8 @@ void buildCtdiPhantom(double diameter, CtdiPhantom& ph)
     ph.density.assign(n, 0.0);
     ph.material.assign(n, 0);
     ph.hole.assign(n, -1);
+    for (size_t& v : ph.holeCount)
+        v = 0;
     const double airRho = nistFind("Air, Dry (near sea level)")->density;
     const double pmmaRho = nistFind("Polymethyl Methacralate (Lucite, Perspex)")->density;
     const double R = 0.5 * diameter, rh = 0.655, off = R - 1.0;
@@ -672,7 +483,7 @@ void buildCtdiPhantom(double diameter, CtdiPhantom& ph)
                             ph.material[idx] = 0;
                             if (std::fabs(z) <= 5.0) {
                                 ph.material[idx] = 2;
-                                ph.hole[idx] = h;
+                                ph.hole[idx] = static_cast<signed char>(h);
                             }
                         }
                     }
@@ -680,6 +491,9 @@ void buildCtdiPhantom(double diameter, CtdiPhantom& ph)
             }
         }
     }
+    for (size_t i = 0; i < n; ++i)
+        if (ph.hole[i] >= 0)
+            ++ph.holeCount[ph.hole[i]];
     ph.mats = { Material::byNistName("Air, Dry (near sea level)"), Material::byNistName("Polymethyl Methacralate (Lucite, Perspex)"),
         Material::byNistName("Air, Dry (near sea level)") };
 }
@@ -689,27 +503,43 @@ bool isCtBeam(int type)
     return type == DXB_BEAM_CT_SPIRAL || type == DXB_BEAM_CT_SPIRAL_DUAL || type == DXB_BEAM_CT_SEQUENTIAL;
 }
 
+// The nested run.  The phantom is built once per diameter and stays resident on every device of the context; the
+// histories of the calibration beam are sharded over the devices like those of any beam, each device sums the kerma
+// tallies of the five holes itself (integers), and the host adds five numbers per device.  The run uses its own
+// Philox stream (beam key ^ DXB_CALIBRATION_KEY_XOR).
 int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOut, double* msOut)
 {
-    DeviceState& d = *c->devs[0];
-    CUDA_TRY(c, cudaSetDevice(d.device));
     const double diameter = b.ctdi_diameter > 0 ? b.ctdi_diameter : 32.0;
-    CtdiPhantom ph;
-    buildCtdiPhantom(diameter, ph);
-    if (!d.ctdi || d.ctdiDiameter != diameter) {
-        d.ctdi = std::make_unique<World>();
-        d.ctdi->device = d.device;
-        int rc = uploadTables(c, *d.ctdi, ph.mats, d.stream);
-        if (rc != DXB_OK)
-            return rc;
-        rc = uploadGrid(c, *d.ctdi, ph.dim, ph.spacing, ph.density.data(), ph.material.data(), d.stream, 0,
-            static_cast<size_t>(ph.dim[0]) * ph.dim[1] * ph.dim[2], true);
-        if (rc != DXB_OK)
-            return rc;
-        d.ctdiDiameter = diameter;
+    if (!c->ctdi || c->ctdi->diameter != diameter) {
+        c->ctdi = std::make_unique<CtdiPhantom>();
+        buildCtdiPhantom(diameter, *c->ctdi);
     }
-    World& w = *d.ctdi;
-    CUDA_TRY(c, cudaMemsetAsync(w.tally.p, 0, w.nvox * 4 * sizeof(unsigned long long), d.stream));
+    const CtdiPhantom& ph = *c->ctdi;
+    const size_t nPh = static_cast<size_t>(ph.dim[0]) * ph.dim[1] * ph.dim[2];
+    // an IPC-exchanging context (one process per GPU) runs the whole nested beam itself: it is deterministic, so every
+    // rank derives the same factor without a broadcast
+    const uint64_t nDev = c->devs.size();
+    for (uint64_t i = 0; i < nDev; ++i) {
+        DeviceState& d = *c->devs[i];
+        CUDA_TRY(c, cudaSetDevice(d.device));
+        if (!d.ctdi || d.ctdiDiameter != diameter) {
+            d.ctdi = std::make_unique<World>();
+            d.ctdi->device = d.device;
+            int rc = uploadTables(c, *d.ctdi, ph.mats, d.stream);
+            if (rc != DXB_OK)
+                return rc;
+            const bool ipc = c->ipc;
+            c->ipc = false; // the phantom's tally buffer is never shared
+            rc = uploadGrid(c, *d.ctdi, ph.dim, ph.spacing, ph.density.data(), ph.material.data(), d.stream, 0, nPh, true);
+            c->ipc = ipc;
+            if (rc != DXB_OK)
+                return rc;
+            CUDA_TRY(c, d.ctdiHole.upload(ph.hole, d.device, d.stream));
+            CUDA_TRY(c, d.holeSums.alloc(8, d.device));
+            CUDA_TRY(c, cudaStreamSynchronize(d.stream));
+            d.ctdiDiameter = diameter;
+        }
+    }
 
     // the internal axial beam: same tube(s), bowtie(s), collimation, SDD and FOV; 1 degree steps, no AEC
     dxb_beam_desc cb = b;
@@ -732,36 +562,58 @@ int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOu
     if (rc != DXB_OK)
         return rc;
     const float saveE = c->scaleE, saveE2 = c->scaleE2;
+    const uint64_t saveKey = c->runKey;
     chooseScales(c, pb, true);
-    rc = uploadBeam(c, d, pb);
-    TransportResult tr;
-    if (rc == DXB_OK)
-        rc = runOnDevice(c, d, w, pb, mode, true, 2, 0, 1, nullptr, true, &tr);
-    if (rc == DXB_OK)
-        rc = collectStats(c, d, tr);
+    c->runKey = c->beamKey ^ DXB_CALIBRATION_KEY_XOR;
+    std::vector<TransportResult> tr(nDev);
+    for (uint64_t i = 0; i < nDev && rc == DXB_OK; ++i) {
+        DeviceState& d = *c->devs[i];
+        World& w = *d.ctdi;
+        if (cudaSetDevice(d.device) != cudaSuccess || cudaMemsetAsync(w.tally.p, 0, w.nvox * 4 * sizeof(unsigned long long), d.stream) != cudaSuccess
+            || cudaMemsetAsync(d.holeSums.p, 0, 8 * sizeof(unsigned long long), d.stream) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(c, DXB_ECUDA, "calibration: clearing the phantom tallies failed");
+            break;
+        }
+        rc = uploadBeam(c, d, pb);
+        if (rc == DXB_OK)
+            rc = runOnDevice(c, d, w, pb, mode, true, 2, i, nDev, nullptr, true, &tr[i]);
+        if (rc == DXB_OK) {
+            launchHoleSums(w.tally.p, d.ctdiHole.p, w.nvox, d.holeSums.p, d.stream);
+            if (cudaGetLastError() != cudaSuccess)
+                rc = fail(c, DXB_ECUDA, "calibration: hole sums");
+        }
+    }
+    unsigned long long sums[5] = { 0, 0, 0, 0, 0 };
+    double msMax = 0;
+    for (uint64_t i = 0; i < nDev && rc == DXB_OK; ++i) {
+        DeviceState& d = *c->devs[i];
+        rc = collectStats(c, d, tr[i]);
+        if (rc != DXB_OK)
+            break;
+        unsigned long long h[5];
+        if (cudaMemcpy(h, d.holeSums.p, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(c, DXB_ECUDA, "calibration: reading the hole sums failed");
+            break;
+        }
+        for (int k = 0; k < 5; ++k)
+            sums[k] += h[k];
+        msMax = std::max(msMax, tr[i].ms);
+    }
     const double invE = 1.0 / c->scaleE;
     c->scaleE = saveE;
     c->scaleE2 = saveE2;
+    c->runKey = saveKey;
+    cudaSetDevice(c->devs[0]->device);
     if (rc != DXB_OK)
         return rc;
     if (msOut)
-        *msOut = tr.ms;
-    // read back the kerma tallies of the hole voxels
-    std::vector<unsigned long long> tally(w.nvox * 4);
-    CUDA_TRY(c, cudaMemcpy(tally.data(), w.tally.p, tally.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    double sum[5] = { 0, 0, 0, 0, 0 };
-    size_t cnt[5] = { 0, 0, 0, 0, 0 };
-    for (size_t i = 0; i < w.nvox; ++i) {
-        const int h = ph.hole[i];
-        if (h >= 0) {
-            sum[h] += static_cast<double>(tally[i * 4]) * invE;
-            ++cnt[h];
-        }
-    }
+        *msOut = msMax;
     const double vol = ph.spacing[0] * ph.spacing[1] * ph.spacing[2];
     double kerma[5];
     for (int h = 0; h < 5; ++h)
-        kerma[h] = cnt[h] ? sum[h] / (cnt[h] * vol) : 0.0; // keV/g, mean over the 10 cm chamber length
+        kerma[h] = ph.holeCount[h] ? static_cast<double>(sums[h]) * invE / (static_cast<double>(ph.holeCount[h]) * vol) : 0.0; // keV/g, mean over the 10 cm chamber length
     // CTDI100 = (1/NT) * integral_{-5}^{5} K dz = Kmean * 10 cm / collimation
     const double ctdi100c = kerma[0] * 10.0 / b.collimation;
     const double ctdi100p = 0.25 * (kerma[1] + kerma[2] + kerma[3] + kerma[4]) * 10.0 / b.collimation;
@@ -792,7 +644,7 @@ int initDevice(dxb_ctx* c, DeviceState& d)
     return DXB_OK;
 }
 
-} // namespace
+} // namespace dxb
 
 // ============================================================================ C ABI
 extern "C" {
@@ -830,6 +682,10 @@ int dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices)
             devices.push_back(cuda_devices[i]);
         }
     }
+    for (size_t i = 0; i < devices.size(); ++i)
+        for (size_t j = 0; j < i; ++j)
+            if (devices[i] == devices[j])
+                return DXB_EINVAL;
     for (int dev : devices) {
         auto d = std::make_unique<DeviceState>();
         d->device = dev;
@@ -840,16 +696,11 @@ int dxb_create(dxb_ctx** out, const int* cuda_devices, int n_devices)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, devices[0]) == cudaSuccess)
         c->smCount = prop.multiProcessorCount;
-    // peer access for the in-process tally reduce
-    for (size_t i = 1; i < c->devs.size(); ++i) {
-        int can = 0;
-        cudaDeviceCanAccessPeer(&can, c->devs[0]->device, c->devs[i]->device);
-        if (can) {
-            cudaSetDevice(c->devs[0]->device);
-            cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[i]->device, 0);
-            if (e != cudaSuccess)
-                cudaGetLastError();
-        }
+    setLaunchSmCount(c->smCount);
+    // several devices: peer access all-to-all, exchange streams and events (exchange.cu)
+    if (c->devs.size() > 1 && mgInit(c.get()) != DXB_OK) {
+        mgDestroy(c.get());
+        return DXB_ECUDA;
     }
     cudaSetDevice(devices[0]);
     *out = c.release();
@@ -860,6 +711,7 @@ void dxb_destroy(dxb_ctx* c)
 {
     if (!c)
         return;
+    mgDestroy(c);
     for (auto& d : c->devs) {
         cudaSetDevice(d->device);
         cudaStreamSynchronize(d->stream);
@@ -910,14 +762,19 @@ int dxb_set_grid(dxb_ctx* c, const uint64_t dim[3], const double spacing_cm[3], 
     for (int i = 0; i < 3; ++i)
         if (!(spacing_cm[i] > 0))
             return fail(c, DXB_EINVAL, "set_grid: spacing must be positive");
-    for (auto& d : c->devs) {
-        CUDA_TRY(c, cudaSetDevice(d->device));
-        int rc = uploadGrid(c, d->world, dim, spacing_cm, density, material, d->stream, 0, n, true);
-        if (rc != DXB_OK)
-            return rc;
-    }
-    // dose score lives on device 0
+    c->tallyValid = false;
+    if (c->devs.size() > 1) // every device uploads its slab; the dose score is distributed the same way (exchange.cu)
+        return mgSetGrid(c, dim, spacing_cm, density, material);
+    int rc = mgFlush(c);
+    if (rc != DXB_OK)
+        return rc;
     DeviceState& d0 = *c->devs[0];
+    CUDA_TRY(c, cudaSetDevice(d0.device));
+    rc = uploadGrid(c, d0.world, dim, spacing_cm, density, material, d0.stream, 0, n, true);
+    if (rc != DXB_OK)
+        return rc;
+    if (c->exchanging && (rc = mgPrepareExchange(c)) != DXB_OK)
+        return rc;
     CUDA_TRY(c, cudaSetDevice(d0.device));
     CUDA_TRY(c, d0.dose.alloc(n, d0.device));
     CUDA_TRY(c, d0.variance.alloc(n, d0.device));
@@ -945,8 +802,13 @@ int dxb_set_grid_sharded(dxb_ctx* c, const uint64_t dim[3], const double spacing
         return fail(c, DXB_EINVAL, "set_grid_sharded: voxel range outside the grid");
     DeviceState& d0 = *c->devs[0];
     CUDA_TRY(c, cudaSetDevice(d0.device));
-    int rc = uploadGrid(c, d0.world, dim, spacing_cm, density, material, d0.stream, voxel_begin, voxel_end, false);
+    int rc = mgFlush(c);
     if (rc != DXB_OK)
+        return rc;
+    rc = uploadGrid(c, d0.world, dim, spacing_cm, density, material, d0.stream, voxel_begin, voxel_end, false);
+    if (rc != DXB_OK)
+        return rc;
+    if (c->exchanging && (rc = mgPrepareExchange(c)) != DXB_OK)
         return rc;
     CUDA_TRY(c, d0.dose.alloc(n, d0.device));
     CUDA_TRY(c, d0.variance.alloc(n, d0.device));
@@ -996,13 +858,20 @@ int dxb_clear_dose(dxb_ctx* c)
 {
     if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
         return fail(c, DXB_ESTATE, "clear_dose: no grid");
-    DeviceState& d0 = *c->devs[0];
-    const size_t n = d0.world.nvox;
-    CUDA_TRY(c, cudaSetDevice(d0.device));
-    CUDA_TRY(c, cudaMemsetAsync(d0.dose.p, 0, n * sizeof(double), d0.stream));
-    CUDA_TRY(c, cudaMemsetAsync(d0.variance.p, 0, n * sizeof(double), d0.stream));
-    CUDA_TRY(c, cudaMemsetAsync(d0.events.p, 0, n * sizeof(unsigned long long), d0.stream));
-    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    int rc = mgFlush(c);
+    if (rc != DXB_OK)
+        return rc;
+    const size_t n = c->devs[0]->world.nvox;
+    for (auto& d : c->devs) {
+        if (!d->dose.p)
+            continue;
+        CUDA_TRY(c, cudaSetDevice(d->device));
+        CUDA_TRY(c, cudaMemsetAsync(d->dose.p, 0, n * sizeof(double), d->stream));
+        CUDA_TRY(c, cudaMemsetAsync(d->variance.p, 0, n * sizeof(double), d->stream));
+        CUDA_TRY(c, cudaMemsetAsync(d->events.p, 0, n * sizeof(unsigned long long), d->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(d->stream));
+    }
+    CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
     return DXB_OK;
 }
 
@@ -1011,8 +880,11 @@ int dxb_set_seed(dxb_ctx* c, uint64_t seed)
     if (!c)
         return DXB_EINVAL;
     c->seed = seed;
+    c->beamCounter = 0; // the next beam runs on key `seed` itself
     return DXB_OK;
 }
+
+uint64_t dxb_last_beam_key(const dxb_ctx* c) { return c ? c->beamKey : 0; }
 
 int dxb_set_history_range(dxb_ctx* c, uint64_t rank, uint64_t world)
 {
@@ -1144,21 +1016,42 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
     }
     c->stats = dxb_run_stats {};
     c->tallyValid = false;
+    // Every beam gets its own Philox key (the reference's driver calls transport() once per beam on one world,
+    // R:src/libopendxmc/simulationpipeline.cpp:161-167: identical streams would make identical beams add no information
+    // while their variances are summed as if independent).  All ranks / devices of a job count the same beams, so the
+    // key - and with it the result - stays independent of the GPU count.
+    c->beamKey = c->seed + c->beamCounter * DXB_BEAM_KEY_STRIDE;
+    c->runKey = c->beamKey;
+    ++c->beamCounter;
     std::vector<TransportResult> results(nDev);
     // clear tallies, upload the beam and launch on every device (launches are asynchronous, so the devices run concurrently)
     for (uint64_t i = 0; i < nDev; ++i) {
         DeviceState& d = *c->devs[i];
         CUDA_TRY(c, cudaSetDevice(d.device));
-        CUDA_TRY(c, cudaMemsetAsync(d.world.tally.p, 0, d.world.nvox * 4 * sizeof(unsigned long long), d.stream));
+        if (c->exchanging) {
+            // double-buffered tallies: the buffer of this beam was cleared by the exchange of the beam before the last one
+            if (!d.needsClear[d.world.cur])
+                CUDA_TRY(c, cudaStreamWaitEvent(d.stream, d.evBufReady[d.world.cur], 0));
+            else // the last beam was never finished (its tallies are dropped, as without an exchange)
+                CUDA_TRY(c, cudaMemsetAsync(d.world.tallyCur(), 0, d.world.nvox * 4 * sizeof(unsigned long long), d.stream));
+        } else {
+            CUDA_TRY(c, cudaMemsetAsync(d.world.tallyCur(), 0, d.world.nvox * 4 * sizeof(unsigned long long), d.stream));
+        }
         rc = uploadBeam(c, d, pb);
         if (rc != DXB_OK)
             return rc;
     }
+    c->exchanged = false;
     for (uint64_t i = 0; i < nDev; ++i) {
         rc = runOnDevice(c, *c->devs[i], c->devs[i]->world, pb, physics_mode, false, -1, c->rank * nDev + i, effWorld, progress,
             nDev > 1, &results[i]);
         if (rc != DXB_OK)
             return rc;
+        if (c->exchanging) {
+            DeviceState& d = *c->devs[i];
+            d.needsClear[d.world.cur] = true; // scored into, not yet exchanged
+            CUDA_TRY(c, cudaEventRecord(d.evTransportDone[d.world.cur], d.stream));
+        }
     }
     bool cancelled = false;
     double msMax = 0;
@@ -1180,18 +1073,15 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         progress->done.store(progress->total.load());
     if (cancelled)
         return fail(c, DXB_ECANCELLED, "cancelled");
-    // in-process reduce: device 0 pulls the peers' tallies over NVLink peer memory
-    if (nDev > 1) {
-        DeviceState& d0 = *c->devs[0];
-        CUDA_TRY(c, cudaSetDevice(d0.device));
-        std::vector<const unsigned long long*> peers;
-        for (uint64_t i = 1; i < nDev; ++i)
-            peers.push_back(c->devs[i]->world.tally.p);
-        DevBuf<const unsigned long long*> dPeers;
-        CUDA_TRY(c, dPeers.upload(peers, d0.device, d0.stream));
-        launchPeerReduce(d0.world.tally.p, dPeers.p, static_cast<int>(peers.size()), d0.world.nvox * 4, d0.stream);
-        CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    if (c->ipc) {
+        // one process per GPU: before the caller's barrier tells the peers that they may clear the buffer of the PREVIOUS
+        // beam, this rank's pulls from it must have finished (they ran under the transport kernels just awaited)
+        DeviceState& d = *c->devs[0];
+        const int prev = d.world.cur ^ 1;
+        if (d.pullsPending[prev]) {
+            CUDA_TRY(c, cudaEventSynchronize(d.evPullsDone[prev]));
+            d.pullsPending[prev] = false;
+        }
     }
     c->tallyValid = true;
     return DXB_OK;
@@ -1202,7 +1092,7 @@ int dxb_finish_beam(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int
     if (!c || !beam)
         return DXB_EINVAL;
     if (!c->tallyValid)
-        return fail(c, DXB_ESTATE, "finish_beam: no tallies (call dxb_run_transport first)");
+        return fail(c, DXB_ESTATE, "finish_beam: no tallies (call dxb_run_transport first; a beam is finished once)");
     DeviceState& d0 = *c->devs[0];
     double factor = kKeVperGramToMilliGray;
     double calibMs = 0;
@@ -1216,13 +1106,23 @@ int dxb_finish_beam(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int
         }
     }
     CUDA_TRY(c, cudaSetDevice(d0.device));
-    World& w = d0.world;
-    const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
-    launchEnergyToDose(w.tally.p, w.voxels.p, d0.dose.p, d0.variance.p, d0.events.p, w.nvox, 1.0 / c->scaleE, 1.0 / c->scaleE2,
-        factor, vol, d0.stream);
-    CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));
-    CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    if (c->exchanging) {
+        // several participants: the exchange (peer pulls, slab reduce -> dose, clear) is enqueued on the exchange streams and
+        // runs underneath the next beam's transport; read-out calls wait for it (exchange.cu)
+        const int rc = mgEnqueueExchange(c, factor);
+        if (rc != DXB_OK)
+            return rc;
+    } else {
+        World& w = d0.world;
+        const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
+        launchEnergyToDose(w.tallyCur(), w.voxels.p, d0.dose.p, d0.variance.p, d0.events.p, w.nvox, 1.0 / c->scaleE, 1.0 / c->scaleE2,
+            factor, vol, d0.stream);
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));
+        CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    }
+    // a second finish of the same beam would add its dose, variance and events once more
+    c->tallyValid = false;
     c->stats.calibration_factor = factor;
     c->stats.calibration_ms = calibMs;
     if (factor_out)
@@ -1234,8 +1134,8 @@ int dxb_set_tally_storage(dxb_ctx* c, void* device_ptr, uint64_t n_words)
 {
     if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
         return fail(c, DXB_ESTATE, "set_tally_storage: set the grid first");
-    if (c->devs.size() != 1)
-        return fail(c, DXB_ESTATE, "set_tally_storage: single-device contexts only (one process per GPU)");
+    if (c->devs.size() != 1 || c->exchanging)
+        return fail(c, DXB_ESTATE, "set_tally_storage: single-device contexts without a library-managed exchange only");
     DeviceState& d0 = *c->devs[0];
     World& w = d0.world;
     CUDA_TRY(c, cudaSetDevice(d0.device));
@@ -1265,8 +1165,8 @@ int dxb_finish_beam_sharded(dxb_ctx* c, const dxb_beam_desc* beam, int physics_m
         return DXB_EINVAL;
     if (!c->tallyValid)
         return fail(c, DXB_ESTATE, "finish_beam_sharded: no tallies (call dxb_run_transport first)");
-    if (c->devs.size() != 1)
-        return fail(c, DXB_ESTATE, "finish_beam_sharded: single-device contexts only (one process per GPU)");
+    if (c->devs.size() != 1 || c->exchanging)
+        return fail(c, DXB_ESTATE, "finish_beam_sharded: single-device contexts without a library-managed exchange only");
     DeviceState& d0 = *c->devs[0];
     World& w = d0.world;
     if (voxel_begin > voxel_end || voxel_end > w.nvox || n_peers < 0 || n_peers > 63 || (n_peers > 0 && !peer_tallies && !multicast_tally))
@@ -1300,6 +1200,7 @@ int dxb_finish_beam_sharded(dxb_ctx* c, const dxb_beam_desc* beam, int physics_m
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(d0.evEnd, d0.stream));
     CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    c->tallyValid = false; // a beam is finished once
     c->stats.calibration_factor = factor;
     c->stats.calibration_ms = calibMs;
     if (factor_out)
@@ -1311,6 +1212,9 @@ int dxb_dose_buffers(dxb_ctx* c, void** dose, void** variance, void** n_events, 
 {
     if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
         return fail(c, DXB_ESTATE, "dose_buffers: no grid");
+    const int grc = mgGatherDose(c);
+    if (grc != DXB_OK)
+        return grc;
     DeviceState& d0 = *c->devs[0];
     if (dose)
         *dose = d0.dose.p;
@@ -1330,7 +1234,7 @@ int dxb_run(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int use_bea
     if (rc != DXB_OK)
         return rc;
     if (c->world > 1)
-        return fail(c, DXB_ESTATE, "dxb_run on a sharded context: use run_transport + external reduce + finish_beam");
+        return fail(c, DXB_ESTATE, "dxb_run on a context that is one shard of a multi-process job: use dxb_run_transport, a barrier over the ranks, dxb_finish_beam");
     rc = dxb_finish_beam(c, beam, physics_mode, use_beam_calibration, nullptr);
     if (rc != DXB_OK)
         return rc;
@@ -1342,6 +1246,8 @@ int dxb_tally_buffer(dxb_ctx* c, void** device_ptr, uint64_t* n_words)
 {
     if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
         return fail(c, DXB_ESTATE, "tally_buffer: no grid");
+    if (c->exchanging)
+        return fail(c, DXB_ESTATE, "tally_buffer: the library exchanges the tallies of this context itself");
     if (device_ptr)
         *device_ptr = c->devs[0]->world.tally.p;
     if (n_words)
@@ -1355,6 +1261,11 @@ int dxb_get_dose(dxb_ctx* c, double* dose, double* variance, uint64_t* n_events)
         return fail(c, DXB_ESTATE, "get_dose: no grid");
     DeviceState& d0 = *c->devs[0];
     const size_t n = d0.world.nvox;
+    if (c->devs.size() > 1) // every device copies its slab of the dose score over its own PCIe link
+        return mgGetDose(c, 0, n, dose, variance, n_events);
+    int rc = mgFlush(c);
+    if (rc != DXB_OK)
+        return rc;
     CUDA_TRY(c, cudaSetDevice(d0.device));
     if (dose)
         CUDA_TRY(c, cudaMemcpyAsync(dose, d0.dose.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
@@ -1375,6 +1286,11 @@ int dxb_get_dose_range(dxb_ctx* c, uint64_t voxel_begin, uint64_t voxel_end, dou
     if (voxel_begin > voxel_end || voxel_end > n)
         return fail(c, DXB_EINVAL, "get_dose_range: voxel range outside the grid");
     const size_t b = voxel_begin, m = voxel_end - voxel_begin;
+    if (c->devs.size() > 1)
+        return mgGetDose(c, voxel_begin, voxel_end, dose, variance, n_events);
+    int rc = mgFlush(c);
+    if (rc != DXB_OK)
+        return rc;
     CUDA_TRY(c, cudaSetDevice(d0.device));
     if (m > 0) {
         if (dose)
@@ -1395,7 +1311,17 @@ int dxb_get_energy_scored(dxb_ctx* c, double* energy, double* energy_sq, uint64_
     DeviceState& d0 = *c->devs[0];
     World& w = d0.world;
     const size_t n = w.nvox;
+    if (c->exchanging && c->exchanged)
+        return fail(c, DXB_ESTATE, "get_energy_scored: the tallies of the last beam have been handed to the exchange (read them before dxb_finish_beam)");
     CUDA_TRY(c, cudaSetDevice(d0.device));
+    DevBuf<unsigned long long> summed; // several devices: sum of their buffers (integers: identical to one device)
+    const unsigned long long* tally = w.tallyCur();
+    if (c->devs.size() > 1) {
+        const int rc = mgSumTallies(c, summed);
+        if (rc != DXB_OK)
+            return rc;
+        tally = summed.p;
+    }
     DevBuf<double> e, e2;
     DevBuf<unsigned long long> cnt;
     if (energy)
@@ -1404,7 +1330,7 @@ int dxb_get_energy_scored(dxb_ctx* c, double* energy, double* energy_sq, uint64_
         CUDA_TRY(c, e2.alloc(n, d0.device));
     if (n_events)
         CUDA_TRY(c, cnt.alloc(n, d0.device));
-    launchTallyToEnergy(w.tally.p, e.p, e2.p, cnt.p, n, 1.0 / c->scaleE, 1.0 / c->scaleE2, d0.stream);
+    launchTallyToEnergy(tally, e.p, e2.p, cnt.p, n, 1.0 / c->scaleE, 1.0 / c->scaleE2, d0.stream);
     CUDA_TRY(c, cudaGetLastError());
     if (energy)
         CUDA_TRY(c, cudaMemcpyAsync(energy, e.p, n * sizeof(double), cudaMemcpyDeviceToHost, d0.stream));
@@ -1423,6 +1349,9 @@ int dxb_get_dose_postprocessed(dxb_ctx* c, int delete_air_dose, double* dose, do
     DeviceState& d0 = *c->devs[0];
     World& w = d0.world;
     const size_t n = w.nvox;
+    const int grc = mgGatherDose(c); // waits for pending exchanges; several devices: all slabs of the dose score -> device 0
+    if (grc != DXB_OK)
+        return grc;
     CUDA_TRY(c, cudaSetDevice(d0.device));
     // max(dose) < 1 mGy -> report uGy (dose x 1e3, variance x 1e6), R:src/libopendxmc/simulationpipeline.cpp:187-195,227-229
     DevBuf<unsigned long long> dMax;
@@ -1467,6 +1396,9 @@ int dxb_organ_dose(dxb_ctx* c, const uint8_t* organ, uint32_t n_organs, double* 
     DeviceState& d0 = *c->devs[0];
     World& w = d0.world;
     const size_t n = w.nvox;
+    const int grc = mgGatherDose(c);
+    if (grc != DXB_OK)
+        return grc;
     CUDA_TRY(c, cudaSetDevice(d0.device));
     DevBuf<unsigned char> dOrg;
     DevBuf<double> acc; // energy[256], mass[256], var[256]

@@ -13,6 +13,8 @@ int transportMuxOccupancy(int mode, bool calib, bool smemTable, int slots, int t
 cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream);
 int transportPoolSlots(int mode, bool calib, bool smemTable, int slots);
 int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks);
+void setLaunchSmCount(int sms);
+void launchHoleSums(const unsigned long long* tally, const signed char* hole, size_t n, unsigned long long* sums, cudaStream_t s);
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s);
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s);
 void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,

@@ -605,6 +605,28 @@ __global__ void peerReduceKernel(unsigned long long* __restrict__ dst, const uns
     }
 }
 
+// CT calibration: integer sums of the kerma tally (word 0) over the voxels of each of the five CTDI measurement holes
+__global__ void holeSumKernel(const unsigned long long* __restrict__ tally, const signed char* __restrict__ hole, size_t n,
+    unsigned long long* __restrict__ sums /*[5]*/)
+{
+    __shared__ unsigned long long s_sum[5];
+    if (threadIdx.x < 5)
+        s_sum[threadIdx.x] = 0ull;
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int h = hole[i];
+        if (h >= 0) {
+            const unsigned long long v = tally[i * 4];
+            if (v)
+                atomicAdd(&s_sum[h], v);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && s_sum[threadIdx.x])
+        atomicAdd(&sums[threadIdx.x], s_sum[threadIdx.x]);
+}
+
 // reference post-processing (R:src/libopendxmc/simulationpipeline.cpp:180-185,206-211,221-229)
 __global__ void postprocessKernel(const double* __restrict__ in, const unsigned int* __restrict__ voxels, double* __restrict__ out,
     size_t n, int maskAir, double scale)
@@ -802,9 +824,13 @@ int transportOccupancy(int mode, bool calib, bool smemTable, int threads, size_t
     return e == cudaSuccess ? nb : 0;
 }
 
+// grid size of the HBM-streaming kernels: 8 blocks of 256 threads per SM of the device the context runs on
+static int g_streamBlocks = 148 * 8;
+void setLaunchSmCount(int sms) { g_streamBlocks = (sms > 0 ? sms : 148) * 8; }
+
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s)
 {
-    packVoxelsKernel<<<148 * 8, 256, 0, s>>>(density, material, out, n, maxBits);
+    packVoxelsKernel<<<g_streamBlocks, 256, 0, s>>>(density, material, out, n, maxBits);
 }
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s)
 {
@@ -813,43 +839,47 @@ void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, fl
 void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,
     unsigned long long* events, size_t n, double inv_e, double inv_e2, double factor, double vol, cudaStream_t s)
 {
-    energyToDoseKernel<<<148 * 8, 256, 0, s>>>(tally, voxels, dose, variance, events, n, inv_e, inv_e2, factor, vol);
+    energyToDoseKernel<<<g_streamBlocks, 256, 0, s>>>(tally, voxels, dose, variance, events, n, inv_e, inv_e2, factor, vol);
 }
 void launchFusedReduceToDose(const unsigned long long* tally, bool multicast, const unsigned long long* const* peers, int n_peers,
     int first_peer, const unsigned int* voxels, double* dose, double* variance, unsigned long long* events, size_t begin, size_t end,
     double inv_e, double inv_e2, double factor, double vol, cudaStream_t s)
 {
     if (multicast)
-        fusedMulticastToDoseKernel<<<148 * 8, 256, 0, s>>>(tally, voxels, dose, variance, events, begin, end, inv_e, inv_e2, factor, vol);
+        fusedMulticastToDoseKernel<<<g_streamBlocks, 256, 0, s>>>(tally, voxels, dose, variance, events, begin, end, inv_e, inv_e2, factor, vol);
     else
-        fusedPullToDoseKernel<<<148 * 8, 256, 0, s>>>(tally, peers, n_peers, first_peer, voxels, dose, variance, events, begin, end, inv_e,
+        fusedPullToDoseKernel<<<g_streamBlocks, 256, 0, s>>>(tally, peers, n_peers, first_peer, voxels, dose, variance, events, begin, end, inv_e,
             inv_e2, factor, vol);
 }
 void launchTallyToEnergy(const unsigned long long* tally, double* e, double* e2, unsigned long long* cnt, size_t n,
     double inv_e, double inv_e2, cudaStream_t s)
 {
-    tallyToEnergyKernel<<<148 * 8, 256, 0, s>>>(tally, e, e2, cnt, n, inv_e, inv_e2);
+    tallyToEnergyKernel<<<g_streamBlocks, 256, 0, s>>>(tally, e, e2, cnt, n, inv_e, inv_e2);
 }
 void launchPeerReduce(unsigned long long* dst, const unsigned long long* const* peers, int n_peers, size_t n_words, cudaStream_t s)
 {
-    peerReduceKernel<<<148 * 8, 256, 0, s>>>(dst, peers, n_peers, n_words);
+    peerReduceKernel<<<g_streamBlocks, 256, 0, s>>>(dst, peers, n_peers, n_words);
+}
+void launchHoleSums(const unsigned long long* tally, const signed char* hole, size_t n, unsigned long long* sums, cudaStream_t s)
+{
+    holeSumKernel<<<g_streamBlocks / 4, 256, 0, s>>>(tally, hole, n, sums);
 }
 void launchPostprocess(const double* in, const unsigned int* voxels, double* out, size_t n, int maskAir, double scale, cudaStream_t s)
 {
-    postprocessKernel<<<148 * 8, 256, 0, s>>>(in, voxels, out, n, maskAir, scale);
+    postprocessKernel<<<g_streamBlocks, 256, 0, s>>>(in, voxels, out, n, maskAir, scale);
 }
 void launchU64ToDouble(const unsigned long long* in, const unsigned int* voxels, double* out, size_t n, int maskAir, cudaStream_t s)
 {
-    u64ToDoubleKernel<<<148 * 8, 256, 0, s>>>(in, voxels, out, n, maskAir);
+    u64ToDoubleKernel<<<g_streamBlocks, 256, 0, s>>>(in, voxels, out, n, maskAir);
 }
 void launchMax(const double* in, const unsigned int* voxels, size_t n, int maskAir, unsigned long long* outBits, cudaStream_t s)
 {
-    maxKernel<<<148 * 4, 256, 0, s>>>(in, voxels, n, maskAir, outBits);
+    maxKernel<<<g_streamBlocks / 2, 256, 0, s>>>(in, voxels, n, maskAir, outBits);
 }
 void launchOrganDose(const double* dose, const double* variance, const unsigned int* voxels, const unsigned char* organ, size_t n,
     double vol, double* energy, double* mass, unsigned long long* count, double* varEnergy, cudaStream_t s)
 {
-    organDoseKernel<<<148 * 4, 256, 0, s>>>(dose, variance, voxels, organ, n, vol, energy, mass, count, varEnergy);
+    organDoseKernel<<<g_streamBlocks / 2, 256, 0, s>>>(dose, variance, voxels, organ, n, vol, energy, mass, count, varEnergy);
 }
 void launchAttenuationProbe(const TablesDev& tab, int mat, const float* energy, int n, float* out4, cudaStream_t s)
 {
@@ -862,7 +892,7 @@ void launchMajorantProbe(const float* majorant, const float* energy, int n, floa
 void launchSegment(const double* hu, size_t n, const double* sep, int n_sep, const double* matAtt, double waterAttDens,
     double airAttDens, unsigned char* material, double* density, cudaStream_t s)
 {
-    segmentKernel<<<148 * 8, 256, 0, s>>>(hu, n, sep, n_sep, matAtt, waterAttDens, airAttDens, material, density);
+    segmentKernel<<<g_streamBlocks, 256, 0, s>>>(hu, n, sep, n_sep, matAtt, waterAttDens, airAttDens, material, density);
 }
 
 } // namespace dxb

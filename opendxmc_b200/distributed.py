@@ -46,10 +46,15 @@ def reduce_tallies(tally, dst=0, group=None):
 def run_beam(world, beam, tally, rank, use_beam_calibration=True, progress=None, group=None):
     """Transport::operator() across ranks: shard tallies -> reduce -> (rank 0) calibration + energy->dose.
     Returns the calibration factor on rank 0, None elsewhere."""
+    import torch
     from .api import Transport
     tr = Transport()
-    tr.run_transport(world, beam, progress)
+    tr.run_transport(world, beam, progress)  # returns after the transport kernels have finished (library stream)
     reduce_tallies(tally, 0, group)
+    # the reduce is enqueued on torch's current stream, energy->dose runs on the library's own stream: nothing else
+    # orders the two, so wait for the reduce before the tallies are converted
+    if tally.is_cuda:
+        torch.cuda.current_stream(tally.device).synchronize()
     if rank == 0:
         return tr.finish_beam(world, beam, use_beam_calibration)
     return None
@@ -79,6 +84,10 @@ def set_grid_sharded(world, dim, spacing, density, material, device_index, group
     csp = (C.c_double * 3)(*[float(v) for v in spacing])
     density = np.ascontiguousarray(density, dtype=np.float64)
     material = np.ascontiguousarray(material, dtype=np.uint8)
+    # a context with a library-managed exchange: no peer may still be pulling from the tally buffers this call clears
+    lib.dxb_flush(ctx)
+    if size > 1:
+        dist.barrier(group=group)
     rc = lib.dxb_set_grid_sharded(ctx, cdim, csp, density.ctypes.data_as(K.c_double_p), material.ctypes.data_as(K.c_u8_p), b, e)
     if rc != K.DXB_OK:
         raise K.DxbError(rc, "dxb_set_grid_sharded", (lib.dxb_last_error(ctx) or b"").decode())
@@ -223,6 +232,82 @@ class FusedExchange:
 def run_beam_fused(world, beam, exchange, use_beam_calibration=True, progress=None):
     """Transport::operator() across ranks with the fused exchange: shard tallies -> (barrier) -> every rank converts
     its slab of the multicast-summed tallies.  Returns the calibration factor."""
+    from .api import Transport
+    Transport().run_transport(world, beam, progress)
+    return exchange.finish_beam(beam, world._item.lowEnergyCorrection, use_beam_calibration)
+
+
+class PipelinedExchange:
+    """The library-managed exchange for one process per GPU (include/dxb.h: dxb_exchange_export / dxb_exchange_import).
+
+    The two tally buffers of every rank are mapped into every other rank through CUDA IPC.  Per beam the caller runs
+    dxb_run_transport, a barrier over the ranks (the one synchronisation the library cannot do across processes) and
+    dxb_finish_beam, which only ENQUEUES the exchange: copy-engine pulls of this rank's voxel slab from every peer,
+    slab reduce -> dose, clear of the previous buffer.  They run underneath the next beam's transport kernels; the dose
+    score of slab r stays on rank r (dxb_get_dose_range) and read-out calls wait for pending exchanges.
+    torch.distributed moves 128 bytes of handles per rank and provides the barrier; nothing else."""
+
+    kind = "ipc-copy-engine-pipelined"
+
+    def __init__(self, world, local_rank, group=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.world = world
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.size = dist.get_world_size(self.group)
+        self.device = torch.device("cuda", local_rank)
+        lib = K.load()
+        ctx = world.ctx()
+        mine = C.create_string_buffer(K.DXB_EXCHANGE_HANDLE_BYTES)
+        rc = lib.dxb_exchange_export(ctx, mine)
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_exchange_export", (lib.dxb_last_error(ctx) or b"").decode())
+        gathered = [None] * self.size
+        dist.all_gather_object(gathered, bytes(mine.raw), group=self.group)
+        blob = b"".join(gathered)
+        rc = lib.dxb_exchange_import(ctx, self.rank, self.size, blob)
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_exchange_import", (lib.dxb_last_error(ctx) or b"").decode())
+        n = world._item.size()
+        self.n_voxels = n
+        self.begin, self.end = slab(n, self.rank, self.size)
+
+    def barrier(self):
+        self._dist.barrier(group=self.group)
+
+    def finish_beam(self, beam, physics_mode, use_beam_calibration=True):
+        """after dxb_run_transport on every rank: barrier, then enqueue the exchange; returns the calibration factor."""
+        lib = K.load()
+        self.barrier()
+        f = C.c_double()
+        rc = lib.dxb_finish_beam(self.world.ctx(), C.byref(beam.desc()), int(physics_mode), 1 if use_beam_calibration else 0, C.byref(f))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_finish_beam", (lib.dxb_last_error(self.world.ctx()) or b"").decode())
+        return f.value
+
+    def flush(self):
+        rc = K.load().dxb_flush(self.world.ctx())
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_flush")
+
+    def times_ms(self):
+        """device time of the last flushed exchange on this rank: (pulls, slab reduce -> dose, clear)."""
+        t = (C.c_double * 3)()
+        K.load().dxb_exchange_times(self.world.ctx(), t)
+        return tuple(t)
+
+    def close(self):
+        """every rank's pending pulls must have finished before any rank frees the buffers they read"""
+        self.flush()
+        self.barrier()
+        K.load().dxb_exchange_close(self.world.ctx())
+        self.barrier()
+
+
+def run_beam_pipelined(world, beam, exchange, use_beam_calibration=True, progress=None):
+    """Transport::operator() across ranks with the library-managed exchange.  Returns the calibration factor."""
     from .api import Transport
     Transport().run_transport(world, beam, progress)
     return exchange.finish_beam(beam, world._item.lowEnergyCorrection, use_beam_calibration)

@@ -23,6 +23,7 @@ struct dxb_ctx {
     std::vector<uint64_t> events;
     std::string error;
     uint64_t seed = 0x0DDC0FFEEull;
+    uint64_t beamCounter = 0; // like the library: beam k runs on key seed + k * DXB_BEAM_KEY_STRIDE (include/dxb.h)
     uint64_t calibrationHistories = 720000; // small: this is a CPU run (env DXB_DOUBLE_CALIB overrides)
 };
 
@@ -117,7 +118,8 @@ int dxb_run(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, int use_bea
         return DXB_ECANCELLED;
     orc_stats st;
     // accumulates into dose / variance / events like repeated transport() calls on one world
-    const int rc = orc_transport(c->world, beam, physics_mode, use_beam_calibration, c->seed, c->calibrationHistories, 0, c->dose.data(),
+    const uint64_t key = c->seed + c->beamCounter++ * DXB_BEAM_KEY_STRIDE;
+    const int rc = orc_transport(c->world, beam, physics_mode, use_beam_calibration, key, c->calibrationHistories, 0, c->dose.data(),
         c->variance.data(), c->events.data(), &st);
     if (rc != 0) {
         c->error = "run: oracle transport failed";

@@ -52,6 +52,15 @@ constexpr double RUSSIAN_ROULETTE_PROBABILITY = 0.9;
 constexpr double KEV_PER_GRAM_TO_MGY = 1.602176634e-10;
 constexpr uint64_t SHARD_BLOCK = 65536;
 
+// ------------------------------------------------------------------ device mirroring
+// By default the oracle reproduces the places where the device stores a QUANTISED copy of its input (24-bit voxel
+// densities, f32 majorant / bowtie knots / alias acceptance values / shell constants / exposure geometry), so that both
+// sides consume the same numbers and differ by arithmetic rounding only.  orc_set_device_mirroring(0) switches all of
+// that off: the oracle then runs on the caller's f64 data as handed over.  tests/test_oracle_known_answers.py and the
+// GPU suite use the un-mirrored mode to show that those quantisations are harmless, not merely shared.
+bool g_mirror = true;
+inline double mf(double v) { return g_mirror ? static_cast<double>(static_cast<float>(v)) : v; }
+
 // ------------------------------------------------------------------ RandomState [D]
 void philox(const uint32_t key[2], const uint32_t ctr[4], uint32_t out[4])
 {
@@ -347,10 +356,10 @@ bool dopplerBroaden(const OMaterial& material, double energy, double e0, double 
     double r = rShell, U = 0, j0 = 0;
     bool bound = false;
     for (uint32_t i = 0; i < material.nShells; ++i) {
-        const double f = static_cast<float>(material.shells[i].n_electrons_fraction);
+        const double f = mf(material.shells[i].n_electrons_fraction);
         if (r < f) {
-            U = static_cast<float>(material.shells[i].binding_energy_kev);
-            j0 = static_cast<float>(material.shells[i].compton_j0);
+            U = mf(material.shells[i].binding_energy_kev);
+            j0 = mf(material.shells[i].compton_j0);
             bound = true;
             break;
         }
@@ -358,7 +367,7 @@ bool dopplerBroaden(const OMaterial& material, double energy, double e0, double 
     }
     eOut = e0;
     if (!bound) {
-        j0 = static_cast<float>(material.restJ0); // the electrons outside the table: unbound, one common profile
+        j0 = mf(material.restJ0); // the electrons outside the table: unbound, one common profile
         if (!(j0 > 0))
             return true;
     }
@@ -385,12 +394,12 @@ double photoFluorescence(const OMaterial& material, double energy, double rShell
     double r = rShell;
     for (uint32_t i = 0; i < material.nShells; ++i) {
         const dxb_shell& s = material.shells[i];
-        if (!(static_cast<float>(s.binding_energy_kev) < energy))
+        if (!(mf(s.binding_energy_kev) < energy))
             continue;
-        const double f = static_cast<float>(s.photo_fraction_above);
+        const double f = mf(s.photo_fraction_above);
         if (r < f) {
-            const double ef = static_cast<float>(s.fluor_energy_kev);
-            if (rYield < static_cast<float>(s.fluor_yield) && ef >= MIN_ENERGY && ef < energy)
+            const double ef = mf(s.fluor_energy_kev);
+            if (rYield < mf(s.fluor_yield) && ef >= MIN_ENERGY && ef < energy)
                 return ef;
             return 0;
         }
@@ -525,13 +534,16 @@ struct AAVoxelGrid {
         std::vector<double> maxDens(materials.size(), 0.0);
         for (size_t i = 0; i < density.size(); ++i) {
             // the device grid stores the top 24 bits of the f32 density (round to nearest; DESIGN.md: voxel layout)
-            const float rf = static_cast<float>(density[i] > 0 ? density[i] : 0.0);
-            uint32_t bits;
-            std::memcpy(&bits, &rf, 4);
-            bits = (bits + 0x80u) & 0xFFFFFF00u;
-            float rq;
-            std::memcpy(&rq, &bits, 4);
-            const double rho = static_cast<double>(rq);
+            double rho = density[i] > 0 ? density[i] : 0.0;
+            if (g_mirror) {
+                const float rf = static_cast<float>(rho);
+                uint32_t bits;
+                std::memcpy(&bits, &rf, 4);
+                bits = (bits + 0x80u) & 0xFFFFFF00u;
+                float rq;
+                std::memcpy(&rq, &bits, 4);
+                rho = static_cast<double>(rq);
+            }
             density[i] = rho;
             maxDens[materialIndex[i]] = std::max(maxDens[materialIndex[i]], rho);
         }
@@ -541,8 +553,8 @@ struct AAVoxelGrid {
             double m = 0;
             for (size_t k = 0; k < materials.size(); ++k) {
                 // the device majorant is built from the f32 total table
-                const double tot = static_cast<double>(static_cast<float>(materials[k].photo[e] + materials[k].incoh[e] + materials[k].coh[e]));
-                m = std::max(m, static_cast<double>(static_cast<float>(static_cast<float>(maxDens[k]) * static_cast<float>(tot))));
+                const double tot = mf(materials[k].photo[e] + materials[k].incoh[e] + materials[k].coh[e]);
+                m = std::max(m, g_mirror ? static_cast<double>(static_cast<float>(maxDens[k]) * static_cast<float>(tot)) : maxDens[k] * tot);
             }
             woodcockStepTable[e] = std::max(m, 1e-12);
         }
@@ -697,8 +709,8 @@ struct Bowtie {
                 w /= mean;
         // the device evaluates the profile from f32 knots
         for (size_t i = 0; i < angle.size(); ++i) {
-            angle[i] = static_cast<float>(angle[i]);
-            weight[i] = static_cast<float>(weight[i]);
+            angle[i] = mf(angle[i]);
+            weight[i] = mf(weight[i]);
         }
     }
     double operator()(double a) const
@@ -983,7 +995,7 @@ struct SpecterDistribution {
             small.pop_back();
             const size_t lg = large.back();
             large.pop_back();
-            prob[sm] = static_cast<double>(static_cast<float>(q[sm])); // device keeps f32 acceptance values
+            prob[sm] = mf(q[sm]); // device keeps f32 acceptance values
             alias[sm] = lg;
             q[lg] = (q[lg] + q[sm]) - 1.0;
             (q[lg] < 1.0 ? small : large).push_back(lg);
@@ -1031,7 +1043,7 @@ struct BeamModel {
     {
         // exposure geometry is held in f32 on the device; mirror that rounding so that both sides start
         // from the same rays
-        auto f = [](double v) { return static_cast<double>(static_cast<float>(v)); };
+        auto f = [](double v) { return mf(v); };
         const double angx = (2.0 * state.randomUniform() - 1.0) * f(e.halfAngles[0]);
         const double angy = (2.0 * state.randomUniform() - 1.0) * f(e.halfAngles[1]);
         Particle p;
@@ -1176,7 +1188,8 @@ double ctCalibration(const orc_world& w, const dxb_beam_desc& b, int correction,
         cb.spectrum[1].n = 0;
     const uint64_t nExp = numberOfExposures(cb);
     cb.particles_per_exposure = std::max<uint64_t>(1, calibHistories / nExp);
-    runBeam(ph, cb, correction, seed, nThreads, 0, 1, nullptr);
+    // the nested run draws from its own stream: beam key ^ DXB_CALIBRATION_KEY_XOR (include/dxb.h)
+    runBeam(ph, cb, correction, seed ^ DXB_CALIBRATION_KEY_XOR, nThreads, 0, 1, nullptr);
 
     double sum[5] = { 0, 0, 0, 0, 0 };
     size_t cnt[5] = { 0, 0, 0, 0, 0 };
@@ -1225,6 +1238,9 @@ double analyticCalibration(const orc_world& w, const dxb_beam_desc& b)
 
 // =========================================================================== C interface
 extern "C" {
+
+void orc_set_device_mirroring(int on) { g_mirror = on != 0; }
+int orc_get_device_mirroring(void) { return g_mirror ? 1 : 0; }
 
 orc_world* orc_world_create(const uint64_t dim[3], const double spacing[3], const double* density, const uint8_t* material,
     uint32_t n_materials, const dxb_material_tables* tables)

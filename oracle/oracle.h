@@ -29,6 +29,12 @@ typedef struct orc_stats {
     int threads;
 } orc_stats;
 
+/* Device mirroring (default on): the oracle quantises its inputs where the device stores a quantised copy (24-bit voxel
+ * density, f32 majorant, bowtie knots, alias acceptance values, shell constants, exposure geometry).  0 switches all
+ * of it off - pure f64 on the caller's data; process-wide, set it BEFORE orc_world_create. */
+void orc_set_device_mirroring(int on);
+int orc_get_device_mirroring(void);
+
 /* World<AAVoxelGrid>: copies everything it needs (tables are deep-copied). */
 orc_world* orc_world_create(const uint64_t dim[3], const double spacing_cm[3], const double* density,
                             const uint8_t* material, uint32_t n_materials, const dxb_material_tables* tables);

@@ -44,6 +44,8 @@ def load():
     sig = {
         "orc_world_create": (VP, [K.c_u64_p, K.c_double_p, K.c_double_p, K.c_u8_p, C.c_uint32, MT]),
         "orc_world_destroy": (None, [VP]),
+        "orc_set_device_mirroring": (None, [C.c_int]),
+        "orc_get_device_mirroring": (C.c_int, []),
         "orc_world_set_reference_materials": (None, [VP, MT, MT, C.c_double, C.c_double]),
         "orc_run": (C.c_int, [VP, BD, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, K.c_double_p, K.c_double_p, K.c_u64_p,
                               C.POINTER(orc_stats)]),
@@ -77,6 +79,19 @@ def load():
 
 def _dp(a):
     return a.ctypes.data_as(K.c_double_p)
+
+
+class unmirrored:
+    """context manager: oracle worlds created inside run on the caller's f64 data as handed over, WITHOUT the
+    quantisations that mirror the device's storage formats (oracle.h: orc_set_device_mirroring)."""
+
+    def __enter__(self):
+        load().orc_set_device_mirroring(0)
+        return self
+
+    def __exit__(self, *a):
+        load().orc_set_device_mirroring(1)
+        return False
 
 
 def philox(key, ctr):

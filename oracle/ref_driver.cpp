@@ -52,6 +52,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -601,7 +602,7 @@ static std::shared_ptr<Beam> makeRunBeam(const std::string& kind, unsigned long 
     return beam;
 }
 
-static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix, double ctdiw, const std::string& kind)
+static int runMode(int mode, bool deleteAir, unsigned long long perExposure, const std::string& prefix, double ctdiw, const std::string& kind, bool repeat)
 {
     auto vol = makeCylinder(0.5, 64, 32);
     unsigned long long nExposures = 0;
@@ -632,6 +633,34 @@ static int runMode(int mode, bool deleteAir, unsigned long long perExposure, con
         std::fprintf(stderr, "ref_driver: no result\n");
         return 3;
     }
+    // A second startSimulation() on the SAME pipeline object: the worker leaves the stop flag of the pipeline's single
+    // TransportProgress raised (R:src/libopendxmc/simulationpipeline.cpp:234) and nothing in OpenDXMC clears it, so
+    // dxmc::Transport must (progress->start()).  The second run builds a new world, hence draws the same Philox keys:
+    // its result must arrive and equal the first one.
+    int secondRun = -1;
+    if (repeat) {
+        const std::vector<double> firstDose = g_simulated->getDoseArray();
+        g_simulated.reset();
+        g_running = -1;
+        sim.startSimulation();
+        for (int i = 0; i < 60000 && !g_simulated; ++i) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+            sim.timerEvent(nullptr);
+        }
+        if (!g_simulated) {
+            std::fprintf(stderr, "ref_driver: the second startSimulation() on the same pipeline produced no result\n");
+            return 4;
+        }
+        // (the CPU double adds doubles from several threads: last bits move with the thread order)
+        const std::vector<double>& second = g_simulated->getDoseArray();
+        double sum = 0, worst = 0, top = 0;
+        for (std::size_t i = 0; i < second.size() && i < firstDose.size(); ++i) {
+            sum += second[i];
+            top = std::max(top, std::fabs(firstDose[i]));
+            worst = std::max(worst, std::fabs(second[i] - firstDose[i]));
+        }
+        secondRun = (second.size() == firstDose.size() && sum > 0 && worst <= 1e-9 * top) ? 1 : 0;
+    }
     const auto& d = *g_simulated;
     writeRaw(prefix + ".density.bin", d.getDensityArray());
     writeRaw(prefix + ".material.bin", d.getMaterialArray());
@@ -641,7 +670,7 @@ static int runMode(int mode, bool deleteAir, unsigned long long perExposure, con
     std::ofstream j(prefix + ".json");
     j << "{\"dim\": [" << d.dimensions()[0] << ", " << d.dimensions()[1] << ", " << d.dimensions()[2] << "], \"spacing\": [" << d.spacing()[0] << ", "
       << d.spacing()[1] << ", " << d.spacing()[2] << "], \"mode\": " << mode << ", \"delete_air\": " << (deleteAir ? 1 : 0)
-      << ", \"ctdiw\": " << ctdiw << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << nExposures << ", \"beam\": \"" << kind << "\", \"dose_units\": \""
+      << ", \"ctdiw\": " << ctdiw << ", \"per_exposure\": " << perExposure << ", \"exposures\": " << nExposures << ", \"beam\": \"" << kind << "\", \"second_run_identical\": " << secondRun << ", \"dose_units\": \""
       << d.units(DataContainer::ImageType::Dose) << "\"}\n";
     return 0;
 }
@@ -662,7 +691,7 @@ int main(int argc, char** argv)
     if (what == "icrp" && argc >= 9)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
-        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0, argc > 7 ? argv[7] : "sequential");
-    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [level] [beam kind]\n");
+        return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0, argc > 7 ? argv[7] : "sequential", argc > 8 && std::atoi(argv[8]) != 0);
+    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [level] [beam kind] [1: start twice]\n");
     return 1;
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_capi.LIB_PATH)
     for name in _declared_functions():
         assert hasattr(lib, name), f"libdxmc_b200.so does not export {name}"
-    assert _capi.load().dxb_abi_version() == 1
+    assert _capi.load().dxb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -9,6 +9,8 @@ import time
 import numpy as np
 import pytest
 
+from parity import assert_same_stream_parity
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 SEED = 0x0DDC0FFEE
@@ -27,6 +29,7 @@ def _compare_run(dx, orc, wl, mode=1, rois=None, tol=5e-3):
     assert abs(e.sum() - oe.sum()) / oe.sum() <= tol, (e.sum(), oe.sum())
     for k in ("steps", "interactions", "deposits"):
         assert abs(st[k] - ost[k]) / max(ost[k], 1) < tol, (k, st[k], ost[k])
+    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, "", counter_floor=30)
     for name, m in (rois or {}).items():
         a, b = e[m].sum(), oe[m].sum()
         s = np.sqrt(e2[m].sum() + oe2[m].sum())
@@ -187,7 +190,8 @@ def test_calibrated_dose_dx_and_ct(dx, orc):
     assert d.sum() == pytest.approx(od.sum(), rel=5e-3)
     sel = n > 20
     assert np.all(v[sel] > 0)
-    # a second beam accumulates into the same dose score (repeated transport() on one world)
+    # a second beam accumulates into the same dose score (repeated transport() on one world); replayed with the same key
+    world.set_seed(SEED)
     assert tr(world, beam, None, True)
     d2, v2, n2 = world._item.doseArrays()
     assert d2.sum() == pytest.approx(2 * d.sum(), rel=1e-9) and int(n2.sum()) == 2 * int(n.sum())
@@ -201,7 +205,7 @@ def test_calibrated_dose_dx_and_ct(dx, orc):
     world.set_calibration_histories(3_600_000)
     assert tr(world, ct, None, True)
     f_gpu = world.run_stats()["calibration_factor"]
-    f_cpu = ow.ct_calibration(ct, 1, SEED, 3_600_000)
+    f_cpu = ow.ct_calibration(ct, 1, world.last_beam_key(), 3_600_000)
     assert f_gpu == pytest.approx(f_cpu, rel=0.02)
     world.close()
 
@@ -312,20 +316,80 @@ def test_progress_and_cancel(dx):
 
 
 def test_in_process_multi_gpu_is_bit_identical(dx):
+    """dxb_create with several devices (what dxmc::Transport reaches with DXMC_B200_DEVICES=0,1,...): sharded upload,
+    sharded nested calibration run, double-buffered tallies with the pipelined copy-engine exchange, distributed dose
+    score.  Tallies, calibration factor, DOSE, variance, events, the reference's post-processing and the per-organ
+    dose must equal the single-GPU results bit for bit."""
     from opendxmc_b200 import _capi as K
-    if K.load().dxb_device_count() < 2:
+    lib = K.load()
+    n_dev = lib.dxb_device_count()
+    if n_dev < 2:
         pytest.skip("needs 2 GPUs")
-    wl = dx.workloads.ctdi_body_phantom(n=32, histories=1_000_000, step_deg=5.0)
+    devs = list(range(min(n_dev, 4)))
+    wl = dx.workloads.ct_spiral_patient(scale=4, histories=2_000_000, step_deg=5.0)
     w1 = wl.build_world(1, [0])
-    w2 = wl.build_world(1, [0, 1])
+    wn = wl.build_world(1, devs)
     tr = dx.Transport()
+    # (1) the tallies of one beam, read before any exchange
     tr.run_transport(w1, wl.beam)
-    tr.run_transport(w2, wl.beam)
-    a, b = w1.energy_scored(), w2.energy_scored()
-    for x, y in zip(a, b):
+    tr.run_transport(wn, wl.beam)
+    for x, y in zip(w1.energy_scored(), wn.energy_scored()):
         assert np.array_equal(x, y)
+    s1, sn = w1.run_stats(), wn.run_stats()
+    for k in ("histories", "steps", "interactions", "deposits"):
+        assert s1[k] == sn[k], k
+    # (2) four beams back to back without reading anything in between: the exchange of beam i runs under the transport
+    # of beam i + 1 and the tally buffers alternate; the first and the last beam are CT-calibrated (nested run)
+    desc = wl.beam.desc()
+    factors = {}
+    for w in (w1, wn):
+        w.set_seed(SEED)
+        w.set_calibration_histories(720_000)
+        factors[id(w)] = []
+        for k in range(4):
+            assert lib.dxb_run_transport(w.ctx(), C.byref(desc), 1, None) == 0, lib.dxb_last_error(w.ctx())
+            f = C.c_double()
+            assert lib.dxb_finish_beam(w.ctx(), C.byref(desc), 1, 1 if k in (0, 3) else 0, C.byref(f)) == 0, lib.dxb_last_error(w.ctx())
+            # a beam is finished once
+            assert lib.dxb_finish_beam(w.ctx(), C.byref(desc), 1, 0, None) == K.DXB_ESTATE
+            factors[id(w)].append(f.value)
+    assert factors[id(w1)] == factors[id(wn)]
+    d1, dn = [a.copy() for a in w1.fetch_dose()], [a.copy() for a in wn.fetch_dose()]
+    for a, b, name in zip(d1, dn, ("dose", "variance", "events")):
+        assert np.array_equal(a, b), f"{name}: {np.count_nonzero(a != b)} voxels differ"
+    assert d1[2].sum() > 0
+    # (3) ranged read-out, the reference's post-processing and the per-organ dose run on the gathered score
+    nvox = d1[0].size
+    part = wn.fetch_dose_range(nvox // 5, nvox // 2 + 3)
+    assert np.array_equal(part[0][nvox // 5:nvox // 2 + 3], d1[0][nvox // 5:nvox // 2 + 3]) and part[0][:nvox // 5].sum() == 0
+    for delete_air in (False, True):
+        for a, b in zip(w1.dose_postprocessed(delete_air), wn.dose_postprocessed(delete_air)):
+            assert np.array_equal(a, b)
+    for a, b in zip(w1.organ_dose(wl.organ, len(wl.organ_names)), wn.organ_dose(wl.organ, len(wl.organ_names))):
+        assert np.array_equal(a, b)
+    # (4) a new grid on the same context (setData again), then one more beam
+    for w in (w1, wn):
+        w.build()
+        w.set_seed(SEED + 5)
+        assert tr(w, wl.beam, None, False)
+    for a, b in zip(w1.fetch_dose(), wn.fetch_dose()):
+        assert np.array_equal(a, b)
     w1.close()
-    w2.close()
+    wn.close()
+
+
+def test_ipc_pipelined_exchange_matches_single_gpu_bit_for_bit():
+    """one process per GPU with the library-managed exchange (CUDA IPC peers, copy-engine pulls under the next beam's
+    transport) against the single-GPU dose score - tests/mp_ipc_exchange.py under torchrun."""
+    import subprocess
+    from opendxmc_b200 import _capi as K
+    n = K.load().dxb_device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "mp_ipc_exchange.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "IPC_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 def test_fused_exchange_matches_single_gpu_bit_for_bit():
@@ -345,8 +409,8 @@ def test_fused_exchange_matches_single_gpu_bit_for_bit():
     assert out.returncode == 0 and "FUSED_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-@pytest.mark.skipif(os.environ.get("DXB_RUN_REF_PIPELINE") != "1" or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref")),
-                    reason="opt-in (DXB_RUN_REF_PIPELINE=1): needs oracle/_ref/opendxmc_ref built where the reference tree is mounted")
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref")),
+                    reason="needs oracle/_ref/opendxmc_ref, built where the reference tree is mounted (the binary travels to the GPU box)")
 def test_reference_pipeline_binary_matches_python_mirror():
     """OpenDXMC's own SimulationPipeline (compiled unmodified, oracle/ref_driver.cpp) against the Python mirror."""
     sys.path.insert(0, os.path.join(ROOT, "profiles"))

@@ -10,6 +10,8 @@ At these sizes the oracle can only follow a few million histories in seconds, so
 import numpy as np
 import pytest
 
+from parity import assert_same_stream_parity
+
 pytestmark = pytest.mark.gpu
 
 SEED = 0x0DDC0FFEE
@@ -46,6 +48,8 @@ def test_c2_full_volume_matches_oracle(dx, orc, c2_full):
     # the roofline's per-history counters must agree between kernel and oracle
     for k in ("steps", "interactions", "deposits"):
         assert abs(st[k] - ost[k]) / ost[k] < 2e-3, (k, st[k], ost[k])
+    # ... and, tighter, what the shared random streams deliver (tests/parity.py)
+    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, "C2 full", counter_floor=30)
     # per-organ and per-slab energy within 3 combined standard errors
     for name, m in _slab_rois(wl).items():
         a, b = e[m].sum(), oe[m].sum()
@@ -63,8 +67,15 @@ def test_c2_full_volume_is_deterministic_and_shard_invariant(dx, c2_full):
     tr = dx.Transport()
     tr.run_transport(world, wl.beam)
     e, e2, cnt = [a.copy() for a in world.energy_scored()]
-    # idempotence: same seed, same histories -> the same integers
+    # the next beam on the same world draws from its own Philox key (base + k * stride): a different answer ...
     tr.run_transport(world, wl.beam)
+    assert world.last_beam_key() != SEED
+    f, f2, fcnt = world.energy_scored()
+    assert not np.array_equal(e, f)
+    # ... and idempotence: same key, same histories -> the same integers
+    world.set_seed(SEED)
+    tr.run_transport(world, wl.beam)
+    assert world.last_beam_key() == SEED
     f, f2, fcnt = world.energy_scored()
     assert np.array_equal(e, f) and np.array_equal(e2, f2) and np.array_equal(cnt, fcnt)
     # a different seed gives a different (but statistically equal) answer
@@ -73,11 +84,11 @@ def test_c2_full_volume_is_deterministic_and_shard_invariant(dx, c2_full):
     g, _, _ = world.energy_scored()
     assert not np.array_equal(e, g)
     assert abs(g.sum() - e.sum()) / e.sum() < 5e-3
-    world.set_seed(SEED)
     # the sum over 4 shards is the whole, bit for bit
     acc = [np.zeros_like(e), np.zeros_like(e2), np.zeros_like(cnt)]
     for rank in range(4):
         world.set_history_range(rank, 4)
+        world.set_seed(SEED)
         tr.run_transport(world, wl.beam)
         for a, b in zip(acc, world.energy_scored()):
             a += b
@@ -112,12 +123,18 @@ def test_dose_score_accumulates_linearly_over_beams(dx, c2_full):
     tr = dx.Transport()
     assert tr(world, wl.beam, None, False)
     d1, v1, n1 = [a.copy() for a in world.fetch_dose()]
+    world.set_seed(SEED)  # replay the same beam (same Philox key): the score must double exactly
     assert tr(world, wl.beam, None, False)
-    d2, v2, n2 = world.fetch_dose()
+    d2, v2, n2 = [a.copy() for a in world.fetch_dose()]
     assert np.array_equal(n2, 2 * n1)
     nz = d1 > 0
     assert np.allclose(d2[nz], 2.0 * d1[nz], rtol=1e-12, atol=0.0)
     assert np.allclose(v2[nz], 2.0 * v1[nz], rtol=1e-12, atol=0.0)
+    # without a re-seed the next beam is an independent sample (key base + 1 * stride): statistically equal, not identical
+    assert tr(world, wl.beam, None, False)
+    d3, v3, n3 = world.fetch_dose()
+    assert not np.array_equal(n3 - n2, n1)
+    assert abs((d3.sum() - d2.sum()) - d1.sum()) / d1.sum() < 5e-3
     world.close()
 
 
@@ -137,6 +154,7 @@ def test_c4_full_shape_dual_source_properties(dx):
     acc_c = np.zeros_like(cnt)
     for rank in range(2):
         world.set_history_range(rank, 2)
+        world.set_seed(SEED)
         tr.run_transport(world, wl.beam)
         a, _, c = world.energy_scored()
         acc += a

@@ -392,3 +392,58 @@ def test_segmentation_rule(orc):
     assert list(mat) == [0, 1, 1, 2, 3, 4, 4]
     expect = np.maximum(((wa - aa) * hu / 1000 + wa) / att[mat], 0.0)
     assert dens == pytest.approx(expect)
+
+
+def _foreign_water(dx):
+    """water-like tables with different numbers, same format: photoelectric x 1.3, coherent x 0.7, a warped scatter
+    function - what an externally built (e.g. EPICS-derived) blob looks like to the library"""
+    water = dx.Material.byNistName("Water, Liquid")
+    a = water.table_arrays()
+    b = dict(a)
+    b["photo"] = a["photo"] * 1.3
+    b["coh"] = a["coh"] * 0.7
+    b["etr"] = a["etr"] * 1.1
+    b["sf"] = np.clip(a["sf"] ** 1.2, 0.0, 1.0)
+    return water, a, b, dx.Material.fromTables(b, water)
+
+
+def test_external_material_tables_drop_in(dx, orc):
+    """dxb_material_from_tables: the EPICS drop-in route.  Host lookups, the exported master tables and the oracle's
+    lookups all follow the supplied arrays; wrong geometry or bad numbers are refused."""
+    water, a, b, ext = _foreign_water(dx)
+    assert ext is not None
+    got = ext.table_arrays()
+    for k in ("photo", "incoh", "coh", "etr", "ff_cdf", "sf"):
+        assert np.array_equal(got[k], b[k]), k
+    for e in (15.0, 33.3, 60.0, 118.0):
+        w, x = water.attenuationValues(e), ext.attenuationValues(e)
+        assert x.photoelectric == pytest.approx(1.3 * w.photoelectric, rel=1e-12)
+        assert x.incoherent == pytest.approx(w.incoherent, rel=1e-12)
+        assert x.coherent == pytest.approx(0.7 * w.coherent, rel=1e-12)
+        assert orc.attenuation(ext, e)[:3] == pytest.approx([x.photoelectric, x.incoherent, x.coherent], rel=1e-12)
+        assert ext.massEnergyTransferAttenuation(e) == pytest.approx(1.1 * water.massEnergyTransferAttenuation(e), rel=1e-12)
+    # the oracle transports through it: 30 % more photoelectric absorption shows up as fewer scatter events per history
+    dim, sp = [16, 16, 16], [1.0, 1.0, 1.0]
+    beam = dx.PencilBeam([0.0, 0.0, -20.0], [0, 0, 1], 40.0)
+    beam.setNumberOfExposures(2)
+    beam.setNumberOfParticlesPerExposure(20_000)
+    res = {}
+    for name, m in (("water", water), ("ext", ext)):
+        ow = orc.OracleWorld(dim, sp, np.ones(16 ** 3), np.zeros(16 ** 3, dtype=np.uint8), [m])
+        e, e2, cnt, st = ow.run(beam, 1)
+        res[name] = (e.sum(), st["interactions"] / st["histories"])
+    assert res["ext"][1] < 0.97 * res["water"][1]
+    # refused: wrong grid geometry, negative values, non-monotone cumulative
+    from opendxmc_b200 import _capi as K
+    import ctypes as C
+    t = water.tables()
+    t.n_energy -= 1
+    h = K.VP()
+    assert K.load().dxb_material_from_tables(C.byref(h), C.byref(t)) == K.DXB_EINVAL
+    bad = dict(b)
+    bad["photo"] = b["photo"].copy()
+    bad["photo"][7] = -1.0
+    assert dx.Material.fromTables(bad, water) is None
+    bad = dict(b)
+    bad["ff_cdf"] = b["ff_cdf"][::-1].copy()
+    assert dx.Material.fromTables(bad, water) is None

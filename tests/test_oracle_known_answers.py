@@ -244,3 +244,45 @@ def test_energy_conservation_all_modes_with_fluorescence(dx, orc, mode):
         # fluorescence photons add scoring events: more deposits per history than in mode 1
         _, _, _, st1 = ow.run(beam, 1, seed=9)
         assert st["deposits"] > st1["deposits"]
+
+
+def _roi_sigma(e_a, e2_a, e_b, e2_b, masks):
+    worst = 0.0
+    for m in masks.values():
+        s = math.sqrt(e2_a[m].sum() + e2_b[m].sum())
+        if s > 0:
+            worst = max(worst, abs(e_a[m].sum() - e_b[m].sum()) / s)
+    return worst
+
+
+@pytest.mark.parametrize("config", ["C1", "C2-small"])
+def test_device_mirroring_quantisations_are_harmless(dx, orc, config):
+    """The oracle normally mirrors the device's storage formats (24-bit voxel densities, f32 majorant, bowtie knots,
+    alias acceptance values, shell constants, exposure geometry) so that GPU and oracle differ by rounding only.  With
+    the mirroring switched OFF the oracle runs on the f64 inputs as handed over; both modes draw the same Philox
+    streams, so their dose maps must agree far inside the statistics (a quantisation that biased the transport would
+    show up here): totals within 2e-4, every ROI within a fraction of a standard error, and almost all voxels equal."""
+    if config == "C1":
+        wl = dx.workloads.ctdi_body_phantom(n=32, histories=400_000, step_deg=5.0)
+        masks = {"pmma": wl.material == 1, "air": wl.material == 0}
+    else:
+        wl = dx.workloads.ct_spiral_patient(scale=8, histories=400_000, step_deg=10.0)
+        masks = {nm: wl.organ == i for i, nm in enumerate(wl.organ_names)}
+    assert orc.load().orc_get_device_mirroring() == 1
+    e, e2, cnt, st = orc.OracleWorld.from_workload(wl).run(wl.beam, 1)
+    with orc.unmirrored():
+        assert orc.load().orc_get_device_mirroring() == 0
+        ow = orc.OracleWorld.from_workload(wl)
+        f, f2, fcnt, ft = ow.run(wl.beam, 1)
+        # the un-mirrored majorant is the exact f64 maximum of density x total attenuation
+        tot = max(m.attenuationValues(60.0).sum() * float(wl.density[wl.material == i].max()) for i, m in enumerate(wl.materials)
+                  if np.any(wl.material == i))
+        assert ow.majorant(60.0) == pytest.approx(tot, rel=1e-9)
+    assert orc.load().orc_get_device_mirroring() == 1
+    assert st["histories"] == ft["histories"]
+    assert abs(e.sum() - f.sum()) / e.sum() <= 2e-4
+    for k in ("steps", "interactions", "deposits"):
+        assert abs(st[k] - ft[k]) / st[k] <= 2e-4, k
+    assert _roi_sigma(e, e2, f, f2, masks) <= 0.5
+    assert np.count_nonzero(cnt == fcnt) / cnt.size >= 0.995
+    assert not np.array_equal(e, f)  # the switch does change the inputs

@@ -606,3 +606,17 @@ def test_reference_simulation_pipeline_end_to_end_on_the_cpu_double(dx, orc, ref
     assert np.allclose(vv, ref[1], rtol=1e-9, atol=1e-13 * float(vv.max()))
     air = mat == 0
     assert (ref[0][air].sum() == 0) == bool(delete_air) and ref[0][~air].sum() > 0
+
+
+def test_second_start_simulation_on_the_same_pipeline(tmp_path):
+    """The reference's worker raises the stop flag of the pipeline's single TransportProgress at the end of every run
+    (R:src/libopendxmc/simulationpipeline.cpp:234) and nothing in OpenDXMC clears it: dxmc::Transport::operator() must
+    start the progress object itself, or the second startSimulation() is 'cancelled' before it begins and the 3 s timer
+    re-publishes the stale first result."""
+    prefix = str(tmp_path / "twice")
+    env = dict(os.environ, DXB_DOUBLE_CALIB="180000")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref_cpu"), "run", "1", "1", "600", prefix, "1.0", "sequential", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    meta = json.load(open(prefix + ".json"))
+    assert meta["second_run_identical"] == 1
