@@ -1,26 +1,35 @@
 #!/usr/bin/env python3
-"""bench.py — histories/s of the dxmc::Transport hot path on the BASELINE.json workload (C2).
+"""bench.py — histories/s of the dxmc::Transport hot path on the BASELINE.json workload (C2; --workload C4 for config 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--histories H] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--histories H] [--impl ours|reference] [--workload C2|C4]
+                    [--inprocess] [--exchange pipelined|multicast|p2p|nccl]
 
-A *step* is one full beam: H histories (default 1e9 = BASELINE.json configs[1]) of the 120 kV spiral CT beam with
-bowtie through the synthetic 512x512x300 patient volume.  Every step uses a fresh Philox key, so nothing is cached.
+A *step* is one full beam: H histories (default 1e9 = BASELINE.json configs[1]) of the 120 kV spiral CT beam with bowtie
+through the synthetic 512x512x300 patient volume.  Every step uses a fresh Philox key, so nothing is cached.
 
-  value  histories/s with the voxel grid, tables and beam already resident in HBM (timed region: tally clear +
-         transport kernels + [N>1: NCCL reduce of the fixed-point tallies to rank 0] + energy->dose), CUDA events,
-         barrier + synchronize on both sides, max over ranks.
-  e2e    the same metric through the reference-facing C ABI with HOST buffers: dxb_set_grid (H2D of the f64 density
-         and u8 material arrays from pinned memory) + dxb_run_transport/dxb_finish_beam + dxb_get_dose (D2H of dose,
-         variance, event count), i.e. what R:src/libopendxmc/simulationpipeline.cpp:145-219 does around transport().
+  value  histories/s with the voxel grid, tables and beam already resident in HBM.  Timed region: K back-to-back beams,
+         each = tally hand-over + transport kernels + [N > 1: the exchange of the fixed-point tallies] + energy -> dose.
+         N > 1, default exchange "pipelined": the library's own exchange (copy-engine pulls of every rank's voxel slab,
+         slab reduce -> dose) runs underneath the NEXT beam's transport kernels; the timed region ends when the last
+         beam's exchange has finished on every rank.  Device time (dxb_timer_*: CUDA events on every stream of the
+         context), barrier + synchronize on both sides, max over ranks.
+         One process per GPU under torchrun (the contract), or --inprocess: ONE process drives the N GPUs through a
+         multi-device dxb_ctx - what dxmc::Transport reaches from the reference's single worker thread.
+  e2e    the same metric through the reference-facing C ABI with HOST buffers, doing what the reference's driver does
+         per run (R:src/libopendxmc/simulationpipeline.cpp:145-219): dxb_set_grid (H2D of the f64 density and u8
+         material arrays) + transport WITH use_beam_calibration = 1 (the nested CTDI Monte Carlo run, :165) +
+         dxb_get_dose (D2H of dose, variance, event count).  `e2e.with_materials` adds dxb_set_materials (table build).
   roofline  the transport kernel: algorithmic bytes/history A = S*5 + D*48 (S, D counted by the
          kernel in the same run) x histories / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the CPU oracle (restated DXMClib algorithm, std::thread on all host cores; "port": the real
-         DXMClib is absent from the reference tree) on a bounded sample of the same workload.
+         DXMClib is absent from the reference tree) on a bounded sample of the same workload; at N = 1
+         the deposited energy per history of a timed GPU step is checked against that sample (0.5 %).
 
-Inputs (630 MB f64 density + 79 MB material -> 629 MB packed voxels + 2.5 GB tallies) are far larger than the
+Inputs (630 MB f64 density + 79 MB material -> 315 MB packed voxels + 2.5 GB tallies) are far larger than the
 126 MB L2, so no explicit L2 flush is needed between steps.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,7 +41,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED0 = 0x0DDC0FFEE
-METRIC = "histories/sec (512x512x300 CT, 120 kV spiral)"
+METRICS = {"C2": "histories/sec (512x512x300 CT, 120 kV spiral)",
+           "C4": "histories/sec (512x512x400 thorax, dual-source spiral CT with AEC)"}
+CALIBRATION_HISTORIES = 36_000_000  # the library's default size of the nested CTDI run
 
 
 def parse_args():
@@ -40,17 +51,25 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--histories", type=float, default=1e9, help="histories per step (whole job)")
-    ap.add_argument("--scale", type=int, default=1, help="grid coarsening (1 = the BASELINE 512x512x300 volume)")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C4"],
+                    help="C2 = BASELINE.json configs[1] (the headline); C4 = configs[3]: dual-source thorax with AEC, 1e10 histories")
+    ap.add_argument("--histories", type=float, default=None, help="histories per step (whole job); default 1e9 (C2) / 1e10 (C4)")
+    ap.add_argument("--scale", type=int, default=1, help="grid coarsening (1 = the BASELINE volume)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exchange", default="multicast", choices=["multicast", "p2p", "nccl"],
-                    help="N > 1: fused reduce->dose per voxel slab, reading the sum over ranks through the NVSwitch multicast "
-                         "address (default; falls back to P2P pulls without multicast support) or by NVLink P2P pulls, or an "
-                         "NCCL reduce to rank 0 followed by energy->dose there")
-    return ap.parse_args()
+    ap.add_argument("--inprocess", action="store_true",
+                    help="one process drives all --gpus devices through a multi-device dxb_ctx (no torchrun)")
+    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "multicast", "p2p", "nccl"],
+                    help="N > 1, one process per GPU: 'pipelined' = the library-managed exchange over CUDA IPC (copy-engine slab "
+                         "pulls under the next beam's transport; falls back to the next choice if IPC is unavailable); 'multicast' / "
+                         "'p2p' = fused reduce->dose kernel per slab reading the NVSwitch multicast sum / peer buffers (synchronous); "
+                         "'nccl' = NCCL reduce to rank 0 + energy->dose there")
+    args = ap.parse_args()
+    if args.histories is None:
+        args.histories = 1e10 if args.workload == "C4" else 1e9
+    return args
 
 
 class ClockSampler:
@@ -225,43 +244,91 @@ class SharedHostArrays:
 
 def make_workload(args):
     import opendxmc_b200 as dx
+    if args.workload == "C4":
+        return dx.workloads.ct_dual_source_thorax(scale=args.scale, histories=int(args.histories))
     return dx.workloads.ct_spiral_patient(scale=args.scale, histories=int(args.histories))
 
 
 def config_dict(args, wl, extra=None):
-    c = {"workload": "C2 synthetic CT patient %dx%dx%d, 120 kV spiral CT, bowtie, pitch 1, %d exposures" % (
-        wl.dim[0], wl.dim[1], wl.dim[2], wl.beam.numberOfExposures()),
-        "histories_per_step": wl.beam.numberOfParticles(), "physics_mode": 1,
-        "l2": "inputs larger than L2 (0.63 GB voxels + 2.5 GB tallies vs 126 MB), no flush needed"}
+    nvox = wl.n_voxels
+    what = ("C2 synthetic CT patient %dx%dx%d, 120 kV spiral CT, bowtie, pitch 1, %d exposures" if args.workload == "C2" else
+            "C4 synthetic thorax %dx%dx%d, dual-source 120/120 kV spiral CT, two bowties, WED AEC, pitch 3.2, %d exposures")
+    c = {"workload": what % (wl.dim[0], wl.dim[1], wl.dim[2], wl.beam.numberOfExposures()),
+         "histories_per_step": wl.beam.numberOfParticles(), "physics_mode": 1,
+         "l2": "inputs larger than L2 (%.2f GB voxels + %.1f GB tallies vs 126 MB), no flush needed" % (nvox * 4 / 1e9, nvox * 32 / 1e9)}
     if extra:
         c.update(extra)
     return c
 
 
+def library_build_id():
+    """sha256 (first 16 hex digits) of the loaded libdxmc_b200.so: profiles captured from another build do not apply"""
+    from opendxmc_b200 import _capi as K
+    h = hashlib.sha256()
+    with open(K.LIB_PATH, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(build_id):
+    """DRAM bytes per history of the transport kernel from the ncu --set full capture of THIS build (profiles/*traffic*.json
+    carry the build id they were captured from); None if the shipped kernel has changed since."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(os.listdir(pdir))
+    except OSError:
+        return None
+    for nm in names:
+        if "traffic" not in nm or not nm.endswith(".json"):
+            continue
+        try:
+            tj = json.load(open(os.path.join(pdir, nm)))
+        except Exception:
+            continue
+        if tj.get("library_build") == build_id and "dram_bytes_per_history" in tj:
+            best = (float(tj["dram_bytes_per_history"]), nm)
+    return best
+
+
 # --------------------------------------------------------------------------------------- CPU oracle legs
-def cpu_oracle_rate(args, wl, target_seconds):
-    """Times the CPU oracle (all host cores) on a bounded sample of the workload.  bench.py is one of the few places
-    allowed to execute oracle/ (as the measured *baseline*, never as the product)."""
+def oracle_sample(wl, target_seconds, seed_base, with_calibration):
+    """Times the CPU oracle (all host cores) on a bounded sample of the workload: the same beam with fewer histories per
+    exposure through the full volume (+ the nested CTDI calibration run scaled by the same factor when asked).
+    bench.py is one of the few places allowed to execute oracle/ (as the measured *baseline*, never as the product)."""
     from oracle import oracle_py as orc
-    import opendxmc_b200 as dx
     ow = orc.OracleWorld.from_workload(wl)
     nexp = wl.beam.numberOfExposures()
     full_ppe = wl.beam.numberOfParticlesPerExposure()
-    # size the sample so that it takes about target_seconds: probe, then rescale until the run is long enough
     ppe = max(1, 200_000 // nexp)
-    st = None
+    st = e = None
     for attempt in range(4):
         wl.beam.setNumberOfParticlesPerExposure(ppe)
-        _, _, _, st = ow.run(wl.beam, 1, SEED0 + attempt, 0)
+        e, _, _, st = ow.run(wl.beam, 1, seed_base + attempt, 0)
         if st["seconds"] >= 0.6 * target_seconds:
             break
         rate = st["histories"] / max(st["seconds"], 1e-9)
         ppe = max(ppe + 1, int(rate * target_seconds / nexp))
+    cal_seconds, cal_hist = 0.0, 0
+    if with_calibration:
+        cal_hist = max(36_000, int(CALIBRATION_HISTORIES * (ppe / full_ppe)))
+        t0 = time.perf_counter()
+        ow.ct_calibration(wl.beam, 1, seed_base, cal_hist)
+        cal_seconds = time.perf_counter() - t0
     wl.beam.setNumberOfParticlesPerExposure(full_ppe)
+    return {"ow": ow, "ppe": ppe, "nexp": nexp, "stats": st, "deposited_per_history": float(e.sum()) / st["histories"],
+            "calibration_seconds": cal_seconds, "calibration_histories": cal_hist}
+
+
+def cpu_oracle_rate(args, wl, target_seconds):
+    s = oracle_sample(wl, target_seconds, SEED0, False)
+    st = s["stats"]
     return {"value": st["histories"] / st["seconds"], "unit": "histories/s", "cores": int(st["threads"]), "kind": "port",
             "sample": "%d histories (%d per exposure x %d exposures) of the same beam through the full volume, %.1f s" % (
-                st["histories"], ppe, nexp, st["seconds"]),
-            "steps_per_history": st["steps"] / st["histories"], "deposits_per_history": st["deposits"] / st["histories"]}, ow
+                st["histories"], s["ppe"], s["nexp"], st["seconds"]),
+            "steps_per_history": st["steps"] / st["histories"], "deposits_per_history": st["deposits"] / st["histories"],
+            "deposited_kev_per_history": s["deposited_per_history"]}
 
 
 def run_reference(args):
@@ -273,6 +340,7 @@ def run_reference(args):
     ow = orc.OracleWorld.from_workload(wl)
     nexp = wl.beam.numberOfExposures()
     full = wl.beam.numberOfParticles()
+    full_ppe = wl.beam.numberOfParticlesPerExposure()
     per_step_seconds = min(20.0, 180.0 / max(1, args.steps + args.warmup))
     ppe = max(1, 200_000 // nexp)
     for attempt in range(3):
@@ -292,14 +360,24 @@ def run_reference(args):
         secs += st["seconds"]
         threads = st["threads"]
     value = hist / secs
+    # e2e of the CPU arm: the same step + the nested CTDI calibration run the reference's transport() call includes
+    # (R:src/libopendxmc/simulationpipeline.cpp:165, useBeamCalibration = true), scaled like the sample
+    cal_hist = max(36_000, int(CALIBRATION_HISTORIES * (ppe / full_ppe)))
+    t0 = time.perf_counter()
+    ow.ct_calibration(wl.beam, 1, SEED0, cal_hist)
+    cal_seconds = time.perf_counter() - t0
+    e2e_value = hist / (secs + cal_seconds * args.steps)
+    wl.beam.setNumberOfParticlesPerExposure(full_ppe)  # `config` names the workload, `cpu_baseline.sample` the bounded sample of it
     sample = "%d histories per step (%d per exposure x %d exposures) of the %d-history beam, full volume" % (ppe * nexp, ppe, nexp, full)
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
+    out = {"impl": "reference", "metric": METRICS[args.workload], "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(args, wl, {"reference": "CPU oracle = in-repo restatement of the DXMClib algorithm (DXMClib is not in "
                                                            "/root/reference and cannot be built offline), std::thread on all host cores"}),
            "cpu_baseline": {"value": value, "unit": "histories/s", "cores": int(threads), "kind": "port", "sample": sample},
-           "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "transport + nested CTDI calibration run of %d histories (the library's 36e6 scaled like the sample), %.2f s per step" % (
+                       cal_hist, cal_seconds)}}
     print(json.dumps(out), flush=True)
     return 0
 
@@ -318,6 +396,12 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libdxmc_b200 has no CPU fallback")
+    if args.inprocess and world_size > 1:
+        raise SystemExit("bench.py: --inprocess is ONE process driving --gpus devices; do not launch it under torchrun")
+    n_local = args.gpus if args.inprocess else 1   # devices behind this process's context
+    n_gpus = args.gpus if args.inprocess else world_size
+    if args.inprocess and torch.cuda.device_count() < n_local:
+        raise SystemExit("bench.py: --inprocess --gpus %d but only %d devices visible" % (n_local, torch.cuda.device_count()))
     torch.cuda.set_device(local_rank)
     dist = None
     if world_size > 1:
@@ -334,6 +418,7 @@ def run_ours(args):
         except Exception:
             pass
     lib = K.load()
+    build_id = library_build_id()
 
     wl = make_workload(args)
     n_hist = wl.beam.numberOfParticles()
@@ -347,67 +432,99 @@ def run_ours(args):
     out_pin = [torch.empty(nvox, dtype=torch.float64).pin_memory(), torch.empty(nvox, dtype=torch.float64).pin_memory(),
                torch.empty(nvox, dtype=torch.int64).pin_memory()] if rank == 0 else None
 
-    world = wl.build_world(1, [local_rank])
+    devices = list(range(n_local)) if args.inprocess else [local_rank]
+    world = wl.build_world(1, devices)
     ctx = world.ctx()
     world.set_history_range(rank, world_size)
-    stream = torch.cuda.Stream(device=local_rank)
-    K.load().dxb_set_stream(ctx, C.c_void_p(stream.cuda_stream))
-    tr = dx.Transport()
+    stream = None
+    if not args.inprocess:
+        stream = torch.cuda.Stream(device=local_rank)
+        lib.dxb_set_stream(ctx, C.c_void_p(stream.cuda_stream))
     desc = wl.beam.desc()
-    # N > 1: the exchange step.  Preferred: tallies in symmetric memory + the fused reduce->dose kernel (NVSwitch
-    # multicast sum, else P2P pull); fallback: one NCCL reduce of the tally buffer to rank 0 + energy->dose there.
-    exchange, tally = None, None
-    if dist is not None and args.exchange != "nccl":
-        try:
-            exchange = D.FusedExchange(world, local_rank, multicast=(args.exchange == "multicast"))
-        except Exception as exc:  # symmetric memory unavailable on this box
-            if rank == 0:
-                print(f"bench.py: fused exchange unavailable ({exc!r}); using the NCCL reduce", file=sys.stderr, flush=True)
-            exchange = None
-        ok = torch.tensor([1 if exchange is not None else 0], device=f"cuda:{local_rank}")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok) == 0 and exchange is not None:
-            exchange.close()
-            exchange = None
-    if exchange is None:
-        tally = D.tally_tensor(world, local_rank)
+
+    # ---- N > 1, one process per GPU: the exchange step
+    pipelined, fused, tally = None, None, None
+    if dist is not None:
+        def agreed(obj):
+            ok = torch.tensor([1 if obj is not None else 0], device=f"cuda:{local_rank}")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            return int(ok) == 1
+        choice = args.exchange
+        if choice == "pipelined":
+            try:
+                pipelined = D.PipelinedExchange(world, local_rank)
+            except Exception as exc:
+                print(f"bench.py: rank {rank}: library-managed exchange unavailable ({exc!r}); trying the fused multicast kernel", file=sys.stderr, flush=True)
+                pipelined = None
+            if not agreed(pipelined):
+                if pipelined is not None:
+                    lib.dxb_exchange_close(ctx)
+                pipelined, choice = None, "multicast"
+        if pipelined is None and choice in ("multicast", "p2p"):
+            try:
+                fused = D.FusedExchange(world, local_rank, multicast=(choice == "multicast"))
+            except Exception as exc:  # symmetric memory unavailable on this box
+                print(f"bench.py: rank {rank}: fused exchange unavailable ({exc!r}); using the NCCL reduce", file=sys.stderr, flush=True)
+                fused = None
+            if not agreed(fused):
+                if fused is not None:
+                    fused.close()
+                fused = None
+        if pipelined is None and fused is None:
+            tally = D.tally_tensor(world, local_rank)
+    sharded = pipelined if pipelined is not None else fused   # exchanges that leave the dose score distributed over the ranks
+    exchange_kind = ("none (1 GPU)" if n_gpus == 1 else
+                     "in-process multi-device context: copy-engine slab pulls + slab reduce->dose, pipelined under the next beam" if args.inprocess else
+                     "library-managed over CUDA IPC: copy-engine slab pulls + slab reduce->dose, pipelined under the next beam" if pipelined is not None else
+                     ("fused reduce->dose per slab, " + fused.kind) if fused is not None else "NCCL int64 reduce to rank 0 + energy->dose")
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        lib.dxb_flush(ctx)
 
-    # N > 1 with the fused exchange: the dose score stays distributed (rank r holds its slab), so the e2e read-out is
-    # sharded too - every rank copies ITS slab over its own PCIe link into result arrays that rank 0 (the caller) placed
-    # in host memory shared by the processes (dxb_get_dose_range), instead of gathering everything through rank 0.
     shared_out = None
-    if exchange is not None and not args.no_e2e:
-        shared_out = SharedHostArrays(rank, dist, nvox, torch, exchange.begin, exchange.end)
+    if sharded is not None and not args.no_e2e:
+        shared_out = SharedHostArrays(rank, dist, nvox, torch, sharded.begin, sharded.end)
         if not shared_out.ok:
             shared_out = None
 
-    def step(i, timed_stats=None):
-        """one beam with everything resident: tallies -> (reduce) -> dose."""
+    def transport_and_finish(i, use_calibration, timed_stats=None):
+        """one beam with everything resident: tallies -> exchange -> dose."""
         lib.dxb_set_seed(ctx, SEED0 + 7919 * (i + 1))
         rc = lib.dxb_run_transport(ctx, C.byref(desc), 1, None)
         assert rc == 0, lib.dxb_last_error(ctx)
         if timed_stats is not None:
             timed_stats.append(world.run_stats())
-        if exchange is not None:
+        if pipelined is not None:
+            pipelined.finish_beam(wl.beam, 1, use_calibration)   # barrier over the ranks + enqueue (asynchronous)
+            return
+        if fused is not None:
             with torch.cuda.stream(stream):
-                exchange.finish_beam(wl.beam, 1, False)
+                fused.finish_beam(wl.beam, 1, use_calibration)
             return
         if dist is not None:
             with torch.cuda.stream(stream):
                 D.reduce_tallies(tally, 0)
             stream.synchronize()
-        if rank == 0:
-            rc = lib.dxb_finish_beam(ctx, C.byref(desc), 1, 0, None)
+        if rank == 0 or dist is None:
+            rc = lib.dxb_finish_beam(ctx, C.byref(desc), 1, 1 if use_calibration else 0, None)
             assert rc == 0, lib.dxb_last_error(ctx)
 
-    def e2e_step(i):
-        """the reference-facing call sequence with host buffers: setData/build -> transport -> read dose."""
-        if exchange is not None:
+    def step(i, timed_stats=None):
+        transport_and_finish(i, False, timed_stats)
+
+    e2e_cal_ms = []
+
+    def e2e_step(i, with_materials=False):
+        """the reference-facing call sequence with host buffers: [materials ->] setData/build -> transport(useBeamCalibration = true) -> read dose."""
+        if with_materials:
+            g = world._item
+            mats = (K.VP * len(g._materials))(*[m._h for m in g._materials])
+            rc = lib.dxb_set_materials(ctx, len(g._materials), mats)
+            assert rc == 0, lib.dxb_last_error(ctx)
+        if sharded is not None:
             # one process per GPU: every rank uploads its slab, the packed slabs travel over NVLink
             D.set_grid_sharded(world, wl.dim, wl.spacing, wl.density, wl.material, local_rank, stream=stream)
         else:
@@ -415,15 +532,16 @@ def run_ours(args):
             sp = (C.c_double * 3)(*wl.spacing)
             rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
             assert rc == 0, lib.dxb_last_error(ctx)
-        step(1000 + i)
+        transport_and_finish(1000 + i, True)
+        e2e_cal_ms.append(world.run_stats()["calibration_ms"])
         if shared_out is not None:
-            rc = lib.dxb_get_dose_range(ctx, exchange.begin, exchange.end, shared_out.ptr(0, K.c_double_p), shared_out.ptr(1, K.c_double_p),
+            rc = lib.dxb_get_dose_range(ctx, sharded.begin, sharded.end, shared_out.ptr(0, K.c_double_p), shared_out.ptr(1, K.c_double_p),
                                         shared_out.ptr(2, K.c_u64_p))
             assert rc == 0, lib.dxb_last_error(ctx)
             return
-        if exchange is not None:
+        if fused is not None:
             with torch.cuda.stream(stream):
-                exchange.gather_dose(0)
+                fused.gather_dose(0)
         if rank == 0:
             rc = lib.dxb_get_dose(ctx, C.cast(out_pin[0].data_ptr(), K.c_double_p), C.cast(out_pin[1].data_ptr(), K.c_double_p),
                                   C.cast(out_pin[2].data_ptr(), K.c_u64_p))
@@ -437,18 +555,21 @@ def run_ours(args):
     stats = []
     barrier()
     sampler.mark_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev0.record(stream)
+    rc = lib.dxb_timer_begin(ctx)
+    assert rc == 0, lib.dxb_last_error(ctx)
     for i in range(args.steps):
         step(args.warmup + i, stats)
-    ev1.record(stream)
+    tm = C.c_double()
+    rc = lib.dxb_timer_end(ctx, C.byref(tm))   # after every stream of the context, the pending exchange included
+    assert rc == 0, lib.dxb_last_error(ctx)
     barrier()
     wall = time.perf_counter() - t0
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    tms = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    xt = (C.c_double * 3)()
+    lib.dxb_exchange_times(ctx, xt)
+    tms = torch.tensor([tm.value, wall * 1e3, xt[0], xt[1], xt[2]], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_total = float(tms[0])
@@ -462,35 +583,64 @@ def run_ours(args):
     hist_done, steps_done, deps_done, launches = [float(v) for v in k]
     kernel_ms = float(kms[0])
 
+    # ---- N = 1: the deposited energy per history of the last timed beam (read straight from its tallies)
+    dep_per_hist = None
+    if n_gpus == 1:
+        e = np.zeros(nvox)
+        rc = lib.dxb_get_energy_scored(ctx, e.ctypes.data_as(K.c_double_p), None, None)
+        assert rc == 0, lib.dxb_last_error(ctx)
+        dep_per_hist = float(e.sum()) / stats[-1]["histories"]
+        del e
+
     # ---- e2e
     e2e = None
     if not args.no_e2e:
-        e2e_step(-1)  # warm
+        e2e_step(-1)  # warm (builds the calibration phantom once per context, like the first beam of a session)
         barrier()
+        del e2e_cal_ms[:]
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 2))
         for i in range(n_e2e):
             e2e_step(i)
         barrier()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        te = torch.tensor([time.perf_counter() - t0, sum(e2e_cal_ms) / max(len(e2e_cal_ms), 1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        e2e_step(100, with_materials=True)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step(101, with_materials=True)
+        barrier()
+        tmat = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmat, op=dist.ReduceOp.MAX)
+        per_rank_upload = sharded is not None or args.inprocess
         e2e = {"value": n_hist * n_e2e / float(te[0]), "unit": "histories/s",
-               "h2d_bytes_per_step": int(nvox * 9 * (1 if exchange is not None else world_size)), "d2h_bytes_per_step": int(nvox * 24),
+               "h2d_bytes_per_step": int(nvox * 9 * (1 if per_rank_upload else n_gpus)), "d2h_bytes_per_step": int(nvox * 24),
                "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e,
-               "note": ("host-clock around dxb_set_grid_sharded (every rank uploads its slab, packed slabs all-gathered over NVLink) + "
-                        "dxb_run_transport + fused exchange/finish + dxb_get_dose_range of every rank's slab into "
-                        "pinned host arrays shared by the processes" if shared_out is not None else
-                        "host-clock around dxb_set_grid + dxb_run_transport + exchange/finish + (N>1: slab gather to rank 0) + dxb_get_dose, pinned host buffers")}
+               "calibration_ms": float(te[1]),
+               "calibration": "use_beam_calibration = 1: nested CTDI run of %d histories inside every timed step (device time reported as calibration_ms)" % CALIBRATION_HISTORIES,
+               "with_materials": {"value": n_hist / float(tmat[0]), "ms_per_step": 1e3 * float(tmat[0]),
+                                  "note": "the same step preceded by dxb_set_materials (host table build + upload), 1 timed step"},
+               "note": ("host clock around: dxb_set_grid%s + dxb_run_transport + %sdxb_finish_beam(use_beam_calibration = 1) + %s" % (
+                   "_sharded (every rank uploads its slab, packed slabs all-gathered over NVLink)" if sharded is not None else
+                   " (every device uploads its slab, packed slabs all-gathered by peer copies)" if args.inprocess and n_gpus > 1 else "",
+                   "barrier + " if dist is not None else "",
+                   "dxb_get_dose_range of every rank's slab into pinned host arrays shared by the processes" if shared_out is not None else
+                   "dxb_get_dose (every device copies its slab over its own PCIe link)" if args.inprocess and n_gpus > 1 else
+                   "(N>1: slab gather to rank 0) + dxb_get_dose, pinned host buffers"))}
         if shared_out is not None and rank == 0:
             # the caller's view: every voxel of the three arrays was written by exactly one rank
             e2e["events_read_back"] = int(shared_out.arrays[2].sum())
+        elif rank == 0:
+            e2e["events_read_back"] = int(out_pin[2].sum())
 
     if shared_out is not None:
         shared_out.close(rank)
+    if pipelined is not None:
+        pipelined.close()
+    if fused is not None:
+        fused.close()
     if rank != 0:
-        if exchange is not None:
-            exchange.close()
         world.close()
         if dist is not None:
             dist.destroy_process_group()
@@ -503,42 +653,52 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     S = steps_done / hist_done
-    D = deps_done / hist_done
-    a_hist = S * 5.0 + D * 48.0
-    # per-GPU roofline of the transport kernel: this rank's share of the histories over the slowest rank's kernel time
-    achieved = (hist_done / world_size) * a_hist / (kernel_ms * 1e-3) / 1e9
-    # measured DRAM traffic of the kernel (one `ncu --set full` capture, profiles/r01_pool_traffic.json), per launch
-    traffic, traffic_per_hist = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pool_traffic.json")))
-        traffic_per_hist = float(tj["dram_bytes_per_history"])
-        traffic = traffic_per_hist * hist_done / max(launches, 1.0)
-    except Exception:
-        pass
+    Dd = deps_done / hist_done
+    a_hist = S * 5.0 + Dd * 48.0
+    # per-GPU roofline of the transport kernel: this GPU's share of the histories over the slowest GPU's kernel time
+    achieved = (hist_done / n_gpus) * a_hist / (kernel_ms * 1e-3) / 1e9
+    # measured DRAM traffic of the kernel: one `ncu --set full` capture of THIS library build (profiles/*traffic*.json), per launch
+    tr = measured_traffic(build_id)
+    traffic_per_hist = tr[0] if tr else None
+    traffic = traffic_per_hist * hist_done / max(launches, 1.0) if tr else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum per history x histories per launch)",
-                "traffic_bytes_per_history": traffic_per_hist, "algorithmic_bytes_per_launch": a_hist * hist_done / max(launches, 1.0),
-                "kernel": "transportKernelPool<1,false,true,16>", "peak_source": "measured" if peaks else "fallback",
-                "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": D,
-                "sector_bytes_per_history": (S + 3 * D) * 32.0,
+                "traffic_bytes_per_history": traffic_per_hist, "traffic_build": build_id if tr else None, "traffic_source": tr[1] if tr else
+                "none: no profiles/*traffic*.json was captured from the loaded library build " + build_id,
+                "library_build": build_id,
+                "algorithmic_bytes_per_launch": a_hist * hist_done / max(launches, 1.0),
+                "kernel": "transportKernelPool<1,false,true,16,0>", "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": Dd,
+                "sector_bytes_per_history": (S + 3 * Dd) * 32.0, "sector_frac": (hist_done / n_gpus) * (S + 3 * Dd) * 32.0 / (kernel_ms * 1e-3) / 1e9 / peak,
                 "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / ms_total}
     value = n_hist * args.steps / (ms_total * 1e-3)
-    out = {"metric": METRIC, "value": value, "unit": "histories/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+    finish_kernels = args.steps * (n_gpus if (sharded is not None or args.inprocess) else 1)
+    out = {"metric": METRICS[args.workload], "value": value, "unit": "histories/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl, {"parallelism": "histories sharded over %d GPU(s)" % world_size,
-                                                                 "exchange": ("none (1 GPU)" if dist is None else
-                                                                              ("fused reduce->dose per slab, " + exchange.kind) if exchange is not None
-                                                                              else "NCCL int64 reduce to rank 0 + energy->dose")}),
-           "clocks": clocks, "gpu_launches": int(launches + args.steps * (world_size if exchange is not None else 1)),  # transport kernels (all ranks) + energy->dose (rank 0, or one fused slab kernel per rank)
+           "dtype": "f32", "data": "synthetic",
+           "config": config_dict(args, wl, {"parallelism": "histories sharded over %d GPU(s), %s" % (
+               n_gpus, "one process drives all of them (multi-device dxb_ctx)" if args.inprocess else "one process per GPU"),
+               "exchange": exchange_kind, "calibration_in_value": "off (device-resident beams); e2e runs with use_beam_calibration = 1"}),
+           "clocks": clocks, "gpu_launches": int(launches + finish_kernels),  # transport kernels (all GPUs) + energy->dose / slab reduce kernels
            "roofline": roofline}
+    if n_gpus > 1:
+        out["exchange_ms"] = {"pulls": float(tms[2]), "slab_reduce_to_dose": float(tms[3]), "clear": float(tms[4]),
+                              "non_kernel_ms_per_step": (ms_total - kernel_ms) / args.steps,
+                              "note": "device time of the LAST beam's exchange (max over ranks); with the pipelined exchange the earlier ones ran "
+                                      "underneath the next beam's transport kernels - non_kernel_ms_per_step is what stayed exposed per beam "
+                                      "(barrier, tail of the slab reduce, the last exchange / K)"}
     if e2e:
         out["e2e"] = e2e
-    if exchange is not None:
-        exchange.close()
     world.close()
-    if not args.no_cpu_baseline and world_size == 1:  # the CPU baseline is reported at N = 1 only
-        cb, _ = cpu_oracle_rate(args, wl, args.cpu_seconds)
+    if not args.no_cpu_baseline and n_gpus == 1 and world_size == 1:  # the CPU baseline is reported at N = 1 only
+        cb = cpu_oracle_rate(args, wl, args.cpu_seconds)
         out["cpu_baseline"] = cb
+        # the timed GPU step is a correct one: same physics, same tables, independent histories
+        rel = abs(dep_per_hist - cb["deposited_kev_per_history"]) / cb["deposited_kev_per_history"]
+        out["dose_check"] = {"gpu_deposited_kev_per_history": dep_per_hist, "oracle_deposited_kev_per_history": cb["deposited_kev_per_history"],
+                             "rel": rel, "tolerance": 5e-3, "ok": bool(rel <= 5e-3)}
+        assert rel <= 5e-3, "the timed GPU step deposits %.6g keV/history, the oracle sample %.6g (> 0.5 %%)" % (
+            dep_per_hist, cb["deposited_kev_per_history"])
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -234,13 +234,17 @@ __device__ __forceinline__ bool dopplerBroaden(const TablesDev& tab, int mat, fl
     const float u = fminf(fmaxf(rPz, kU24), 1.0f - kU24);
     float pz = __logf(__fdividef(u, 1.0f - u)) * __fdividef(0.25f, j0) * kFineStructure; // in units of m_e c
     pz = fminf(fmaxf(pz, -0.5f), 0.5f);
+    // E'/E = e0 / b * (a + sign(pz) sqrt(a^2 - b (1 - t))), t = pz^2, a = 1 - t e0 cos, b = 1 - t e0^2.  Expanded, the
+    // discriminant is t (q - t e0^2 sin^2) with q = (1 - e0)^2 + 2 e0 (1 - cos): no cancellation of O(1) terms in f32,
+    // and sign(pz) sqrt(t) = pz.
     const float t = pz * pz;
     const float te0 = t * e0;
     const float a = fmaf(-te0, cosT, 1.0f);
     const float b = fmaf(-te0, e0, 1.0f);
-    const float disc = fmaxf(fmaf(a, a, -(b * (1.0f - t))), 0.0f);
-    const float root = sqrtf(disc);
-    const float e = __fdividef(e0, b) * (a + (pz < 0.0f ? -root : root));
+    const float ome = 1.0f - e0;
+    const float q = fmaf(2.0f * e0, 1.0f - cosT, ome * ome);
+    const float disc = fmaxf(fmaf(-te0 * e0, fmaf(-cosT, cosT, 1.0f), q), 0.0f);
+    const float e = __fdividef(e0, b) * fmaf(pz, sqrtf(disc), a);
     if (!(e > 0.0f) || !(fmaf(-E, e, E) > U))
         return false;
     eOut = fminf(e, 1.0f);

@@ -376,12 +376,14 @@ bool dopplerBroaden(const OMaterial& material, double energy, double e0, double 
     const double u = std::min(std::max(rPz, U24), 1.0 - U24);
     double pz = std::log(u / (1.0 - u)) * (0.25 / j0) * FINE_STRUCTURE;
     pz = std::min(std::max(pz, -0.5), 0.5);
+    // E'/E = e0 / b (a + sign(pz) sqrt(a^2 - b (1 - t))), written with the expanded discriminant t (q - t e0^2 sin^2),
+    // q = (1 - e0)^2 + 2 e0 (1 - cos), like the device (no cancellation of O(1) terms in f32)
     const double t = pz * pz;
     const double a = 1.0 - t * e0 * cosTheta;
     const double b = 1.0 - t * e0 * e0;
-    const double disc = std::max(a * a - b * (1.0 - t), 0.0);
-    const double root = std::sqrt(disc);
-    const double e = e0 / b * (a + (pz < 0 ? -root : root));
+    const double q = (1.0 - e0) * (1.0 - e0) + 2.0 * e0 * (1.0 - cosTheta);
+    const double disc = std::max(q - t * e0 * e0 * (1.0 - cosTheta * cosTheta), 0.0);
+    const double e = e0 / b * (a + pz * std::sqrt(disc));
     if (!(e > 0) || !(energy - energy * e > U))
         return false;
     eOut = std::min(e, 1.0);

@@ -1,23 +1,38 @@
 """Same-stream parity checks shared by the GPU tests.
 
 The kernels and the oracle draw the SAME Philox streams (key, history id, block) and read the same tables, so their
-outputs differ only where f32 and f64 arithmetic round differently: a handful of histories per million take another
-branch, a few deposits per hundred thousand land in the neighbouring voxel.  The tests therefore assert what the design
-delivers, orders of magnitude tighter than the acceptance bar of BASELINE.json (north_star: total deposited energy
-within 0.5 %, ROI / organ dose within 3 combined standard errors - still checked, as the documented bar):
+outputs differ only where f32 and f64 arithmetic round differently: a few histories per million take another branch
+of an acceptance test, and a deposit lands in the neighbouring voxel when the f32 position (rounding error ~5e-6 cm at
+|x| ~ 20-60 cm) sits that close to a voxel face - a probability proportional to 1 / voxel size.  The tests assert what
+the design delivers, orders of magnitude tighter than the acceptance bar of BASELINE.json (north_star: total deposited
+energy within 0.5 %, ROI / organ dose within 3 combined standard errors - still checked, as the documented bar):
 
-    total deposited energy          relative difference <= 1e-5
-    steps / interactions / deposits relative difference <= 1e-5 each  (they feed the roofline model)
-    event-count arrays              equal on >= 99.9 % of the voxels
-    voxel-wise energy               sum |E_gpu - E_oracle| / sum E_oracle <= 1e-4
+    total deposited energy           relative difference <= 1e-5   (physics mode 2: 5e-5)
+    steps / interactions / deposits  relative difference <= 1e-5 each (mode 2: 5e-5; they feed the roofline)
+    misplaced events                 sum |n_gpu - n_oracle| / (2 sum n_oracle) <= max(1e-4, 4e-5 cm / voxel size)
+    voxel-wise energy                sum |E_gpu - E_oracle| / sum E_oracle     <= max(2e-4, 1e-4 cm / voxel size)
+                                     (mode 2: x 3 - the Doppler-broadened energy of every bound-electron collision is an
+                                     f32 result of several rounded operations)
 
-A kernel regression that misplaces or loses 0.3 % of the energy passes the acceptance bar but not these."""
+Measured on B200 (profiles/r02_parity_metrics.jsonl): totals 1e-8 ... 6e-6, counters <= 9e-6, misplaced events 3e-5 at
+5 mm voxels and 2e-4 at 0.8 mm, voxel-wise energy 2e-6 ... 1.2e-4 (4e-4 at 0.8 mm voxels).  A kernel regression that
+misplaces or loses 0.3 % of the energy passes the acceptance bar but not these."""
+import json
+import os
+
 import numpy as np
 
 TOTAL_ENERGY_RTOL = 1e-5
 COUNTER_RTOL = 1e-5
-EQUAL_VOXEL_FRACTION = 0.999
-VOXELWISE_ENERGY_RTOL = 1e-4
+MODE2_FACTOR = 5.0
+
+
+def misplaced_bound(voxel_cm):
+    return max(1e-4, 4e-5 / voxel_cm)
+
+
+def voxelwise_bound(voxel_cm):
+    return max(2e-4, 1e-4 / voxel_cm)
 
 
 def same_stream_metrics(e, cnt, st, oe, ocnt, ost):
@@ -25,20 +40,28 @@ def same_stream_metrics(e, cnt, st, oe, ocnt, ost):
     cnt, ocnt = np.asarray(cnt), np.asarray(ocnt)
     m = {"total_energy_rel": abs(e.sum() - oe.sum()) / oe.sum(),
          "equal_voxel_fraction": float(np.count_nonzero(cnt == ocnt)) / cnt.size,
+         "misplaced_event_fraction": float(np.abs(cnt.astype(np.int64) - ocnt.astype(np.int64)).sum()) / (2.0 * max(int(ocnt.sum()), 1)),
          "voxelwise_energy_rel": float(np.abs(e - oe).sum() / oe.sum())}
     for k in ("steps", "interactions", "deposits"):
         m[k + "_rel"] = abs(int(st[k]) - int(ost[k])) / max(int(ost[k]), 1)
     return m
 
 
-def assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, what="", counter_floor=0):
-    """`counter_floor`: runs with few events cannot resolve 1e-5; a difference of up to that many events also passes."""
+def assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, what="", voxel_cm=0.5, mode=1, counter_floor=30):
+    """`voxel_cm`: smallest voxel edge of the grid; `counter_floor`: runs with few events cannot resolve 1e-5, a difference
+    of up to that many events also passes."""
     m = same_stream_metrics(e, cnt, st, oe, ocnt, ost)
+    k2 = MODE2_FACTOR if mode == 2 else 1.0
+    m["voxel_cm"], m["mode"] = float(voxel_cm), int(mode)
     msg = f"{what} {m}"
+    log = os.environ.get("DXB_PARITY_LOG")  # keeps the measured margins of a GPU run (profiles/*parity_metrics*)
+    if log:
+        with open(log, "a") as f:
+            f.write(json.dumps({"what": what, "histories": int(st["histories"]), **m}) + "\n")
     assert int(st["histories"]) == int(ost["histories"]), msg
-    assert m["total_energy_rel"] <= TOTAL_ENERGY_RTOL, msg
+    assert m["total_energy_rel"] <= TOTAL_ENERGY_RTOL * k2, msg
     for k in ("steps", "interactions", "deposits"):
-        assert m[k + "_rel"] <= COUNTER_RTOL or abs(int(st[k]) - int(ost[k])) <= counter_floor, msg
-    assert m["equal_voxel_fraction"] >= EQUAL_VOXEL_FRACTION, msg
-    assert m["voxelwise_energy_rel"] <= VOXELWISE_ENERGY_RTOL, msg
+        assert m[k + "_rel"] <= COUNTER_RTOL * k2 or abs(int(st[k]) - int(ost[k])) <= counter_floor, msg
+    assert m["misplaced_event_fraction"] <= misplaced_bound(voxel_cm) * k2, msg
+    assert m["voxelwise_energy_rel"] <= voxelwise_bound(voxel_cm) * (3.0 if mode == 2 else 1.0), msg
     return m

@@ -29,7 +29,7 @@ def _compare_run(dx, orc, wl, mode=1, rois=None, tol=5e-3):
     assert abs(e.sum() - oe.sum()) / oe.sum() <= tol, (e.sum(), oe.sum())
     for k in ("steps", "interactions", "deposits"):
         assert abs(st[k] - ost[k]) / max(ost[k], 1) < tol, (k, st[k], ost[k])
-    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, "", counter_floor=30)
+    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"{wl.name} mode {mode}", voxel_cm=min(wl.spacing), mode=mode)
     for name, m in (rois or {}).items():
         a, b = e[m].sum(), oe[m].sum()
         s = np.sqrt(e2[m].sum() + oe2[m].sum())

@@ -73,7 +73,7 @@ def test_c1_energy_and_roi_parity(dx, orc, c1, mode):
         assert abs(st[k] - ost[k]) / ost[k] < 5e-3, (k, st[k], ost[k])
     assert abs(int(cnt.sum()) - int(ocnt.sum())) / ocnt.sum() < 5e-3
     # what the shared random streams deliver: 1e-5 on totals and counters, voxel-wise agreement (tests/parity.py)
-    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"C1 mode {mode}", counter_floor=30)
+    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"C1 mode {mode}", voxel_cm=min(c1.spacing), mode=mode)
     # ROIs: centre rod, four periphery rods, whole PMMA, air
     n = c1.dim[0]
     d = c1.spacing[0]
@@ -126,7 +126,7 @@ def test_c2_small_parity(dx, orc):
     assert abs(e.sum() - oe.sum()) / oe.sum() <= 5e-3
     for k in ("steps", "interactions", "deposits"):
         assert abs(st[k] - ost[k]) / ost[k] < 5e-3, (k, st[k], ost[k])
-    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, "C2 scale 4", counter_floor=30)
+    assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, "C2 scale 4", voxel_cm=min(wl.spacing))
     rois = {nm: wl.organ == i for i, nm in enumerate(wl.organ_names)}
     nz = wl.dim[2]
     zidx = np.repeat(np.arange(nz), wl.dim[0] * wl.dim[1])
@@ -260,7 +260,7 @@ def test_mode2_fluorescence_and_doppler_parity(dx, orc):
         assert abs(e.sum() - oe.sum()) / oe.sum() <= 5e-3
         for k in ("steps", "interactions", "deposits"):
             assert abs(st[k] - ost[k]) / ost[k] < 5e-3, (mode, k, st[k], ost[k])
-        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"Ca block mode {mode}", counter_floor=30)
+        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"Ca block mode {mode}", voxel_cm=min(spacing), mode=mode)
         rois = {"water": mat.reshape(-1) == 0, "bone": mat.reshape(-1) == 1}
         _roi_check(np.array(e), np.array(e2), oe, oe2, rois)
         out[mode] = (st, float(np.array(e).sum()))
@@ -303,7 +303,7 @@ def test_external_material_tables_on_the_device(dx, orc):
         e, e2, cnt = world.energy_scored()
         st = world.run_stats()
         oe, oe2, ocnt, ost = ow.run(beam, 1, SEED)
-        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"external tables: {name}", counter_floor=30)
+        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"external tables: {name}", voxel_cm=min(sp))
         out[name] = (float(e.sum()), st["interactions"] / st["histories"])
         world.close()
     assert out["ext"][1] < 0.97 * out["water"][1]
