@@ -8,7 +8,7 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -ftz=true -prec-div=fals
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
-OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o build/exchange.o
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o build/exchange.o build/icrp.o build/import_kernels.o
 
 all: $(LIB) oracle ref
 

@@ -442,6 +442,31 @@ int dxb_segment_ct(dxb_ctx*, const double* hu, uint64_t n, const dxb_tube_desc* 
                    uint8_t* material_out, double* density_out,
                    dxb_material** materials_out /* [5], caller destroys */);
 
+/* ICRP 110 / 143 voxel-phantom import, SURVEY §8f-2: what ICRPPhantomImportPipeline::importPhantom does with the
+ * phantom's organ array and its two text tables (R:src/libopendxmc/icrpphantomimportpipeline.cpp:209-351; parsers :59-205):
+ * "Air" appended as organ 0 / medium 0; with remove_arms the organs named *arm*, *hand*, *Humeri*, *Ulnae* become air;
+ * organs absent from the array are dropped and the rest renumbered consecutively, unused media likewise; material and
+ * density arrays by organ lookup.  The tables are passed as the TEXT of `<phantom>_organs.dat` / `<phantom>_media.dat`.
+ *   dxb_icrp_import  device path: presence scan + one look-up-table gather per voxel over the organ array (n = nx*ny*nz
+ *                    bytes, x fastest), writes organ / material (u8) and density (f64) arrays of n elements;
+ *   dxb_icrp_plan    the host-side rules alone, given which organ values occur (`present[v] != 0`); dxb_icrp_luts returns
+ *                    the three 256-entry tables the device pass applies (organ value -> organ index, medium, density).
+ * The plan lists the surviving organs (name, density, medium index) and media (name, composition in mass %, zero
+ * entries kept like the reference, to hand to dxb_material_by_weight). */
+typedef struct dxb_icrp dxb_icrp;
+int dxb_icrp_import(dxb_ctx*, const uint8_t* organ_in, uint64_t n, const char* organs_dat, const char* media_dat, int remove_arms,
+                    uint8_t* organ_out, uint8_t* material_out, double* density_out, dxb_icrp** plan_out);
+int dxb_icrp_plan(dxb_icrp** out, const char* organs_dat, const char* media_dat, int remove_arms, const uint8_t present[256]);
+int dxb_icrp_luts(const dxb_icrp*, uint8_t organ_lut[256], uint8_t material_lut[256], double density_lut[256]);
+void dxb_icrp_destroy(dxb_icrp*);
+uint32_t dxb_icrp_n_organs(const dxb_icrp*);
+const char* dxb_icrp_organ_name(const dxb_icrp*, uint32_t index);
+double dxb_icrp_organ_density(const dxb_icrp*, uint32_t index);
+uint32_t dxb_icrp_organ_medium(const dxb_icrp*, uint32_t index);
+uint32_t dxb_icrp_n_media(const dxb_icrp*);
+const char* dxb_icrp_medium_name(const dxb_icrp*, uint32_t index);
+int dxb_icrp_medium_composition(const dxb_icrp*, uint32_t index, uint32_t* Z, double* weight, int cap); /* returns the element count */
+
 int dxb_abi_version(void);
 int dxb_device_count(void);
 

@@ -190,6 +190,17 @@ SIGNATURES = {
     "dxb_get_run_stats": (C.c_int, [VP, C.POINTER(dxb_run_stats)]),
     "dxb_device_attenuation": (C.c_int, [VP, C.c_uint32, C.c_int, c_double_p, C.c_uint32, c_float_p]),
     "dxb_device_majorant": (C.c_int, [VP, c_double_p, C.c_uint32, c_float_p]),
+    "dxb_icrp_import": (C.c_int, [VP, c_u8_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int, c_u8_p, c_u8_p, c_double_p, C.POINTER(VP)]),
+    "dxb_icrp_plan": (C.c_int, [C.POINTER(VP), C.c_char_p, C.c_char_p, C.c_int, c_u8_p]),
+    "dxb_icrp_luts": (C.c_int, [VP, c_u8_p, c_u8_p, c_double_p]),
+    "dxb_icrp_destroy": (None, [VP]),
+    "dxb_icrp_n_organs": (C.c_uint32, [VP]),
+    "dxb_icrp_organ_name": (C.c_char_p, [VP, C.c_uint32]),
+    "dxb_icrp_organ_density": (C.c_double, [VP, C.c_uint32]),
+    "dxb_icrp_organ_medium": (C.c_uint32, [VP, C.c_uint32]),
+    "dxb_icrp_n_media": (C.c_uint32, [VP]),
+    "dxb_icrp_medium_name": (C.c_char_p, [VP, C.c_uint32]),
+    "dxb_icrp_medium_composition": (C.c_int, [VP, C.c_uint32, c_u32_p, c_double_p, C.c_int]),
     "dxb_segment_ct": (C.c_int, [VP, c_double_p, C.c_uint64, C.POINTER(dxb_tube_desc), c_u8_p, c_double_p, C.POINTER(VP)]),
 }
 

@@ -221,6 +221,72 @@ def ct_dual_source_thorax(scale=1, histories=10_000_000_000, step_deg=1.0):
                     beam, organ=material.copy(), organ_names=["air", "lung", "soft tissue", "bone"])
 
 
+def icrp_dat_text(phantom):
+    """The phantom's `<phantom>_organs.dat` / `<phantom>_media.dat` tables as TEXT in the layout of the ICRP files (id at
+    column 0, name from column 6, tissue number and density behind a name field at least 50 characters wide; media:
+    id, name, 13 mass-% columns for Z = 1,6,7,8,11,12,15,16,17,19,20,26,53), regenerated from the packaged
+    icrp_tables.json - the input of dxb_icrp_import / dxb_icrp_plan (include/dxb.h).  The reference's own parser reads
+    this text to the same tables as the original files (tests/test_reference_sources_compile.py)."""
+    t = icrp_tables()[phantom]
+    organs = ["Organs and tissues of the %s reference computational phantom" % phantom, "", "Organ Organ" + " " * 42 + "Tissue Density",
+              "ID" + " " * 51 + "number"]
+    for o in t["organs"]:
+        d = "%.3f" % o["density"]
+        if float(d) != o["density"]:
+            d = repr(float(o["density"]))
+        organs.append("%-6d%-49s%2d%9s" % (o["id"], o["name"], o["medium"], d))
+    zs = [1, 6, 7, 8, 11, 12, 15, 16, 17, 19, 20, 26, 53]
+    media = [" " * 80 + "".join("%6d" % z for z in zs), "No." + " " * 100 + "(% by mass)"]
+    for m in t["media"]:
+        cols = []
+        for z in zs:
+            w = m["composition"][str(z)]
+            c = "%.1f" % w
+            cols.append(c if float(c) == w else repr(float(w)))
+        media.append("%-6d%-72s%s" % (m["id"], m["name"], "".join("%6s" % c for c in cols)))
+    return "\n".join(organs) + "\n", "\n".join(media) + "\n"
+
+
+def icrp_import(organ_array, organs_text, media_text, remove_arms=False, world=None):
+    """ICRPPhantomImportPipeline::importPhantom through the C ABI (R:src/libopendxmc/icrpphantomimportpipeline.cpp:258-351).
+    With a `world` (a built api.World: any context with a device) the O(N) passes run on the GPU (dxb_icrp_import);
+    without one the host-side rules alone are evaluated (dxb_icrp_plan) and the three look-up tables applied with numpy.
+    Returns (organ, organ_names, material, density, media_names, compositions) like import_icrp_tables."""
+    import ctypes as C
+    from . import _capi as K
+    lib = K.load()
+    organ_array = np.ascontiguousarray(organ_array, dtype=np.uint8).reshape(-1)
+    n = organ_array.size
+    plan = K.VP()
+    if world is not None:
+        organ, material, density = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8), np.zeros(n)
+        rc = lib.dxb_icrp_import(world.ctx(), organ_array.ctypes.data_as(K.c_u8_p), n, organs_text.encode(), media_text.encode(),
+                                 1 if remove_arms else 0, organ.ctypes.data_as(K.c_u8_p), material.ctypes.data_as(K.c_u8_p),
+                                 density.ctypes.data_as(K.c_double_p), C.byref(plan))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_icrp_import", (lib.dxb_last_error(world.ctx()) or b"").decode())
+    else:
+        present = np.zeros(256, dtype=np.uint8)
+        present[np.unique(organ_array)] = 1
+        rc = lib.dxb_icrp_plan(C.byref(plan), organs_text.encode(), media_text.encode(), 1 if remove_arms else 0, present.ctypes.data_as(K.c_u8_p))
+        if rc != K.DXB_OK:
+            raise K.DxbError(rc, "dxb_icrp_plan")
+        lo, lm, ld = np.zeros(256, dtype=np.uint8), np.zeros(256, dtype=np.uint8), np.zeros(256)
+        lib.dxb_icrp_luts(plan, lo.ctypes.data_as(K.c_u8_p), lm.ctypes.data_as(K.c_u8_p), ld.ctypes.data_as(K.c_double_p))
+        organ, material, density = lo[organ_array], lm[organ_array], ld[organ_array]
+    try:
+        names = [lib.dxb_icrp_organ_name(plan, i).decode() for i in range(lib.dxb_icrp_n_organs(plan))]
+        media_names, comps = [], []
+        for i in range(lib.dxb_icrp_n_media(plan)):
+            media_names.append(lib.dxb_icrp_medium_name(plan, i).decode())
+            z, w = np.zeros(16, dtype=np.uint32), np.zeros(16)
+            k = lib.dxb_icrp_medium_composition(plan, i, z.ctypes.data_as(K.c_u32_p), w.ctypes.data_as(K.c_double_p), 16)
+            comps.append({int(z[j]): float(w[j]) for j in range(k)})
+    finally:
+        lib.dxb_icrp_destroy(plan)
+    return organ, names, material, density, media_names, comps
+
+
 def import_icrp_tables(phantom, organ_array):
     """ICRPPhantomImportPipeline::importPhantom remap rules — R:src/libopendxmc/icrpphantomimportpipeline.cpp:209-351:
     air appended as organ 0 / medium 0 (rho 0.001, {N:0.8,O:0.2}); organs absent from the array pruned and ids made

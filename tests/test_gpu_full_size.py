@@ -134,7 +134,9 @@ def test_dose_score_accumulates_linearly_over_beams(dx, c2_full):
     assert tr(world, wl.beam, None, False)
     d3, v3, n3 = world.fetch_dose()
     assert not np.array_equal(n3 - n2, n1)
-    assert abs((d3.sum() - d2.sum()) - d1.sum()) / d1.sum() < 5e-3
+    assert abs(int(n3.sum() - n2.sum()) - int(n1.sum())) / n1.sum() < 5e-3
+    body = wl.material > 0  # (the dose of a single event in an air voxel is huge: compare where the statistics are)
+    assert abs((d3[body].sum() - d2[body].sum()) - d1[body].sum()) / d1[body].sum() < 2e-2
     world.close()
 
 

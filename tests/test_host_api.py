@@ -447,3 +447,64 @@ def test_external_material_tables_drop_in(dx, orc):
     bad = dict(b)
     bad["ff_cdf"] = b["ff_cdf"][::-1].copy()
     assert dx.Material.fromTables(bad, water) is None
+
+
+def _arms_removed(dx, phantom, raw):
+    out = raw.copy()
+    for o in dx.workloads.icrp_tables()[phantom]["organs"]:
+        if any(k in o["name"] for k in ("arm", "hand", "Humeri", "Ulnae")):
+            out[out == o["id"]] = 0
+    return out
+
+
+@pytest.mark.parametrize("phantom", ["AM", "AF", "10M", "00F", "15F"])
+@pytest.mark.parametrize("remove_arms", [False, True])
+def test_icrp_plan_equals_the_python_import_rules(dx, phantom, remove_arms):
+    """dxb_icrp_plan (C++: parses the *_organs.dat / *_media.dat TEXT, folds arm removal, organ pruning / renumbering and
+    media pruning into three 256-entry tables) against workloads.import_icrp_tables, the Python restatement that
+    tests/test_reference_sources_compile.py checks against the reference's own importPhantom."""
+    organs_text, media_text = dx.workloads.icrp_dat_text(phantom)
+    ids = np.array([o["id"] for o in dx.workloads.icrp_tables()[phantom]["organs"]], dtype=np.uint8)
+    rng = np.random.default_rng(len(phantom) + 17 * remove_arms)
+    cases = [np.concatenate([ids, ids[::-1], np.zeros(7, dtype=np.uint8)]),                      # every organ occurs
+             rng.choice(np.concatenate([ids[::3], [0]]).astype(np.uint8), 4099).astype(np.uint8),   # a sparse subset (+ air)
+             rng.choice(ids[5:40], 515).astype(np.uint8)]                                          # no air voxel at all
+    for raw in cases:
+        organ, names, material, density, media_names, comps = dx.workloads.icrp_import(raw, organs_text, media_text, remove_arms)
+        ref_raw = _arms_removed(dx, phantom, raw) if remove_arms else raw
+        r_organ, r_names, r_material, r_density, r_media, r_comps = dx.workloads.import_icrp_tables(phantom, ref_raw)
+        assert np.array_equal(organ, r_organ) and names == r_names
+        assert np.array_equal(material, r_material) and np.array_equal(density, r_density)
+        assert media_names == r_media
+        for c, rc in zip(comps, r_comps):
+            assert {z: w for z, w in c.items() if w > 0} == rc
+        assert int(material.max()) < len(media_names) and int(organ.max()) < len(names)
+
+
+def test_icrp_plan_rejects_empty_tables(dx):
+    from opendxmc_b200 import _capi as K
+    import ctypes as C
+    organs_text, media_text = dx.workloads.icrp_dat_text("AM")
+    present = np.ones(256, dtype=np.uint8)
+    plan = K.VP()
+    assert K.load().dxb_icrp_plan(C.byref(plan), b"no organ line here\n", media_text.encode(), 0, present.ctypes.data_as(K.c_u8_p)) == K.DXB_EINVAL
+    assert K.load().dxb_icrp_plan(C.byref(plan), organs_text.encode(), b"\n\n", 0, present.ctypes.data_as(K.c_u8_p)) == K.DXB_EINVAL
+
+
+def test_icrp_import_golden_from_the_reference(dx):
+    """tests/golden/icrp_import_golden.json: outputs of the reference's own ICRPPhantomImportPipeline::importPhantom
+    (oracle/_ref/opendxmc_ref icrp, generated by tests/golden/make_icrp_golden.py where /root/reference is mounted) on the
+    regenerated table text and small organ arrays; the host-side plan must reproduce them exactly."""
+    import json
+    import os
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icrp_import_golden.json")))
+    assert len(golden["cases"]) >= 6
+    for case in golden["cases"]:
+        organs_text, media_text = dx.workloads.icrp_dat_text(case["phantom"])
+        raw = np.array(case["input"], dtype=np.uint8)
+        organ, names, material, density, media_names, comps = dx.workloads.icrp_import(raw, organs_text, media_text, case["remove_arms"])
+        assert np.array_equal(organ, case["organ"]) and names == case["organ_names"], case["name"]
+        assert np.array_equal(material, case["material"]) and np.array_equal(density, np.array(case["density"])), case["name"]
+        assert media_names == case["media_names"]
+        for c, rc in zip(comps, case["media_composition"]):
+            assert c == {int(z): w for z, w in rc.items()}
