@@ -8,13 +8,13 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -ftz=true -prec-div=fals
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall
 
 LIB := $(LIBDIR)/libdxmc_b200.so
-OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o build/exchange.o build/icrp.o build/import_kernels.o
+OBJS := build/atom.o build/material.o build/tube.o build/beams.o build/capi.o build/transport.o build/transport_mux.o build/transport_pool.o build/context.o build/exchange.o build/icrp.o build/import_kernels.o build/h5mini.o build/h5_capi.o build/scene_io.o
 
 all: $(LIB) oracle ref
 
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz
 
 CSRC_HDRS := $(wildcard $(CSRC)/*.hpp $(CSRC)/*.cuh)
 

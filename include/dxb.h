@@ -373,9 +373,12 @@ int dxb_finish_beam_sharded(dxb_ctx*, const dxb_beam_desc*, int physics_mode, in
  *                          and returns; dxb_get_dose_range / dxb_flush wait for it.  Per beam the caller runs
  *                              dxb_run_transport;  barrier over the ranks;  dxb_finish_beam
  *                          (the barrier is the only synchronisation the library cannot do itself across processes).
+ *                          The nested CTDI calibration run of a beam is sharded over the ranks too: every rank runs its
+ *                          share of the calibration histories and publishes five integer sums in a small mailbox the
+ *                          peers read (so dxb_finish_beam with use_beam_calibration waits for all ranks to get there).
  *   dxb_flush            - waits until every enqueued transport / exchange of the context has completed.
  *   dxb_exchange_times   - device time of the last flushed exchange on device 0: {pulls, slab reduce -> dose, clear} [ms]. */
-#define DXB_EXCHANGE_HANDLE_BYTES 128
+#define DXB_EXCHANGE_HANDLE_BYTES 192
 int dxb_exchange_export(dxb_ctx*, void* handles);
 int dxb_exchange_import(dxb_ctx*, uint64_t rank, uint64_t world, const void* all_handles /* world x DXB_EXCHANGE_HANDLE_BYTES */);
 int dxb_exchange_close(dxb_ctx*); /* unmaps the peers' buffers (after a flush and a barrier, before any rank destroys its context) */
@@ -466,6 +469,48 @@ uint32_t dxb_icrp_organ_medium(const dxb_icrp*, uint32_t index);
 uint32_t dxb_icrp_n_media(const dxb_icrp*);
 const char* dxb_icrp_medium_name(const dxb_icrp*, uint32_t index);
 int dxb_icrp_medium_composition(const dxb_icrp*, uint32_t index, uint32_t* Z, double* weight, int cap); /* returns the element count */
+
+/* ====================================================================== */
+/* HDF5 save files, SURVEY §8f-3 (R:src/libopendxmc/hdf5wrapper.cpp)        */
+/* ====================================================================== */
+/* A minimal reader / writer for the subset of the HDF5 format OpenDXMC's save files use (opendxmc_b200/csrc/h5mini.*:
+ * superblock version 0, old-style groups, version-1 object headers, attributes, f64 / u64 / u8 / variable-length string
+ * datasets stored contiguously or as one deflate-6 chunk; the reader also walks multi-chunk B-trees).  The image has no
+ * HDF5 library: the reader is pinned on a genuine libhdf5-written file, the writer on the reader, and the reference's own
+ * hdf5wrapper.cpp round-trips through both (tests/stubs/H5Cpp.h is a shim over this API).
+ * Object-level API: an in-memory image of a file is built (create + put_*) and written by dxb_h5_save, or parsed by
+ * dxb_h5_open and queried.  Paths are "/group/sub/name"; dims are in HDF5 order (slowest first). */
+typedef struct dxb_h5 dxb_h5;
+enum { DXB_H5_UNKNOWN = 0, DXB_H5_F64 = 1, DXB_H5_U64 = 2, DXB_H5_U8 = 3, DXB_H5_STRING = 4, DXB_H5_I64 = 5, DXB_H5_I32 = 6,
+       DXB_H5_U32 = 7, DXB_H5_F32 = 8, DXB_H5_U16 = 9, DXB_H5_I16 = 10, DXB_H5_I8 = 11 };
+dxb_h5* dxb_h5_create(void);
+int dxb_h5_open(dxb_h5** out, const char* path);
+void dxb_h5_close(dxb_h5*);
+const char* dxb_h5_error(const dxb_h5*);
+int dxb_h5_save(dxb_h5*, const char* path);
+int dxb_h5_exists(const dxb_h5*, const char* path);               /* 0 no, 1 group, 2 dataset (H5File::nameExists) */
+int dxb_h5_make_group(dxb_h5*, const char* path);                 /* creates missing parents */
+const char* dxb_h5_list(dxb_h5*, const char* group_path);         /* "g name\n" / "d name\n" / "a name\n" lines; valid until the next call */
+int dxb_h5_put_dataset(dxb_h5*, const char* path, int type, int rank, const uint64_t* dims, const void* data, int deflate);
+int dxb_h5_put_strings(dxb_h5*, const char* path, uint64_t n, const char* const* strings);
+int dxb_h5_put_attribute(dxb_h5*, const char* group_path, const char* name, int type, int64_t n /* < 0: scalar */, const void* data);
+int dxb_h5_dataset_info(const dxb_h5*, const char* path, int* type, int* rank, uint64_t dims[8], int* deflate);
+int dxb_h5_dataset_read(const dxb_h5*, const char* path, void* out, uint64_t out_bytes);
+const char* dxb_h5_dataset_string(const dxb_h5*, const char* path, uint64_t index);
+int dxb_h5_attribute_info(const dxb_h5*, const char* group_path, const char* name, int* type, int64_t* n /* -1: scalar */);
+int dxb_h5_attribute_read(const dxb_h5*, const char* group_path, const char* name, void* out, uint64_t out_bytes);
+const char* dxb_h5_attribute_string(const dxb_h5*, const char* group_path, const char* name, uint64_t index);
+
+/* Scene-level: drive the engine head-less from a file the GUI wrote, and hand the result back in the same format.
+ *   dxb_load_scene  reads "dimensions", "spacing", "densityarray", "materialarray", "materialnames", "materialcomposition"
+ *                   (R:src/libopendxmc/hdf5wrapper.cpp:1070-1118), builds the materials like the worker does
+ *                   (parseCompoundStr -> Material::byWeight, R:...simulationpipeline.cpp:136) and calls dxb_set_materials +
+ *                   dxb_set_grid; the file's other content (organ array, names, AEC data) stays with the context;
+ *   dxb_save_dose   writes everything dxb_load_scene read plus "dosearray", "dosevariancearray", "doseeventcountarray"
+ *                   (f64, HDF5 dims (nz, ny, nx), one deflate-6 chunk each, :121-151, :436-447) after the driver's
+ *                   post-processing (air mask if delete_air_dose, uGy rule; units_out = "mGy" / "uGy"). */
+int dxb_load_scene(dxb_ctx*, const char* path, uint64_t dim_out[3], double spacing_cm_out[3], uint32_t* n_materials_out);
+int dxb_save_dose(dxb_ctx*, const char* path, int delete_air_dose, char units_out[4]);
 
 int dxb_abi_version(void);
 int dxb_device_count(void);

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdxmc_b200.so")
 
-DXB_EXCHANGE_HANDLE_BYTES = 128
+DXB_EXCHANGE_HANDLE_BYTES = 192
 DXB_OK, DXB_EINVAL, DXB_EMATERIAL, DXB_ECUDA, DXB_ESTATE, DXB_ECANCELLED, DXB_ENOMEM = range(7)
 STATUS_NAMES = ["DXB_OK", "DXB_EINVAL", "DXB_EMATERIAL", "DXB_ECUDA", "DXB_ESTATE", "DXB_ECANCELLED", "DXB_ENOMEM"]
 
@@ -201,6 +201,25 @@ SIGNATURES = {
     "dxb_icrp_n_media": (C.c_uint32, [VP]),
     "dxb_icrp_medium_name": (C.c_char_p, [VP, C.c_uint32]),
     "dxb_icrp_medium_composition": (C.c_int, [VP, C.c_uint32, c_u32_p, c_double_p, C.c_int]),
+    "dxb_h5_create": (VP, []),
+    "dxb_h5_open": (C.c_int, [C.POINTER(VP), C.c_char_p]),
+    "dxb_h5_close": (None, [VP]),
+    "dxb_h5_error": (C.c_char_p, [VP]),
+    "dxb_h5_save": (C.c_int, [VP, C.c_char_p]),
+    "dxb_h5_exists": (C.c_int, [VP, C.c_char_p]),
+    "dxb_h5_make_group": (C.c_int, [VP, C.c_char_p]),
+    "dxb_h5_list": (C.c_char_p, [VP, C.c_char_p]),
+    "dxb_h5_put_dataset": (C.c_int, [VP, C.c_char_p, C.c_int, C.c_int, c_u64_p, VP, C.c_int]),
+    "dxb_h5_put_strings": (C.c_int, [VP, C.c_char_p, C.c_uint64, C.POINTER(C.c_char_p)]),
+    "dxb_h5_put_attribute": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, VP]),
+    "dxb_h5_dataset_info": (C.c_int, [VP, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), c_u64_p, C.POINTER(C.c_int)]),
+    "dxb_h5_dataset_read": (C.c_int, [VP, C.c_char_p, VP, C.c_uint64]),
+    "dxb_h5_dataset_string": (C.c_char_p, [VP, C.c_char_p, C.c_uint64]),
+    "dxb_h5_attribute_info": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "dxb_h5_attribute_read": (C.c_int, [VP, C.c_char_p, C.c_char_p, VP, C.c_uint64]),
+    "dxb_h5_attribute_string": (C.c_char_p, [VP, C.c_char_p, C.c_char_p, C.c_uint64]),
+    "dxb_load_scene": (C.c_int, [VP, C.c_char_p, c_u64_p, c_double_p, C.POINTER(C.c_uint32)]),
+    "dxb_save_dose": (C.c_int, [VP, C.c_char_p, C.c_int, C.c_char_p]),
     "dxb_segment_ct": (C.c_int, [VP, c_double_p, C.c_uint64, C.POINTER(dxb_tube_desc), c_u8_p, c_double_p, C.POINTER(VP)]),
 }
 

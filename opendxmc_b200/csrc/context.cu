@@ -516,9 +516,13 @@ int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOu
     }
     const CtdiPhantom& ph = *c->ctdi;
     const size_t nPh = static_cast<size_t>(ph.dim[0]) * ph.dim[1] * ph.dim[2];
-    // an IPC-exchanging context (one process per GPU) runs the whole nested beam itself: it is deterministic, so every
-    // rank derives the same factor without a broadcast
+    // shards of the nested beam: the devices of this context, or - one process per GPU with the library-managed exchange -
+    // the ranks of the job, whose five sums travel through IPC mailboxes (exchange.cu).  A context that is sharded by the
+    // caller alone (dxb_set_history_range without dxb_exchange_import) runs the whole nested beam itself: it is
+    // deterministic, so every rank derives the same factor without a broadcast.
     const uint64_t nDev = c->devs.size();
+    const bool overRanks = c->ipc && c->exchanging && c->world > 1 && c->devs[0]->mailbox.p;
+    const uint64_t shardBase = overRanks ? c->rank : 0, shardWorld = overRanks ? c->world : nDev;
     for (uint64_t i = 0; i < nDev; ++i) {
         DeviceState& d = *c->devs[i];
         CUDA_TRY(c, cudaSetDevice(d.device));
@@ -577,7 +581,7 @@ int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOu
         }
         rc = uploadBeam(c, d, pb);
         if (rc == DXB_OK)
-            rc = runOnDevice(c, d, w, pb, mode, true, 2, i, nDev, nullptr, true, &tr[i]);
+            rc = runOnDevice(c, d, w, pb, mode, true, 2, shardBase + i, shardWorld, nullptr, true, &tr[i]);
         if (rc == DXB_OK) {
             launchHoleSums(w.tally.p, d.ctdiHole.p, w.nvox, d.holeSums.p, d.stream);
             if (cudaGetLastError() != cudaSuccess)
@@ -592,7 +596,11 @@ int ctCalibration(dxb_ctx* c, const dxb_beam_desc& b, int mode, double* factorOu
         if (rc != DXB_OK)
             break;
         unsigned long long h[5];
-        if (cudaMemcpy(h, d.holeSums.p, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        if (overRanks) {
+            rc = mgShareHoleSums(c, d.holeSums.p, h);
+            if (rc != DXB_OK)
+                break;
+        } else if (cudaMemcpy(h, d.holeSums.p, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
             cudaGetLastError();
             rc = fail(c, DXB_ECUDA, "calibration: reading the hole sums failed");
             break;
@@ -869,6 +877,9 @@ int dxb_clear_dose(dxb_ctx* c)
         CUDA_TRY(c, cudaMemsetAsync(d->dose.p, 0, n * sizeof(double), d->stream));
         CUDA_TRY(c, cudaMemsetAsync(d->variance.p, 0, n * sizeof(double), d->stream));
         CUDA_TRY(c, cudaMemsetAsync(d->events.p, 0, n * sizeof(unsigned long long), d->stream));
+    }
+    for (auto& d : c->devs) {
+        CUDA_TRY(c, cudaSetDevice(d->device));
         CUDA_TRY(c, cudaStreamSynchronize(d->stream));
     }
     CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
@@ -1053,6 +1064,9 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
             CUDA_TRY(c, cudaEventRecord(d.evTransportDone[d.world.cur], d.stream));
         }
     }
+    // the previous beam's exchange is enqueued now, while every device runs this beam's kernels (exchange.cu)
+    if (c->exchanging && (rc = mgEnqueuePending(c)) != DXB_OK)
+        return rc;
     bool cancelled = false;
     double msMax = 0;
     for (uint64_t i = 0; i < nDev; ++i) {

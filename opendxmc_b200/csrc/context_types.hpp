@@ -172,6 +172,10 @@ struct DeviceState {
     bool needsClear[2] = { false, false };
     DevBuf<unsigned long long> staging; // (parts - 1) slabs of 4 x u64 per voxel
     std::vector<const unsigned long long*> peerTally[2]; // [buffer][participant]: device pointers valid on THIS device
+    // one process per GPU: {sequence number, five hole sums} of this rank's shard of the nested calibration run, readable
+    // by the peers through CUDA IPC
+    DevBuf<unsigned long long> mailbox;
+    std::vector<const unsigned long long*> peerMailbox;
 };
 
 // CT calibration phantom (host side), cached per diameter
@@ -226,6 +230,7 @@ struct dxb_ctx {
     float scaleE = 16777216.0f, scaleE2 = 65536.0f; // 2^24, 2^16 fixed-point quanta per keV, keV^2
     int smCount = 148;
     bool tallyValid = false;
+    std::shared_ptr<void> scene;            // the save file dxb_load_scene read (an h5mini::File), written back by dxb_save_dose
     std::unique_ptr<dxb::CtdiPhantom> ctdi; // host copy of the calibration phantom, built once per diameter
     // ---- tally exchange (exchange.cu).  In-process: one participant per device of this context; one process per GPU:
     // one participant per rank, peers mapped through CUDA IPC (dxb_exchange_export / dxb_exchange_import).
@@ -234,7 +239,14 @@ struct dxb_ctx {
     int parts = 1;           // participants
     bool exchanged = false;  // the last beam's tallies have been handed to the exchange (no longer readable)
     std::vector<void*> ipcOpened;
+    struct {                 // the exchange dxb_finish_beam asked for and mgEnqueuePending still has to enqueue (in-process)
+        bool active = false;
+        int buffer = 0;
+        double factor = 0;
+        float scaleE = 1, scaleE2 = 1;
+    } pending;
     bool exchangeTimed = false;
+    uint64_t mailSeq = 0;    // calibrated beams so far (the mailbox sequence number)
     double exchangeMs[4] = { 0, 0, 0, 0 }; // last flush: pulls, reduce, clear (CUDA events on the exchange stream of device 0)
 };
 
@@ -280,9 +292,12 @@ void mgDestroy(dxb_ctx* c);
 int mgSetGrid(dxb_ctx* c, const uint64_t dim[3], const double spacing[3], const double* density, const uint8_t* material);
 int mgPrepareExchange(dxb_ctx* c);                        // second tally buffer, staging, slabs (after the grid is known)
 int mgEnqueueExchange(dxb_ctx* c, double factor);         // pulls + slab reduce -> dose + clear, asynchronous
+int mgEnqueuePending(dxb_ctx* c);                         // in-process: the deferred enqueue (after the next beam's launch, or at a flush)
 int mgFlush(dxb_ctx* c);                                  // every enqueued exchange has completed
 int mgGetDose(dxb_ctx* c, size_t begin, size_t end, double* dose, double* variance, uint64_t* events);
 int mgGatherDose(dxb_ctx* c);                             // device 0 receives every slab of the dose score
 int mgSumTallies(dxb_ctx* c, DevBuf<unsigned long long>& out); // device 0: sum over the devices' current tally buffers
+// one process per GPU: publishes this rank's five calibration hole sums and adds those of all peers (waits for them)
+int mgShareHoleSums(dxb_ctx* c, const unsigned long long* devSums, unsigned long long total[5]);
 
 } // namespace dxb

@@ -17,6 +17,7 @@
 // and packs slab r of the caller's arrays, the packed 4-byte slabs are all-gathered by peer copies.
 #include "context_types.hpp"
 
+#include <chrono>
 #include <thread>
 
 namespace dxb {
@@ -92,6 +93,17 @@ int overDevices(dxb_ctx* c, F f)
         if (r != DXB_OK)
             return r;
     return DXB_OK;
+}
+
+// mailbox = {sequence number, five sums}: the sums are visible system-wide before the sequence number announces them
+__global__ void publishMailboxKernel(unsigned long long* __restrict__ mailbox, const unsigned long long* __restrict__ sums, unsigned long long seq)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int k = 0; k < 5; ++k)
+            mailbox[1 + k] = sums[k];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(mailbox) = seq;
+    }
 }
 
 size_t maxSlab(size_t n, int parts) { return (n + static_cast<size_t>(parts) - 1) / static_cast<size_t>(parts); }
@@ -208,12 +220,11 @@ int mgSetGrid(dxb_ctx* c, const uint64_t dim[3], const double spacing[3], const 
                                 (e - b) * sizeof(unsigned int), d.stream));
         }
     }
-    for (auto& d : c->devs) {
-        CUDA_TRY(c, cudaSetDevice(d->device));
-        rc = finishGrid(c, d->world, d->stream); // majorant, material-index check; synchronises the stream
-        if (rc != DXB_OK)
-            return rc;
-    }
+    rc = overDevices(c, [&](size_t i) -> int { // majorant, material-index check; synchronises the device's stream
+        return finishGrid(c, c->devs[i]->world, c->devs[i]->stream);
+    });
+    if (rc != DXB_OK)
+        return rc;
     CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
     return mgPrepareExchange(c);
 }
@@ -237,8 +248,12 @@ int mgPrepareExchange(dxb_ctx* c)
             d.pullsPending[b] = false;
             d.needsClear[b] = false;
         }
-        CUDA_TRY(c, cudaStreamSynchronize(d.xstream));
         w.cur = 0;
+    }
+    c->pending.active = false;
+    for (auto& dp : c->devs) { // (all devices clear concurrently)
+        CUDA_TRY(c, cudaSetDevice(dp->device));
+        CUDA_TRY(c, cudaStreamSynchronize(dp->xstream));
     }
     if (!c->ipc) {
         for (auto& dp : c->devs)
@@ -253,10 +268,32 @@ int mgPrepareExchange(dxb_ctx* c)
     return DXB_OK;
 }
 
+// The exchange of the beam that was just finished.  One process per GPU: enqueued at once (the caller has just put a barrier
+// between the ranks' transport and this call).  In-process: only NOTED here and enqueued by mgEnqueuePending - from the
+// next dxb_run_transport right after its kernels have been launched on every device, or from a flush - because one host
+// thread issues some 30 driver calls per device for it, and the GPUs would idle meanwhile if that happened between two
+// beams; this way it happens while they run the next beam.
 int mgEnqueueExchange(dxb_ctx* c, double factor)
 {
+    c->pending.active = true;
+    c->pending.buffer = c->devs[0]->world.cur;
+    c->pending.factor = factor;
+    c->pending.scaleE = c->scaleE;
+    c->pending.scaleE2 = c->scaleE2;
+    for (auto& dp : c->devs)
+        dp->world.cur = c->pending.buffer ^ 1;
+    c->exchanged = true;
+    return c->ipc ? mgEnqueuePending(c) : DXB_OK;
+}
+
+int mgEnqueuePending(dxb_ctx* c)
+{
+    if (!c->pending.active)
+        return DXB_OK;
+    c->pending.active = false;
     const int parts = c->parts;
-    const int b = c->devs[0]->world.cur;
+    const int b = c->pending.buffer;
+    const double factor = c->pending.factor;
     const size_t n = c->devs[0]->world.nvox;
     const size_t ms = maxSlab(n, parts);
     const World& w0 = c->devs[0]->world;
@@ -266,13 +303,10 @@ int mgEnqueueExchange(dxb_ctx* c, double factor)
         World& w = d.world;
         cudaStream_t xs = d.xstream;
         CUDA_TRY(c, cudaSetDevice(d.device));
-        // the transport kernels that scored into buffer b have finished: on this device and, in-process, on every peer
-        // (one process per GPU: the caller separates dxb_run_transport from dxb_finish_beam by a barrier over the ranks)
+        // the transport kernels that scored into buffer b have finished on every participant: dxb_run_transport returns
+        // after synchronising the transport streams of all devices of the context, and with one process per GPU the
+        // caller separates it from dxb_finish_beam by a barrier over the ranks.  (The event wait is free.)
         CUDA_TRY(c, cudaStreamWaitEvent(xs, d.evTransportDone[b], 0));
-        if (!c->ipc)
-            for (auto& pp : c->devs)
-                if (pp.get() != &d)
-                    CUDA_TRY(c, cudaStreamWaitEvent(xs, pp->evTransportDone[b], 0));
         if (c->ipc && d.needsClear[b ^ 1]) {
             // one process per GPU: the same barrier also tells that every peer has pulled the PREVIOUS beam's buffer
             // (each rank waits for its own pulls at the end of dxb_run_transport), so it can be cleared now
@@ -295,7 +329,7 @@ int mgEnqueueExchange(dxb_ctx* c, double factor)
         const unsigned long long* local = b ? w.tally1.p : w.tally.p;
         if (d.ve > d.vb)
             reduceSlabsToDoseKernel<<<g_exchangeBlocks, 256, 0, xs>>>(local, d.staging.p, parts - 1, ms, w.voxels.p, d.dose.p, d.variance.p,
-                d.events.p, d.vb, d.ve, 1.0 / c->scaleE, 1.0 / c->scaleE2, factor, vol);
+                d.events.p, d.vb, d.ve, 1.0 / c->pending.scaleE, 1.0 / c->pending.scaleE2, factor, vol);
         CUDA_TRY(c, cudaGetLastError());
         CUDA_TRY(c, cudaEventRecord(d.evX[2], xs));
         d.needsClear[b] = true;
@@ -315,9 +349,6 @@ int mgEnqueueExchange(dxb_ctx* c, double factor)
             d.needsClear[b] = false;
         }
     }
-    for (auto& dp : c->devs)
-        dp->world.cur = b ^ 1;
-    c->exchanged = true;
     c->exchangeTimed = true;
     CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
     return DXB_OK;
@@ -327,6 +358,9 @@ int mgFlush(dxb_ctx* c)
 {
     if (!c->exchanging)
         return DXB_OK;
+    const int prc = mgEnqueuePending(c);
+    if (prc != DXB_OK)
+        return prc;
     for (auto& dp : c->devs) {
         if (!dp->xstream)
             continue;
@@ -413,6 +447,39 @@ int mgSumTallies(dxb_ctx* c, DevBuf<unsigned long long>& out)
     return DXB_OK;
 }
 
+int mgShareHoleSums(dxb_ctx* c, const unsigned long long* devSums, unsigned long long total[5])
+{
+    DeviceState& d = *c->devs[0];
+    if (!c->ipc || !d.mailbox.p || d.peerMailbox.size() != static_cast<size_t>(c->parts))
+        return fail(c, DXB_ESTATE, "calibration exchange: no mailboxes (dxb_exchange_import)");
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    const unsigned long long seq = ++c->mailSeq;
+    publishMailboxKernel<<<1, 32, 0, d.stream>>>(d.mailbox.p, devSums, seq);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(d.stream));
+    for (int k = 0; k < 5; ++k)
+        total[k] = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int p = 0; p < c->parts; ++p) {
+        unsigned long long h[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (;;) {
+            CUDA_TRY(c, cudaMemcpy(h, d.peerMailbox[p], sizeof(h), cudaMemcpyDeviceToHost));
+            if (h[0] == seq) {
+                // the sums were made visible before the number: read them (again) now that the number is known
+                CUDA_TRY(c, cudaMemcpy(h, d.peerMailbox[p], sizeof(h), cudaMemcpyDeviceToHost));
+                break;
+            }
+            if (h[0] > seq)
+                return fail(c, DXB_ESTATE, "calibration exchange: rank " + std::to_string(p) + " is ahead (the ranks must finish the same beams with the same flags)");
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0)
+                return fail(c, DXB_ESTATE, "calibration exchange: timed out waiting for rank " + std::to_string(p));
+        }
+        for (int k = 0; k < 5; ++k)
+            total[k] += h[1 + k];
+    }
+    return DXB_OK;
+}
+
 } // namespace dxb
 
 using namespace dxb;
@@ -439,10 +506,14 @@ int dxb_exchange_export(dxb_ctx* c, void* handles)
             return rc;
     }
     CUDA_TRY(c, w.tally1.alloc(w.nvox * 4, d.device));
-    static_assert(2 * sizeof(cudaIpcMemHandle_t) == DXB_EXCHANGE_HANDLE_BYTES, "handle size");
-    cudaIpcMemHandle_t h[2];
+    // the mailbox gets an allocation of its own (2 MiB: not carved out of a block shared with other small buffers)
+    CUDA_TRY(c, d.mailbox.alloc((2u << 20) / sizeof(unsigned long long), d.device));
+    CUDA_TRY(c, cudaMemset(d.mailbox.p, 0, 64));
+    static_assert(3 * sizeof(cudaIpcMemHandle_t) == DXB_EXCHANGE_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h[3];
     CUDA_TRY(c, cudaIpcGetMemHandle(&h[0], w.tally.p));
     CUDA_TRY(c, cudaIpcGetMemHandle(&h[1], w.tally1.p));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[2], d.mailbox.p));
     std::memcpy(handles, h, sizeof(h));
     return DXB_OK;
 }
@@ -462,18 +533,24 @@ int dxb_exchange_import(dxb_ctx* c, uint64_t rank, uint64_t world, const void* a
     const auto* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int b = 0; b < 2; ++b)
         d.peerTally[b].assign(world, nullptr);
+    d.peerMailbox.assign(world, nullptr);
     for (uint64_t p = 0; p < world; ++p) {
-        for (int b = 0; b < 2; ++b) {
-            if (p == rank) {
-                d.peerTally[b][p] = b ? w.tally1.p : w.tally.p;
-                continue;
+        for (int b = 0; b < 3; ++b) {
+            const unsigned long long* ptr = b == 0 ? w.tally.p : (b == 1 ? w.tally1.p : d.mailbox.p);
+            if (p != rank) {
+                void* opened = nullptr;
+                CUDA_TRY(c, cudaIpcOpenMemHandle(&opened, h[p * 3 + b], cudaIpcMemLazyEnablePeerAccess));
+                c->ipcOpened.push_back(opened);
+                ptr = static_cast<const unsigned long long*>(opened);
             }
-            void* ptr = nullptr;
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&ptr, h[p * 2 + b], cudaIpcMemLazyEnablePeerAccess));
-            c->ipcOpened.push_back(ptr);
-            d.peerTally[b][p] = static_cast<const unsigned long long*>(ptr);
+            if (b < 2)
+                d.peerTally[b][p] = ptr;
+            else
+                d.peerMailbox[p] = ptr;
         }
     }
+    c->mailSeq = 0;
+    CUDA_TRY(c, cudaMemset(d.mailbox.p, 0, 64));
     c->ipc = true;
     c->parts = static_cast<int>(world);
     c->exchanging = world > 1;

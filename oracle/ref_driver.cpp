@@ -416,7 +416,7 @@ static int beamModelMode()
     return 0;
 }
 
-static int h5RoundTripMode()
+static int h5RoundTripMode(const std::string& file)
 {
     BeamSettingsModel model;
     addDefaultBeams(model);
@@ -426,13 +426,13 @@ static int h5RoundTripMode()
     vol->setAecData(vol->calculateAECfilterFromWaterEquivalentDiameter(true));
     int nSaved = 0;
     {
-        HDF5Wrapper out("memory.h5", HDF5Wrapper::FileOpenMode::WriteOver);
+        HDF5Wrapper out(file, HDF5Wrapper::FileOpenMode::WriteOver);
         if (!out.save(vol))
             return 7;
         for (const auto& a : saved)
             nSaved += out.save(a) ? 1 : 0; // the pencil beam has no save() overload (R:hdf5wrapper.cpp:1050-1068)
     }
-    HDF5Wrapper in("memory.h5", HDF5Wrapper::FileOpenMode::ReadOnly);
+    HDF5Wrapper in(file, HDF5Wrapper::FileOpenMode::ReadOnly);
     auto back = in.load();
     auto beams = in.loadBeams();
     if (!back)
@@ -464,6 +464,28 @@ static int h5RoundTripMode()
     for (const auto& a : beams)
         model2.addBeam(a);
     dumpModel(model2, "loaded", beams.size());
+    return 0;
+}
+
+// HDF5Wrapper::load() (the reference's loader, R:src/libopendxmc/hdf5wrapper.cpp:1070-1150) on a file written elsewhere,
+// e.g. by dxb_save_dose
+static int h5LoadMode(const std::string& file)
+{
+    HDF5Wrapper in(file, HDF5Wrapper::FileOpenMode::ReadOnly);
+    auto d = in.load();
+    if (!d)
+        return 8;
+    double dose = 0, count = 0, density = 0;
+    for (double v : d->getDoseArray())
+        dose += v;
+    for (double v : d->getDoseEventCountArray())
+        count += v;
+    for (double v : d->getDensityArray())
+        density += v;
+    std::printf("{\"kind\": \"h5load\", \"dimensions\": [%zu, %zu, %zu], \"spacing\": [%.17g, %.17g, %.17g], \"materials\": %zu, "
+                "\"dose_sum\": %.17g, \"count_sum\": %.17g, \"density_sum\": %.17g, \"variance_size\": %zu}\n",
+        d->dimensions()[0], d->dimensions()[1], d->dimensions()[2], d->spacing()[0], d->spacing()[1], d->spacing()[2], d->getMaterials().size(),
+        dose, count, density, d->getDoseVarianceArray().size());
     return 0;
 }
 
@@ -685,13 +707,15 @@ int main(int argc, char** argv)
     if (what == "beammodel")
         return beamModelMode();
     if (what == "h5roundtrip")
-        return h5RoundTripMode();
+        return h5RoundTripMode(argc > 2 ? argv[2] : "/tmp/opendxmc_ref_roundtrip.h5");
+    if (what == "h5load" && argc >= 3)
+        return h5LoadMode(argv[2]);
     if (what == "dosetable" && argc >= 10)
         return doseTableMode(argv);
     if (what == "icrp" && argc >= 9)
         return icrpMode(argv);
     if (what == "run" && argc >= 6)
         return runMode(std::atoi(argv[2]), std::atoi(argv[3]) != 0, std::strtoull(argv[4], nullptr, 10), argv[5], argc > 6 ? std::atof(argv[6]) : 1.0, argc > 7 ? argv[7] : "sequential", argc > 8 && std::atoi(argv[8]) != 0);
-    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [level] [beam kind] [1: start twice]\n");
+    std::fprintf(stderr, "usage: opendxmc_ref host | bowtie | beammodel | h5roundtrip [file] | h5load <file> | icrp <organ array> <organs.dat> <media.dat> <nx> <ny> <nz> <remove arms> | dosetable <prefix> <nx> <ny> <nz> <dx> <dy> <dz> <n organs> | run <mode> <delete_air> <histories per exposure> <out prefix> [level] [beam kind] [1: start twice]\n");
     return 1;
 }

@@ -1,7 +1,13 @@
-// In-memory stand-in for the HDF5 C++ API (<H5Cpp.h>), tests only (see QObject in this directory): files, groups,
-// data sets and attributes live in process memory, keyed by the file path, so that OpenDXMC's hdf5wrapper.cpp can save
-// a scene and load it back in the same process.  Not a file format.
+// <H5Cpp.h> for a box without the HDF5 library: the part of the HDF5 C++ API that OpenDXMC's hdf5wrapper.cpp calls
+// (R:src/libopendxmc/hdf5wrapper.cpp:73-360), implemented over libdxmc_b200's own HDF5 reader / writer (include/dxb.h:
+// dxb_h5_*, opendxmc_b200/csrc/h5mini.*).  Files are REAL files in the HDF5 format: H5File(path, H5F_ACC_TRUNC) builds an
+// image that close() / the destructor writes, H5File(path, H5F_ACC_RDONLY) parses one.  Test infrastructure (like the Qt
+// stand-ins in this directory): it lets the reference's own save / load code, compiled unmodified, round-trip scenes and
+// beams through the file format (oracle/ref_driver.cpp: h5roundtrip).
 #pragma once
+#include "dxb.h"
+
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -39,30 +45,57 @@ class AttributeIException : public Exception { using Exception::Exception; };
 class DataType {
 public:
     DataType() = default;
-    DataType(H5T_class_t c, std::size_t s) : cls(c), size(s) { }
+    DataType(H5T_class_t c, std::size_t s, bool sign = false) : cls(c), size(s), isSigned(sign) { }
     std::size_t getSize() const { return size; }
     H5T_class_t getClass() const { return cls; }
+    // dxb_h5 type code of this in-memory type
+    int code() const
+    {
+        if (cls == H5T_FLOAT)
+            return size == 8 ? DXB_H5_F64 : (size == 4 ? DXB_H5_F32 : DXB_H5_UNKNOWN);
+        if (cls == H5T_STRING)
+            return DXB_H5_STRING;
+        if (cls == H5T_INTEGER)
+            switch (size) {
+            case 8: return isSigned ? DXB_H5_I64 : DXB_H5_U64;
+            case 4: return isSigned ? DXB_H5_I32 : DXB_H5_U32;
+            case 2: return isSigned ? DXB_H5_I16 : DXB_H5_U16;
+            case 1: return isSigned ? DXB_H5_I8 : DXB_H5_U8;
+            default: break;
+            }
+        return DXB_H5_UNKNOWN;
+    }
+    static DataType fromCode(int c)
+    {
+        switch (c) {
+        case DXB_H5_F64: return { H5T_FLOAT, 8 };
+        case DXB_H5_F32: return { H5T_FLOAT, 4 };
+        case DXB_H5_U64: return { H5T_INTEGER, 8 };
+        case DXB_H5_I64: return { H5T_INTEGER, 8, true };
+        case DXB_H5_U32: return { H5T_INTEGER, 4 };
+        case DXB_H5_I32: return { H5T_INTEGER, 4, true };
+        case DXB_H5_U16: return { H5T_INTEGER, 2 };
+        case DXB_H5_I16: return { H5T_INTEGER, 2, true };
+        case DXB_H5_U8: return { H5T_INTEGER, 1 };
+        case DXB_H5_I8: return { H5T_INTEGER, 1, true };
+        case DXB_H5_STRING: return { H5T_STRING, H5T_VARIABLE };
+        default: return {};
+        }
+    }
     H5T_class_t cls = H5T_NO_CLASS;
     std::size_t size = 0;
+    bool isSigned = false;
 };
 class PredType : public DataType {
 public:
     using DataType::DataType;
-    static inline const DataType& mk(H5T_class_t c, std::size_t s)
-    {
-        static std::map<std::pair<int, std::size_t>, PredType> all;
-        auto& t = all[{ c, s }];
-        t.cls = c;
-        t.size = s;
-        return t;
-    }
     static const PredType NATIVE_DOUBLE, NATIVE_UINT64, NATIVE_UINT8, NATIVE_UINT, NATIVE_INT, C_S1;
 };
 inline const PredType PredType::NATIVE_DOUBLE { H5T_FLOAT, 8 };
 inline const PredType PredType::NATIVE_UINT64 { H5T_INTEGER, 8 };
 inline const PredType PredType::NATIVE_UINT8 { H5T_INTEGER, 1 };
 inline const PredType PredType::NATIVE_UINT { H5T_INTEGER, 4 };
-inline const PredType PredType::NATIVE_INT { H5T_INTEGER, 4 };
+inline const PredType PredType::NATIVE_INT { H5T_INTEGER, 4, true };
 inline const PredType PredType::C_S1 { H5T_STRING, 1 };
 class StrType : public DataType {
 public:
@@ -95,93 +128,131 @@ public:
 
 class DSetCreatPropList {
 public:
-    void setChunk(int, const hsize_t*) { }
-    void setDeflate(int) { }
+    void setChunk(int, const hsize_t*) { chunked = true; }
+    void setDeflate(int level) { deflate = level > 0; }
+    bool chunked = false, deflate = false;
 };
 
-struct Node { // data set or attribute payload
-    DataType type;
-    DataSpace space;
-    std::vector<unsigned char> bytes;
-    std::vector<std::string> strings;
-};
-struct Store {
-    std::map<std::string, std::shared_ptr<Node>> datasets;
-    std::map<std::string, std::map<std::string, std::shared_ptr<Node>>> groups; // group path -> attributes
-};
-
-class AbstractDs {
-public:
-    explicit AbstractDs(std::shared_ptr<Node> n = nullptr) : node(std::move(n)) { }
-    DataSpace getSpace() const { return node->space; }
-    H5T_class_t getTypeClass() const { return node->type.cls; }
-    FloatType getFloatType() const { return FloatType(node->type.cls, node->type.size); }
-    IntType getIntType() const { return IntType(node->type.cls, node->type.size); }
-    DataType getDataType() const { return node->type; }
-
-protected:
-    void put(const void* buf, const DataType& t)
+// the file image behind an H5File and everything opened from it
+struct Image {
+    dxb_h5* h = nullptr;
+    std::string path;
+    bool writing = false, closed = false;
+    ~Image() { flush(); }
+    void flush()
     {
-        node->type = t;
-        const auto n = static_cast<std::size_t>(node->space.getSimpleExtentNpoints());
-        if (t.cls == H5T_STRING) {
-            const char* const* s = static_cast<const char* const*>(buf);
-            node->strings.assign(s, s + n);
-        } else {
-            node->bytes.assign(static_cast<const unsigned char*>(buf), static_cast<const unsigned char*>(buf) + n * t.size);
-        }
+        if (h && writing && !closed)
+            dxb_h5_save(h, path.c_str());
+        closed = true;
+        if (h)
+            dxb_h5_close(h);
+        h = nullptr;
     }
-    void get(void* buf, const DataType& t) const
+};
+
+class DataSet {
+public:
+    DataSet() = default;
+    DataSet(std::shared_ptr<Image> i, std::string p, DataType t, DataSpace s, bool z) : img(std::move(i)), path(std::move(p)), type(t), space(std::move(s)), deflate(z) { }
+    DataSpace getSpace() const { return space; }
+    H5T_class_t getTypeClass() const { return type.cls; }
+    DataType getDataType() const { return type; }
+    void write(const void* buf, const DataType& memType)
     {
-        if (t.cls == H5T_STRING) {
+        const auto n = static_cast<std::size_t>(space.getSimpleExtentNpoints());
+        int rc;
+        if (memType.cls == H5T_STRING) {
+            rc = dxb_h5_put_strings(img->h, path.c_str(), n, static_cast<const char* const*>(buf));
+        } else {
+            std::vector<uint64_t> d(space.dims.begin(), space.dims.end());
+            rc = dxb_h5_put_dataset(img->h, path.c_str(), memType.code(), static_cast<int>(d.size()), d.data(), buf, deflate ? 1 : 0);
+        }
+        if (rc != DXB_OK)
+            throw DataSetIException("DataSet::write", path);
+    }
+    void read(void* buf, const DataType& memType) const
+    {
+        const auto n = static_cast<std::size_t>(space.getSimpleExtentNpoints());
+        if (memType.cls == H5T_STRING) {
+            // like H5Dread of variable-length strings: one malloc'ed C string per element
             char** out = static_cast<char**>(buf);
-            for (std::size_t i = 0; i < node->strings.size(); ++i) {
-                out[i] = static_cast<char*>(std::malloc(node->strings[i].size() + 1));
-                std::memcpy(out[i], node->strings[i].c_str(), node->strings[i].size() + 1);
+            for (std::size_t i = 0; i < n; ++i) {
+                const char* s = dxb_h5_dataset_string(img->h, path.c_str(), i);
+                if (!s)
+                    throw DataSetIException("DataSet::read", path);
+                out[i] = static_cast<char*>(std::malloc(std::strlen(s) + 1));
+                std::strcpy(out[i], s);
             }
         } else {
-            std::memcpy(buf, node->bytes.data(), node->bytes.size());
+            if (memType.code() != type.code() || dxb_h5_dataset_read(img->h, path.c_str(), buf, n * type.size) != DXB_OK)
+                throw DataSetIException("DataSet::read", path + ": stored type differs from the requested one (no conversion in this shim)");
         }
     }
-    std::shared_ptr<Node> node;
+
+private:
+    std::shared_ptr<Image> img;
+    std::string path;
+    DataType type;
+    DataSpace space;
+    bool deflate = false;
 };
-class DataSet : public AbstractDs {
+
+class Attribute {
 public:
-    using AbstractDs::AbstractDs;
-    void write(const void* buf, const DataType& t) { put(buf, t); }
-    void read(void* buf, const DataType& t) const { get(buf, t); }
-};
-class Attribute : public AbstractDs {
-public:
-    using AbstractDs::AbstractDs;
-    void write(const DataType& t, const void* buf) { put(buf, t); }
-    void read(const DataType& t, void* buf) const { get(buf, t); }
+    Attribute() = default;
+    Attribute(std::shared_ptr<Image> i, std::string g, std::string n, DataType t, DataSpace s) : img(std::move(i)), group(std::move(g)), name(std::move(n)), type(t), space(std::move(s)) { }
+    DataSpace getSpace() const { return space; }
+    H5T_class_t getTypeClass() const { return type.cls; }
+    FloatType getFloatType() const { return FloatType(type.cls, type.size); }
+    IntType getIntType() const { return IntType(type.cls, type.size); }
+    void write(const DataType& memType, const void* buf)
+    {
+        const long long n = space.dims.empty() ? -1 : static_cast<long long>(space.dims[0]);
+        if (dxb_h5_put_attribute(img->h, group.c_str(), name.c_str(), memType.code(), n, buf) != DXB_OK)
+            throw AttributeIException("Attribute::write", name);
+    }
+    void read(const DataType& memType, void* buf) const
+    {
+        const auto n = static_cast<std::size_t>(space.getSimpleExtentNpoints());
+        if (memType.code() != type.code() || dxb_h5_attribute_read(img->h, group.c_str(), name.c_str(), buf, n * type.size) != DXB_OK)
+            throw AttributeIException("Attribute::read", name);
+    }
+
+private:
+    std::shared_ptr<Image> img;
+    std::string group, name;
+    DataType type;
+    DataSpace space;
 };
 
 class H5Location {
 public:
     H5Location() = default;
-    H5Location(std::shared_ptr<Store> s, std::string p) : store(std::move(s)), path(std::move(p)) { }
-    bool attrExists(const char* name) const { return store->groups[path].count(name) != 0; }
+    H5Location(std::shared_ptr<Image> i, std::string p) : img(std::move(i)), path(std::move(p)) { }
+    bool attrExists(const char* name) const { return dxb_h5_attribute_info(img->h, path.c_str(), name, nullptr, nullptr) == DXB_OK; }
     bool attrExists(const std::string& name) const { return attrExists(name.c_str()); }
     Attribute createAttribute(const char* name, const DataType& t, const DataSpace& sp)
     {
-        auto n = std::make_shared<Node>();
-        n->type = t;
-        n->space = sp;
-        store->groups[path][name] = n;
-        return Attribute(n);
+        if (sp.dims.size() > 1)
+            throw AttributeIException("createAttribute", "rank > 1");
+        return Attribute(img, path, name, t, sp);
     }
     Attribute openAttribute(const char* name) const
     {
-        auto it = store->groups[path].find(name);
-        if (it == store->groups[path].end())
+        int code = 0;
+        int64_t n = 0;
+        if (dxb_h5_attribute_info(img->h, path.c_str(), name, &code, &n) != DXB_OK)
             throw AttributeIException("openAttribute", name);
-        return Attribute(it->second);
+        DataSpace sp;
+        if (n >= 0) {
+            const hsize_t d = static_cast<hsize_t>(n);
+            sp = DataSpace(1, &d);
+        }
+        return Attribute(img, path, name, DataType::fromCode(code), sp);
     }
 
 protected:
-    std::shared_ptr<Store> store;
+    std::shared_ptr<Image> img;
     std::string path;
 };
 class Group : public H5Location {
@@ -192,47 +263,45 @@ class H5File : public H5Location {
 public:
     H5File(const char* name, unsigned flags)
     {
-        static std::map<std::string, std::shared_ptr<Store>> files;
-        if (flags == H5F_ACC_TRUNC || !files.count(name)) {
-            if (flags == H5F_ACC_RDONLY)
-                throw FileIException("H5File", std::string("no such file: ") + name);
-            files[name] = std::make_shared<Store>();
-        }
-        store = files[name];
+        img = std::make_shared<Image>();
+        img->path = name;
         path = "/";
-        store->groups["/"];
+        if (flags == H5F_ACC_TRUNC) {
+            img->h = dxb_h5_create();
+            img->writing = true;
+        } else if (dxb_h5_open(&img->h, name) != DXB_OK) {
+            throw FileIException("H5File", std::string("cannot open ") + name);
+        }
     }
     H5File(const std::string& name, unsigned flags) : H5File(name.c_str(), flags) { }
-    static std::string norm(const std::string& p) { return !p.empty() && p[0] == '/' ? p : "/" + p; }
-    bool nameExists(const char* p) const { return store->groups.count(norm(p)) || store->datasets.count(norm(p)); }
+    bool nameExists(const char* p) const { return dxb_h5_exists(img->h, p) != 0; }
     bool nameExists(const std::string& p) const { return nameExists(p.c_str()); }
     Group createGroup(const char* p)
     {
-        store->groups[norm(p)];
-        return Group(store, norm(p));
+        if (dxb_h5_make_group(img->h, p) != DXB_OK)
+            throw GroupIException("createGroup", p);
+        return Group(img, p);
     }
     Group openGroup(const char* p) const
     {
-        if (!store->groups.count(norm(p)))
+        if (dxb_h5_exists(img->h, p) != 1)
             throw GroupIException("openGroup", p);
-        return Group(store, norm(p));
+        return Group(img, p);
     }
-    DataSet createDataSet(const char* p, const DataType& t, const DataSpace& sp, const DSetCreatPropList& = DSetCreatPropList())
+    DataSet createDataSet(const char* p, const DataType& t, const DataSpace& sp, const DSetCreatPropList& plist = DSetCreatPropList())
     {
-        auto n = std::make_shared<Node>();
-        n->type = t;
-        n->space = sp;
-        store->datasets[norm(p)] = n;
-        return DataSet(n);
+        return DataSet(img, p, t, sp, plist.chunked && plist.deflate);
     }
     DataSet openDataSet(const char* p) const
     {
-        auto it = store->datasets.find(norm(p));
-        if (it == store->datasets.end())
+        int code = 0, rank = 0, z = 0;
+        uint64_t dims[8];
+        if (dxb_h5_dataset_info(img->h, p, &code, &rank, dims, &z) != DXB_OK)
             throw DataSetIException("openDataSet", p);
-        return DataSet(it->second);
+        std::vector<hsize_t> d(dims, dims + rank);
+        return DataSet(img, p, DataType::fromCode(code), DataSpace(rank, d.data()), z != 0);
     }
-    void close() { }
+    void close() { img->flush(); }
 };
 
 } // namespace H5

@@ -1,6 +1,7 @@
 """GPU parity, part 2: every beam type, the scaled C3/C4/C5 configurations, calibration, post-processing, per-organ
 dose, CT segmentation, progress / cancel, and in-process multi-GPU invariance — CUDA path through the C ABI vs the oracle."""
 import ctypes as C
+import json
 import os
 import sys
 import threading
@@ -449,3 +450,76 @@ def test_icrp_import_on_the_device(dx):
         for a, b in zip(dev, host):
             assert np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b
     world.close()
+
+
+def test_scene_file_in_dose_file_out(dx, tmp_path):
+    """a save file in OpenDXMC's HDF5 layout (written here with the library's own writer, the way
+    R:src/libopendxmc/hdf5wrapper.cpp:384-459 lays it out) drives the engine head-less - dxb_load_scene builds materials
+    and grid from it - and dxb_save_dose hands dose / variance / event count back in the same file format, in z-y-x
+    order, after the reference's post-processing.  Where the reference's own loader is available (oracle/_ref), it reads
+    the result file."""
+    import subprocess
+    from opendxmc_b200 import _capi as K
+    lib = K.load()
+    wl = dx.workloads.ctdi_body_phantom(n=24, histories=200_000, step_deg=10.0)
+    # the scene file
+    h = lib.dxb_h5_create()
+
+    def put(path, a, deflate):
+        a = np.ascontiguousarray(a)
+        code = {np.dtype(np.float64): 1, np.dtype(np.uint64): 2, np.dtype(np.uint8): 3}[a.dtype]
+        dims = (C.c_uint64 * a.ndim)(*a.shape)
+        assert lib.dxb_h5_put_dataset(h, path, code, a.ndim, dims, a.ctypes.data_as(K.VP), deflate) == 0
+    nx, ny, nz = wl.dim
+    put(b"/dimensions", np.array(wl.dim, dtype=np.uint64), 0)
+    put(b"/spacing", np.array(wl.spacing), 0)
+    put(b"/densityarray", wl.density.reshape(nz, ny, nx), 1)
+    put(b"/materialarray", wl.material.reshape(nz, ny, nx), 1)
+    names = wl.material_names
+    comps = []
+    for nm in names:
+        comp = dx.NISTMaterials.Composition(nm)
+        comps.append("".join("%s%s" % (dx.AtomHandler.toSymbol(z), "%.6f" % w) for z, w in sorted(comp.items())))
+    for path, strings in ((b"/materialnames", names), (b"/materialcomposition", comps)):
+        arr = (C.c_char_p * len(strings))(*[s.encode() for s in strings])
+        assert lib.dxb_h5_put_strings(h, path, len(strings), arr) == 0
+    scene = tmp_path / "scene.h5"
+    assert lib.dxb_h5_save(h, str(scene).encode()) == 0
+    lib.dxb_h5_close(h)
+    # head-less run
+    ctx = K.VP()
+    assert lib.dxb_create(C.byref(ctx), None, 0) == 0
+    dim, sp, nm = (C.c_uint64 * 3)(), (C.c_double * 3)(), C.c_uint32()
+    assert lib.dxb_load_scene(ctx, str(scene).encode(), dim, sp, C.byref(nm)) == 0, lib.dxb_last_error(ctx)
+    assert list(dim) == wl.dim and list(sp) == pytest.approx(wl.spacing) and nm.value == len(names)
+    lib.dxb_set_calibration_histories(ctx, 360_000)
+    assert lib.dxb_run(ctx, C.byref(wl.beam.desc()), 1, 1, None) == 0, lib.dxb_last_error(ctx)
+    n = wl.n_voxels
+    d, v, cnt = np.zeros(n), np.zeros(n), np.zeros(n)
+    units = C.create_string_buffer(4)
+    assert lib.dxb_get_dose_postprocessed(ctx, 1, d.ctypes.data_as(K.c_double_p), v.ctypes.data_as(K.c_double_p), cnt.ctypes.data_as(K.c_double_p), units) == 0
+    result = tmp_path / "result.h5"
+    u2 = C.create_string_buffer(4)
+    assert lib.dxb_save_dose(ctx, str(result).encode(), 1, u2) == 0, lib.dxb_last_error(ctx)
+    assert u2.value == units.value
+    lib.dxb_destroy(ctx)
+    # the result file: scene + three result arrays, z-y-x, deflated
+    r = K.VP()
+    assert lib.dxb_h5_open(C.byref(r), str(result).encode()) == 0
+    t, rk, dd, z = C.c_int(), C.c_int(), (C.c_uint64 * 8)(), C.c_int()
+    for name, ref in (("dosearray", d), ("dosevariancearray", v), ("doseeventcountarray", cnt), ("densityarray", wl.density)):
+        assert lib.dxb_h5_dataset_info(r, ("/" + name).encode(), C.byref(t), C.byref(rk), dd, C.byref(z)) == 0
+        assert (t.value, list(dd)[:3], z.value) == (1, [nz, ny, nx], 1)
+        got = np.zeros(n)
+        assert lib.dxb_h5_dataset_read(r, ("/" + name).encode(), got.ctypes.data_as(K.VP), got.nbytes) == 0
+        assert np.array_equal(got, ref), name
+    assert d.sum() > 0 and lib.dxb_h5_dataset_string(r, b"/materialnames", 1) == names[1].encode()
+    lib.dxb_h5_close(r)
+    # the reference's own HDF5Wrapper::load() (compiled unmodified over the H5Cpp shim) reads the file
+    exe = os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref")
+    if os.path.exists(exe):
+        out = subprocess.run([exe, "h5load", str(result)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        info = json.loads(out.stdout)
+        assert info["dimensions"] == wl.dim and info["materials"] == len(names)
+        assert info["dose_sum"] == pytest.approx(d.sum(), rel=1e-12) and info["count_sum"] == pytest.approx(cnt.sum(), rel=1e-12)

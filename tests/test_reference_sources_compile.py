@@ -456,13 +456,40 @@ def test_reference_beam_settings_model_matches_the_python_mirror(dx, ref_rows, t
     assert all(("Bowtie filter" in k) or ("Use current AEC profile" in k) or k.endswith("Rotation center (x, y, z) [cm]") for k in extra), extra
 
 
-def test_reference_hdf5_wrapper_round_trip_over_the_shims(ref_rows):
-    """HDF5Wrapper (the reference's code, R:src/libopendxmc/hdf5wrapper.cpp) saves the scene and loads it back against the
-    in-memory stand-in for the HDF5 C++ API: every setting of the loadable beam types survives (radian accessors, tube
-    filtration, organ AEC ...), and so do the grid and the materials (AtomHandler::toSymbol -> parseCompoundStr)."""
-    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "h5roundtrip"], capture_output=True, text=True, cwd="/root/reference")
+def test_reference_hdf5_wrapper_round_trip_over_the_shims(ref_rows, tmp_path):
+    """HDF5Wrapper (the reference's code, R:src/libopendxmc/hdf5wrapper.cpp, compiled unmodified) saves the scene to a REAL
+    file in the HDF5 format and loads it back - tests/stubs/H5Cpp.h maps the HDF5 C++ API onto libdxmc_b200's own reader /
+    writer (include/dxb.h: dxb_h5_*): every setting of the loadable beam types survives (radian accessors, tube
+    filtration, organ AEC ...), and so do the grid and the materials (AtomHandler::toSymbol -> parseCompoundStr).  The
+    file is then inspected independently of the reference's code."""
+    import ctypes as C
+    from opendxmc_b200 import _capi as K
+    path = tmp_path / "scene.h5"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref"), "h5roundtrip", str(path)], capture_output=True, text=True, cwd="/root/reference")
     assert r.returncode == 0, r.stderr
     head = json.loads(r.stdout.splitlines()[0])
+    # the file the reference's save() produced: HDF5 signature, arrays in z-y-x order (:121-124), one deflated chunk for
+    # the big arrays (:145-151), variable-length strings, beam groups numbered from 1 with attributes
+    raw = path.read_bytes()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    lib = K.load()
+    h = K.VP()
+    assert lib.dxb_h5_open(C.byref(h), str(path).encode()) == K.DXB_OK
+    t, rk, d, z = C.c_int(), C.c_int(), (C.c_uint64 * 8)(), C.c_int()
+    dims = np.zeros(3, dtype=np.uint64)
+    assert lib.dxb_h5_dataset_read(h, b"/dimensions", dims.ctypes.data_as(K.VP), 24) == K.DXB_OK
+    assert list(dims) == [24, 24, 5]
+    for name, code in (("densityarray", 1), ("materialarray", 3), ("organarray", 3)):
+        assert lib.dxb_h5_dataset_info(h, ("/" + name).encode(), C.byref(t), C.byref(rk), d, C.byref(z)) == K.DXB_OK
+        assert (t.value, rk.value, list(d)[:3], z.value) == (code, 3, [5, 24, 24], 1), name
+    assert lib.dxb_h5_dataset_info(h, b"/materialnames", C.byref(t), C.byref(rk), d, C.byref(z)) == K.DXB_OK and t.value == 4
+    assert lib.dxb_h5_dataset_string(h, b"/materialnames", 0) == b"Air, Dry (near sea level)"
+    assert lib.dxb_h5_dataset_string(h, b"/materialcomposition", 1).startswith(b"H")   # PMMA: H, C, O
+    groups = lib.dxb_h5_list(h, b"/beams").decode().split()
+    assert "CTSpiralBeams" in groups and "DXBeams" in groups and "CTSpiralDualEnergyBeams" in groups
+    attrs = lib.dxb_h5_list(h, b"/beams/CTSpiralBeams/1").decode()
+    assert "a pitch" in attrs or "a " in attrs
+    lib.dxb_h5_close(h)
     assert head["same_grid"] and head["same_materials"] and head["worst_composition_rel"] < 1e-12
     # the pencil beam has no save() overload (R:hdf5wrapper.cpp:1050-1068)
     assert head["beams_saved"] == 5
