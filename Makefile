@@ -22,9 +22,13 @@ build/%.o: $(CSRC)/%.cpp $(CSRC_HDRS) include/dxb.h Makefile
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
+# identity of the shipped transport kernel: its sources + the compiler flags (bench.py only trusts an ncu traffic capture
+# whose id equals the one compiled into the loaded library, dxb_kernel_build_id)
+KERNEL_ID := $(shell cat $(CSRC)/transport_pool.cu $(CSRC)/transport_common.cuh $(CSRC)/device_types.cuh | sha256sum | cut -c1-16)-$(shell echo '$(NVFLAGS)' | sha256sum | cut -c1-8)
+
 build/%.o: $(CSRC)/%.cu $(CSRC_HDRS) include/dxb.h Makefile
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) -DDXB_KERNEL_BUILD_ID='"$(KERNEL_ID)"' -c $< -o $@
 
 oracle: oracle/liboracle.so
 oracle/liboracle.so: oracle/oracle.cpp oracle/oracle.h include/dxb.h Makefile

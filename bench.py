@@ -262,13 +262,10 @@ def config_dict(args, wl, extra=None):
 
 
 def library_build_id():
-    """sha256 (first 16 hex digits) of the loaded libdxmc_b200.so: profiles captured from another build do not apply"""
+    """identity of the transport kernel compiled into the LOADED libdxmc_b200.so (hash of its sources + compiler flags,
+    dxb_kernel_build_id): an ncu capture taken from another kernel build does not describe it"""
     from opendxmc_b200 import _capi as K
-    h = hashlib.sha256()
-    with open(K.LIB_PATH, "rb") as f:
-        for chunk in iter(lambda: f.read(1 << 20), b""):
-            h.update(chunk)
-    return h.hexdigest()[:16]
+    return K.load().dxb_kernel_build_id().decode()
 
 
 def measured_traffic(build_id):

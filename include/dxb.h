@@ -513,6 +513,9 @@ int dxb_load_scene(dxb_ctx*, const char* path, uint64_t dim_out[3], double spaci
 int dxb_save_dose(dxb_ctx*, const char* path, int delete_air_dose, char units_out[4]);
 
 int dxb_abi_version(void);
+/* identity of the transport kernel compiled into this library: hash of its sources and compiler flags (profiles taken
+ * from another build do not describe it; bench.py compares it with the id stored next to an ncu traffic capture) */
+const char* dxb_kernel_build_id(void);
 int dxb_device_count(void);
 
 #ifdef __cplusplus

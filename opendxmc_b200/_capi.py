@@ -107,6 +107,7 @@ VP = C.c_void_p
 # name -> (restype, argtypes); this table is also what tests/test_capi_symbols.py checks against include/dxb.h
 SIGNATURES = {
     "dxb_abi_version": (C.c_int, []),
+    "dxb_kernel_build_id": (C.c_char_p, []),
     "dxb_device_count": (C.c_int, []),
     "dxb_material_by_weight": (C.c_int, [C.POINTER(VP), C.c_uint32, c_u32_p, c_double_p]),
     "dxb_material_by_nist_name": (C.c_int, [C.POINTER(VP), C.c_char_p]),

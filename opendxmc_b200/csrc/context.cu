@@ -321,7 +321,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     P.interact_bias = std::clamp(c->opt.interactBias == -999 ? (pool ? 24 : 16) : c->opt.interactBias, -32, 32);
     P.service_warps = std::clamp(c->opt.serviceWarps, 0, 32);
     P.diag = c->opt.diag;
-    P.step_quad = pool && c->opt.stepQuad && P.step_pairs == 2;
+    P.step_quad = (pool && c->opt.stepQuad && P.step_pairs == 2) ? c->opt.stepQuad : 0;
     P.work_counter = d.counters.p;
     P.stats = d.counters.p + 8;
 
@@ -656,6 +656,11 @@ int initDevice(dxb_ctx* c, DeviceState& d)
 
 // ============================================================================ C ABI
 extern "C" {
+
+#ifndef DXB_KERNEL_BUILD_ID
+#define DXB_KERNEL_BUILD_ID "unknown"
+#endif
+const char* dxb_kernel_build_id(void) { return DXB_KERNEL_BUILD_ID; }
 
 int dxb_device_count(void)
 {

@@ -614,6 +614,10 @@ int dxb_timer_end(dxb_ctx* c, double* ms_max)
 {
     if (!c || c->devs.empty() || !ms_max)
         return DXB_EINVAL;
+    // an exchange that is still only noted (in-process) belongs to the timed work
+    const int prc = mgEnqueuePending(c);
+    if (prc != DXB_OK)
+        return prc;
     double mx = 0;
     for (auto& d : c->devs) {
         if (!d->evTimer[0])

@@ -229,10 +229,22 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         c0 = loadVoxel(G.voxels + v0);
                     if (in1)
                         c1 = loadVoxel(G.voxels + v1);
-                    if (in2)
-                        c2 = loadVoxel(G.voxels + v2);
-                    if (in3)
-                        c3 = loadVoxel(G.voxels + v3);
+                    // step_quad == 2 (experiment): the speculative second pair is only PREFETCHED into L2 and loaded when the
+                    // walk gets there, so that no unconsumed load is outstanding when the slot is published (the release
+                    // fence waits for every load in flight)
+                    const bool prefetchOnly = P.step_quad == 2;
+                    if (in2) {
+                        if (prefetchOnly)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(G.voxels + v2));
+                        else
+                            c2 = loadVoxel(G.voxels + v2);
+                    }
+                    if (in3) {
+                        if (prefetchOnly)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(G.voxels + v3));
+                        else
+                            c3 = loadVoxel(G.voxels + v3);
+                    }
                     // walk the four tentative collisions in order; stop at the first real one or at the exit
                     const float* tt = totTable + epos.i;
                     newPhase = kPhDead;
@@ -253,6 +265,12 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                                 newPhase = kPhInt;
                             } else {
                                 blk += 1u; // the second pair is now consumed
+                                if (prefetchOnly) {
+                                    if (in2)
+                                        c2 = loadVoxel(G.voxels + v2);
+                                    if (in3)
+                                        c3 = loadVoxel(G.voxels + v3);
+                                }
                                 if (in2) {
                                     ++nSteps;
                                     mat = voxelMaterial(c2);

@@ -7,16 +7,17 @@ of an acceptance test, and a deposit lands in the neighbouring voxel when the f3
 the design delivers, orders of magnitude tighter than the acceptance bar of BASELINE.json (north_star: total deposited
 energy within 0.5 %, ROI / organ dose within 3 combined standard errors - still checked, as the documented bar):
 
-    total deposited energy           relative difference <= 1e-5   (physics mode 2: 5e-5)
-    steps / interactions / deposits  relative difference <= 1e-5 each (mode 2: 5e-5; they feed the roofline)
+    total deposited energy           relative difference <= 1e-5
+    steps / interactions / deposits  relative difference <= 1e-5 each (they feed the roofline model)
     misplaced events                 sum |n_gpu - n_oracle| / (2 sum n_oracle) <= max(1e-4, 4e-5 cm / voxel size)
     voxel-wise energy                sum |E_gpu - E_oracle| / sum E_oracle     <= max(2e-4, 1e-4 cm / voxel size)
-                                     (mode 2: x 3 - the Doppler-broadened energy of every bound-electron collision is an
-                                     f32 result of several rounded operations)
+for all three physics modes.  (Mode 2 first measured 10 x worse: the Doppler-broadened energy E'/E was evaluated as a
+difference of O(1) terms in f32; the discriminant is now expanded analytically on both sides, transport_common.cuh:
+dopplerBroaden.)
 
-Measured on B200 (profiles/r02_parity_metrics.jsonl): totals 1e-8 ... 6e-6, counters <= 9e-6, misplaced events 3e-5 at
-5 mm voxels and 2e-4 at 0.8 mm, voxel-wise energy 2e-6 ... 1.2e-4 (4e-4 at 0.8 mm voxels).  A kernel regression that
-misplaces or loses 0.3 % of the energy passes the acceptance bar but not these."""
+Measured on B200 (profiles/r02_parity_metrics.jsonl, 23 comparisons): totals 5e-10 ... 6e-6, counters <= 9e-6, misplaced
+events 4e-7 ... 5e-5 at 3 - 7 mm voxels and 2e-4 at 0.8 mm, voxel-wise energy 9e-7 ... 1.2e-4 (4e-4 at 0.8 mm voxels).  A
+kernel regression that misplaces or loses 0.3 % of the energy passes the acceptance bar but not these."""
 import json
 import os
 
@@ -24,7 +25,7 @@ import numpy as np
 
 TOTAL_ENERGY_RTOL = 1e-5
 COUNTER_RTOL = 1e-5
-MODE2_FACTOR = 5.0
+MODE2_FACTOR = 1.0  # (kept as a knob: see the note on mode 2 above)
 
 
 def misplaced_bound(voxel_cm):
@@ -63,5 +64,5 @@ def assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, what="", voxel_cm=0.5, 
     for k in ("steps", "interactions", "deposits"):
         assert m[k + "_rel"] <= COUNTER_RTOL * k2 or abs(int(st[k]) - int(ost[k])) <= counter_floor, msg
     assert m["misplaced_event_fraction"] <= misplaced_bound(voxel_cm) * k2, msg
-    assert m["voxelwise_energy_rel"] <= voxelwise_bound(voxel_cm) * (3.0 if mode == 2 else 1.0), msg
+    assert m["voxelwise_energy_rel"] <= voxelwise_bound(voxel_cm) * k2, msg
     return m
