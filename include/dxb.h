@@ -428,6 +428,9 @@ typedef struct dxb_run_stats {
     double   calibration_factor;
     double   energy_emitted_kev;   /* sum of E*w over sampled histories */
     double   energy_deposited_kev; /* sum over tallies */
+    uint64_t hops;            /* slab-local majorants: tentative steps that ended on a slab face (no voxel fetch) */
+    int32_t  local_majorant;  /* 1: the last beam ran on the slab-local majorant build of the kernel */
+    int32_t  reserved;
 } dxb_run_stats;
 int dxb_get_run_stats(const dxb_ctx*, dxb_run_stats* out);
 
@@ -438,6 +441,11 @@ int dxb_device_attenuation(dxb_ctx*, uint32_t material_index, int physics_mode,
                            const double* energy_kev, uint32_t n, float* out4);
 /* majorant mu_max(E) [1/cm] as the kernels interpolate it */
 int dxb_device_majorant(dxb_ctx*, const double* energy_kev, uint32_t n, float* out);
+/* The slab-local majorant table built with the grid (option "local_majorant": -1 auto, 0 off, 1 on; "slab_cm": target slab
+ * thickness): slabs of 2^shift voxel layers along z; inside slab s and energy band b (= energy node index >> 5) the kernels
+ * track with mu_max(E) / inv_ratio[s * 16 + b].  *useful = 1 when auto mode would use it.  inv_ratio may be NULL (sizes
+ * only); it receives n_slabs * 16 floats.  This is what a test hands to the CPU oracle so that both track identically. */
+int dxb_get_local_majorant(dxb_ctx*, int* n_slabs, int* shift, int* useful, float* inv_ratio);
 
 /* CT segmentation, SURVEY §8f-1: HU -> (material, density)
  * R:src/libopendxmc/ctsegmentationpipeline.cpp:113-169 */

@@ -1236,6 +1236,15 @@ class World:
                                              out.ctypes.data_as(K.c_float_p)), "dxb_device_attenuation", self._ctx)
         return out
 
+    def local_majorant(self):
+        """the slab-local majorant table built with the grid: (n_slabs, shift, useful, inv_ratio[n_slabs, 16])"""
+        n, sh, us = C.c_int(), C.c_int(), C.c_int()
+        _check(_lib().dxb_get_local_majorant(self._ctx, C.byref(n), C.byref(sh), C.byref(us), None), "dxb_get_local_majorant", self._ctx)
+        t = np.ones((max(n.value, 1), 16), dtype=np.float32)
+        if n.value > 0:
+            _check(_lib().dxb_get_local_majorant(self._ctx, None, None, None, t.ctypes.data_as(K.c_float_p)), "dxb_get_local_majorant", self._ctx)
+        return n.value, sh.value, bool(us.value), t
+
     def device_majorant(self, energies):
         e = np.ascontiguousarray(energies, dtype=np.float64)
         out = np.zeros(len(e), dtype=np.float32)

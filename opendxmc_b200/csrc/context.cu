@@ -98,6 +98,7 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
         }
     }
     w.n_mat = n;
+    w.hostTot = tot;
     CUDA_TRY(c, w.att.upload(att, w.device, s));
     CUDA_TRY(c, w.tot.upload(tot, w.device, s));
     CUDA_TRY(c, w.etr.upload(etr, w.device, s));
@@ -109,6 +110,72 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
     CUDA_TRY(c, w.majorant.alloc(kDevNE, w.device));
     CUDA_TRY(c, cudaStreamSynchronize(s)); // host vectors go out of scope
     w.hasTables = true;
+    return DXB_OK;
+}
+
+// Slab-local majorants (transport_pool.cu, LM builds).  Slabs of 2^shift voxel layers along z, about opt.slabCm thick.  The
+// device finds, per slab and material, the largest density (exact integer maxima of the 24-bit densities); the small table
+//   inv_ratio(slab, band) = 1 / max over the band's energy nodes of [ max_m rho_max(slab, m) * tot_m(node) / majorant(node) ]
+// is then computed HERE with single IEEE f32 operations on the same f32 tables the device reads, so that the oracle, which
+// receives the table through dxb_get_local_majorant, tracks with exactly the numbers the kernel uses.
+int buildLocalMajorant(dxb_ctx* c, World& w, cudaStream_t s)
+{
+    w.lmSlabs = 0;
+    w.lmUseful = false;
+    const int nz = static_cast<int>(w.dim[2]);
+    int shift = 0;
+    while ((2 << shift) * w.spacing[2] <= c->opt.slabCm * 1.5 && (nz >> (shift + 1)) >= 1 && shift < 12)
+        ++shift;
+    int slabs = (nz + (1 << shift) - 1) >> shift;
+    while (slabs > kLmMaxSlabs) {
+        ++shift;
+        slabs = (nz + (1 << shift) - 1) >> shift;
+    }
+    if (slabs < 2 || w.hostTot.size() != static_cast<size_t>(w.n_mat) * kDevNE)
+        return DXB_OK; // a single slab is the global majorant
+    CUDA_TRY(c, w.slabMax.alloc(static_cast<size_t>(slabs) * 256, w.device));
+    CUDA_TRY(c, cudaMemsetAsync(w.slabMax.p, 0, static_cast<size_t>(slabs) * 256 * sizeof(unsigned int), s));
+    launchSlabMax(w.voxels.p, static_cast<size_t>(w.dim[0]) * w.dim[1], nz, shift, slabs, w.slabMax.p, s);
+    CUDA_TRY(c, cudaGetLastError());
+    std::vector<unsigned int> bits(static_cast<size_t>(slabs) * 256);
+    std::vector<float> maj(kDevNE);
+    CUDA_TRY(c, cudaMemcpyAsync(bits.data(), w.slabMax.p, bits.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaMemcpyAsync(maj.data(), w.majorant.p, kDevNE * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    w.lmHost.assign(static_cast<size_t>(slabs) * kLmBands, 1.0f);
+    double meanRatio = 0;
+    const int refBand = 378 >> 5; // the band of 60 keV (node 378): where a diagnostic spectrum has most of its photons
+    for (int sl = 0; sl < slabs; ++sl) {
+        for (int b = 0; b < kLmBands; ++b) {
+            const int n0 = b * 32, n1 = std::min(b * 32 + 32, kDevNE - 1);
+            if (n0 >= kDevNE)
+                break;
+            float r = 0.0f;
+            for (int node = n0; node <= n1; ++node) {
+                float mu = 0.0f;
+                for (int m = 0; m < w.n_mat; ++m) {
+                    float rho;
+                    const unsigned int q = bits[static_cast<size_t>(sl) * 256 + m];
+                    std::memcpy(&rho, &q, sizeof(float));
+                    const float v = rho * w.hostTot[static_cast<size_t>(m) * kDevNE + node];
+                    mu = v > mu ? v : mu;
+                }
+                const float ratio = mu / maj[node];
+                r = ratio > r ? ratio : r;
+            }
+            // a little head-room (2^-20) keeps local attenuation * inv_ratio <= majorant under f32 rounding
+            r = std::min(1.0f, std::max(r, 1.0e-6f) * (1.0f + 9.5367431640625e-7f));
+            w.lmHost[static_cast<size_t>(sl) * kLmBands + b] = r >= 1.0f ? 1.0f : 1.0f / r;
+            if (b == refBand)
+                meanRatio += r;
+        }
+    }
+    meanRatio /= slabs;
+    CUDA_TRY(c, w.lmInvRatio.upload(w.lmHost, w.device, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    w.lmShift = shift;
+    w.lmSlabs = slabs;
+    w.lmUseful = meanRatio < 0.8; // hops and the longer step code must be paid for
     return DXB_OK;
 }
 
@@ -124,6 +191,14 @@ int finishGrid(dxb_ctx* c, World& w, cudaStream_t s)
     CUDA_TRY(c, cudaStreamSynchronize(s));
     if (mmax >= static_cast<unsigned int>(w.n_mat))
         return fail(c, DXB_EINVAL, "set_grid: material index out of range");
+    if (c->opt.localMajorant != 0) {
+        const int rc = buildLocalMajorant(c, w, s);
+        if (rc != DXB_OK)
+            return rc;
+    } else {
+        w.lmSlabs = 0;
+        w.lmUseful = false;
+    }
     w.hasGrid = true;
     return DXB_OK;
 }
@@ -272,7 +347,7 @@ uint64_t localCount(uint64_t nTotal, uint64_t rank, uint64_t world)
 struct TransportResult {
     double ms = 0;
     uint64_t launches = 0;
-    uint64_t stats[5] = { 0, 0, 0, 0, 0 };
+    uint64_t stats[6] = { 0, 0, 0, 0, 0, 0 }; // steps, interactions, deposits, emitted, histories, hops
     bool cancelled = false;
 };
 
@@ -332,14 +407,25 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.slots = 0;
     cfg.pool = pool;
     cfg.min_blocks = c->opt.poolMinBlocks;
+    cfg.local_majorant = false;
     if (pool) {
+        // slab-local majorants: the pool kernel's scoring builds; auto = when the table built with the grid predicts a gain
+        const bool lm = !calib && w.lmSlabs >= 2 && (c->opt.localMajorant == 1 || (c->opt.localMajorant < 0 && w.lmUseful));
+        cfg.local_majorant = lm;
+        const int lmSlabs = lm ? w.lmSlabs : 0;
         cfg.threads = std::clamp(c->opt.poolThreads, 64, 512) / 32 * 32;
-        cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots);
-        cfg.smem = poolSmemBytes(cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0);
+        cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots, lm);
+        cfg.smem = poolSmemBytes(cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0, lmSlabs);
         if (cfg.table_in_smem && cfg.smem > 56 * 1024) {
             cfg.table_in_smem = false;
-            cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots);
-            cfg.smem = poolSmemBytes(cfg.slots, 0);
+            cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots, lm);
+            cfg.smem = poolSmemBytes(cfg.slots, 0, lmSlabs);
+        }
+        if (lm) {
+            P.lm_inv_ratio = w.lmInvRatio.p;
+            P.lm_slabs = w.lmSlabs;
+            P.lm_shift = w.lmShift;
+            P.lm_thickness = static_cast<float>(static_cast<double>(1 << w.lmShift) * w.spacing[2]);
         }
     } else if (mux) {
         // the table shares the SM's shared memory with the photon slots: keep it only while two blocks still fit
@@ -356,13 +442,15 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks)
+        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks, cfg.local_majorant)
             : mux  ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)
             return fail(c, DXB_ECUDA, "transport kernel cannot be resident (occupancy 0)");
     }
     cfg.blocks = c->smCount * perSm;
+    if (!calib)
+        c->stats.local_majorant = cfg.local_majorant ? 1 : 0;
 
     const uint64_t nLocal = localCount(pb.nTotal, rank, world);
     CUDA_TRY(c, cudaMemsetAsync(d.counters.p + 8, 0, 24 * sizeof(unsigned long long), d.stream));
@@ -407,9 +495,9 @@ int collectStats(dxb_ctx* c, DeviceState& d, TransportResult& res)
 {
     CUDA_TRY(c, cudaSetDevice(d.device));
     CUDA_TRY(c, cudaStreamSynchronize(d.stream));
-    unsigned long long h[5];
+    unsigned long long h[6];
     CUDA_TRY(c, cudaMemcpy(h, d.counters.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 6; ++i)
         res.stats[i] = h[i];
     if (c->opt.diag) {
         // pool kernel diagnostics: executions and claimed lanes per phase (step, interaction, Rayleigh, refill)
@@ -988,6 +1076,15 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.poolMinBlocks = static_cast<int>(value);
     } else if (k == "step_quad") {
         c->opt.stepQuad = static_cast<int>(value);
+    } else if (k == "local_majorant") {
+        const int v = static_cast<int>(value);
+        if (v < -1 || v > 1)
+            return fail(c, DXB_EINVAL, "local_majorant must be -1 (auto), 0 (off) or 1 (on)");
+        c->opt.localMajorant = v; // takes effect with the next dxb_set_grid (the table is built with the grid)
+    } else if (k == "slab_cm") {
+        if (!(value > 0))
+            return DXB_EINVAL;
+        c->opt.slabCm = value;
     } else if (k == "diag") {
         c->opt.diag = static_cast<int>(value);
     } else if (k == "service_warps") {
@@ -1085,6 +1182,7 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         c->stats.deposits += results[i].stats[2];
         c->stats.energy_emitted_kev += static_cast<double>(results[i].stats[3]) / 65536.0;
         c->stats.histories += results[i].stats[4];
+        c->stats.hops += results[i].stats[5];
         c->stats.kernel_launches += results[i].launches;
     }
     c->stats.transport_ms = msMax;
@@ -1477,6 +1575,22 @@ int dxb_device_attenuation(dxb_ctx* c, uint32_t material_index, int physics_mode
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(out4, dOut.p, static_cast<size_t>(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
     CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_get_local_majorant(dxb_ctx* c, int* n_slabs, int* shift, int* useful, float* inv_ratio)
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_local_majorant: no grid");
+    const World& w = c->devs[0]->world;
+    if (n_slabs)
+        *n_slabs = w.lmSlabs;
+    if (shift)
+        *shift = w.lmShift;
+    if (useful)
+        *useful = w.lmUseful ? 1 : 0;
+    if (inv_ratio && w.lmSlabs > 0)
+        std::memcpy(inv_ratio, w.lmHost.data(), static_cast<size_t>(w.lmSlabs) * kLmBands * sizeof(float));
     return DXB_OK;
 }
 

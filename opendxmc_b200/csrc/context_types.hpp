@@ -101,6 +101,13 @@ struct World {
     DevBuf<double> stageDensity;         // staging for the caller's f64 density / u8 material (kept between set_grid calls)
     DevBuf<unsigned char> stageMaterial;
     bool hasGrid = false, hasTables = false;
+    // slab-local majorants (pool kernel, LM builds)
+    std::vector<float> hostTot;          // [n_mat * kDevNE] the f32 total-attenuation table as uploaded
+    DevBuf<unsigned int> slabMax;        // [lmSlabs * 256] per slab and material: largest density (24-bit float bits)
+    DevBuf<float> lmInvRatio;            // [lmSlabs * kLmBands]
+    std::vector<float> lmHost;           // host copy of lmInvRatio
+    int lmShift = 0, lmSlabs = 0;
+    bool lmUseful = false;               // the table predicts a gain (mean ratio below the threshold)
 
     GridDev gridDev() const
     {
@@ -208,6 +215,8 @@ struct Options {
     int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
+    int localMajorant = -1;      // pool kernel: slab-local majorants; -1 auto (on when the table predicts a gain), 0 off, 1 on
+    double slabCm = 2.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
     int interactBias = -999;     // -999: kernel default (mux 16: interaction phase when waiting lanes + bias >= stepping lanes;
                                  // pool 24: stepper warps keep stepping while at least this many lanes can claim a photon)

@@ -103,12 +103,19 @@ struct RunParams {
     int service_warps;              // pool kernel: warps per block that prefer interaction / refill phases
     int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes;
                                     // pool kernel: stepper warps keep stepping while at least this many lanes can
+    // slab-local majorants (pool kernel, LM builds): the grid is cut into slabs of 2^lm_shift voxel layers along z; inside
+    // slab s and energy band b (32 energy nodes) the tracking majorant is mu_max(E) / lm_inv_ratio[s * kLmBands + b]
+    const float* __restrict__ lm_inv_ratio; // [lm_slabs * kLmBands], >= 1
+    int lm_slabs, lm_shift;
+    float lm_thickness;              // slab thickness [cm] = 2^lm_shift * dz
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
 };
 
 constexpr unsigned int kShardBlock = 65536; // histories per sharding block
+constexpr int kLmBands = 16;                // energy bands of the slab-local majorant table: band = energy node index >> 5
+constexpr int kLmMaxSlabs = 256;
 
 // dynamic shared memory of the transport kernel:
 //   [per warp: 4 x u64 history-pool words][per warp: source buffer, kSourceBufWords x 32 words]
@@ -130,9 +137,9 @@ __host__ __device__ inline size_t muxSmemBytes(int threads, int slots, int table
 }
 
 // the block-pooled kernel (transport_pool.cu): 32 classes x `slots` photons per block + 2 status words per class
-__host__ __device__ inline size_t poolSmemBytes(int slots, int table_floats)
+__host__ __device__ inline size_t poolSmemBytes(int slots, int table_floats, int lm_slabs = 0)
 {
-    return (static_cast<size_t>(table_floats) + kDevNE + 64 + static_cast<size_t>(kSlotWords) * slots * 32) * 4;
+    return (static_cast<size_t>(table_floats) + kDevNE + 64 + static_cast<size_t>(kSlotWords) * slots * 32 + static_cast<size_t>(lm_slabs) * kLmBands) * 4;
 }
 
 // launch wrappers (transport.cu, transport_mux.cu, transport_pool.cu)
@@ -143,6 +150,7 @@ struct LaunchConfig {
     int slots; // 0: one photon per lane in registers (transport.cu); >= 2: slots per lane (mux) / per class (pool)
     bool pool; // block-pooled kernel instead of the lane-multiplexed one
     int min_blocks; // pool kernel: 5 / 6 = the 48 / 40-register builds (5 / 6 blocks of <= 256 threads per SM), else 64 registers
+    bool local_majorant; // pool kernel: the slab-local majorant build
 };
 
 } // namespace dxb

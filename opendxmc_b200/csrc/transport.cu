@@ -448,6 +448,28 @@ __global__ void packVoxelsKernel(const double* __restrict__ density, const unsig
             atomicMax(&maxDensityBits[i], s_max[i]);
 }
 
+// slab-local majorants: per slab of 2^shift voxel layers and per material the largest (24-bit) density that occurs.
+// Block (slab, part) scans one part of the slab's voxels; maxima meet in shared memory, then in out[slab * 256 + material].
+__global__ void slabMaxKernel(const unsigned int* __restrict__ voxels, size_t layerSize, int nz, int shift, int parts,
+    unsigned int* __restrict__ out)
+{
+    __shared__ unsigned int s_max[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_max[i] = 0u;
+    __syncthreads();
+    const int slab = blockIdx.x / parts, part = blockIdx.x % parts;
+    const int z0 = slab << shift, z1 = min(nz, (slab + 1) << shift);
+    const size_t begin = static_cast<size_t>(z0) * layerSize, end = static_cast<size_t>(z1) * layerSize;
+    for (size_t i = begin + static_cast<size_t>(part) * blockDim.x + threadIdx.x; i < end; i += static_cast<size_t>(parts) * blockDim.x) {
+        const unsigned int v = voxels[i];
+        atomicMax(&s_max[v & 0xFFu], v & 0xFFFFFF00u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (s_max[i])
+            atomicMax(&out[slab * 256 + i], s_max[i]);
+}
+
 __global__ void majorantKernel(const float* __restrict__ tot, const unsigned int* __restrict__ maxDensityBits,
     int n_mat, float* __restrict__ majorant)
 {
@@ -831,6 +853,11 @@ void setLaunchSmCount(int sms) { g_streamBlocks = (sms > 0 ? sms : 148) * 8; }
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s)
 {
     packVoxelsKernel<<<g_streamBlocks, 256, 0, s>>>(density, material, out, n, maxBits);
+}
+void launchSlabMax(const unsigned int* voxels, size_t layerSize, int nz, int shift, int nslabs, unsigned int* out, cudaStream_t s)
+{
+    const int parts = max(1, g_streamBlocks / max(nslabs, 1));
+    slabMaxKernel<<<nslabs * parts, 256, 0, s>>>(voxels, layerSize, nz, shift, parts, out);
 }
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s)
 {

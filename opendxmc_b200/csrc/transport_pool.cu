@@ -80,7 +80,12 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
 
 // LB: register budget through the launch bounds.  0: 64 registers (<= 512 threads per block, 1024 resident threads per SM);
 // 5 / 6: <= 256 threads per block with 5 / 6 resident blocks per SM (48 / 40 registers, a few spilled words).
-template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB>
+// LM: slab-local majorants.  The grid is cut into slabs of 2^lm_shift voxel layers along z; inside a slab the
+// tracking majorant is mu_max(E) / inv_ratio(slab, energy band) - the largest attenuation that occurs IN THAT SLAB instead
+// of anywhere in the grid.  A tentative step that would cross a slab face stops on the face and the walk continues in the
+// next slab with a fresh draw (the exponential free path is memoryless, so the estimator stays unbiased).  Pays when the
+// densest material is confined to part of the z range (teeth in a whole-body phantom during a chest scan).
+template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false>
 __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transportKernelPool(const __grid_constant__ RunParams P)
 {
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
@@ -98,6 +103,10 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     const int nTab = SMEM_TABLE ? P.tab.n_mat * kDevNE : 0;
     float* __restrict__ s_maj = reinterpret_cast<float*>(s_raw) + kSlotWords * kStride + 64;
     float* __restrict__ s_tot = s_maj + kDevNE;
+    float* __restrict__ s_lm = s_tot + nTab; // [lm_slabs x kLmBands] inverse majorant ratios (LM builds)
+    if (LM)
+        for (int i = threadIdx.x; i < P.lm_slabs * kLmBands; i += blockDim.x)
+            s_lm[i] = P.lm_inv_ratio[i];
     const int rot = static_cast<int>(((threadIdx.x >> 5) * SPC) / (blockDim.x >> 5)); // first slot this warp tries to claim
     for (int i = threadIdx.x; i < nTab; i += blockDim.x)
         s_tot[i] = P.tab.tot[i];
@@ -116,7 +125,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     unsigned long long poolNext = 0, poolEnd = 0;
     bool drained = false;
     // per-lane
-    unsigned int nSteps = 0, nInteractions = 0, nDeposits = 0, nHistories = 0;
+    unsigned int nSteps = 0, nInteractions = 0, nDeposits = 0, nHistories = 0, nHops = 0;
     unsigned long long emitted = 0;
 
     for (;;) {
@@ -204,6 +213,101 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             bool stepping = active;
             int newPhase = kPhStep;
             int mat = 0;
+            if (LM && !CALIB) {
+                // ---- slab-local majorants: four sub-steps, each either a tentative collision (voxel gather) or a hop to the
+                // face of the current slab; positions and kinds do not depend on voxel data, so all gathers are in flight at once
+                if (stepping) {
+                    const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
+                    const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
+                    const bool up = dz > 0.0f;
+                    const float invdz = dz != 0.0f ? __fdividef(1.0f, dz) : 0.0f;
+                    const int band = epos.i >> 5;
+                    int slab = min(max(__float2int_rd(fmaf(pz, G.inv_dz, G.offz)), 0), G.nz - 1) >> P.lm_shift;
+                    float x = px, y = py, z = pz;
+                    float xs[4], ys[4], zs[4], ir[4];
+                    unsigned int cell[4];
+                    int kind[4]; // 0: left the grid, 1: hop, 2: tentative collision
+                    bool alive = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        kind[j] = 0;
+                        cell[j] = 0u;
+                        ir[j] = 1.0f;
+                        if (alive) {
+                            const float invr = s_lm[slab * kLmBands + band];
+                            const float u = j == 0 ? r1.k(0) : (j == 1 ? r1.k(2) : (j == 2 ? r2.k(0) : r2.k(2)));
+                            const float sl = __log2f(fmaf(u, -kU24, 1.0f)) * stepScale * invr;
+                            const float zf = fmaf(static_cast<float>(slab + (up ? 1 : 0)), P.lm_thickness, G.z0);
+                            const float tb = dz != 0.0f ? (zf - z) * invdz : 3.0e38f;
+                            if (sl < tb) {
+                                x = fmaf(dx, sl, x);
+                                y = fmaf(dy, sl, y);
+                                z = fmaf(dz, sl, z);
+                                unsigned int v;
+                                if (voxelIndex(G, x, y, z, v)) {
+                                    kind[j] = 2;
+                                    cell[j] = loadVoxel(G.voxels + v);
+                                    ir[j] = invr;
+                                } else {
+                                    alive = false;
+                                }
+                            } else {
+                                x = fmaf(dx, tb, x);
+                                y = fmaf(dy, tb, y);
+                                z = zf;
+                                slab += up ? 1 : -1;
+                                // the end point must map into the first (last) voxel layer of the slab it enters: the face
+                                // coordinate is moved by single ulps until the layer index says so (0 - 2 iterations)
+                                const int want = up ? (slab << P.lm_shift) : (((slab + 1) << P.lm_shift) - 1);
+                                for (int it = 0; it < 8; ++it) {
+                                    const int izc = __float2int_rd(fmaf(z, G.inv_dz, G.offz));
+                                    if (up ? izc >= want : izc <= want)
+                                        break;
+                                    z = nextafterf(z, up ? 3.0e38f : -3.0e38f);
+                                }
+                                unsigned int v;
+                                if (slab >= 0 && slab < P.lm_slabs && voxelIndex(G, x, y, z, v))
+                                    kind[j] = 1;
+                                else
+                                    alive = false;
+                            }
+                            xs[j] = x;
+                            ys[j] = y;
+                            zs[j] = z;
+                        }
+                    }
+                    const float* tt = totTable + epos.i;
+                    newPhase = kPhDead;
+                    blk += 1u;
+                    bool walking = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (walking) {
+                            if (j == 2)
+                                blk += 1u; // the second pair is now consumed
+                            if (kind[j] == 0) {
+                                walking = false; // newPhase stays dead
+                            } else {
+                                px = xs[j], py = ys[j], pz = zs[j];
+                                if (kind[j] == 1) {
+                                    ++nHops;
+                                } else {
+                                    ++nSteps;
+                                    mat = voxelMaterial(cell[j]);
+                                    const float mu = voxelDensity(cell[j]) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                    const float ra = j == 0 ? r1.k(1) : (j == 1 ? r1.k(3) : (j == 2 ? r2.k(1) : r2.k(3)));
+                                    if (ra * muMaxU24 < mu * ir[j]) {
+                                        newPhase = kPhInt;
+                                        walking = false;
+                                    }
+                                }
+                                if (walking && j == 3)
+                                    newPhase = kPhStep;
+                            }
+                        }
+                    }
+                }
+            } else
             if (!CALIB && P.step_quad) {
                 // Two step pairs with all four voxel gathers in flight at once: the second pair (block blk + 1) is
                 // speculative and is simply not consumed if the first pair ends in a real collision or outside the grid
@@ -543,9 +647,9 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     }
 
     // ---------------- statistics
-    unsigned long long v[5] = { nSteps, nInteractions, nDeposits, emitted, nHistories };
+    unsigned long long v[6] = { nSteps, nInteractions, nDeposits, emitted, nHistories, nHops };
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < 6; ++k) {
         unsigned long long x = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
@@ -555,10 +659,10 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     }
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false>
 cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t stream)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
     if (e != cudaSuccess)
         return e;
@@ -566,10 +670,10 @@ cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t
     return cudaGetLastError();
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false>
 int occupancyPool(int threads, size_t smem)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -588,6 +692,15 @@ int occupancyPool(int threads, size_t smem)
 #define DXB_POOL_DISPATCH(CALL)                                                  \
     const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
+    if (localMajorant && !calib)                                                \
+        switch (key) {                                                          \
+        case 0: return CALL(0, false, false, 16, 0, true);                      \
+        case 1: return CALL(0, false, true, 16, 0, true);                       \
+        case 4: return CALL(1, false, false, 16, 0, true);                      \
+        case 5: return CALL(1, false, true, 16, 0, true);                       \
+        case 8: return CALL(2, false, false, 16, 0, true);                      \
+        default: return CALL(2, false, true, 16, 0, true);                      \
+        }                                                                       \
     switch (key) {                                                              \
     case 8: return CALL(2, false, false, 16, 0);                                    \
     case 9: return CALL(2, false, true, 16, 0);                                     \
@@ -620,25 +733,28 @@ int occupancyPool(int threads, size_t smem)
 cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream)
 {
     const bool smemTable = cfg.table_in_smem;
+    const bool localMajorant = cfg.local_majorant;
     const int slots = cfg.slots;
     const int lb = (cfg.threads <= 256 && (cfg.min_blocks == 5 || cfg.min_blocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? cfg.min_blocks : 0;
-#define DXB_CALL(MO, CA, SM, MM, LB) launchPool<MO, CA, SM, MM, LB>(p, cfg, stream)
+#define DXB_CALL(...) launchPool<__VA_ARGS__>(p, cfg, stream)
     DXB_POOL_DISPATCH(DXB_CALL)
 #undef DXB_CALL
 }
 
-int transportPoolSlots(int mode, bool calib, bool smemTable, int slots)
+int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant)
 {
     // must mirror DXB_POOL_DISPATCH: only the production variant is built for several slot counts
+    if (localMajorant && !calib)
+        return 16;
     if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 12))
         return slots;
     return 16;
 }
 
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks)
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant)
 {
     const int lb = (threads <= 256 && (minBlocks == 5 || minBlocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? minBlocks : 0;
-#define DXB_CALL(MO, CA, SM, MM, LB) occupancyPool<MO, CA, SM, MM, LB>(threads, smem)
+#define DXB_CALL(...) occupancyPool<__VA_ARGS__>(threads, smem)
     DXB_POOL_DISPATCH(DXB_CALL)
 #undef DXB_CALL
 }

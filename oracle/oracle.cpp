@@ -505,7 +505,7 @@ inline void atomicInc(uint64_t& target, uint64_t v = 1)
 }
 
 struct WorkerStats {
-    uint64_t histories = 0, steps = 0, interactions = 0, deposits = 0;
+    uint64_t histories = 0, steps = 0, interactions = 0, deposits = 0, hops = 0;
     double emitted = 0;
 };
 
@@ -522,6 +522,10 @@ struct AAVoxelGrid {
     std::vector<double> energyImparted, energyImpartedSquared;
     std::vector<uint64_t> nEvents;
     int scoreMaterial = -1; // calibration: collision kerma estimator in this material
+    // [D] slab-local majorants (transport_pool.cu, LM builds): slabs of 2^lmShift voxel layers along z; inside slab s and
+    // energy band b (= energy node index >> 5) the tracking majorant is majorant(E) / lmInvRatio[s * 16 + b]
+    int lmShift = 0, lmSlabs = 0;
+    std::vector<double> lmInvRatio;
 
     size_t size() const { return density.size(); }
     double voxelVolume() const { return spacing[0] * spacing[1] * spacing[2]; }
@@ -667,6 +671,74 @@ struct AAVoxelGrid {
         }
     }
 
+    long layerOf(double z) const { return static_cast<long>(std::floor((z - aabb[2]) / spacing[2])); }
+
+    // [D] Woodcock tracking with slab-local majorants.  Same random-number protocol as woodcockTransport (one Philox block
+    // per pair of tentative steps); a tentative step that would cross the face of the current slab stops ON the face (no
+    // collision test, its acceptance number is not used) and tracking continues in the next slab with the next draw: the
+    // exponential free path is memoryless, so the result is unbiased whatever the slab table.
+    void woodcockTransportSlabs(Particle& p, int correction, RandomState& state, WorkerStats& st)
+    {
+        const double thickness = static_cast<double>(1 << lmShift) * spacing[2];
+        bool still_inside = true;
+        while (still_inside) {
+            const double attMax = majorant(p.energy);
+            const double attMaxInv = 1.0 / attMax;
+            const size_t node = std::min<size_t>(static_cast<size_t>(std::max(0.0, materials[0].eCoord(p.energy))), materials[0].nE - 2);
+            const int band = static_cast<int>(node >> 5);
+            long slab = std::min<long>(std::max<long>(layerOf(p.pos[2]), 0), static_cast<long>(dim[2]) - 1) >> lmShift;
+            const std::array<double, 4> u = state.block();
+            for (int half = 0; half < 2 && still_inside; ++half) {
+                const double invr = lmInvRatio[static_cast<size_t>(slab) * 16 + band];
+                const double steplen = -std::log(1.0 - u[2 * half]) * attMaxInv * invr;
+                const bool up = p.dir[2] > 0;
+                const double zf = aabb[2] + static_cast<double>(slab + (up ? 1 : 0)) * thickness;
+                const double tb = p.dir[2] != 0 ? (zf - p.pos[2]) / p.dir[2] : 3.0e38;
+                const double toExit = exitDistance(p);
+                if (steplen < tb) {
+                    if (!(steplen < toExit)) {
+                        still_inside = false;
+                        break;
+                    }
+                    ++st.steps;
+                    p.translate(steplen);
+                    const size_t flat = flatIndex(p.pos);
+                    const uint8_t matInd = materialIndex[flat];
+                    const OMaterial& mat = materials[matInd];
+                    const auto att = mat.attenuationValues(p.energy);
+                    const double attSum = att.sum() * density[flat];
+                    if (u[2 * half + 1] * attMax < attSum * invr) {
+                        ++st.interactions;
+                        const auto res = interact(att, p, mat, correction, state);
+                        if (res.energyImparted > 0) {
+                            ++st.deposits;
+                            scoreEnergy(flat, res.energyImparted);
+                        }
+                        still_inside = res.particleAlive;
+                        break; // the energy (band, majorant) or the direction may have changed: new block
+                    }
+                } else {
+                    slab += up ? 1 : -1;
+                    if (!(tb < toExit) || slab < 0 || slab >= lmSlabs) {
+                        still_inside = false;
+                        break;
+                    }
+                    ++st.hops;
+                    p.translate(tb);
+                    // exactly on the face, then single ulps until the point maps into the voxel layer it enters
+                    p.pos[2] = zf;
+                    const long want = up ? (slab << lmShift) : (((slab + 1) << lmShift) - 1);
+                    for (int it = 0; it < 8; ++it) {
+                        const long l = layerOf(p.pos[2]);
+                        if (up ? l >= want : l <= want)
+                            break;
+                        p.pos[2] = std::nextafter(p.pos[2], up ? 3.0e38 : -3.0e38);
+                    }
+                }
+            }
+        }
+    }
+
     // World::transport: move to the AABB, then track
     void transport(Particle& p, int correction, RandomState& state, WorkerStats& st)
     {
@@ -674,7 +746,10 @@ struct AAVoxelGrid {
         if (p.energy < MIN_ENERGY || !intersect(p, tmin, tmax))
             return;
         p.translate(tmin);
-        woodcockTransport(p, correction, state, st);
+        if (lmSlabs >= 2 && scoreMaterial < 0)
+            woodcockTransportSlabs(p, correction, state, st);
+        else
+            woodcockTransport(p, correction, state, st);
     }
 };
 
@@ -1117,6 +1192,7 @@ void runBeam(AAVoxelGrid& grid, const dxb_beam_desc& b, int correction, uint64_t
         for (const auto& w : ws) {
             stats->histories += w.histories;
             stats->steps += w.steps;
+            stats->hops += w.hops;
             stats->interactions += w.interactions;
             stats->deposits += w.deposits;
             stats->energy_emitted_kev += w.emitted;
@@ -1240,6 +1316,49 @@ double analyticCalibration(const orc_world& w, const dxb_beam_desc& b)
 
 // =========================================================================== C interface
 extern "C" {
+
+// slab-local majorants: the table the device built (dxb_get_local_majorant), or none (n_slabs < 2)
+void orc_world_set_local_majorant(orc_world* w, int shift, int n_slabs, const float* inv_ratio)
+{
+    AAVoxelGrid& g = w->grid;
+    g.lmShift = shift;
+    g.lmSlabs = (n_slabs >= 2 && inv_ratio) ? n_slabs : 0;
+    g.lmInvRatio.clear();
+    if (g.lmSlabs)
+        g.lmInvRatio.assign(inv_ratio, inv_ratio + static_cast<size_t>(n_slabs) * 16);
+}
+// ... or the oracle's own table in f64 (no GPU needed): slabs of 2^shift voxel layers; returns the number of slabs
+int orc_world_build_local_majorant(orc_world* w, int shift)
+{
+    AAVoxelGrid& g = w->grid;
+    const long nz = static_cast<long>(g.dim[2]);
+    const int slabs = static_cast<int>((nz + (1 << shift) - 1) >> shift);
+    g.lmShift = shift;
+    g.lmSlabs = slabs >= 2 ? slabs : 0;
+    g.lmInvRatio.assign(static_cast<size_t>(slabs) * 16, 1.0);
+    if (!g.lmSlabs)
+        return 0;
+    const size_t layer = g.dim[0] * g.dim[1];
+    const uint32_t nE = g.materials[0].nE;
+    for (int sl = 0; sl < slabs; ++sl) {
+        std::vector<double> maxDens(g.materials.size(), 0.0);
+        const size_t b = static_cast<size_t>(sl << shift) * layer, e = std::min(g.density.size(), static_cast<size_t>((sl + 1) << shift) * layer);
+        for (size_t i = b; i < e; ++i)
+            maxDens[g.materialIndex[i]] = std::max(maxDens[g.materialIndex[i]], g.density[i]);
+        for (uint32_t band = 0; band * 32 < nE; ++band) {
+            double r = 0;
+            for (uint32_t node = band * 32; node <= std::min(band * 32 + 32, nE - 1); ++node) {
+                double mu = 0;
+                for (size_t k = 0; k < g.materials.size(); ++k)
+                    mu = std::max(mu, maxDens[k] * (g.materials[k].photo[node] + g.materials[k].incoh[node] + g.materials[k].coh[node]));
+                r = std::max(r, mu / g.woodcockStepTable[node]);
+            }
+            r = std::min(1.0, std::max(r, 1e-6) * (1.0 + 1e-6));
+            g.lmInvRatio[static_cast<size_t>(sl) * 16 + band] = 1.0 / r;
+        }
+    }
+    return g.lmSlabs;
+}
 
 void orc_set_device_mirroring(int on) { g_mirror = on != 0; }
 int orc_get_device_mirroring(void) { return g_mirror ? 1 : 0; }

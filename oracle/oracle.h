@@ -27,6 +27,7 @@ typedef struct orc_stats {
     double calibration_factor;
     double seconds;
     int threads;
+    uint64_t hops; /* slab-local majorants: tentative steps that ended on a slab face */
 } orc_stats;
 
 /* Device mirroring (default on): the oracle quantises its inputs where the device stores a quantised copy (24-bit voxel
@@ -39,6 +40,11 @@ int orc_get_device_mirroring(void);
 orc_world* orc_world_create(const uint64_t dim[3], const double spacing_cm[3], const double* density,
                             const uint8_t* material, uint32_t n_materials, const dxb_material_tables* tables);
 void orc_world_destroy(orc_world*);
+/* Slab-local majorants (the kernel's LM builds): track with the table the device built (dxb_get_local_majorant; n_slabs * 16
+ * floats; n_slabs < 2 switches it off) or with the oracle's own f64 table for slabs of 2^shift voxel layers (returns the
+ * number of slabs). */
+void orc_world_set_local_majorant(orc_world*, int shift, int n_slabs, const float* inv_ratio);
+int orc_world_build_local_majorant(orc_world*, int shift);
 /* air + PMMA tables for the nested CTDI calibration and the DAP / air-kerma calibrations */
 void orc_world_set_reference_materials(orc_world*, const dxb_material_tables* air, const dxb_material_tables* pmma,
                                        double air_density, double pmma_density);

@@ -20,7 +20,7 @@ class orc_stats(C.Structure):
     _fields_ = [
         ("histories", C.c_uint64), ("steps", C.c_uint64), ("interactions", C.c_uint64), ("deposits", C.c_uint64),
         ("energy_emitted_kev", C.c_double), ("energy_deposited_kev", C.c_double), ("calibration_factor", C.c_double),
-        ("seconds", C.c_double), ("threads", C.c_int),
+        ("seconds", C.c_double), ("threads", C.c_int), ("hops", C.c_uint64),
     ]
 
 
@@ -44,6 +44,8 @@ def load():
     sig = {
         "orc_world_create": (VP, [K.c_u64_p, K.c_double_p, K.c_double_p, K.c_u8_p, C.c_uint32, MT]),
         "orc_world_destroy": (None, [VP]),
+        "orc_world_set_local_majorant": (None, [VP, C.c_int, C.c_int, K.c_float_p]),
+        "orc_world_build_local_majorant": (C.c_int, [VP, C.c_int]),
         "orc_set_device_mirroring": (None, [C.c_int]),
         "orc_get_device_mirroring": (C.c_int, []),
         "orc_world_set_reference_materials": (None, [VP, MT, MT, C.c_double, C.c_double]),
@@ -131,6 +133,15 @@ class OracleWorld:
             load().orc_world_destroy(self._h)
         except Exception:
             pass
+
+    def build_local_majorant(self, shift):
+        """slab-local majorants from the oracle's own f64 table: slabs of 2**shift voxel layers; returns the slab count"""
+        return int(load().orc_world_build_local_majorant(self._h, int(shift)))
+
+    def set_local_majorant(self, shift, n_slabs, inv_ratio):
+        """track with the table the device built (World.local_majorant()); n_slabs < 2 switches it off"""
+        t = np.ascontiguousarray(inv_ratio, dtype=np.float32) if inv_ratio is not None else np.zeros(1, dtype=np.float32)
+        load().orc_world_set_local_majorant(self._h, int(shift), int(n_slabs), t.ctypes.data_as(K.c_float_p))
 
     def run(self, beam, physics_mode=1, seed=0x0DDC0FFEE, threads=0, rank=0, world=1):
         """energy tallies of one beam: (energy[keV], energy_sq, n_events, stats dict)."""

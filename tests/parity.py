@@ -66,3 +66,15 @@ def assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, what="", voxel_cm=0.5, 
     assert m["misplaced_event_fraction"] <= misplaced_bound(voxel_cm) * k2, msg
     assert m["voxelwise_energy_rel"] <= voxelwise_bound(voxel_cm) * k2, msg
     return m
+
+
+def mirror_local_majorant(world, oracle_world):
+    """The pool kernel tracks with slab-local majorants when the table built with the grid predicts a gain (option
+    local_majorant = -1, the default).  The oracle then has to track with the same table to stay on the same random-number
+    stream.  Returns True if the table was handed over."""
+    n, shift, useful, table = world.local_majorant()
+    if n >= 2 and useful:
+        oracle_world.set_local_majorant(shift, n, table)
+        return True
+    oracle_world.set_local_majorant(0, 0, None)
+    return False

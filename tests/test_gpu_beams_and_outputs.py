@@ -10,7 +10,7 @@ import time
 import numpy as np
 import pytest
 
-from parity import assert_same_stream_parity
+from parity import assert_same_stream_parity, mirror_local_majorant
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
@@ -24,8 +24,10 @@ def _compare_run(dx, orc, wl, mode=1, rois=None, tol=5e-3):
     e, e2, cnt = world.energy_scored()
     st = world.run_stats()
     ow = orc.OracleWorld.from_workload(wl)
+    assert mirror_local_majorant(world, ow) == bool(st["local_majorant"])
     oe, oe2, ocnt, ost = ow.run(wl.beam, mode, SEED)
     assert st["histories"] == ost["histories"] == wl.beam.numberOfParticles()
+    assert st["hops"] == pytest.approx(ost["hops"], rel=1e-4, abs=30)
     assert abs(st["energy_emitted_kev"] - ost["energy_emitted_kev"]) / ost["energy_emitted_kev"] < 1e-5
     assert abs(e.sum() - oe.sum()) / oe.sum() <= tol, (e.sum(), oe.sum())
     for k in ("steps", "interactions", "deposits"):
@@ -132,6 +134,8 @@ def test_c3_icrp_shape_per_organ_dose(dx, orc):
     assert tr(world, wl.beam, None, False)
     d, v, n = world._item.doseArrays()
     ow = orc.OracleWorld.from_workload(wl)
+    # 54 media, teeth (2.75 g/cm3) set the global majorant: the kernel tracks with slab-local majorants here
+    assert mirror_local_majorant(world, ow) and world.run_stats()["local_majorant"] == 1 and world.run_stats()["hops"] > 0
     od, ov, on, ost = ow.transport(wl.beam, 1, False, SEED)
     vol = wl.spacing[0] * wl.spacing[1] * wl.spacing[2]
     n_org = len(wl.organ_names)
@@ -186,6 +190,7 @@ def test_calibrated_dose_dx_and_ct(dx, orc):
     assert tr(world, beam, None, True)
     d, v, n = world._item.doseArrays()
     ow = orc.OracleWorld.from_workload(wl)
+    mirror_local_majorant(world, ow)
     od, ov, on, ost = ow.transport(beam, 1, True, SEED)
     assert world.run_stats()["calibration_factor"] == pytest.approx(ost["calibration_factor"], rel=1e-9)
     assert d.sum() == pytest.approx(od.sum(), rel=5e-3)
@@ -523,3 +528,50 @@ def test_scene_file_in_dose_file_out(dx, tmp_path):
         info = json.loads(out.stdout)
         assert info["dimensions"] == wl.dim and info["materials"] == len(names)
         assert info["dose_sum"] == pytest.approx(d.sum(), rel=1e-12) and info["count_sum"] == pytest.approx(cnt.sum(), rel=1e-12)
+
+
+def test_slab_local_majorants_on_the_device(dx, orc):
+    """SURVEY §7 step 7 (region-local majorants), as z slabs: on the ICRP-shaped phantom the densest medium (teeth) lives in
+    a few slabs, so the pool kernel's LM build needs a fraction of the tentative steps.  It must (a) follow the oracle
+    on the same table draw for draw, (b) give a dose statistically equal to global tracking, (c) stay GPU-count
+    invariant, (d) switch itself off where it cannot pay (C2: bone in every slab)."""
+    wl = dx.workloads.icrp_phantom("AM", scale=3, histories=2_000_000)
+    res = {}
+    for lm in (0, -1):
+        world = wl.build_world(1, [0])
+        world.set_option("local_majorant", lm)
+        dx.Transport().run_transport(world, wl.beam)
+        e, e2, cnt = [a.copy() for a in world.energy_scored()]
+        st = world.run_stats()
+        assert st["local_majorant"] == (1 if lm else 0)
+        ow = orc.OracleWorld.from_workload(wl)
+        if lm:
+            assert mirror_local_majorant(world, ow)
+            # shards of the histories sum to the whole, bit for bit, with hops in the walk too
+            acc = [np.zeros_like(e), np.zeros_like(e2), np.zeros_like(cnt)]
+            for rank in range(3):
+                world.set_history_range(rank, 3)
+                world.set_seed(SEED)
+                dx.Transport().run_transport(world, wl.beam)
+                for a, b in zip(acc, world.energy_scored()):
+                    a += b
+            assert all(np.array_equal(a, b) for a, b in zip(acc, (e, e2, cnt)))
+        oe, oe2, ocnt, ost = ow.run(wl.beam, 1, SEED)
+        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"AM scale 3 local_majorant={lm}", voxel_cm=min(wl.spacing))
+        assert abs(st["hops"] - ost["hops"]) <= max(30, 1e-5 * ost["hops"])
+        res[lm] = (e, e2, st)
+        world.close()
+    (e0, s0, st0), (e1, s1, st1) = res[0], res[-1]
+    assert st1["hops"] > 0 and st0["hops"] == 0 and st1["steps"] < 0.5 * st0["steps"]
+    sigma = np.sqrt(s0.sum() + s1.sum())
+    assert abs(e0.sum() - e1.sum()) / sigma < 4.0
+    for name, m in {"dense": wl.density > 1.2, "soft": (wl.density > 0.5) & (wl.density <= 1.2), "lung / air": wl.density <= 0.5}.items():
+        s = np.sqrt(s0[m].sum() + s1[m].sum())
+        assert s == 0 or abs(e0[m].sum() - e1[m].sum()) / s < 4.0, name
+    c2 = dx.workloads.ct_spiral_patient(scale=8, histories=100_000, step_deg=10.0)
+    world = c2.build_world(1, [0])
+    n, shift, useful, table = world.local_majorant()
+    assert n >= 2 and not useful and table.min() >= 1.0
+    dx.Transport().run_transport(world, c2.beam)
+    assert world.run_stats()["local_majorant"] == 0
+    world.close()

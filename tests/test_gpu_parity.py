@@ -7,7 +7,7 @@ unsharded, 1 vs N devices) bit-exact.
 import numpy as np
 import pytest
 
-from parity import assert_same_stream_parity
+from parity import assert_same_stream_parity, mirror_local_majorant
 
 pytestmark = pytest.mark.gpu
 
@@ -217,7 +217,7 @@ def test_kernels_agree_on_calibration_run_and_many_materials(dx):
              dx.workloads.icrp_phantom("AM", scale=4, histories=400_000)]
     for w in cases:
         res = []
-        for o in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 16}):
+        for o in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 16, "local_majorant": 0}):   # same tracking rule on both sides
             world = w.build_world(1, [0])
             world.set_calibration_histories(360_000)
             for k, v in o.items():
@@ -255,6 +255,7 @@ def test_mode2_fluorescence_and_doppler_parity(dx, orc):
         e, e2, cnt = world.energy_scored()
         st = world.run_stats()
         ow = orc.OracleWorld(dim, spacing, dens.reshape(-1), mat.reshape(-1), [water, bone])
+        mirror_local_majorant(world, ow)   # water slabs / bone slabs along z: the kernel tracks slab-locally here
         oe, oe2, ocnt, ost = ow.run(beam, mode, SEED)
         assert st["histories"] == ost["histories"]
         assert abs(e.sum() - oe.sum()) / oe.sum() <= 5e-3
@@ -296,6 +297,7 @@ def test_external_material_tables_on_the_device(dx, orc):
         ref = np.array([orc.attenuation(m, e) for e in energies])
         assert (np.abs(dev - ref) / np.abs(ref)).max() <= 1e-6
         ow = orc.OracleWorld(dim, sp, dens, mat.reshape(-1), [air, m])
+        mirror_local_majorant(world, ow)
         devm = world.device_majorant(energies).astype(np.float64)
         refm = np.array([ow.majorant(e) for e in energies])
         assert (np.abs(devm - refm) / refm).max() <= 1e-6

@@ -286,3 +286,55 @@ def test_device_mirroring_quantisations_are_harmless(dx, orc, config):
     assert _roi_sigma(e, e2, f, f2, masks) <= 0.5
     assert np.count_nonzero(cnt == fcnt) / cnt.size >= 0.995
     assert not np.array_equal(e, f)  # the switch does change the inputs
+
+
+@pytest.mark.parametrize("energy", [30.0, 80.0])
+def test_beer_lambert_layered_with_slab_local_majorants(dx, orc, energy):
+    """Woodcock tracking with SLAB-LOCAL majorants (steps stop on slab faces, the walk restarts with a fresh draw) must
+    still give the first-collision probability 1 - exp(-sum mu t) of a layered water / bone / air column, with fewer
+    tentative steps than under the global (bone) majorant."""
+    water = dx.Material.byNistName("Water, Liquid")
+    bone = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    air = dx.Material.byNistName("Air, Dry (near sea level)")
+    mats, dens = [water, bone, air], [1.0, 1.92, 1.2e-3]
+    n, t = 64, 8.0
+    layer = lambda k: 0 if k < 24 else (1 if k < 36 else (2 if k < 48 else 0))
+    beam = dx.PencilBeam([0.0, 0.0, -10.0], [0, 0, 1], energy)
+    beam.setNumberOfExposures(4)
+    beam.setNumberOfParticlesPerExposure(100_000)
+    res = {}
+    for local in (False, True):
+        ow, density, material, spacing = _column_world(dx, orc, mats, dens, layer, n, t)
+        if local:
+            assert ow.build_local_majorant(2) == 16     # slabs of 4 layers: none straddles two media
+        e, e2, cnt, st = ow.run(beam, 1)
+        res[local] = st
+    thick = t / n
+    tau = sum(dens[layer(k)] * mats[layer(k)].attenuationValues(energy).sum() * thick for k in range(n))
+    expect = 1.0 - math.exp(-tau)
+    nh = res[True]["histories"]
+    for local in (False, True):
+        p = res[local]["interactions"] / nh
+        sigma = math.sqrt(expect * (1 - expect) / nh)
+        assert abs(p - expect) < 4 * sigma, (local, p, expect, sigma)
+    assert res[True]["hops"] > 0 and res[False]["hops"] == 0
+    assert res[True]["steps"] < 0.75 * res[False]["steps"]
+
+
+def test_slab_local_majorants_leave_the_dose_unchanged(dx, orc):
+    """ICRP-shaped phantom (54 media, teeth at 2.75 g/cm3 set the global majorant) under a chest spiral: with slab-local
+    majorants the oracle takes far fewer tentative steps and scores a statistically identical dose."""
+    wl = dx.workloads.icrp_phantom("AM", scale=4, histories=300_000)
+    a = orc.OracleWorld.from_workload(wl)
+    e, e2, cnt, st = a.run(wl.beam, 1)
+    b = orc.OracleWorld.from_workload(wl)
+    assert b.build_local_majorant(0) >= 2
+    f, f2, fcnt, ft = b.run(wl.beam, 1)
+    assert ft["hops"] > 0 and ft["steps"] < 0.8 * st["steps"]
+    s = math.sqrt(e2.sum() + f2.sum())
+    assert abs(e.sum() - f.sum()) / s < 4.0
+    assert abs(st["interactions"] - ft["interactions"]) / st["interactions"] < 0.01
+    masks = {"upper": np.repeat(np.arange(wl.dim[2]), wl.dim[0] * wl.dim[1]) >= wl.dim[2] // 2}
+    masks["lower"] = ~masks["upper"]
+    masks["dense"] = wl.density > 1.2
+    assert _roi_sigma(e, e2, f, f2, masks) < 4.0
