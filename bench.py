@@ -513,14 +513,24 @@ def run_ours(args):
         transport_and_finish(i, False, timed_stats)
 
     e2e_cal_ms = []
+    e2e_parts = {"set_materials": 0.0, "set_grid": 0.0, "transport": 0.0, "finish_beam": 0.0, "get_dose": 0.0}
+
+    def timed(name, fn):
+        t = time.perf_counter()
+        r = fn()
+        e2e_parts[name] += time.perf_counter() - t
+        return r
 
     def e2e_step(i, with_materials=False):
         """the reference-facing call sequence with host buffers: [materials ->] setData/build -> transport(useBeamCalibration = true) -> read dose."""
+        t_mark = time.perf_counter()
         if with_materials:
             g = world._item
             mats = (K.VP * len(g._materials))(*[m._h for m in g._materials])
             rc = lib.dxb_set_materials(ctx, len(g._materials), mats)
             assert rc == 0, lib.dxb_last_error(ctx)
+            e2e_parts["set_materials"] += time.perf_counter() - t_mark
+            t_mark = time.perf_counter()
         if sharded is not None:
             # one process per GPU: every rank uploads its slab, the packed slabs travel over NVLink
             D.set_grid_sharded(world, wl.dim, wl.spacing, wl.density, wl.material, local_rank, stream=stream)
@@ -529,12 +539,17 @@ def run_ours(args):
             sp = (C.c_double * 3)(*wl.spacing)
             rc = lib.dxb_set_grid(ctx, dim, sp, wl.density.ctypes.data_as(K.c_double_p), wl.material.ctypes.data_as(K.c_u8_p))
             assert rc == 0, lib.dxb_last_error(ctx)
+        e2e_parts["set_grid"] += time.perf_counter() - t_mark
+        t_mark = time.perf_counter()
         transport_and_finish(1000 + i, True)
+        e2e_parts["transport"] += time.perf_counter() - t_mark   # transport + (barrier) + calibration + finish / exchange enqueue
+        t_mark = time.perf_counter()
         e2e_cal_ms.append(world.run_stats()["calibration_ms"])
         if shared_out is not None:
             rc = lib.dxb_get_dose_range(ctx, sharded.begin, sharded.end, shared_out.ptr(0, K.c_double_p), shared_out.ptr(1, K.c_double_p),
                                         shared_out.ptr(2, K.c_u64_p))
             assert rc == 0, lib.dxb_last_error(ctx)
+            e2e_parts["get_dose"] += time.perf_counter() - t_mark
             return
         if fused is not None:
             with torch.cuda.stream(stream):
@@ -543,6 +558,7 @@ def run_ours(args):
             rc = lib.dxb_get_dose(ctx, C.cast(out_pin[0].data_ptr(), K.c_double_p), C.cast(out_pin[1].data_ptr(), K.c_double_p),
                                   C.cast(out_pin[2].data_ptr(), K.c_u64_p))
             assert rc == 0, lib.dxb_last_error(ctx)
+        e2e_parts["get_dose"] += time.perf_counter() - t_mark
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -595,12 +611,15 @@ def run_ours(args):
         e2e_step(-1)  # warm (builds the calibration phantom once per context, like the first beam of a session)
         barrier()
         del e2e_cal_ms[:]
+        for k in e2e_parts:
+            e2e_parts[k] = 0.0
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 2))
         for i in range(n_e2e):
             e2e_step(i)
         barrier()
         te = torch.tensor([time.perf_counter() - t0, sum(e2e_cal_ms) / max(len(e2e_cal_ms), 1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        parts_ms = {k: 1e3 * v / n_e2e for k, v in e2e_parts.items() if k != "set_materials"}
         e2e_step(100, with_materials=True)  # warm
         barrier()
         t0 = time.perf_counter()
@@ -615,6 +634,9 @@ def run_ours(args):
                "h2d_bytes_per_step": int(nvox * 9 * (1 if per_rank_upload else n_gpus)), "d2h_bytes_per_step": int(nvox * 24),
                "steps": n_e2e, "ms_per_step": 1e3 * float(te[0]) / n_e2e,
                "calibration_ms": float(te[1]),
+               "parts_ms": dict(parts_ms, note="host clock of rank 0 per step: set_grid = upload + pack + (all-gather) + majorant; transport = "
+                                               "dxb_run_transport + (barrier) + nested calibration run + dxb_finish_beam (with the pipelined exchange: "
+                                               "enqueue only); get_dose = wait for the exchange + D2H of this rank's slab"),
                "calibration": "use_beam_calibration = 1: nested CTDI run of %d histories inside every timed step (device time reported as calibration_ms)" % CALIBRATION_HISTORIES,
                "with_materials": {"value": n_hist / float(tmat[0]), "ms_per_step": 1e3 * float(tmat[0]),
                                   "note": "the same step preceded by dxb_set_materials (host table build + upload), 1 timed step"},

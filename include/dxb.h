@@ -443,9 +443,9 @@ int dxb_device_attenuation(dxb_ctx*, uint32_t material_index, int physics_mode,
 int dxb_device_majorant(dxb_ctx*, const double* energy_kev, uint32_t n, float* out);
 /* The slab-local majorant table built with the grid (option "local_majorant": -1 auto, 0 off, 1 on; "slab_cm": target slab
  * thickness): slabs of 2^shift voxel layers along z; inside slab s and energy band b (= energy node index >> 5) the kernels
- * track with mu_max(E) / inv_ratio[s * 16 + b].  *useful = 1 when auto mode would use it.  inv_ratio may be NULL (sizes
- * only); it receives n_slabs * 16 floats.  This is what a test hands to the CPU oracle so that both track identically. */
-int dxb_get_local_majorant(dxb_ctx*, int* n_slabs, int* shift, int* useful, float* inv_ratio);
+ * track with mu_max(E) * ratio[s * 16 + b], ratio in (0, 1].  *useful = 1 when auto mode would use it.  ratio may be NULL
+ * (sizes only); it receives n_slabs * 16 floats.  This is what a test hands to the CPU oracle so that both track identically. */
+int dxb_get_local_majorant(dxb_ctx*, int* n_slabs, int* shift, int* useful, float* ratio);
 
 /* CT segmentation, SURVEY §8f-1: HU -> (material, density)
  * R:src/libopendxmc/ctsegmentationpipeline.cpp:113-169 */

@@ -1237,7 +1237,7 @@ class World:
         return out
 
     def local_majorant(self):
-        """the slab-local majorant table built with the grid: (n_slabs, shift, useful, inv_ratio[n_slabs, 16])"""
+        """the slab-local majorant table built with the grid: (n_slabs, shift, useful, ratio[n_slabs, 16], local / global majorant in (0, 1])"""
         n, sh, us = C.c_int(), C.c_int(), C.c_int()
         _check(_lib().dxb_get_local_majorant(self._ctx, C.byref(n), C.byref(sh), C.byref(us), None), "dxb_get_local_majorant", self._ctx)
         t = np.ones((max(n.value, 1), 16), dtype=np.float32)

@@ -115,7 +115,7 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
 
 // Slab-local majorants (transport_pool.cu, LM builds).  Slabs of 2^shift voxel layers along z, about opt.slabCm thick.  The
 // device finds, per slab and material, the largest density (exact integer maxima of the 24-bit densities); the small table
-//   inv_ratio(slab, band) = 1 / max over the band's energy nodes of [ max_m rho_max(slab, m) * tot_m(node) / majorant(node) ]
+//   ratio(slab, band) = max over the band's energy nodes of [ max_m rho_max(slab, m) * tot_m(node) / majorant(node) ]
 // is then computed HERE with single IEEE f32 operations on the same f32 tables the device reads, so that the oracle, which
 // receives the table through dxb_get_local_majorant, tracks with exactly the numbers the kernel uses.
 int buildLocalMajorant(dxb_ctx* c, World& w, cudaStream_t s)
@@ -163,15 +163,15 @@ int buildLocalMajorant(dxb_ctx* c, World& w, cudaStream_t s)
                 const float ratio = mu / maj[node];
                 r = ratio > r ? ratio : r;
             }
-            // a little head-room (2^-20) keeps local attenuation * inv_ratio <= majorant under f32 rounding
+            // a little head-room (2^-20) keeps the local attenuation below majorant * ratio under f32 rounding
             r = std::min(1.0f, std::max(r, 1.0e-6f) * (1.0f + 9.5367431640625e-7f));
-            w.lmHost[static_cast<size_t>(sl) * kLmBands + b] = r >= 1.0f ? 1.0f : 1.0f / r;
+            w.lmHost[static_cast<size_t>(sl) * kLmBands + b] = r;
             if (b == refBand)
                 meanRatio += r;
         }
     }
     meanRatio /= slabs;
-    CUDA_TRY(c, w.lmInvRatio.upload(w.lmHost, w.device, s));
+    CUDA_TRY(c, w.lmRatio.upload(w.lmHost, w.device, s));
     CUDA_TRY(c, cudaStreamSynchronize(s));
     w.lmShift = shift;
     w.lmSlabs = slabs;
@@ -422,7 +422,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
             cfg.smem = poolSmemBytes(cfg.slots, 0, lmSlabs);
         }
         if (lm) {
-            P.lm_inv_ratio = w.lmInvRatio.p;
+            P.lm_ratio = w.lmRatio.p;
             P.lm_slabs = w.lmSlabs;
             P.lm_shift = w.lmShift;
             P.lm_thickness = static_cast<float>(static_cast<double>(1 << w.lmShift) * w.spacing[2]);
@@ -1578,7 +1578,7 @@ int dxb_device_attenuation(dxb_ctx* c, uint32_t material_index, int physics_mode
     return DXB_OK;
 }
 
-int dxb_get_local_majorant(dxb_ctx* c, int* n_slabs, int* shift, int* useful, float* inv_ratio)
+int dxb_get_local_majorant(dxb_ctx* c, int* n_slabs, int* shift, int* useful, float* ratio)
 {
     if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
         return fail(c, DXB_ESTATE, "get_local_majorant: no grid");
@@ -1589,8 +1589,8 @@ int dxb_get_local_majorant(dxb_ctx* c, int* n_slabs, int* shift, int* useful, fl
         *shift = w.lmShift;
     if (useful)
         *useful = w.lmUseful ? 1 : 0;
-    if (inv_ratio && w.lmSlabs > 0)
-        std::memcpy(inv_ratio, w.lmHost.data(), static_cast<size_t>(w.lmSlabs) * kLmBands * sizeof(float));
+    if (ratio && w.lmSlabs > 0)
+        std::memcpy(ratio, w.lmHost.data(), static_cast<size_t>(w.lmSlabs) * kLmBands * sizeof(float));
     return DXB_OK;
 }
 

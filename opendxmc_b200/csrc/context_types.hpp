@@ -104,8 +104,8 @@ struct World {
     // slab-local majorants (pool kernel, LM builds)
     std::vector<float> hostTot;          // [n_mat * kDevNE] the f32 total-attenuation table as uploaded
     DevBuf<unsigned int> slabMax;        // [lmSlabs * 256] per slab and material: largest density (24-bit float bits)
-    DevBuf<float> lmInvRatio;            // [lmSlabs * kLmBands]
-    std::vector<float> lmHost;           // host copy of lmInvRatio
+    DevBuf<float> lmRatio;            // [lmSlabs * kLmBands]
+    std::vector<float> lmHost;           // host copy of lmRatio: local / global majorant, in (0, 1]
     int lmShift = 0, lmSlabs = 0;
     bool lmUseful = false;               // the table predicts a gain (mean ratio below the threshold)
 

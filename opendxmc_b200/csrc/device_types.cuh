@@ -104,8 +104,8 @@ struct RunParams {
     int interact_bias;              // mux kernel: an interaction phase runs when waiting lanes + bias >= stepping lanes;
                                     // pool kernel: stepper warps keep stepping while at least this many lanes can
     // slab-local majorants (pool kernel, LM builds): the grid is cut into slabs of 2^lm_shift voxel layers along z; inside
-    // slab s and energy band b (32 energy nodes) the tracking majorant is mu_max(E) / lm_inv_ratio[s * kLmBands + b]
-    const float* __restrict__ lm_inv_ratio; // [lm_slabs * kLmBands], >= 1
+    // slab s and energy band b (32 energy nodes) the tracking majorant is mu_max(E) * lm_ratio[s * kLmBands + b]
+    const float* __restrict__ lm_ratio; // [lm_slabs * kLmBands], in (0, 1]
     int lm_slabs, lm_shift;
     float lm_thickness;              // slab thickness [cm] = 2^lm_shift * dz
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)

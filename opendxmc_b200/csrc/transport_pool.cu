@@ -81,10 +81,10 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
 // LB: register budget through the launch bounds.  0: 64 registers (<= 512 threads per block, 1024 resident threads per SM);
 // 5 / 6: <= 256 threads per block with 5 / 6 resident blocks per SM (48 / 40 registers, a few spilled words).
 // LM: slab-local majorants.  The grid is cut into slabs of 2^lm_shift voxel layers along z; inside a slab the
-// tracking majorant is mu_max(E) / inv_ratio(slab, energy band) - the largest attenuation that occurs IN THAT SLAB instead
-// of anywhere in the grid.  A tentative step that would cross a slab face stops on the face and the walk continues in the
-// next slab with a fresh draw (the exponential free path is memoryless, so the estimator stays unbiased).  Pays when the
-// densest material is confined to part of the z range (teeth in a whole-body phantom during a chest scan).
+// tracking majorant is mu_max(E) * ratio(slab, energy band) - the largest attenuation that occurs IN THAT SLAB instead of
+// anywhere in the grid.  The optical depth drawn for a tentative step is marched through the slabs (piecewise constant
+// majorant), so the estimator stays unbiased.  Pays when the densest material is confined to part of the z range (teeth in
+// a whole-body phantom during a chest scan).
 template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false>
 __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transportKernelPool(const __grid_constant__ RunParams P)
 {
@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     const int nTab = SMEM_TABLE ? P.tab.n_mat * kDevNE : 0;
     float* __restrict__ s_maj = reinterpret_cast<float*>(s_raw) + kSlotWords * kStride + 64;
     float* __restrict__ s_tot = s_maj + kDevNE;
-    float* __restrict__ s_lm = s_tot + nTab; // [lm_slabs x kLmBands] inverse majorant ratios (LM builds)
+    float* __restrict__ s_lm = s_tot + nTab; // [kLmBands x lm_slabs] local / global majorant ratios (LM builds), band-major:
+                                             // the lanes of a warp read different slabs of mostly one band (no bank conflicts)
     if (LM)
         for (int i = threadIdx.x; i < P.lm_slabs * kLmBands; i += blockDim.x)
-            s_lm[i] = P.lm_inv_ratio[i];
+            s_lm[(i % kLmBands) * P.lm_slabs + i / kLmBands] = P.lm_ratio[i];
     const int rot = static_cast<int>(((threadIdx.x >> 5) * SPC) / (blockDim.x >> 5)); // first slot this warp tries to claim
     for (int i = threadIdx.x; i < nTab; i += blockDim.x)
         s_tot[i] = P.tab.tot[i];
@@ -214,62 +215,68 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             int newPhase = kPhStep;
             int mat = 0;
             if (LM && !CALIB) {
-                // ---- slab-local majorants: four sub-steps, each either a tentative collision (voxel gather) or a hop to the
-                // face of the current slab; positions and kinds do not depend on voxel data, so all gathers are in flight at once
+                // ---- slab-local majorants.  Each sub-step draws ONE optical depth tau = -ln(1 - u) and marches it
+                // through the slabs: while tau exceeds what the rest of the current slab can absorb at its local majorant, the
+                // ray moves to the slab face and tau is reduced accordingly; the tentative collision lies where tau is used
+                // up.  Crossing a face consumes no random number and the collision point is a continuous function of the
+                // face distance, so f32 / f64 rounding cannot flip a decision there.  Positions and local majorants do not
+                // depend on voxel data: both gathers of a pair are in flight before the walk looks at the first one.
+                // One Philox block = one PAIR of sub-steps per phase (not the quad of the global-majorant path): under a local
+                // majorant most tentative collisions are real, so further speculative sub-steps would mostly be thrown away.
                 if (stepping) {
                     const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
-                    const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
                     const bool up = dz > 0.0f;
                     const float invdz = dz != 0.0f ? __fdividef(1.0f, dz) : 0.0f;
-                    const int band = epos.i >> 5;
+                    const float muMax = muMaxU24 * 16777216.0f;
+                    const float* __restrict__ lm = s_lm + (epos.i >> 5) * P.lm_slabs; // this energy band's ratios, by slab
                     int slab = min(max(__float2int_rd(fmaf(pz, G.inv_dz, G.offz)), 0), G.nz - 1) >> P.lm_shift;
                     float x = px, y = py, z = pz;
-                    float xs[4], ys[4], zs[4], ir[4];
-                    unsigned int cell[4];
-                    int kind[4]; // 0: left the grid, 1: hop, 2: tentative collision
+                    float xs[2], ys[2], zs[2], rr[2];
+                    unsigned int cell[2];
+                    unsigned int hp[2];
+                    bool ok[2];
                     bool alive = true;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        kind[j] = 0;
+                    for (int j = 0; j < 2; ++j) {
+                        ok[j] = false;
                         cell[j] = 0u;
-                        ir[j] = 1.0f;
+                        rr[j] = 1.0f;
+                        hp[j] = 0u;
                         if (alive) {
-                            const float invr = s_lm[slab * kLmBands + band];
-                            const float u = j == 0 ? r1.k(0) : (j == 1 ? r1.k(2) : (j == 2 ? r2.k(0) : r2.k(2)));
-                            const float sl = __log2f(fmaf(u, -kU24, 1.0f)) * stepScale * invr;
-                            const float zf = fmaf(static_cast<float>(slab + (up ? 1 : 0)), P.lm_thickness, G.z0);
-                            const float tb = dz != 0.0f ? (zf - z) * invdz : 3.0e38f;
-                            if (sl < tb) {
-                                x = fmaf(dx, sl, x);
-                                y = fmaf(dy, sl, y);
-                                z = fmaf(dz, sl, z);
-                                unsigned int v;
-                                if (voxelIndex(G, x, y, z, v)) {
-                                    kind[j] = 2;
-                                    cell[j] = loadVoxel(G.voxels + v);
-                                    ir[j] = invr;
-                                } else {
-                                    alive = false;
+                            float tau = __log2f(fmaf(j == 0 ? r1.k(0) : r1.k(2), -kU24, 1.0f)) * -kLn2;
+                            for (;;) {
+                                const float r = lm[slab];
+                                const float mus = muMax * r;
+                                const float zf = fmaf(static_cast<float>(slab + (up ? 1 : 0)), P.lm_thickness, G.z0);
+                                const float tb = dz != 0.0f ? (zf - z) * invdz : 3.0e38f;
+                                const float need = __fdividef(tau, mus);
+                                if (need < tb) {
+                                    x = fmaf(dx, need, x);
+                                    y = fmaf(dy, need, y);
+                                    z = fmaf(dz, need, z);
+                                    rr[j] = r;
+                                    break;
                                 }
-                            } else {
+                                tau = fmaxf(fmaf(-tb, mus, tau), 0.0f);
                                 x = fmaf(dx, tb, x);
                                 y = fmaf(dy, tb, y);
                                 z = zf;
                                 slab += up ? 1 : -1;
-                                // the end point must map into the first (last) voxel layer of the slab it enters: the face
-                                // coordinate is moved by single ulps until the layer index says so (0 - 2 iterations)
-                                const int want = up ? (slab << P.lm_shift) : (((slab + 1) << P.lm_shift) - 1);
-                                for (int it = 0; it < 8; ++it) {
-                                    const int izc = __float2int_rd(fmaf(z, G.inv_dz, G.offz));
-                                    if (up ? izc >= want : izc <= want)
-                                        break;
-                                    z = nextafterf(z, up ? 3.0e38f : -3.0e38f);
-                                }
-                                unsigned int v;
-                                if (slab >= 0 && slab < P.lm_slabs && voxelIndex(G, x, y, z, v))
-                                    kind[j] = 1;
-                                else
+                                ++hp[j];
+                                // left through the top / bottom, or sideways (a straight line never comes back)
+                                if (slab < 0 || slab >= P.lm_slabs || !(x >= G.x0 && x <= G.x1 && y >= G.y0 && y <= G.y1)) {
                                     alive = false;
+                                    break;
+                                }
+                            }
+                            if (alive) {
+                                unsigned int v;
+                                if (voxelIndex(G, x, y, z, v)) {
+                                    ok[j] = true;
+                                    cell[j] = loadVoxel(G.voxels + v);
+                                } else {
+                                    alive = false;
+                                }
                             }
                             xs[j] = x;
                             ys[j] = y;
@@ -281,28 +288,22 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     blk += 1u;
                     bool walking = true;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 2; ++j) {
                         if (walking) {
-                            if (j == 2)
-                                blk += 1u; // the second pair is now consumed
-                            if (kind[j] == 0) {
-                                walking = false; // newPhase stays dead
+                            nHops += hp[j];
+                            if (!ok[j]) {
+                                walking = false; // left the grid: newPhase stays dead
                             } else {
+                                ++nSteps;
                                 px = xs[j], py = ys[j], pz = zs[j];
-                                if (kind[j] == 1) {
-                                    ++nHops;
-                                } else {
-                                    ++nSteps;
-                                    mat = voxelMaterial(cell[j]);
-                                    const float mu = voxelDensity(cell[j]) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
-                                    const float ra = j == 0 ? r1.k(1) : (j == 1 ? r1.k(3) : (j == 2 ? r2.k(1) : r2.k(3)));
-                                    if (ra * muMaxU24 < mu * ir[j]) {
-                                        newPhase = kPhInt;
-                                        walking = false;
-                                    }
-                                }
-                                if (walking && j == 3)
+                                mat = voxelMaterial(cell[j]);
+                                const float mu = voxelDensity(cell[j]) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                if ((j == 0 ? r1.k(1) : r1.k(3)) * muMaxU24 * rr[j] < mu) {
+                                    newPhase = kPhInt;
+                                    walking = false;
+                                } else if (j == 1) {
                                     newPhase = kPhStep;
+                                }
                             }
                         }
                     }

@@ -523,9 +523,9 @@ struct AAVoxelGrid {
     std::vector<uint64_t> nEvents;
     int scoreMaterial = -1; // calibration: collision kerma estimator in this material
     // [D] slab-local majorants (transport_pool.cu, LM builds): slabs of 2^lmShift voxel layers along z; inside slab s and
-    // energy band b (= energy node index >> 5) the tracking majorant is majorant(E) / lmInvRatio[s * 16 + b]
+    // energy band b (= energy node index >> 5) the tracking majorant is majorant(E) * lmRatio[s * 16 + b]
     int lmShift = 0, lmSlabs = 0;
-    std::vector<double> lmInvRatio;
+    std::vector<double> lmRatio;
 
     size_t size() const { return density.size(); }
     double voxelVolume() const { return spacing[0] * spacing[1] * spacing[2]; }
@@ -674,66 +674,69 @@ struct AAVoxelGrid {
     long layerOf(double z) const { return static_cast<long>(std::floor((z - aabb[2]) / spacing[2])); }
 
     // [D] Woodcock tracking with slab-local majorants.  Same random-number protocol as woodcockTransport (one Philox block
-    // per pair of tentative steps); a tentative step that would cross the face of the current slab stops ON the face (no
-    // collision test, its acceptance number is not used) and tracking continues in the next slab with the next draw: the
-    // exponential free path is memoryless, so the result is unbiased whatever the slab table.
+    // per pair of tentative steps).  The optical depth tau = -ln(1 - u) drawn for a tentative step is marched through the
+    // slabs: while it exceeds what the rest of the current slab absorbs at the slab's majorant, the ray moves to the slab
+    // face and tau shrinks accordingly; the tentative collision lies where tau is used up and is accepted with
+    // mu(x) / (slab majorant).  Unbiased for any table that bounds mu inside each slab; crossing a face consumes no
+    // random number.
     void woodcockTransportSlabs(Particle& p, int correction, RandomState& state, WorkerStats& st)
     {
         const double thickness = static_cast<double>(1 << lmShift) * spacing[2];
         bool still_inside = true;
         while (still_inside) {
             const double attMax = majorant(p.energy);
-            const double attMaxInv = 1.0 / attMax;
             const size_t node = std::min<size_t>(static_cast<size_t>(std::max(0.0, materials[0].eCoord(p.energy))), materials[0].nE - 2);
             const int band = static_cast<int>(node >> 5);
             long slab = std::min<long>(std::max<long>(layerOf(p.pos[2]), 0), static_cast<long>(dim[2]) - 1) >> lmShift;
             const std::array<double, 4> u = state.block();
             for (int half = 0; half < 2 && still_inside; ++half) {
-                const double invr = lmInvRatio[static_cast<size_t>(slab) * 16 + band];
-                const double steplen = -std::log(1.0 - u[2 * half]) * attMaxInv * invr;
+                double tau = -std::log(1.0 - u[2 * half]);
+                double ratio = 1.0;
                 const bool up = p.dir[2] > 0;
-                const double zf = aabb[2] + static_cast<double>(slab + (up ? 1 : 0)) * thickness;
-                const double tb = p.dir[2] != 0 ? (zf - p.pos[2]) / p.dir[2] : 3.0e38;
-                const double toExit = exitDistance(p);
-                if (steplen < tb) {
-                    if (!(steplen < toExit)) {
-                        still_inside = false;
+                for (;;) {
+                    ratio = lmRatio[static_cast<size_t>(slab) * 16 + band];
+                    const double mus = attMax * ratio;
+                    const double zf = aabb[2] + static_cast<double>(slab + (up ? 1 : 0)) * thickness;
+                    const double tb = p.dir[2] != 0 ? (zf - p.pos[2]) / p.dir[2] : 3.0e38;
+                    const double need = tau / mus;
+                    if (need < tb) {
+                        if (!(need < exitDistance(p)))
+                            still_inside = false;
+                        else
+                            p.translate(need);
                         break;
                     }
-                    ++st.steps;
-                    p.translate(steplen);
-                    const size_t flat = flatIndex(p.pos);
-                    const uint8_t matInd = materialIndex[flat];
-                    const OMaterial& mat = materials[matInd];
-                    const auto att = mat.attenuationValues(p.energy);
-                    const double attSum = att.sum() * density[flat];
-                    if (u[2 * half + 1] * attMax < attSum * invr) {
-                        ++st.interactions;
-                        const auto res = interact(att, p, mat, correction, state);
-                        if (res.energyImparted > 0) {
-                            ++st.deposits;
-                            scoreEnergy(flat, res.energyImparted);
-                        }
-                        still_inside = res.particleAlive;
-                        break; // the energy (band, majorant) or the direction may have changed: new block
-                    }
-                } else {
-                    slab += up ? 1 : -1;
-                    if (!(tb < toExit) || slab < 0 || slab >= lmSlabs) {
-                        still_inside = false;
+                    tau = std::max(tau - tb * mus, 0.0);
+                    if (!(tb < exitDistance(p))) {
+                        still_inside = false; // leaves through the side (or the top / bottom) before the face
                         break;
                     }
-                    ++st.hops;
                     p.translate(tb);
-                    // exactly on the face, then single ulps until the point maps into the voxel layer it enters
                     p.pos[2] = zf;
-                    const long want = up ? (slab << lmShift) : (((slab + 1) << lmShift) - 1);
-                    for (int it = 0; it < 8; ++it) {
-                        const long l = layerOf(p.pos[2]);
-                        if (up ? l >= want : l <= want)
-                            break;
-                        p.pos[2] = std::nextafter(p.pos[2], up ? 3.0e38 : -3.0e38);
+                    slab += up ? 1 : -1;
+                    ++st.hops;
+                    if (slab < 0 || slab >= lmSlabs) {
+                        still_inside = false;
+                        break;
                     }
+                }
+                if (!still_inside)
+                    break;
+                ++st.steps;
+                const size_t flat = flatIndex(p.pos);
+                const uint8_t matInd = materialIndex[flat];
+                const OMaterial& mat = materials[matInd];
+                const auto att = mat.attenuationValues(p.energy);
+                const double attSum = att.sum() * density[flat];
+                if (u[2 * half + 1] * attMax * ratio < attSum) {
+                    ++st.interactions;
+                    const auto res = interact(att, p, mat, correction, state);
+                    if (res.energyImparted > 0) {
+                        ++st.deposits;
+                        scoreEnergy(flat, res.energyImparted);
+                    }
+                    still_inside = res.particleAlive;
+                    break; // the energy (band, majorant) or the direction may have changed: new block
                 }
             }
         }
@@ -1318,14 +1321,14 @@ double analyticCalibration(const orc_world& w, const dxb_beam_desc& b)
 extern "C" {
 
 // slab-local majorants: the table the device built (dxb_get_local_majorant), or none (n_slabs < 2)
-void orc_world_set_local_majorant(orc_world* w, int shift, int n_slabs, const float* inv_ratio)
+void orc_world_set_local_majorant(orc_world* w, int shift, int n_slabs, const float* ratio)
 {
     AAVoxelGrid& g = w->grid;
     g.lmShift = shift;
-    g.lmSlabs = (n_slabs >= 2 && inv_ratio) ? n_slabs : 0;
-    g.lmInvRatio.clear();
+    g.lmSlabs = (n_slabs >= 2 && ratio) ? n_slabs : 0;
+    g.lmRatio.clear();
     if (g.lmSlabs)
-        g.lmInvRatio.assign(inv_ratio, inv_ratio + static_cast<size_t>(n_slabs) * 16);
+        g.lmRatio.assign(ratio, ratio + static_cast<size_t>(n_slabs) * 16);
 }
 // ... or the oracle's own table in f64 (no GPU needed): slabs of 2^shift voxel layers; returns the number of slabs
 int orc_world_build_local_majorant(orc_world* w, int shift)
@@ -1335,7 +1338,7 @@ int orc_world_build_local_majorant(orc_world* w, int shift)
     const int slabs = static_cast<int>((nz + (1 << shift) - 1) >> shift);
     g.lmShift = shift;
     g.lmSlabs = slabs >= 2 ? slabs : 0;
-    g.lmInvRatio.assign(static_cast<size_t>(slabs) * 16, 1.0);
+    g.lmRatio.assign(static_cast<size_t>(slabs) * 16, 1.0);
     if (!g.lmSlabs)
         return 0;
     const size_t layer = g.dim[0] * g.dim[1];
@@ -1354,7 +1357,7 @@ int orc_world_build_local_majorant(orc_world* w, int shift)
                 r = std::max(r, mu / g.woodcockStepTable[node]);
             }
             r = std::min(1.0, std::max(r, 1e-6) * (1.0 + 1e-6));
-            g.lmInvRatio[static_cast<size_t>(sl) * 16 + band] = 1.0 / r;
+            g.lmRatio[static_cast<size_t>(sl) * 16 + band] = r;
         }
     }
     return g.lmSlabs;

@@ -43,7 +43,7 @@ void orc_world_destroy(orc_world*);
 /* Slab-local majorants (the kernel's LM builds): track with the table the device built (dxb_get_local_majorant; n_slabs * 16
  * floats; n_slabs < 2 switches it off) or with the oracle's own f64 table for slabs of 2^shift voxel layers (returns the
  * number of slabs). */
-void orc_world_set_local_majorant(orc_world*, int shift, int n_slabs, const float* inv_ratio);
+void orc_world_set_local_majorant(orc_world*, int shift, int n_slabs, const float* ratio);
 int orc_world_build_local_majorant(orc_world*, int shift);
 /* air + PMMA tables for the nested CTDI calibration and the DAP / air-kerma calibrations */
 void orc_world_set_reference_materials(orc_world*, const dxb_material_tables* air, const dxb_material_tables* pmma,

@@ -138,9 +138,9 @@ class OracleWorld:
         """slab-local majorants from the oracle's own f64 table: slabs of 2**shift voxel layers; returns the slab count"""
         return int(load().orc_world_build_local_majorant(self._h, int(shift)))
 
-    def set_local_majorant(self, shift, n_slabs, inv_ratio):
+    def set_local_majorant(self, shift, n_slabs, ratio):
         """track with the table the device built (World.local_majorant()); n_slabs < 2 switches it off"""
-        t = np.ascontiguousarray(inv_ratio, dtype=np.float32) if inv_ratio is not None else np.zeros(1, dtype=np.float32)
+        t = np.ascontiguousarray(ratio, dtype=np.float32) if ratio is not None else np.zeros(1, dtype=np.float32)
         load().orc_world_set_local_majorant(self._h, int(shift), int(n_slabs), t.ctypes.data_as(K.c_float_p))
 
     def run(self, beam, physics_mode=1, seed=0x0DDC0FFEE, threads=0, rank=0, world=1):
