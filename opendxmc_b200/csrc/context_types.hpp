@@ -216,7 +216,7 @@ struct Options {
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
     int localMajorant = -1;      // pool kernel: slab-local majorants; -1 auto (on when the table predicts a gain), 0 off, 1 on
-    double slabCm = 2.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers)
+    double slabCm = 8.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers; profiles/r02_sweep.txt)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases
     int interactBias = -999;     // -999: kernel default (mux 16: interaction phase when waiting lanes + bias >= stepping lanes;
                                  // pool 24: stepper warps keep stepping while at least this many lanes can claim a photon)

@@ -262,12 +262,12 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                                 y = fmaf(dy, tb, y);
                                 z = zf;
                                 slab += up ? 1 : -1;
-                                ++hp[j];
                                 // left through the top / bottom, or sideways (a straight line never comes back)
                                 if (slab < 0 || slab >= P.lm_slabs || !(x >= G.x0 && x <= G.x1 && y >= G.y0 && y <= G.y1)) {
                                     alive = false;
                                     break;
                                 }
+                                ++hp[j]; // face crossings inside the grid
                             }
                             if (alive) {
                                 unsigned int v;
