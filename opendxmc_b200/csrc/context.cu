@@ -449,7 +449,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
             return fail(c, DXB_ECUDA, "transport kernel cannot be resident (occupancy 0)");
     }
     cfg.blocks = c->smCount * perSm;
-    if (!calib)
+    if (!calib && d.part == 0) // (several devices launch from their own host threads: one of them reports)
         c->stats.local_majorant = cfg.local_majorant ? 1 : 0;
 
     const uint64_t nLocal = localCount(pb.nTotal, rank, world);
@@ -1137,8 +1137,9 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
     c->runKey = c->beamKey;
     ++c->beamCounter;
     std::vector<TransportResult> results(nDev);
-    // clear tallies, upload the beam and launch on every device (launches are asynchronous, so the devices run concurrently)
-    for (uint64_t i = 0; i < nDev; ++i) {
+    // Hand over the tally buffer, upload the beam and launch - one host thread per device, so that device 7 does not start
+    // a launch sequence later than device 0 (the sequence is ~40 driver calls per device).
+    auto launchOn = [&](size_t i) -> int {
         DeviceState& d = *c->devs[i];
         CUDA_TRY(c, cudaSetDevice(d.device));
         if (c->exchanging) {
@@ -1150,31 +1151,32 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         } else {
             CUDA_TRY(c, cudaMemsetAsync(d.world.tallyCur(), 0, d.world.nvox * 4 * sizeof(unsigned long long), d.stream));
         }
-        rc = uploadBeam(c, d, pb);
-        if (rc != DXB_OK)
-            return rc;
-    }
-    c->exchanged = false;
-    for (uint64_t i = 0; i < nDev; ++i) {
-        rc = runOnDevice(c, *c->devs[i], c->devs[i]->world, pb, physics_mode, false, -1, c->rank * nDev + i, effWorld, progress,
-            nDev > 1, &results[i]);
-        if (rc != DXB_OK)
-            return rc;
+        int r = uploadBeam(c, d, pb);
+        if (r != DXB_OK)
+            return r;
+        r = runOnDevice(c, d, d.world, pb, physics_mode, false, -1, c->rank * nDev + i, effWorld, progress, nDev > 1, &results[i]);
+        if (r != DXB_OK)
+            return r;
         if (c->exchanging) {
-            DeviceState& d = *c->devs[i];
             d.needsClear[d.world.cur] = true; // scored into, not yet exchanged
             CUDA_TRY(c, cudaEventRecord(d.evTransportDone[d.world.cur], d.stream));
         }
-    }
+        return DXB_OK;
+    };
+    c->exchanged = false;
+    rc = nDev > 1 ? overDevices(c, launchOn) : launchOn(0);
+    if (rc != DXB_OK)
+        return rc;
     // the previous beam's exchange is enqueued now, while every device runs this beam's kernels (exchange.cu)
     if (c->exchanging && (rc = mgEnqueuePending(c)) != DXB_OK)
+        return rc;
+    auto collectOn = [&](size_t i) -> int { return collectStats(c, *c->devs[i], results[i]); };
+    rc = nDev > 1 ? overDevices(c, collectOn) : collectOn(0);
+    if (rc != DXB_OK)
         return rc;
     bool cancelled = false;
     double msMax = 0;
     for (uint64_t i = 0; i < nDev; ++i) {
-        rc = collectStats(c, *c->devs[i], results[i]);
-        if (rc != DXB_OK)
-            return rc;
         cancelled = cancelled || results[i].cancelled;
         msMax = std::max(msMax, results[i].ms);
         c->stats.steps += results[i].stats[0];

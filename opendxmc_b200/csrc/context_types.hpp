@@ -12,6 +12,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -284,6 +285,35 @@ inline int fail(dxb_ctx* c, int code, const std::string& msg)
             return fail(ctx, DXB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
         }                                                                                          \
     } while (0)
+
+// f(device index) on one host thread per device (each bound to its device): host-to-device and device-to-host copies of
+// pageable caller memory are staged by the driver and block the calling thread, so N links need N threads.
+template <typename F>
+inline int overDevices(dxb_ctx* c, F f)
+{
+    const size_t n = c->devs.size();
+    std::vector<int> rc(n, DXB_OK);
+    std::vector<std::thread> threads;
+    for (size_t i = 1; i < n; ++i)
+        threads.emplace_back([&, i]() {
+            if (cudaSetDevice(c->devs[i]->device) != cudaSuccess) {
+                rc[i] = fail(c, DXB_ECUDA, "cudaSetDevice failed");
+                return;
+            }
+            rc[i] = f(i);
+        });
+    if (cudaSetDevice(c->devs[0]->device) != cudaSuccess)
+        rc[0] = fail(c, DXB_ECUDA, "cudaSetDevice failed");
+    else
+        rc[0] = f(0);
+    for (auto& t : threads)
+        t.join();
+    cudaSetDevice(c->devs[0]->device);
+    for (int r : rc)
+        if (r != DXB_OK)
+            return r;
+    return DXB_OK;
+}
 
 // ---- context.cu helpers used by exchange.cu
 int finishGrid(dxb_ctx* c, World& w, cudaStream_t s);

@@ -64,36 +64,6 @@ __global__ void reduceSlabsToDoseKernel(const unsigned long long* __restrict__ l
 }
 
 #define CUDA_TRY_T(ctx, expr) CUDA_TRY(ctx, expr)
-#define failT fail
-
-// f(device index) on one host thread per device (each bound to its device): host-to-device and device-to-host copies of
-// pageable caller memory are staged by the driver and block the calling thread, so N links need N threads.
-template <typename F>
-int overDevices(dxb_ctx* c, F f)
-{
-    const size_t n = c->devs.size();
-    std::vector<int> rc(n, DXB_OK);
-    std::vector<std::thread> threads;
-    for (size_t i = 1; i < n; ++i)
-        threads.emplace_back([&, i]() {
-            if (cudaSetDevice(c->devs[i]->device) != cudaSuccess) {
-                rc[i] = failT(c, DXB_ECUDA, "cudaSetDevice failed");
-                return;
-            }
-            rc[i] = f(i);
-        });
-    if (cudaSetDevice(c->devs[0]->device) != cudaSuccess)
-        rc[0] = failT(c, DXB_ECUDA, "cudaSetDevice failed");
-    else
-        rc[0] = f(0);
-    for (auto& t : threads)
-        t.join();
-    cudaSetDevice(c->devs[0]->device);
-    for (int r : rc)
-        if (r != DXB_OK)
-            return r;
-    return DXB_OK;
-}
 
 // mailbox = {sequence number, five sums}: the sums are visible system-wide before the sequence number announces them
 __global__ void publishMailboxKernel(unsigned long long* __restrict__ mailbox, const unsigned long long* __restrict__ sums, unsigned long long seq)
