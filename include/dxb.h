@@ -431,6 +431,7 @@ typedef struct dxb_run_stats {
     uint64_t hops;            /* slab-local majorants: tentative steps that ended on a slab face (no voxel fetch) */
     int32_t  local_majorant;  /* 1: the last beam ran on the slab-local majorant build of the kernel */
     int32_t  reserved;
+    uint64_t voxel_fetches;   /* voxel gathers actually issued (<= steps: the brick pre-filter skips certainly-virtual collisions) */
 } dxb_run_stats;
 int dxb_get_run_stats(const dxb_ctx*, dxb_run_stats* out);
 

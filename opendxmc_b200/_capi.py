@@ -100,7 +100,7 @@ class dxb_run_stats(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("transport_ms", C.c_double), ("total_ms", C.c_double), ("calibration_ms", C.c_double),
         ("calibration_factor", C.c_double), ("energy_emitted_kev", C.c_double), ("energy_deposited_kev", C.c_double),
-        ("hops", C.c_uint64), ("local_majorant", C.c_int32), ("reserved", C.c_int32),
+        ("hops", C.c_uint64), ("local_majorant", C.c_int32), ("reserved", C.c_int32), ("voxel_fetches", C.c_uint64),
     ]
 
 

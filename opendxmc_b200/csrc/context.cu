@@ -191,6 +191,24 @@ int finishGrid(dxb_ctx* c, World& w, cudaStream_t s)
     CUDA_TRY(c, cudaStreamSynchronize(s));
     if (mmax >= static_cast<unsigned int>(w.n_mat))
         return fail(c, DXB_EINVAL, "set_grid: material index out of range");
+    w.brickN[0] = 0;
+    if (c->opt.brickFilter) {
+        int shift = 0;
+        while ((2 << shift) <= c->opt.brickVoxels && shift < 8)
+            ++shift;
+        const int nb[3] = { static_cast<int>((w.dim[0] + (1u << shift) - 1) >> shift), static_cast<int>((w.dim[1] + (1u << shift) - 1) >> shift),
+            static_cast<int>((w.dim[2] + (1u << shift) - 1) >> shift) };
+        const size_t bricks = static_cast<size_t>(nb[0]) * nb[1] * nb[2];
+        if (bricks < (1u << 28)) {
+            CUDA_TRY(c, w.brickBound.alloc(bricks * 8, w.device));
+            launchBrickBound(w.voxels.p, static_cast<int>(w.dim[0]), static_cast<int>(w.dim[1]), static_cast<int>(w.dim[2]), shift, nb[0], nb[1], nb[2],
+                w.tot.p, w.majorant.p, w.n_mat, w.brickBound.p, s);
+            CUDA_TRY(c, cudaGetLastError());
+            w.brickShift = shift;
+            for (int i = 0; i < 3; ++i)
+                w.brickN[i] = nb[i];
+        }
+    }
     if (c->opt.localMajorant != 0) {
         const int rc = buildLocalMajorant(c, w, s);
         if (rc != DXB_OK)
@@ -347,7 +365,7 @@ uint64_t localCount(uint64_t nTotal, uint64_t rank, uint64_t world)
 struct TransportResult {
     double ms = 0;
     uint64_t launches = 0;
-    uint64_t stats[6] = { 0, 0, 0, 0, 0, 0 }; // steps, interactions, deposits, emitted, histories, hops
+    uint64_t stats[7] = { 0, 0, 0, 0, 0, 0, 0 }; // steps, interactions, deposits, emitted, histories, hops, voxel fetches
     bool cancelled = false;
 };
 
@@ -420,6 +438,12 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
             cfg.table_in_smem = false;
             cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots, lm);
             cfg.smem = poolSmemBytes(cfg.slots, 0, lmSlabs);
+        }
+        if (!lm && !calib && c->opt.brickFilter && w.brickN[0] > 0 && w.brickBound.p) {
+            P.brick = w.brickBound.p;
+            P.brick_shift = w.brickShift;
+            P.brick_nx = w.brickN[0];
+            P.brick_ny = w.brickN[1];
         }
         if (lm) {
             P.lm_ratio = w.lmRatio.p;
@@ -495,10 +519,12 @@ int collectStats(dxb_ctx* c, DeviceState& d, TransportResult& res)
 {
     CUDA_TRY(c, cudaSetDevice(d.device));
     CUDA_TRY(c, cudaStreamSynchronize(d.stream));
-    unsigned long long h[6];
+    unsigned long long h[7];
     CUDA_TRY(c, cudaMemcpy(h, d.counters.p + 8, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 7; ++i)
         res.stats[i] = h[i];
+    if (res.stats[6] == 0)
+        res.stats[6] = res.stats[0]; // kernels without the pre-filter fetch the voxel of every tentative step
     if (c->opt.diag) {
         // pool kernel diagnostics: executions and claimed lanes per phase (step, interaction, Rayleigh, refill)
         unsigned long long g[8];
@@ -1076,6 +1102,13 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         c->opt.poolMinBlocks = static_cast<int>(value);
     } else if (k == "step_quad") {
         c->opt.stepQuad = static_cast<int>(value);
+    } else if (k == "brick_filter") {
+        c->opt.brickFilter = value != 0; // (the table is built with the grid; switching the filter off takes effect at once)
+    } else if (k == "brick_voxels") {
+        const int v = static_cast<int>(value);
+        if (v < 2 || v > 256 || (v & (v - 1)))
+            return fail(c, DXB_EINVAL, "brick_voxels must be a power of two in 2..256");
+        c->opt.brickVoxels = v;
     } else if (k == "local_majorant") {
         const int v = static_cast<int>(value);
         if (v < -1 || v > 1)
@@ -1185,6 +1218,7 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         c->stats.energy_emitted_kev += static_cast<double>(results[i].stats[3]) / 65536.0;
         c->stats.histories += results[i].stats[4];
         c->stats.hops += results[i].stats[5];
+        c->stats.voxel_fetches += results[i].stats[6];
         c->stats.kernel_launches += results[i].launches;
     }
     c->stats.transport_ms = msMax;

@@ -109,6 +109,9 @@ struct World {
     std::vector<float> lmHost;           // host copy of lmRatio: local / global majorant, in (0, 1]
     int lmShift = 0, lmSlabs = 0;
     bool lmUseful = false;               // the table predicts a gain (mean ratio below the threshold)
+    // brick pre-filter (pool kernel, quad step): upper bounds of mu / mu_max per brick and energy octave
+    DevBuf<unsigned char> brickBound;    // [brickN[0] * brickN[1] * brickN[2] * 8]
+    int brickShift = 0, brickN[3] = { 0, 0, 0 };
 
     GridDev gridDev() const
     {
@@ -216,6 +219,8 @@ struct Options {
     int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
+    int brickFilter = 1;         // pool kernel, quad step: skip the gathers of certainly-virtual collisions (bit-identical results)
+    int brickVoxels = 16;        // brick edge in voxels (a power of two)
     int localMajorant = -1;      // pool kernel: slab-local majorants; -1 auto (on when the table predicts a gain), 0 off, 1 on
     double slabCm = 8.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers; profiles/r02_sweep.txt)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases

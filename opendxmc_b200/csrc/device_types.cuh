@@ -108,6 +108,11 @@ struct RunParams {
     const float* __restrict__ lm_ratio; // [lm_slabs * kLmBands], in (0, 1]
     int lm_slabs, lm_shift;
     float lm_thickness;              // slab thickness [cm] = 2^lm_shift * dz
+    // brick pre-filter (pool kernel, quad step): per brick of 2^brick_shift voxels per edge and per energy octave (energy node
+    // index >> 6) an upper bound (q + 1) / 256 of mu(voxel) / mu_max over the brick; a tentative collision whose uniform number
+    // is not below the bound is virtual whatever the voxel holds, so its gather is skipped.  nullptr: no filter.
+    const unsigned char* __restrict__ brick; // [bricks * 8]
+    int brick_shift, brick_nx, brick_ny;
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories

@@ -16,6 +16,8 @@ int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int 
 void setLaunchSmCount(int sms);
 void launchHoleSums(const unsigned long long* tally, const signed char* hole, size_t n, unsigned long long* sums, cudaStream_t s);
 void launchSlabMax(const unsigned int* voxels, size_t layerSize, int nz, int shift, int nslabs, unsigned int* out, cudaStream_t s);
+void launchBrickBound(const unsigned int* voxels, int nx, int ny, int nz, int shift, int nbx, int nby, int nbz, const float* tot,
+    const float* majorant, int n_mat, unsigned char* out, cudaStream_t s);
 void launchPackVoxels(const double* density, const unsigned char* material, unsigned int* out, size_t n, unsigned int* maxBits, cudaStream_t s);
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s);
 void launchEnergyToDose(const unsigned long long* tally, const unsigned int* voxels, double* dose, double* variance,

@@ -470,6 +470,51 @@ __global__ void slabMaxKernel(const unsigned int* __restrict__ voxels, size_t la
             atomicMax(&out[slab * 256 + i], s_max[i]);
 }
 
+// Brick pre-filter table (transport_pool.cu, quad step): one block per brick of 2^shift voxels per edge.  The block finds the
+// largest (24-bit) density per material inside the brick, then for each of the 8 energy octaves the largest ratio
+//   max_m rho_max(m) * tot_m(node) / majorant(node)   over the octave's nodes (both ends included: the kernels interpolate
+// numerator and denominator linearly between nodes, and a ratio of two linear functions is monotone in between),
+// and stores q with (q + 1) / 256 strictly above it.
+__global__ void brickBoundKernel(const unsigned int* __restrict__ voxels, int nx, int ny, int nz, int shift, int nbx, int nby,
+    const float* __restrict__ tot, const float* __restrict__ majorant, int n_mat, unsigned char* __restrict__ out)
+{
+    __shared__ unsigned int s_max[256];
+    __shared__ unsigned int s_r[8];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_max[i] = 0u;
+    if (threadIdx.x < 8)
+        s_r[threadIdx.x] = 0u;
+    __syncthreads();
+    const int b = blockIdx.x;
+    const int bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+    const int edge = 1 << shift, cells = edge * edge * edge;
+    for (int t = threadIdx.x; t < cells; t += blockDim.x) {
+        const int i = (bx << shift) + (t & (edge - 1)), j = (by << shift) + ((t >> shift) & (edge - 1)), k = (bz << shift) + (t >> (2 * shift));
+        if (i < nx && j < ny && k < nz) {
+            const unsigned int v = voxels[(static_cast<size_t>(k) * ny + j) * nx + i];
+            atomicMax(&s_max[v & 0xFFu], v & 0xFFFFFF00u);
+        }
+    }
+    __syncthreads();
+    for (int band = 0; band < 8; ++band) {
+        const int node = band * 64 + threadIdx.x;
+        if (threadIdx.x <= 64 && node < kDevNE) {
+            float mu = 0.0f;
+            for (int m = 0; m < n_mat; ++m)
+                if (s_max[m])
+                    mu = fmaxf(mu, __uint_as_float(s_max[m]) * tot[m * kDevNE + node]);
+            const float r = mu / majorant[node];
+            atomicMax(&s_r[band], __float_as_uint(fmaxf(r, 0.0f))); // non-negative floats order like their bit patterns
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const float r = __uint_as_float(s_r[threadIdx.x]);
+        const int q = min(255, static_cast<int>(floorf(r * 256.0f * (1.0f + 9.5367431640625e-7f))));
+        out[static_cast<size_t>(b) * 8 + threadIdx.x] = static_cast<unsigned char>(max(q, 0));
+    }
+}
+
 __global__ void majorantKernel(const float* __restrict__ tot, const unsigned int* __restrict__ maxDensityBits,
     int n_mat, float* __restrict__ majorant)
 {
@@ -858,6 +903,11 @@ void launchSlabMax(const unsigned int* voxels, size_t layerSize, int nz, int shi
 {
     const int parts = max(1, g_streamBlocks / max(nslabs, 1));
     slabMaxKernel<<<nslabs * parts, 256, 0, s>>>(voxels, layerSize, nz, shift, parts, out);
+}
+void launchBrickBound(const unsigned int* voxels, int nx, int ny, int nz, int shift, int nbx, int nby, int nbz, const float* tot,
+    const float* majorant, int n_mat, unsigned char* out, cudaStream_t s)
+{
+    brickBoundKernel<<<nbx * nby * nbz, 128, 0, s>>>(voxels, nx, ny, nz, shift, nbx, nby, tot, majorant, n_mat, out);
 }
 void launchMajorant(const float* tot, const unsigned int* maxBits, int n_mat, float* majorant, cudaStream_t s)
 {

@@ -104,6 +104,17 @@ __device__ __forceinline__ bool voxelIndex(const GridDev& G, float x, float y, f
     return ix < static_cast<unsigned int>(G.nx) && iy < static_cast<unsigned int>(G.ny) && iz < static_cast<unsigned int>(G.nz);
 }
 
+// the same, plus the index of the brick (2^brick_shift voxels per edge) that holds the voxel
+__device__ __forceinline__ bool voxelIndexBrick(const GridDev& G, const RunParams& P, float x, float y, float z, unsigned int& index, unsigned int& brick)
+{
+    const unsigned int ix = static_cast<unsigned int>(__float2int_rd(fmaf(x, G.inv_dx, G.offx)));
+    const unsigned int iy = static_cast<unsigned int>(__float2int_rd(fmaf(y, G.inv_dy, G.offy)));
+    const unsigned int iz = static_cast<unsigned int>(__float2int_rd(fmaf(z, G.inv_dz, G.offz)));
+    index = (iz * G.ny + iy) * G.nx + ix;
+    brick = ((iz >> P.brick_shift) * P.brick_ny + (iy >> P.brick_shift)) * P.brick_nx + (ix >> P.brick_shift);
+    return ix < static_cast<unsigned int>(G.nx) && iy < static_cast<unsigned int>(G.ny) && iz < static_cast<unsigned int>(G.nz);
+}
+
 __device__ __forceinline__ void deflect(float& dx, float& dy, float& dz, float cosT, float phi)
 {
     // dxmc::vectormath::peturb: rotate the direction by polar angle theta and azimuth phi.

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     unsigned long long poolNext = 0, poolEnd = 0;
     bool drained = false;
     // per-lane
-    unsigned int nSteps = 0, nInteractions = 0, nDeposits = 0, nHistories = 0, nHops = 0;
+    unsigned int nSteps = 0, nInteractions = 0, nDeposits = 0, nHistories = 0, nHops = 0, nFetches = 0;
     unsigned long long emitted = 0;
 
     for (;;) {
@@ -313,6 +313,13 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 // Two step pairs with all four voxel gathers in flight at once: the second pair (block blk + 1) is
                 // speculative and is simply not consumed if the first pair ends in a real collision or outside the grid
                 // (counter-based generator: the same block is regenerated when the history gets there).
+                //
+                // Brick pre-filter (P.brick != nullptr): a tentative collision is real iff  u mu_max < mu(voxel).  The grid
+                // is covered by bricks of 2^brick_shift voxels per edge, and for every brick and energy octave the table
+                // holds an upper bound q/256 of mu(voxel)/mu_max over the brick.  If u >= q/256 the collision is virtual
+                // WHATEVER the voxel holds, so its gather is not issued at all.  Same random numbers, same decisions: the
+                // results are bit-identical to the unfiltered walk; only the DRAM traffic and the wait for it go away
+                // (most of a CT volume is air and soft tissue under a bone-set majorant).
                 if (stepping) {
                     const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
                     const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
@@ -324,27 +331,38 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     const float x1 = fmaf(dx, s1, x0), y1 = fmaf(dy, s1, y0), z1 = fmaf(dz, s1, z0);
                     const float x2 = fmaf(dx, s2, x1), y2 = fmaf(dy, s2, y1), z2 = fmaf(dz, s2, z1);
                     const float x3 = fmaf(dx, s3, x2), y3 = fmaf(dy, s3, y2), z3 = fmaf(dz, s3, z2);
-                    unsigned int v0, v1, v2, v3;
-                    const bool in0 = voxelIndex(G, x0, y0, z0, v0);
-                    const bool in1 = voxelIndex(G, x1, y1, z1, v1) && in0;
-                    const bool in2 = voxelIndex(G, x2, y2, z2, v2) && in1;
-                    const bool in3 = voxelIndex(G, x3, y3, z3, v3) && in2;
+                    unsigned int v0, v1, v2, v3, b0, b1, b2, b3;
+                    const bool in0 = voxelIndexBrick(G, P, x0, y0, z0, v0, b0);
+                    const bool in1 = voxelIndexBrick(G, P, x1, y1, z1, v1, b1) && in0;
+                    const bool in2 = voxelIndexBrick(G, P, x2, y2, z2, v2, b2) && in1;
+                    const bool in3 = voxelIndexBrick(G, P, x3, y3, z3, v3, b3) && in2;
+                    // certainly virtual?  (u as a 24-bit integer against q << 16)
+                    bool sk0 = false, sk1 = false, sk2 = false, sk3 = false;
+                    if (P.brick) {
+                        const unsigned char* __restrict__ bt = P.brick + (epos.i >> 6);
+                        const unsigned int q0 = in0 ? __ldg(bt + b0 * 8u) : 255u, q1 = in1 ? __ldg(bt + b1 * 8u) : 255u;
+                        const unsigned int q2 = in2 ? __ldg(bt + b2 * 8u) : 255u, q3 = in3 ? __ldg(bt + b3 * 8u) : 255u;
+                        sk0 = (r1.w[1] >> 8) >= ((q0 + 1u) << 16);
+                        sk1 = (r1.w[3] >> 8) >= ((q1 + 1u) << 16);
+                        sk2 = (r2.w[1] >> 8) >= ((q2 + 1u) << 16);
+                        sk3 = (r2.w[3] >> 8) >= ((q3 + 1u) << 16);
+                    }
                     unsigned int c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
-                    if (in0)
+                    if (in0 && !sk0)
                         c0 = loadVoxel(G.voxels + v0);
-                    if (in1)
+                    if (in1 && !sk1)
                         c1 = loadVoxel(G.voxels + v1);
                     // step_quad == 2 (experiment): the speculative second pair is only PREFETCHED into L2 and loaded when the
                     // walk gets there, so that no unconsumed load is outstanding when the slot is published (the release
                     // fence waits for every load in flight)
                     const bool prefetchOnly = P.step_quad == 2;
-                    if (in2) {
+                    if (in2 && !sk2) {
                         if (prefetchOnly)
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(G.voxels + v2));
                         else
                             c2 = loadVoxel(G.voxels + v2);
                     }
-                    if (in3) {
+                    if (in3 && !sk3) {
                         if (prefetchOnly)
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(G.voxels + v3));
                         else
@@ -356,39 +374,52 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     blk += 1u;
                     if (in0) {
                         ++nSteps;
-                        mat = voxelMaterial(c0);
-                        const float mu0 = voxelDensity(c0) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                         px = x0, py = y0, pz = z0;
-                        if (r1.k(1) * muMaxU24 < mu0) {
+                        bool real = false;
+                        if (!sk0) {
+                            ++nFetches;
+                            mat = voxelMaterial(c0);
+                            real = r1.k(1) * muMaxU24 < voxelDensity(c0) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                        }
+                        if (real) {
                             newPhase = kPhInt;
                         } else if (in1) {
                             ++nSteps;
-                            mat = voxelMaterial(c1);
-                            const float mu1 = voxelDensity(c1) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                             px = x1, py = y1, pz = z1;
-                            if (r1.k(3) * muMaxU24 < mu1) {
+                            if (!sk1) {
+                                ++nFetches;
+                                mat = voxelMaterial(c1);
+                                real = r1.k(3) * muMaxU24 < voxelDensity(c1) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                            }
+                            if (real) {
                                 newPhase = kPhInt;
                             } else {
                                 blk += 1u; // the second pair is now consumed
                                 if (prefetchOnly) {
-                                    if (in2)
+                                    if (in2 && !sk2)
                                         c2 = loadVoxel(G.voxels + v2);
-                                    if (in3)
+                                    if (in3 && !sk3)
                                         c3 = loadVoxel(G.voxels + v3);
                                 }
                                 if (in2) {
                                     ++nSteps;
-                                    mat = voxelMaterial(c2);
-                                    const float mu2 = voxelDensity(c2) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                                     px = x2, py = y2, pz = z2;
-                                    if (r2.k(1) * muMaxU24 < mu2) {
+                                    if (!sk2) {
+                                        ++nFetches;
+                                        mat = voxelMaterial(c2);
+                                        real = r2.k(1) * muMaxU24 < voxelDensity(c2) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                    }
+                                    if (real) {
                                         newPhase = kPhInt;
                                     } else if (in3) {
                                         ++nSteps;
-                                        mat = voxelMaterial(c3);
-                                        const float mu3 = voxelDensity(c3) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                                         px = x3, py = y3, pz = z3;
-                                        newPhase = (r2.k(3) * muMaxU24 < mu3) ? kPhInt : kPhStep;
+                                        if (!sk3) {
+                                            ++nFetches;
+                                            mat = voxelMaterial(c3);
+                                            real = r2.k(3) * muMaxU24 < voxelDensity(c3) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
+                                        }
+                                        newPhase = real ? kPhInt : kPhStep;
                                     }
                                 }
                             }
@@ -648,9 +679,9 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     }
 
     // ---------------- statistics
-    unsigned long long v[6] = { nSteps, nInteractions, nDeposits, emitted, nHistories, nHops };
+    unsigned long long v[7] = { nSteps, nInteractions, nDeposits, emitted, nHistories, nHops, nFetches };
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 7; ++k) {
         unsigned long long x = v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)

@@ -309,3 +309,32 @@ def test_external_material_tables_on_the_device(dx, orc):
         out[name] = (float(e.sum()), st["interactions"] / st["histories"])
         world.close()
     assert out["ext"][1] < 0.97 * out["water"][1]
+
+
+@pytest.mark.parametrize("brick_voxels", [4, 16, 64])
+def test_brick_pre_filter_is_bit_exact(dx, brick_voxels):
+    """The brick pre-filter of the pool kernel skips the voxel gather of a tentative collision whose uniform number is not
+    below an upper bound of mu / mu_max over the brick: that collision is virtual whatever the voxel holds.  Same random
+    numbers, same decisions: every tally word and counter must equal the unfiltered run, with fewer voxel fetches."""
+    for wl, mode in ((dx.workloads.ct_spiral_patient(scale=4, histories=400_000, step_deg=5.0), 1),
+                     (dx.workloads.ctdi_body_phantom(n=32, histories=300_000, step_deg=5.0), 2)):
+        out = []
+        for filt in (0, 1):
+            world = dx.World([0])
+            grid = world.addItem(dx.AAVoxelGrid(mode))
+            assert grid.setData(wl.dim, wl.density, wl.material, wl.materials)
+            grid.setSpacing(wl.spacing)
+            world.build()                       # creates the context
+            world.set_option("brick_filter", filt)
+            world.set_option("brick_voxels", brick_voxels)
+            world.set_option("local_majorant", 0)
+            world.build()                       # the table is built with the grid
+            dx.Transport().run_transport(world, wl.beam)
+            out.append((*[a.copy() for a in world.energy_scored()], world.run_stats()))
+            world.close()
+        (e0, s0, c0, st0), (e1, s1, c1, st1) = out
+        assert np.array_equal(e0, e1) and np.array_equal(s0, s1) and np.array_equal(c0, c1)
+        for k in ("histories", "steps", "interactions", "deposits"):
+            assert st0[k] == st1[k], k
+        assert st0["voxel_fetches"] == st0["steps"]
+        assert 0 < st1["voxel_fetches"] < 0.8 * st1["steps"]
