@@ -426,20 +426,24 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.pool = pool;
     cfg.min_blocks = c->opt.poolMinBlocks;
     cfg.local_majorant = false;
+    cfg.brick_filter = false;
     if (pool) {
         // slab-local majorants: the pool kernel's scoring builds; auto = when the table built with the grid predicts a gain
         const bool lm = !calib && w.lmSlabs >= 2 && (c->opt.localMajorant == 1 || (c->opt.localMajorant < 0 && w.lmUseful));
         cfg.local_majorant = lm;
         const int lmSlabs = lm ? w.lmSlabs : 0;
         cfg.threads = std::clamp(c->opt.poolThreads, 64, 512) / 32 * 32;
-        cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots, lm);
+        const bool bfWanted = !lm && !calib && c->opt.brickFilter && w.brickN[0] > 0 && w.brickBound.p && c->opt.stepQuad && P.step_pairs == 2;
+        cfg.slots = transportPoolSlots(mode, calib, cfg.table_in_smem, c->opt.poolSlots, lm, bfWanted);
         cfg.smem = poolSmemBytes(cfg.slots, cfg.table_in_smem ? w.n_mat * kDevNE : 0, lmSlabs);
         if (cfg.table_in_smem && cfg.smem > 56 * 1024) {
             cfg.table_in_smem = false;
-            cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots, lm);
+            cfg.slots = transportPoolSlots(mode, calib, false, c->opt.poolSlots, lm, bfWanted);
             cfg.smem = poolSmemBytes(cfg.slots, 0, lmSlabs);
         }
-        if (!lm && !calib && c->opt.brickFilter && w.brickN[0] > 0 && w.brickBound.p) {
+        const bool bf = !lm && !calib && c->opt.brickFilter && w.brickN[0] > 0 && w.brickBound.p && c->opt.stepQuad && P.step_pairs == 2;
+        cfg.brick_filter = bf;
+        if (bf) {
             P.brick = w.brickBound.p;
             P.brick_shift = w.brickShift;
             P.brick_nx = w.brickN[0];
@@ -466,7 +470,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks, cfg.local_majorant)
+        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks, cfg.local_majorant, cfg.brick_filter)
             : mux  ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)

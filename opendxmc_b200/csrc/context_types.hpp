@@ -219,7 +219,8 @@ struct Options {
     int poolMinBlocks = 0;       // pool kernel: 5 / 6 select the 48 / 40-register builds (more resident warps), else 64 registers
     int stepQuad = 1;            // pool kernel, step_pairs == 2: issue the four gathers of both pairs at once
     int diag = 0;                // pool kernel: count phase executions / claimed lanes (slower; printed to stderr)
-    int brickFilter = 1;         // pool kernel, quad step: skip the gathers of certainly-virtual collisions (bit-identical results)
+    int brickFilter = 0;         // pool kernel, quad step: skip the gathers of certainly-virtual collisions (bit-identical results;
+                                 // 4.5x fewer gathers on C2 but no faster: off by default)
     int brickVoxels = 16;        // brick edge in voxels (a power of two)
     int localMajorant = -1;      // pool kernel: slab-local majorants; -1 auto (on when the table predicts a gain), 0 off, 1 on
     double slabCm = 8.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers; profiles/r02_sweep.txt)

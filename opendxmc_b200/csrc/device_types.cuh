@@ -156,6 +156,7 @@ struct LaunchConfig {
     bool pool; // block-pooled kernel instead of the lane-multiplexed one
     int min_blocks; // pool kernel: 5 / 6 = the 48 / 40-register builds (5 / 6 blocks of <= 256 threads per SM), else 64 registers
     bool local_majorant; // pool kernel: the slab-local majorant build
+    bool brick_filter;   // pool kernel: the brick pre-filter build of the quad step
 };
 
 } // namespace dxb

@@ -85,7 +85,7 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
 // anywhere in the grid.  The optical depth drawn for a tentative step is marched through the slabs (piecewise constant
 // majorant), so the estimator stays unbiased.  Pays when the densest material is confined to part of the z range (teeth in
 // a whole-body phantom during a chest scan).
-template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false>
+template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false, bool BF = false>
 __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transportKernelPool(const __grid_constant__ RunParams P)
 {
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
@@ -314,12 +314,14 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 // speculative and is simply not consumed if the first pair ends in a real collision or outside the grid
                 // (counter-based generator: the same block is regenerated when the history gets there).
                 //
-                // Brick pre-filter (P.brick != nullptr): a tentative collision is real iff  u mu_max < mu(voxel).  The grid
+                // Brick pre-filter (BF builds, option brick_filter): a tentative collision is real iff  u mu_max < mu(voxel).  The grid
                 // is covered by bricks of 2^brick_shift voxels per edge, and for every brick and energy octave the table
                 // holds an upper bound q/256 of mu(voxel)/mu_max over the brick.  If u >= q/256 the collision is virtual
                 // WHATEVER the voxel holds, so its gather is not issued at all.  Same random numbers, same decisions: the
-                // results are bit-identical to the unfiltered walk; only the DRAM traffic and the wait for it go away
-                // (most of a CT volume is air and soft tissue under a bone-set majorant).
+                // results are bit-identical to the unfiltered walk and 78 % of the gathers of C2 go away (15.5 -> 3.5 per history)
+                // - but not the time: the kernel is bound by instruction issue and dependent latency, not by DRAM, and the
+                // brick lookup costs what the skipped gathers saved (4.83e9 vs 4.92e9 hist/s, profiles/r02_sweep_brickfilter.txt).
+                // Kept as an option (off): it halves the DRAM traffic, which matters when the memory system is shared.
                 if (stepping) {
                     const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
                     const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
@@ -331,14 +333,14 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     const float x1 = fmaf(dx, s1, x0), y1 = fmaf(dy, s1, y0), z1 = fmaf(dz, s1, z0);
                     const float x2 = fmaf(dx, s2, x1), y2 = fmaf(dy, s2, y1), z2 = fmaf(dz, s2, z1);
                     const float x3 = fmaf(dx, s3, x2), y3 = fmaf(dy, s3, y2), z3 = fmaf(dz, s3, z2);
-                    unsigned int v0, v1, v2, v3, b0, b1, b2, b3;
-                    const bool in0 = voxelIndexBrick(G, P, x0, y0, z0, v0, b0);
-                    const bool in1 = voxelIndexBrick(G, P, x1, y1, z1, v1, b1) && in0;
-                    const bool in2 = voxelIndexBrick(G, P, x2, y2, z2, v2, b2) && in1;
-                    const bool in3 = voxelIndexBrick(G, P, x3, y3, z3, v3, b3) && in2;
+                    unsigned int v0, v1, v2, v3, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
+                    const bool in0 = BF ? voxelIndexBrick(G, P, x0, y0, z0, v0, b0) : voxelIndex(G, x0, y0, z0, v0);
+                    const bool in1 = (BF ? voxelIndexBrick(G, P, x1, y1, z1, v1, b1) : voxelIndex(G, x1, y1, z1, v1)) && in0;
+                    const bool in2 = (BF ? voxelIndexBrick(G, P, x2, y2, z2, v2, b2) : voxelIndex(G, x2, y2, z2, v2)) && in1;
+                    const bool in3 = (BF ? voxelIndexBrick(G, P, x3, y3, z3, v3, b3) : voxelIndex(G, x3, y3, z3, v3)) && in2;
                     // certainly virtual?  (u as a 24-bit integer against q << 16)
                     bool sk0 = false, sk1 = false, sk2 = false, sk3 = false;
-                    if (P.brick) {
+                    if (BF) {
                         const unsigned char* __restrict__ bt = P.brick + (epos.i >> 6);
                         const unsigned int q0 = in0 ? __ldg(bt + b0 * 8u) : 255u, q1 = in1 ? __ldg(bt + b1 * 8u) : 255u;
                         const unsigned int q2 = in2 ? __ldg(bt + b2 * 8u) : 255u, q3 = in3 ? __ldg(bt + b3 * 8u) : 255u;
@@ -377,7 +379,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         px = x0, py = y0, pz = z0;
                         bool real = false;
                         if (!sk0) {
-                            ++nFetches;
+                            if (BF)
+                                ++nFetches;
                             mat = voxelMaterial(c0);
                             real = r1.k(1) * muMaxU24 < voxelDensity(c0) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                         }
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                             ++nSteps;
                             px = x1, py = y1, pz = z1;
                             if (!sk1) {
+                                if (BF)
                                 ++nFetches;
                                 mat = voxelMaterial(c1);
                                 real = r1.k(3) * muMaxU24 < voxelDensity(c1) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
@@ -405,7 +409,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                                     ++nSteps;
                                     px = x2, py = y2, pz = z2;
                                     if (!sk2) {
-                                        ++nFetches;
+                                        if (BF)
+                                ++nFetches;
                                         mat = voxelMaterial(c2);
                                         real = r2.k(1) * muMaxU24 < voxelDensity(c2) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                                     }
@@ -415,7 +420,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                                         ++nSteps;
                                         px = x3, py = y3, pz = z3;
                                         if (!sk3) {
-                                            ++nFetches;
+                                            if (BF)
+                                ++nFetches;
                                             mat = voxelMaterial(c3);
                                             real = r2.k(3) * muMaxU24 < voxelDensity(c3) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                                         }
@@ -691,10 +697,10 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     }
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false>
 cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t stream)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
     if (e != cudaSuccess)
         return e;
@@ -702,10 +708,10 @@ cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t
     return cudaGetLastError();
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false>
 int occupancyPool(int threads, size_t smem)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -724,6 +730,15 @@ int occupancyPool(int threads, size_t smem)
 #define DXB_POOL_DISPATCH(CALL)                                                  \
     const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
+    if (brickFilter && !localMajorant && !calib)                                \
+        switch (key) {                                                          \
+        case 0: return CALL(0, false, false, 16, 0, false, true);               \
+        case 1: return CALL(0, false, true, 16, 0, false, true);                \
+        case 4: return CALL(1, false, false, 16, 0, false, true);               \
+        case 5: return CALL(1, false, true, 16, 0, false, true);                \
+        case 8: return CALL(2, false, false, 16, 0, false, true);               \
+        default: return CALL(2, false, true, 16, 0, false, true);               \
+        }                                                                       \
     if (localMajorant && !calib)                                                \
         switch (key) {                                                          \
         case 0: return CALL(0, false, false, 16, 0, true);                      \
@@ -766,6 +781,7 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
 {
     const bool smemTable = cfg.table_in_smem;
     const bool localMajorant = cfg.local_majorant;
+    const bool brickFilter = cfg.brick_filter;
     const int slots = cfg.slots;
     const int lb = (cfg.threads <= 256 && (cfg.min_blocks == 5 || cfg.min_blocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? cfg.min_blocks : 0;
 #define DXB_CALL(...) launchPool<__VA_ARGS__>(p, cfg, stream)
@@ -773,17 +789,17 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
 #undef DXB_CALL
 }
 
-int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant)
+int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant, bool brickFilter)
 {
     // must mirror DXB_POOL_DISPATCH: only the production variant is built for several slot counts
-    if (localMajorant && !calib)
+    if ((localMajorant || brickFilter) && !calib)
         return 16;
     if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 12))
         return slots;
     return 16;
 }
 
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant)
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant, bool brickFilter)
 {
     const int lb = (threads <= 256 && (minBlocks == 5 || minBlocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? minBlocks : 0;
 #define DXB_CALL(...) occupancyPool<__VA_ARGS__>(threads, smem)

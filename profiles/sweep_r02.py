@@ -11,11 +11,11 @@ import opendxmc_b200 as dx
 nh = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 W = dx.workloads
 cases = [("C2 CT patient 512x512x300, spiral", lambda: W.ct_spiral_patient(scale=1, histories=nh), 1,
-          [{}, {"brick_filter": 0}, {"brick_voxels": 8}, {"brick_voxels": 32}, {"step_quad": 2}, {"local_majorant": 1}]),
+          [{}, {"brick_filter": 1, "brick_voxels": 16}, {"brick_filter": 1, "brick_voxels": 32}, {"step_quad": 2}, {"local_majorant": 1}]),
          ("C3 ICRP AM shape 254x127x222, chest spiral", lambda: W.icrp_phantom("AM", histories=nh), 1, [{}, {"local_majorant": 0}, {"slab_cm": 4.0}, {"slab_cm": 8.0}, {"slab_cm": 16.0}]),
          ("C5 ICRP 10y shape 419x226x576, DX 80 kV", lambda: W.icrp_phantom("10M", histories=nh, beam_kind="dx"), 1, [{}, {"local_majorant": 0}, {"slab_cm": 4.0}, {"slab_cm": 8.0}, {"slab_cm": 16.0}]),
-         ("C4 thorax 512x512x400, dual source + AEC", lambda: W.ct_dual_source_thorax(scale=1, histories=nh), 1, [{}, {"brick_filter": 0}]),
-         ("C1 CTDI body phantom 64^3, axial", lambda: W.ctdi_body_phantom(n=64, histories=nh), 1, [{}, {"brick_filter": 0}, {"brick_voxels": 4}]),
+         ("C4 thorax 512x512x400, dual source + AEC", lambda: W.ct_dual_source_thorax(scale=1, histories=nh), 1, [{}, {"brick_filter": 1, "brick_voxels": 16}]),
+         ("C1 CTDI body phantom 64^3, axial", lambda: W.ctdi_body_phantom(n=64, histories=nh), 1, [{}]),
          ("C2 physics mode 0", lambda: W.ct_spiral_patient(scale=1, histories=nh), 0, [{}]),
          ("C2 physics mode 2", lambda: W.ct_spiral_patient(scale=1, histories=nh), 2, [{}])]
 for name, make, mode, variants in cases:
