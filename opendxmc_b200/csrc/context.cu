@@ -254,15 +254,36 @@ int uploadGrid(dxb_ctx* c, World& w, const uint64_t dim[3], const double spacing
     return finish ? finishGrid(c, w, s) : DXB_OK;
 }
 
-struct PreparedBeam {
-    std::vector<ExposureDev> exposures;
-    uint64_t ppe = 0, nTotal = 0;
-    std::vector<float> prob[2], bowA[2], bowW[2];
-    std::vector<unsigned short> alias[2];
-    int specN[2] = { 1, 1 };
-    float specE0[2] = { 0, 0 }, specStep[2] = { 1, 1 };
-    double maxWeight = 1.0;
-};
+// FNV-1a over everything that defines a beam: the descriptor (pointers blanked) and the arrays it points to
+uint64_t beamHash(const dxb_beam_desc& b)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const auto* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i)
+            h = (h ^ c[i]) * 1099511628211ull;
+    };
+    dxb_beam_desc d = b;
+    for (int t = 0; t < 2; ++t) {
+        d.spectrum[t].energy_kev = d.spectrum[t].weight = nullptr;
+        d.bowtie[t].angle_rad = d.bowtie[t].weight = nullptr;
+    }
+    d.aec.weights = nullptr;
+    mix(&d, sizeof(d));
+    for (int t = 0; t < 2; ++t) {
+        if (b.spectrum[t].n && b.spectrum[t].energy_kev && b.spectrum[t].weight) {
+            mix(b.spectrum[t].energy_kev, b.spectrum[t].n * sizeof(double));
+            mix(b.spectrum[t].weight, b.spectrum[t].n * sizeof(double));
+        }
+        if (b.bowtie[t].n && b.bowtie[t].angle_rad && b.bowtie[t].weight) {
+            mix(b.bowtie[t].angle_rad, b.bowtie[t].n * sizeof(double));
+            mix(b.bowtie[t].weight, b.bowtie[t].n * sizeof(double));
+        }
+    }
+    if (b.aec.n && b.aec.weights)
+        mix(b.aec.weights, b.aec.n * sizeof(double));
+    return h ? h : 1;
+}
 
 int prepareBeam(dxb_ctx* c, const dxb_beam_desc& b, PreparedBeam& out)
 {
@@ -341,6 +362,9 @@ int prepareBeam(dxb_ctx* c, const dxb_beam_desc& b, PreparedBeam& out)
 
 int uploadBeam(dxb_ctx* c, DeviceState& d, const PreparedBeam& pb)
 {
+    if (pb.hash && d.uploadedBeam == pb.hash)
+        return DXB_OK; // the exposures, alias tables and bowtie knots of this very beam are already on the device
+    d.uploadedBeam = 0;
     CUDA_TRY(c, d.exposures.upload(pb.exposures, d.device, d.stream));
     for (int t = 0; t < 2; ++t) {
         CUDA_TRY(c, d.specProb[t].upload(pb.prob[t], d.device, d.stream));
@@ -348,6 +372,8 @@ int uploadBeam(dxb_ctx* c, DeviceState& d, const PreparedBeam& pb)
         CUDA_TRY(c, d.bowAngle[t].upload(pb.bowA[t], d.device, d.stream));
         CUDA_TRY(c, d.bowWeight[t].upload(pb.bowW[t], d.device, d.stream));
     }
+    // (pageable source vectors: the copies above have been staged by the time the calls return)
+    d.uploadedBeam = pb.hash;
     return DXB_OK;
 }
 
@@ -1148,10 +1174,19 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         return fail(c, DXB_EINVAL, "physics_mode must be 0, 1 or 2");
     if (c->devs.empty() || !c->devs[0]->world.hasGrid || !c->devs[0]->world.hasTables)
         return fail(c, DXB_ESTATE, "run: set materials and grid first");
-    PreparedBeam pb;
-    int rc = prepareBeam(c, *beam, pb);
-    if (rc != DXB_OK)
-        return rc;
+    // the same beam as last time (a job usually repeats a beam, or runs it again after a parameter study): the exposure
+    // expansion (thousands of poses), the alias tables and their upload are reused
+    const uint64_t bh = beamHash(*beam);
+    int rc = DXB_OK;
+    if (!c->lastBeam || c->lastBeam->hash != bh) {
+        auto fresh = std::make_unique<PreparedBeam>();
+        rc = prepareBeam(c, *beam, *fresh);
+        if (rc != DXB_OK)
+            return rc;
+        fresh->hash = bh;
+        c->lastBeam = std::move(fresh);
+    }
+    const PreparedBeam& pb = *c->lastBeam;
     chooseScales(c, pb, false);
     const uint64_t nDev = c->devs.size();
     const uint64_t effWorld = c->world * nDev;

@@ -165,7 +165,8 @@ struct DeviceState {
     DevBuf<ExposureDev> exposures;
     DevBuf<float> specProb[2], bowAngle[2], bowWeight[2];
     DevBuf<unsigned short> specAlias[2];
-    DevBuf<unsigned long long> counters; // [0] work cursor, [8..12] stats
+    uint64_t uploadedBeam = 0;           // hash of the beam whose arrays the buffers above hold (0: unknown)
+    DevBuf<unsigned long long> counters; // [0] work cursor, [8..14] stats
     cudaEvent_t evStart = nullptr, evTransport = nullptr, evEnd = nullptr;
     // nested CTDI run: hole id per phantom voxel (-1: none) and the five integer kerma sums
     DevBuf<signed char> ctdiHole;
@@ -187,6 +188,18 @@ struct DeviceState {
     // by the peers through CUDA IPC
     DevBuf<unsigned long long> mailbox;
     std::vector<const unsigned long long*> peerMailbox;
+};
+
+// a beam expanded for the device: exposures, alias tables, bowtie knots (context.cu: prepareBeam)
+struct PreparedBeam {
+    std::vector<ExposureDev> exposures;
+    uint64_t ppe = 0, nTotal = 0;
+    std::vector<float> prob[2], bowA[2], bowW[2];
+    std::vector<unsigned short> alias[2];
+    int specN[2] = { 1, 1 };
+    float specE0[2] = { 0, 0 }, specStep[2] = { 1, 1 };
+    double maxWeight = 1.0;
+    uint64_t hash = 0; // beamHash of the descriptor it was prepared from (0: not cached)
 };
 
 // CT calibration phantom (host side), cached per diameter
@@ -246,6 +259,7 @@ struct dxb_ctx {
     float scaleE = 16777216.0f, scaleE2 = 65536.0f; // 2^24, 2^16 fixed-point quanta per keV, keV^2
     int smCount = 148;
     bool tallyValid = false;
+    std::unique_ptr<dxb::PreparedBeam> lastBeam; // the last main beam, expanded (reused when the same beam runs again)
     std::shared_ptr<void> scene;            // the save file dxb_load_scene read (an h5mini::File), written back by dxb_save_dose
     std::unique_ptr<dxb::CtdiPhantom> ctdi; // host copy of the calibration phantom, built once per diameter
     // ---- tally exchange (exchange.cu).  In-process: one participant per device of this context; one process per GPU:
