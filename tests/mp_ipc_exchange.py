@@ -58,6 +58,30 @@ def main():
         assert ref[2].sum() > 0
         print("IPC_OK ranks=%d exchange_ms(pulls, reduce, clear)=%s" % (world_size, ["%.3f" % t for t in times]), flush=True)
     dist.barrier()
+    # the baseline exchange: distributed.run_beam = shard tallies -> NCCL int64 reduce to rank 0 -> calibration + energy->dose
+    # there (the reduce runs on torch's stream, energy->dose on the library's: run_beam orders the two)
+    world = wl.build_world(1, [local_rank])
+    world.set_history_range(rank, world_size)
+    world.set_calibration_histories(720_000)
+    world.set_seed(SEED)
+    tally = D.tally_tensor(world, local_rank)
+    f = [D.run_beam(world, wl.beam, tally, rank, use_beam_calibration=(k == 0)) for k in range(2)]
+    if rank == 0:
+        got = world.fetch_dose()
+        ref_world = wl.build_world(1, [local_rank])
+        ref_world.set_calibration_histories(720_000)
+        ref_world.set_seed(SEED)
+        tr = dx.Transport()
+        for k in range(2):
+            assert tr(ref_world, wl.beam, None, k == 0)
+        ref = ref_world.fetch_dose()
+        ref_world.close()
+        for a, b, name in zip(got, ref, ("dose", "variance", "events")):
+            assert np.array_equal(a, b), f"run_beam (NCCL reduce): {name} differs"
+        assert f[0] > 0
+        print("NCCL_REDUCE_OK", flush=True)
+    world.close()
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -396,7 +396,7 @@ def test_ipc_pipelined_exchange_matches_single_gpu_bit_for_bit():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mp_ipc_exchange.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert out.returncode == 0 and "IPC_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.returncode == 0 and "IPC_OK" in out.stdout and "NCCL_REDUCE_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
 def test_fused_exchange_matches_single_gpu_bit_for_bit():
