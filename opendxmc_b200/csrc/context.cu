@@ -1215,7 +1215,14 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         DeviceState& d = *c->devs[i];
         CUDA_TRY(c, cudaSetDevice(d.device));
         if (c->exchanging) {
-            // double-buffered tallies: the buffer of this beam was cleared by the exchange of the beam before the last one
+            // in-process: the exchange of the beam before goes onto the exchange stream first (it also clears the
+            // buffer this beam scores into); its pulls and reduce then run under this beam's kernels
+            if (c->pending.active) {
+                const int xr = mgExchangeOnDevice(c, d);
+                if (xr != DXB_OK)
+                    return xr;
+            }
+            // double-buffered tallies: the buffer of this beam is cleared by the exchange of the beam before
             if (!d.needsClear[d.world.cur])
                 CUDA_TRY(c, cudaStreamWaitEvent(d.stream, d.evBufReady[d.world.cur], 0));
             else // the last beam was never finished (its tallies are dropped, as without an exchange)
@@ -1236,12 +1243,14 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         return DXB_OK;
     };
     c->exchanged = false;
+    const bool hadPending = c->exchanging && c->pending.active;
     rc = nDev > 1 ? overDevices(c, launchOn) : launchOn(0);
     if (rc != DXB_OK)
         return rc;
-    // the previous beam's exchange is enqueued now, while every device runs this beam's kernels (exchange.cu)
-    if (c->exchanging && (rc = mgEnqueuePending(c)) != DXB_OK)
-        return rc;
+    if (hadPending) {
+        c->pending.active = false;
+        c->exchangeTimed = true;
+    }
     auto collectOn = [&](size_t i) -> int { return collectStats(c, *c->devs[i], results[i]); };
     rc = nDev > 1 ? overDevices(c, collectOn) : collectOn(0);
     if (rc != DXB_OK)
@@ -1265,15 +1274,20 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         progress->done.store(progress->total.load());
     if (cancelled)
         return fail(c, DXB_ECANCELLED, "cancelled");
-    if (c->ipc) {
-        // one process per GPU: before the caller's barrier tells the peers that they may clear the buffer of the PREVIOUS
-        // beam, this rank's pulls from it must have finished (they ran under the transport kernels just awaited)
-        DeviceState& d = *c->devs[0];
-        const int prev = d.world.cur ^ 1;
-        if (d.pullsPending[prev]) {
-            CUDA_TRY(c, cudaEventSynchronize(d.evPullsDone[prev]));
-            d.pullsPending[prev] = false;
+    if (c->exchanging) {
+        // before the peers may clear the buffer of the PREVIOUS beam (at the next exchange; with one process per GPU the
+        // caller's barrier tells them), this participant's pulls from it must have finished - they ran under the
+        // transport kernels just awaited
+        for (auto& dp : c->devs) {
+            DeviceState& d = *dp;
+            const int prev = d.world.cur ^ 1;
+            if (d.pullsPending[prev]) {
+                CUDA_TRY(c, cudaSetDevice(d.device));
+                CUDA_TRY(c, cudaEventSynchronize(d.evPullsDone[prev]));
+                d.pullsPending[prev] = false;
+            }
         }
+        CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
     }
     c->tallyValid = true;
     return DXB_OK;

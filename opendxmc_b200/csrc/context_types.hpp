@@ -179,7 +179,7 @@ struct DeviceState {
     cudaEvent_t evPullsDone[2] = { nullptr, nullptr };     // this device has pulled its slab of every peer's buffer b
     cudaEvent_t evTransportDone[2] = { nullptr, nullptr }; // the transport kernels scoring into buffer b have finished
     cudaEvent_t evTimer[2] = { nullptr, nullptr };         // dxb_timer_begin / dxb_timer_end
-    cudaEvent_t evX[4] = { nullptr, nullptr, nullptr, nullptr }; // exchange stream: before pulls, after pulls, after reduce, after clear
+    cudaEvent_t evX[4] = { nullptr, nullptr, nullptr, nullptr }; // exchange stream: before pulls, after pulls, after reduce, before the lazy clear
     bool pullsPending[2] = { false, false };
     bool needsClear[2] = { false, false };
     DevBuf<unsigned long long> staging; // (parts - 1) slabs of 4 x u64 per voxel
@@ -351,7 +351,8 @@ void mgDestroy(dxb_ctx* c);
 int mgSetGrid(dxb_ctx* c, const uint64_t dim[3], const double spacing[3], const double* density, const uint8_t* material);
 int mgPrepareExchange(dxb_ctx* c);                        // second tally buffer, staging, slabs (after the grid is known)
 int mgEnqueueExchange(dxb_ctx* c, double factor);         // pulls + slab reduce -> dose + clear, asynchronous
-int mgEnqueuePending(dxb_ctx* c);                         // in-process: the deferred enqueue (after the next beam's launch, or at a flush)
+int mgExchangeOnDevice(dxb_ctx* c, DeviceState& d);       // one device's share of the noted exchange
+int mgEnqueuePending(dxb_ctx* c);                         // the noted exchange on every device (serial; flush / IPC ranks)
 int mgFlush(dxb_ctx* c);                                  // every enqueued exchange has completed
 int mgGetDose(dxb_ctx* c, size_t begin, size_t end, double* dose, double* variance, uint64_t* events);
 int mgGatherDose(dxb_ctx* c);                             // device 0 receives every slab of the dose score

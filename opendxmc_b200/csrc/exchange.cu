@@ -239,10 +239,9 @@ int mgPrepareExchange(dxb_ctx* c)
 }
 
 // The exchange of the beam that was just finished.  One process per GPU: enqueued at once (the caller has just put a barrier
-// between the ranks' transport and this call).  In-process: only NOTED here and enqueued by mgEnqueuePending - from the
-// next dxb_run_transport right after its kernels have been launched on every device, or from a flush - because one host
-// thread issues some 30 driver calls per device for it, and the GPUs would idle meanwhile if that happened between two
-// beams; this way it happens while they run the next beam.
+// between the ranks' transport and this call).  In-process: only NOTED here; every device's launch thread of the next
+// dxb_run_transport enqueues its own share (mgExchangeOnDevice) right before it launches the next beam, so the ~30 driver
+// calls per device run in parallel over the devices, and a flush enqueues whatever is still only noted.
 int mgEnqueueExchange(dxb_ctx* c, double factor)
 {
     c->pending.active = true;
@@ -256,69 +255,61 @@ int mgEnqueueExchange(dxb_ctx* c, double factor)
     return c->ipc ? mgEnqueuePending(c) : DXB_OK;
 }
 
+// One device's share of the noted exchange, enqueued on its exchange stream: clear the OTHER buffer (lazily - see below),
+// pull this device's voxel slab of buffer b from every peer, reduce the slabs to dose.  No cross-device event is involved:
+//   * buffer b is complete on every participant - dxb_run_transport returned after synchronising the transport streams of
+//     all devices of the context, and with one process per GPU the caller separates it from dxb_finish_beam by a barrier;
+//   * buffer b^1 (the beam before) has been pulled by every peer - each participant waits for its own pulls at the end of
+//     dxb_run_transport (they ran under that beam's kernels), before the same barrier / before this call.
+int mgExchangeOnDevice(dxb_ctx* c, DeviceState& d)
+{
+    const int parts = c->parts;
+    const int b = c->pending.buffer;
+    World& w = d.world;
+    const size_t n = w.nvox;
+    const size_t ms = maxSlab(n, parts);
+    const double vol = w.spacing[0] * w.spacing[1] * w.spacing[2];
+    cudaStream_t xs = d.xstream;
+    CUDA_TRY(c, cudaSetDevice(d.device));
+    CUDA_TRY(c, cudaStreamWaitEvent(xs, d.evTransportDone[b], 0)); // (free: the host has already seen it)
+    CUDA_TRY(c, cudaEventRecord(d.evX[3], xs));
+    if (d.needsClear[b ^ 1]) {
+        unsigned long long* other = (b ^ 1) ? w.tally1.p : w.tally.p;
+        CUDA_TRY(c, cudaMemsetAsync(other, 0, n * 4 * sizeof(unsigned long long), xs));
+        CUDA_TRY(c, cudaEventRecord(d.evBufReady[b ^ 1], xs));
+        d.needsClear[b ^ 1] = false;
+    }
+    CUDA_TRY(c, cudaEventRecord(d.evX[0], xs));
+    const size_t bytes = (d.ve - d.vb) * 4 * sizeof(unsigned long long);
+    for (int k = 1; k < parts && bytes > 0; ++k) {
+        const int p = (d.part + k) % parts; // staggered: at any moment every participant serves one reader
+        const unsigned long long* src = d.peerTally[b][p] + d.vb * 4;
+        unsigned long long* dst = d.staging.p + static_cast<size_t>(k - 1) * ms * 4;
+        CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, xs));
+    }
+    CUDA_TRY(c, cudaEventRecord(d.evPullsDone[b], xs));
+    CUDA_TRY(c, cudaEventRecord(d.evX[1], xs));
+    d.pullsPending[b] = true;
+    const unsigned long long* local = b ? w.tally1.p : w.tally.p;
+    if (d.ve > d.vb)
+        reduceSlabsToDoseKernel<<<g_exchangeBlocks, 256, 0, xs>>>(local, d.staging.p, parts - 1, ms, w.voxels.p, d.dose.p, d.variance.p,
+            d.events.p, d.vb, d.ve, 1.0 / c->pending.scaleE, 1.0 / c->pending.scaleE2, c->pending.factor, vol);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(d.evX[2], xs));
+    d.needsClear[b] = true; // cleared by the next exchange
+    return DXB_OK;
+}
+
 int mgEnqueuePending(dxb_ctx* c)
 {
     if (!c->pending.active)
         return DXB_OK;
-    c->pending.active = false;
-    const int parts = c->parts;
-    const int b = c->pending.buffer;
-    const double factor = c->pending.factor;
-    const size_t n = c->devs[0]->world.nvox;
-    const size_t ms = maxSlab(n, parts);
-    const World& w0 = c->devs[0]->world;
-    const double vol = w0.spacing[0] * w0.spacing[1] * w0.spacing[2];
     for (auto& dp : c->devs) {
-        DeviceState& d = *dp;
-        World& w = d.world;
-        cudaStream_t xs = d.xstream;
-        CUDA_TRY(c, cudaSetDevice(d.device));
-        // the transport kernels that scored into buffer b have finished on every participant: dxb_run_transport returns
-        // after synchronising the transport streams of all devices of the context, and with one process per GPU the
-        // caller separates it from dxb_finish_beam by a barrier over the ranks.  (The event wait is free.)
-        CUDA_TRY(c, cudaStreamWaitEvent(xs, d.evTransportDone[b], 0));
-        if (c->ipc && d.needsClear[b ^ 1]) {
-            // one process per GPU: the same barrier also tells that every peer has pulled the PREVIOUS beam's buffer
-            // (each rank waits for its own pulls at the end of dxb_run_transport), so it can be cleared now
-            unsigned long long* other = (b ^ 1) ? w.tally1.p : w.tally.p;
-            CUDA_TRY(c, cudaMemsetAsync(other, 0, n * 4 * sizeof(unsigned long long), xs));
-            CUDA_TRY(c, cudaEventRecord(d.evBufReady[b ^ 1], xs));
-            d.needsClear[b ^ 1] = false;
-        }
-        CUDA_TRY(c, cudaEventRecord(d.evX[0], xs));
-        const size_t bytes = (d.ve - d.vb) * 4 * sizeof(unsigned long long);
-        for (int k = 1; k < parts && bytes > 0; ++k) {
-            const int p = (d.part + k) % parts; // staggered: at any moment every participant serves one reader
-            const unsigned long long* src = d.peerTally[b][p] + d.vb * 4;
-            unsigned long long* dst = d.staging.p + static_cast<size_t>(k - 1) * ms * 4;
-            CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, xs));
-        }
-        CUDA_TRY(c, cudaEventRecord(d.evPullsDone[b], xs));
-        CUDA_TRY(c, cudaEventRecord(d.evX[1], xs));
-        d.pullsPending[b] = true;
-        const unsigned long long* local = b ? w.tally1.p : w.tally.p;
-        if (d.ve > d.vb)
-            reduceSlabsToDoseKernel<<<g_exchangeBlocks, 256, 0, xs>>>(local, d.staging.p, parts - 1, ms, w.voxels.p, d.dose.p, d.variance.p,
-                d.events.p, d.vb, d.ve, 1.0 / c->pending.scaleE, 1.0 / c->pending.scaleE2, factor, vol);
-        CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaEventRecord(d.evX[2], xs));
-        d.needsClear[b] = true;
+        const int rc = mgExchangeOnDevice(c, *dp);
+        if (rc != DXB_OK)
+            return rc;
     }
-    if (!c->ipc) {
-        // in-process: buffer b is cleared as soon as every peer has pulled its slab of it (cross-device events)
-        for (auto& dp : c->devs) {
-            DeviceState& d = *dp;
-            World& w = d.world;
-            CUDA_TRY(c, cudaSetDevice(d.device));
-            for (auto& pp : c->devs)
-                if (pp.get() != &d)
-                    CUDA_TRY(c, cudaStreamWaitEvent(d.xstream, pp->evPullsDone[b], 0));
-            CUDA_TRY(c, cudaMemsetAsync(b ? w.tally1.p : w.tally.p, 0, n * 4 * sizeof(unsigned long long), d.xstream));
-            CUDA_TRY(c, cudaEventRecord(d.evBufReady[b], d.xstream));
-            CUDA_TRY(c, cudaEventRecord(d.evX[3], d.xstream));
-            d.needsClear[b] = false;
-        }
-    }
+    c->pending.active = false;
     c->exchangeTimed = true;
     CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
     return DXB_OK;
@@ -345,8 +336,8 @@ int mgFlush(dxb_ctx* c)
             c->exchangeMs[0] = ms;
         if (cudaEventElapsedTime(&ms, d0.evX[1], d0.evX[2]) == cudaSuccess)
             c->exchangeMs[1] = ms;
-        if (!c->ipc && cudaEventElapsedTime(&ms, d0.evX[2], d0.evX[3]) == cudaSuccess)
-            c->exchangeMs[2] = ms;
+        if (cudaEventElapsedTime(&ms, d0.evX[3], d0.evX[0]) == cudaSuccess)
+            c->exchangeMs[2] = ms; // the lazy clear of the other buffer (0 when there was nothing to clear)
         cudaGetLastError();
         c->exchangeTimed = false;
     }
