@@ -868,6 +868,7 @@ void dxb_destroy(dxb_ctx* c)
 {
     if (!c)
         return;
+    c->workers.reset();
     mgDestroy(c);
     for (auto& d : c->devs) {
         cudaSetDevice(d->device);
@@ -1174,6 +1175,7 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         return fail(c, DXB_EINVAL, "physics_mode must be 0, 1 or 2");
     if (c->devs.empty() || !c->devs[0]->world.hasGrid || !c->devs[0]->world.hasTables)
         return fail(c, DXB_ESTATE, "run: set materials and grid first");
+    const auto hostEntry = std::chrono::steady_clock::now();
     // the same beam as last time (a job usually repeats a beam, or runs it again after a parameter study): the exposure
     // expansion (thousands of poses), the alias tables and their upload are reused
     const uint64_t bh = beamHash(*beam);
@@ -1215,13 +1217,6 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         DeviceState& d = *c->devs[i];
         CUDA_TRY(c, cudaSetDevice(d.device));
         if (c->exchanging) {
-            // in-process: the exchange of the beam before goes onto the exchange stream first (it also clears the
-            // buffer this beam scores into); its pulls and reduce then run under this beam's kernels
-            if (c->pending.active) {
-                const int xr = mgExchangeOnDevice(c, d);
-                if (xr != DXB_OK)
-                    return xr;
-            }
             // double-buffered tallies: the buffer of this beam is cleared by the exchange of the beam before
             if (!d.needsClear[d.world.cur])
                 CUDA_TRY(c, cudaStreamWaitEvent(d.stream, d.evBufReady[d.world.cur], 0));
@@ -1243,14 +1238,11 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         return DXB_OK;
     };
     c->exchanged = false;
-    const bool hadPending = c->exchanging && c->pending.active;
+    const auto hostT0 = std::chrono::steady_clock::now();
     rc = nDev > 1 ? overDevices(c, launchOn) : launchOn(0);
     if (rc != DXB_OK)
         return rc;
-    if (hadPending) {
-        c->pending.active = false;
-        c->exchangeTimed = true;
-    }
+    const auto hostT1 = std::chrono::steady_clock::now();
     auto collectOn = [&](size_t i) -> int { return collectStats(c, *c->devs[i], results[i]); };
     rc = nDev > 1 ? overDevices(c, collectOn) : collectOn(0);
     if (rc != DXB_OK)
@@ -1270,6 +1262,15 @@ int dxb_run_transport(dxb_ctx* c, const dxb_beam_desc* beam, int physics_mode, d
         c->stats.kernel_launches += results[i].launches;
     }
     c->stats.transport_ms = msMax;
+    if (traceHost()) {
+        const auto hostT2 = std::chrono::steady_clock::now();
+        const auto us = [](auto a, auto b) { return std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+        std::fprintf(stderr, "[dxb host] run_transport: since last return %lld us, prepare %lld us, launch %lld us, wait+collect %lld us (kernel %.3f ms)\n",
+            static_cast<long long>(c->lastReturn.time_since_epoch().count() ? us(c->lastReturn, hostEntry) : -1),
+            static_cast<long long>(us(hostEntry, hostT0)), static_cast<long long>(us(hostT0, hostT1)),
+            static_cast<long long>(us(hostT1, hostT2)), msMax);
+    }
+    c->lastReturn = std::chrono::steady_clock::now();
     if (progress)
         progress->done.store(progress->total.load());
     if (cancelled)

@@ -7,6 +7,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -244,8 +248,82 @@ struct Options {
 
 } // namespace dxb
 
+namespace dxb {
+
+// One resident host thread per additional device of a context (the calling thread serves device 0): the multi-GPU paths
+// issue their per-device driver calls from these, bound to their device once, instead of spawning threads per call.
+class DeviceWorkers {
+public:
+    explicit DeviceWorkers(const std::vector<int>& devices) // devices[k]: CUDA ordinal served by worker k (device index k + 1)
+    {
+        for (size_t k = 0; k < devices.size(); ++k)
+            threads.emplace_back([this, k, dev = devices[k]]() { loop(k + 1, dev); });
+    }
+    ~DeviceWorkers()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+        }
+        cvWork.notify_all();
+        for (auto& t : threads)
+            t.join();
+    }
+    size_t size() const { return threads.size(); }
+    void post(const std::function<void(size_t)>* f)
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            task = f;
+            remaining = threads.size();
+            ++generation;
+        }
+        cvWork.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lock(m);
+        cvDone.wait(lock, [this]() { return remaining == 0; });
+        task = nullptr;
+    }
+
+private:
+    void loop(size_t index, int device)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(size_t)>* f = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(m);
+                cvWork.wait(lock, [&]() { return stop || generation != seen; });
+                if (stop)
+                    return;
+                seen = generation;
+                f = task;
+            }
+            cudaSetDevice(device);
+            (*f)(index);
+            {
+                std::lock_guard<std::mutex> lock(m);
+                --remaining;
+            }
+            cvDone.notify_one();
+        }
+    }
+    std::mutex m;
+    std::condition_variable cvWork, cvDone;
+    uint64_t generation = 0;
+    size_t remaining = 0;
+    bool stop = false;
+    const std::function<void(size_t)>* task = nullptr;
+    std::vector<std::thread> threads;
+};
+
+} // namespace dxb
+
 struct dxb_ctx {
     std::vector<std::unique_ptr<dxb::DeviceState>> devs;
+    std::unique_ptr<dxb::DeviceWorkers> workers; // created by the first overDevices() of a multi-device context
     std::vector<std::shared_ptr<dxb::Material>> materials;
     uint64_t seed = 0x0DDC0FFEEull;   // base Philox key (dxb_set_seed)
     uint64_t beamCounter = 0;         // dxb_run_transport calls since the last dxb_set_seed
@@ -276,11 +354,19 @@ struct dxb_ctx {
         float scaleE = 1, scaleE2 = 1;
     } pending;
     bool exchangeTimed = false;
+    std::chrono::steady_clock::time_point lastReturn {}; // DXB_TRACE_HOST=1: host time between two dxb_run_transport calls
     uint64_t mailSeq = 0;    // calibrated beams so far (the mailbox sequence number)
     double exchangeMs[4] = { 0, 0, 0, 0 }; // last flush: pulls, reduce, clear (CUDA events on the exchange stream of device 0)
 };
 
 namespace dxb {
+
+// DXB_TRACE_HOST=1: dxb_run_transport prints its host-side phase times to stderr (where does the time between kernels go)
+inline bool traceHost()
+{
+    static const bool on = [] { const char* e = std::getenv("DXB_TRACE_HOST"); return e && e[0] == '1'; }();
+    return on;
+}
 
 // (the multi-device paths report errors from one host thread per device)
 inline std::mutex& errorMutex()
@@ -306,28 +392,29 @@ inline int fail(dxb_ctx* c, int code, const std::string& msg)
         }                                                                                          \
     } while (0)
 
-// f(device index) on one host thread per device (each bound to its device): host-to-device and device-to-host copies of
-// pageable caller memory are staged by the driver and block the calling thread, so N links need N threads.
+// f(device index) on one host thread per device (each bound to its device; the caller's thread serves device 0): host-to-
+// device and device-to-host copies of pageable caller memory are staged by the driver and block the calling thread, so N
+// links need N threads - and N launch sequences issued side by side start the N GPUs together.  Not re-entrant.
 template <typename F>
 inline int overDevices(dxb_ctx* c, F f)
 {
     const size_t n = c->devs.size();
     std::vector<int> rc(n, DXB_OK);
-    std::vector<std::thread> threads;
-    for (size_t i = 1; i < n; ++i)
-        threads.emplace_back([&, i]() {
-            if (cudaSetDevice(c->devs[i]->device) != cudaSuccess) {
-                rc[i] = fail(c, DXB_ECUDA, "cudaSetDevice failed");
-                return;
-            }
-            rc[i] = f(i);
-        });
+    if (n > 1 && (!c->workers || c->workers->size() != n - 1)) {
+        std::vector<int> devices;
+        for (size_t i = 1; i < n; ++i)
+            devices.push_back(c->devs[i]->device);
+        c->workers = std::make_unique<DeviceWorkers>(devices);
+    }
+    const std::function<void(size_t)> task = [&](size_t i) { rc[i] = f(i); };
+    if (n > 1)
+        c->workers->post(&task);
     if (cudaSetDevice(c->devs[0]->device) != cudaSuccess)
         rc[0] = fail(c, DXB_ECUDA, "cudaSetDevice failed");
     else
         rc[0] = f(0);
-    for (auto& t : threads)
-        t.join();
+    if (n > 1)
+        c->workers->wait();
     cudaSetDevice(c->devs[0]->device);
     for (int r : rc)
         if (r != DXB_OK)

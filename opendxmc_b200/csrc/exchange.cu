@@ -238,10 +238,9 @@ int mgPrepareExchange(dxb_ctx* c)
     return DXB_OK;
 }
 
-// The exchange of the beam that was just finished.  One process per GPU: enqueued at once (the caller has just put a barrier
-// between the ranks' transport and this call).  In-process: only NOTED here; every device's launch thread of the next
-// dxb_run_transport enqueues its own share (mgExchangeOnDevice) right before it launches the next beam, so the ~30 driver
-// calls per device run in parallel over the devices, and a flush enqueues whatever is still only noted.
+// The exchange of the beam that was just finished, enqueued at once on every participant's exchange stream (in-process: by
+// the per-device host threads side by side, ~15 driver calls each); it runs underneath the next beam's transport kernels.
+// One process per GPU: the caller has just put a barrier between the ranks' transport and this call.
 int mgEnqueueExchange(dxb_ctx* c, double factor)
 {
     c->pending.active = true;
@@ -252,7 +251,7 @@ int mgEnqueueExchange(dxb_ctx* c, double factor)
     for (auto& dp : c->devs)
         dp->world.cur = c->pending.buffer ^ 1;
     c->exchanged = true;
-    return c->ipc ? mgEnqueuePending(c) : DXB_OK;
+    return mgEnqueuePending(c);
 }
 
 // One device's share of the noted exchange, enqueued on its exchange stream: clear the OTHER buffer (lazily - see below),
@@ -304,11 +303,10 @@ int mgEnqueuePending(dxb_ctx* c)
 {
     if (!c->pending.active)
         return DXB_OK;
-    for (auto& dp : c->devs) {
-        const int rc = mgExchangeOnDevice(c, *dp);
-        if (rc != DXB_OK)
-            return rc;
-    }
+    const int rc = c->devs.size() > 1 ? overDevices(c, [&](size_t i) -> int { return mgExchangeOnDevice(c, *c->devs[i]); })
+                                      : mgExchangeOnDevice(c, *c->devs[0]);
+    if (rc != DXB_OK)
+        return rc;
     c->pending.active = false;
     c->exchangeTimed = true;
     CUDA_TRY(c, cudaSetDevice(c->devs[0]->device));
