@@ -347,7 +347,7 @@ struct dxb_ctx {
     int parts = 1;           // participants
     bool exchanged = false;  // the last beam's tallies have been handed to the exchange (no longer readable)
     std::vector<void*> ipcOpened;
-    struct {                 // the exchange dxb_finish_beam asked for and mgEnqueuePending still has to enqueue (in-process)
+    struct {                 // parameters of the exchange dxb_finish_beam asked for (read by every device's mgExchangeOnDevice)
         bool active = false;
         int buffer = 0;
         double factor = 0;
@@ -439,7 +439,7 @@ int mgSetGrid(dxb_ctx* c, const uint64_t dim[3], const double spacing[3], const 
 int mgPrepareExchange(dxb_ctx* c);                        // second tally buffer, staging, slabs (after the grid is known)
 int mgEnqueueExchange(dxb_ctx* c, double factor);         // pulls + slab reduce -> dose + clear, asynchronous
 int mgExchangeOnDevice(dxb_ctx* c, DeviceState& d);       // one device's share of the noted exchange
-int mgEnqueuePending(dxb_ctx* c);                         // the noted exchange on every device (serial; flush / IPC ranks)
+int mgEnqueuePending(dxb_ctx* c);                         // the noted exchange on every device (side by side on the device threads)
 int mgFlush(dxb_ctx* c);                                  // every enqueued exchange has completed
 int mgGetDose(dxb_ctx* c, size_t begin, size_t end, double* dose, double* variance, uint64_t* events);
 int mgGatherDose(dxb_ctx* c);                             // device 0 receives every slab of the dose score

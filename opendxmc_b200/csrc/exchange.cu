@@ -10,8 +10,9 @@
 //     engines (cudaMemcpyPeerAsync over NVLink 5 / NVSwitch: no SM is involved, so the pulls run underneath the transport
 //     kernels of beam i + 1, which occupy every SM);
 //   * one streaming kernel then adds the N slabs (64-bit integers: order independent, bitwise identical to one GPU),
-//     converts energy to dose for the slab and accumulates it into r's part of the dose score, and the buffer is cleared
-//     once every peer has pulled from it.
+//     converts energy to dose for the slab and accumulates it into r's part of the dose score; the buffer is cleared
+//     lazily, at the head of the next exchange, when every peer is known to have pulled from it (mgExchangeOnDevice).
+// In-process, the per-device driver calls are issued side by side by the context's resident device threads (overDevices).
 // The dose score stays distributed (slab r on participant r) until it is read out: every device copies its own slab to
 // the caller's arrays over its own PCIe link, concurrently.  The grid upload is sharded the same way: device r uploads
 // and packs slab r of the caller's arrays, the packed 4-byte slabs are all-gathered by peer copies.
