@@ -686,7 +686,12 @@ def run_ours(args):
                 "none: no profiles/*traffic*.json was captured from the loaded library build " + build_id,
                 "library_build": build_id,
                 "algorithmic_bytes_per_launch": a_hist * hist_done / max(launches, 1.0),
-                "kernel": "transportKernelPool<1,false,true,16,0>", "peak_source": "measured" if peaks else "fallback",
+                "kernel": "transportKernelPool<1,false,true,16,0%s>" % (",false,false,true" if stats[-1].get("dense_box") else
+                                                                          ",true" if stats[-1].get("local_majorant") else ""),
+                "tracking": ("dense box: flights through the air around the patient, quad step at the global majorant inside"
+                             if stats[-1].get("dense_box") else "slab-local majorants" if stats[-1].get("local_majorant") else "global majorant"),
+                "flights_per_history": sum(s.get("hops", 0) for s in stats) / max(sum(s["histories"] for s in stats), 1),
+                "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_history": a_hist, "steps_per_history": S, "deposits_per_history": Dd,
                 "sector_bytes_per_history": (S + 3 * Dd) * 32.0, "sector_frac": (hist_done / n_gpus) * (S + 3 * Dd) * 32.0 / (kernel_ms * 1e-3) / 1e9 / peak,
                 "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / ms_total}

@@ -430,7 +430,7 @@ typedef struct dxb_run_stats {
     double   energy_deposited_kev; /* sum over tallies */
     uint64_t hops;            /* slab-local majorants: tentative steps that ended on a slab face (no voxel fetch) */
     int32_t  local_majorant;  /* 1: the last beam ran on the slab-local majorant build of the kernel */
-    int32_t  reserved;
+    int32_t  dense_box;       /* 1: the last beam ran on the dense-box build of the kernel (hops = box entries then) */
     uint64_t voxel_fetches;   /* voxel gathers actually issued (<= steps: the brick pre-filter skips certainly-virtual collisions) */
 } dxb_run_stats;
 int dxb_get_run_stats(const dxb_ctx*, dxb_run_stats* out);
@@ -447,6 +447,14 @@ int dxb_device_majorant(dxb_ctx*, const double* energy_kev, uint32_t n, float* o
  * track with mu_max(E) * ratio[s * 16 + b], ratio in (0, 1].  *useful = 1 when auto mode would use it.  ratio may be NULL
  * (sizes only); it receives n_slabs * 16 floats.  This is what a test hands to the CPU oracle so that both track identically. */
 int dxb_get_local_majorant(dxb_ctx*, int* n_slabs, int* shift, int* useful, float* ratio);
+/* The dense box built with the grid (option "dense_box": -1 auto, 0 off, 1 on; "dense_theta": a voxel is thin when its
+ * attenuation stays below this fraction of the majorant at every energy, default 0.02): box = first voxel index x y z and one
+ * past the last x y z of the bounding box of all voxels that are not thin, faces = the same as coordinates [cm] (f32, as the
+ * kernel uses them).  Inside the box the kernels track with mu_max(E), in the rest of the grid with mu_max(E) * ratio[band]
+ * (band = energy node index >> 5) - the air around a patient then costs one flight instead of a tentative step every ~2 cm.
+ * *built = 0: no box (all voxels thin, or the option was 0 when the grid was set); *useful = 1 when auto mode uses it.  Any
+ * pointer may be NULL.  This is what a test hands to the CPU oracle so that both track identically. */
+int dxb_get_dense_box(dxb_ctx*, int* built, int* useful, int box[6], float faces[6], float ratio[16]);
 
 /* CT segmentation, SURVEY §8f-1: HU -> (material, density)
  * R:src/libopendxmc/ctsegmentationpipeline.cpp:113-169 */

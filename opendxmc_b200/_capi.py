@@ -100,7 +100,7 @@ class dxb_run_stats(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("transport_ms", C.c_double), ("total_ms", C.c_double), ("calibration_ms", C.c_double),
         ("calibration_factor", C.c_double), ("energy_emitted_kev", C.c_double), ("energy_deposited_kev", C.c_double),
-        ("hops", C.c_uint64), ("local_majorant", C.c_int32), ("reserved", C.c_int32), ("voxel_fetches", C.c_uint64),
+        ("hops", C.c_uint64), ("local_majorant", C.c_int32), ("dense_box", C.c_int32), ("voxel_fetches", C.c_uint64),
     ]
 
 
@@ -192,6 +192,7 @@ SIGNATURES = {
     "dxb_get_run_stats": (C.c_int, [VP, C.POINTER(dxb_run_stats)]),
     "dxb_device_attenuation": (C.c_int, [VP, C.c_uint32, C.c_int, c_double_p, C.c_uint32, c_float_p]),
     "dxb_get_local_majorant": (C.c_int, [VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_float_p]),
+    "dxb_get_dense_box": (C.c_int, [VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_float_p, c_float_p]),
     "dxb_device_majorant": (C.c_int, [VP, c_double_p, C.c_uint32, c_float_p]),
     "dxb_icrp_import": (C.c_int, [VP, c_u8_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int, c_u8_p, c_u8_p, c_double_p, C.POINTER(VP)]),
     "dxb_icrp_plan": (C.c_int, [C.POINTER(VP), C.c_char_p, C.c_char_p, C.c_int, c_u8_p]),

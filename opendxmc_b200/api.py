@@ -1236,6 +1236,16 @@ class World:
                                              out.ctypes.data_as(K.c_float_p)), "dxb_device_attenuation", self._ctx)
         return out
 
+    def dense_box(self):
+        """the dense box built with the grid: dict(built, useful, box[6] voxel indices, faces[6] cm, ratio[16] outside / global majorant)"""
+        built, useful = C.c_int(), C.c_int()
+        box = (C.c_int * 6)()
+        faces = np.zeros(6, dtype=np.float32)
+        ratio = np.ones(16, dtype=np.float32)
+        _check(_lib().dxb_get_dense_box(self._ctx, C.byref(built), C.byref(useful), box, faces.ctypes.data_as(K.c_float_p),
+                                        ratio.ctypes.data_as(K.c_float_p)), "dxb_get_dense_box", self._ctx)
+        return {"built": bool(built.value), "useful": bool(useful.value), "box": [int(v) for v in box], "faces": faces, "ratio": ratio}
+
     def local_majorant(self):
         """the slab-local majorant table built with the grid: (n_slabs, shift, useful, ratio[n_slabs, 16], local / global majorant in (0, 1])"""
         n, sh, us = C.c_int(), C.c_int(), C.c_int()

@@ -179,6 +179,86 @@ int buildLocalMajorant(dxb_ctx* c, World& w, cudaStream_t s)
     return DXB_OK;
 }
 
+// Dense box (DB builds of the pool kernel): most of a CT volume is air around the patient, and with one majorant a photon pays
+// a tentative step every ~2 cm of it.  A voxel is THIN when its attenuation stays below theta x majorant at every energy node;
+// the dense box is the bounding box of all other voxels.  Inside it the kernel tracks with the global majorant, in the rest
+// of the grid with majorant x ratio[band], ratio = largest attenuation occurring outside the box / majorant (maximised over
+// the band's nodes, as for the slab table).  Box and ratios are what the oracle receives through dxb_get_dense_box.
+int buildDenseBox(dxb_ctx* c, World& w, cudaStream_t s)
+{
+    w.dbBuilt = false;
+    w.dbUseful = false;
+    if (w.hostTot.size() != static_cast<size_t>(w.n_mat) * kDevNE)
+        return DXB_OK;
+    std::vector<float> maj(kDevNE);
+    CUDA_TRY(c, cudaMemcpyAsync(maj.data(), w.majorant.p, kDevNE * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    // thin limit per material: rho * max_E tot_m(E) / majorant(E) <= theta
+    std::vector<unsigned int> scratch(256 + 256 + 6, 0u);
+    for (int m = 0; m < w.n_mat; ++m) {
+        double g = 0;
+        for (int node = 0; node < kDevNE; ++node)
+            if (maj[node] > 0)
+                g = std::max(g, static_cast<double>(w.hostTot[static_cast<size_t>(m) * kDevNE + node]) / maj[node]);
+        const float limit = g > 0 ? static_cast<float>(std::min(c->opt.denseTheta / g, 3.0e38)) : 3.0e38f;
+        unsigned int bits;
+        std::memcpy(&bits, &limit, sizeof(bits));
+        scratch[m] = bits & 0xFFFFFF00u; // (rounded down: a voxel exactly at the limit counts as dense)
+    }
+    const int nx = static_cast<int>(w.dim[0]), ny = static_cast<int>(w.dim[1]), nz = static_cast<int>(w.dim[2]);
+    int* boxInit = reinterpret_cast<int*>(scratch.data() + 512);
+    boxInit[0] = nx, boxInit[1] = ny, boxInit[2] = nz, boxInit[3] = boxInit[4] = boxInit[5] = -1;
+    CUDA_TRY(c, w.dbScratch.upload(scratch, w.device, s));
+    launchDenseBox(w.voxels.p, nx, ny, nz, w.dbScratch.p, reinterpret_cast<int*>(w.dbScratch.p + 512), s);
+    CUDA_TRY(c, cudaGetLastError());
+    launchOutsideMax(w.voxels.p, nx, ny, nz, reinterpret_cast<const int*>(w.dbScratch.p + 512), w.dbScratch.p + 256, s);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(scratch.data(), w.dbScratch.p, scratch.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    const int* box = reinterpret_cast<const int*>(scratch.data() + 512);
+    if (box[3] < 0)
+        return DXB_OK; // nothing but thin voxels: no box
+    double part = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        w.dbBox[a] = box[a];
+        w.dbBox[a + 3] = box[a + 3] + 1;
+        const float d = static_cast<float>(w.spacing[a]);
+        const float lo = static_cast<float>(-0.5 * static_cast<double>(w.dim[a]) * w.spacing[a]);
+        w.dbFaces[a] = std::fmaf(static_cast<float>(w.dbBox[a]), d, lo);
+        w.dbFaces[a + 3] = std::fmaf(static_cast<float>(w.dbBox[a + 3]), d, lo);
+        part *= static_cast<double>(w.dbBox[a + 3] - w.dbBox[a]) / static_cast<double>(w.dim[a]);
+    }
+    const int refBand = 378 >> 5;
+    for (int b = 0; b < kLmBands; ++b) {
+        const int n0 = b * 32, n1 = std::min(b * 32 + 32, kDevNE - 1);
+        float r = 0.0f;
+        for (int node = n0; node <= n1 && n0 < kDevNE; ++node) {
+            float mu = 0.0f;
+            for (int m = 0; m < w.n_mat; ++m) {
+                float rho;
+                const unsigned int q = scratch[256 + m];
+                std::memcpy(&rho, &q, sizeof(float));
+                const float v = rho * w.hostTot[static_cast<size_t>(m) * kDevNE + node];
+                mu = v > mu ? v : mu;
+            }
+            const float ratio = mu / maj[node];
+            r = ratio > r ? ratio : r;
+        }
+        w.dbRatio[b] = std::min(1.0f, std::max(r, 1.0e-6f) * (1.0f + 9.5367431640625e-7f));
+    }
+    w.dbBuilt = true;
+    // Worth it when the flights replace enough tentative steps to pay for themselves (a flight costs about three steps,
+    // profiles/r02_sweep_densebox.txt): the steps saved per history are about mu_max x the path outside the box, estimated
+    // from the linear sizes of grid and box (C2 / C4: 4 steps -> +13 / +15 %; the CTDI phantom: 0.6 steps -> off, it lost 6 %).
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a)
+        vol *= static_cast<double>(w.dim[a]) * w.spacing[a];
+    const double outsidePath = std::cbrt(vol) - std::cbrt(vol * part);
+    const double savedSteps = static_cast<double>(maj[378]) * outsidePath;
+    w.dbUseful = part < 0.85 && w.dbRatio[refBand] < 0.25f && savedSteps >= 2.5;
+    return DXB_OK;
+}
+
 // majorant from the per-material density maxima + the reference's material-index check; the grid becomes usable
 int finishGrid(dxb_ctx* c, World& w, cudaStream_t s)
 {
@@ -216,6 +296,14 @@ int finishGrid(dxb_ctx* c, World& w, cudaStream_t s)
     } else {
         w.lmSlabs = 0;
         w.lmUseful = false;
+    }
+    if (c->opt.denseBox != 0) {
+        const int rc = buildDenseBox(c, w, s);
+        if (rc != DXB_OK)
+            return rc;
+    } else {
+        w.dbBuilt = false;
+        w.dbUseful = false;
     }
     w.hasGrid = true;
     return DXB_OK;
@@ -469,6 +557,25 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
         }
         const bool bf = !lm && !calib && c->opt.brickFilter && w.brickN[0] > 0 && w.brickBound.p && c->opt.stepQuad && P.step_pairs == 2;
         cfg.brick_filter = bf;
+        // dense box: the production variant of the quad step (16 slots, 64 registers); auto = when the box built with the grid
+        // leaves enough of the grid outside
+        const bool db = !lm && !bf && !calib && w.dbBuilt && P.step_quad == 1 && c->opt.poolSlots == 16 && c->opt.poolMinBlocks == 0
+            && (c->opt.denseBox == 1 || (c->opt.denseBox < 0 && w.dbUseful));
+        cfg.dense_box = db;
+        if (db) {
+            for (int a = 0; a < 3; ++a) {
+                P.db_lo[a] = w.dbFaces[a];
+                P.db_hi[a] = w.dbFaces[a + 3];
+                P.db_i0[a] = w.dbBox[a];
+                P.db_n[a] = w.dbBox[a + 3] - w.dbBox[a];
+            }
+            for (int b = 0; b < 16; ++b)
+                P.db_ratio[b] = w.dbRatio[b];
+            double diag2 = 0;
+            for (int a = 0; a < 3; ++a)
+                diag2 += static_cast<double>(w.dim[a]) * w.spacing[a] * static_cast<double>(w.dim[a]) * w.spacing[a];
+            P.db_diag = static_cast<float>(std::sqrt(diag2) * 1.001);
+        }
         if (bf) {
             P.brick = w.brickBound.p;
             P.brick_shift = w.brickShift;
@@ -496,7 +603,7 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     cfg.smem += static_cast<size_t>(std::max(0, c->opt.smemPadKb)) * 1024;
     int perSm = c->opt.blocksPerSm;
     if (perSm <= 0) {
-        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks, cfg.local_majorant, cfg.brick_filter)
+        perSm = pool ? transportPoolOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem, cfg.min_blocks, cfg.local_majorant, cfg.brick_filter, cfg.dense_box)
             : mux  ? transportMuxOccupancy(mode, calib, cfg.table_in_smem, cfg.slots, cfg.threads, cfg.smem)
                    : transportOccupancy(mode, calib, cfg.table_in_smem, cfg.threads, cfg.smem);
         if (perSm <= 0)
@@ -504,7 +611,10 @@ int runOnDevice(dxb_ctx* c, DeviceState& d, World& w, const PreparedBeam& pb, in
     }
     cfg.blocks = c->smCount * perSm;
     if (!calib && d.part == 0) // (several devices launch from their own host threads: one of them reports)
+    {
         c->stats.local_majorant = cfg.local_majorant ? 1 : 0;
+        c->stats.dense_box = cfg.dense_box ? 1 : 0;
+    }
 
     const uint64_t nLocal = localCount(pb.nTotal, rank, world);
     CUDA_TRY(c, cudaMemsetAsync(d.counters.p + 8, 0, 24 * sizeof(unsigned long long), d.stream));
@@ -1140,6 +1250,15 @@ int dxb_set_option(dxb_ctx* c, const char* key, double value)
         if (v < 2 || v > 256 || (v & (v - 1)))
             return fail(c, DXB_EINVAL, "brick_voxels must be a power of two in 2..256");
         c->opt.brickVoxels = v;
+    } else if (k == "dense_box") {
+        const int v = static_cast<int>(value);
+        if (v < -1 || v > 1)
+            return fail(c, DXB_EINVAL, "dense_box must be -1 (auto), 0 (off) or 1 (on)");
+        c->opt.denseBox = v; // the box is built with the grid unless the option is 0 then; switching it off takes effect at once
+    } else if (k == "dense_theta") {
+        if (!(value > 0 && value < 1))
+            return fail(c, DXB_EINVAL, "dense_theta must be in (0, 1)");
+        c->opt.denseTheta = value; // takes effect with the next dxb_set_grid
     } else if (k == "local_majorant") {
         const int v = static_cast<int>(value);
         if (v < -1 || v > 1)
@@ -1665,6 +1784,27 @@ int dxb_device_attenuation(dxb_ctx* c, uint32_t material_index, int physics_mode
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(out4, dOut.p, static_cast<size_t>(n) * 4 * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
     CUDA_TRY(c, cudaStreamSynchronize(d0.stream));
+    return DXB_OK;
+}
+
+int dxb_get_dense_box(dxb_ctx* c, int* built, int* useful, int box[6], float faces[6], float ratio[16])
+{
+    if (!c || c->devs.empty() || !c->devs[0]->world.hasGrid)
+        return fail(c, DXB_ESTATE, "get_dense_box: no grid");
+    const World& w = c->devs[0]->world;
+    if (built)
+        *built = w.dbBuilt ? 1 : 0;
+    if (useful)
+        *useful = w.dbUseful ? 1 : 0;
+    for (int a = 0; a < 6; ++a) {
+        if (box)
+            box[a] = w.dbBuilt ? w.dbBox[a] : 0;
+        if (faces)
+            faces[a] = w.dbBuilt ? w.dbFaces[a] : 0.0f;
+    }
+    if (ratio)
+        for (int b = 0; b < 16; ++b)
+            ratio[b] = w.dbBuilt ? w.dbRatio[b] : 1.0f;
     return DXB_OK;
 }
 

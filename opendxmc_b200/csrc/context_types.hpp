@@ -113,6 +113,12 @@ struct World {
     std::vector<float> lmHost;           // host copy of lmRatio: local / global majorant, in (0, 1]
     int lmShift = 0, lmSlabs = 0;
     bool lmUseful = false;               // the table predicts a gain (mean ratio below the threshold)
+    // dense box (pool kernel, DB builds): bounding box of the voxels that are not thin, outside ratios
+    bool dbBuilt = false, dbUseful = false;
+    int dbBox[6] = { 0, 0, 0, 0, 0, 0 };          // first voxel index x y z, one past the last x y z
+    float dbFaces[6] = { 0, 0, 0, 0, 0, 0 };      // the same as coordinates [cm]: low x y z, high x y z
+    float dbRatio[16] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };
+    DevBuf<unsigned int> dbScratch;               // [256 thin limits][256 outside maxima][6 box words]
     // brick pre-filter (pool kernel, quad step): upper bounds of mu / mu_max per brick and energy octave
     DevBuf<unsigned char> brickBound;    // [brickN[0] * brickN[1] * brickN[2] * 8]
     int brickShift = 0, brickN[3] = { 0, 0, 0 };
@@ -239,6 +245,8 @@ struct Options {
     int brickFilter = 0;         // pool kernel, quad step: skip the gathers of certainly-virtual collisions (bit-identical results;
                                  // 4.5x fewer gathers on C2 but no faster: off by default)
     int brickVoxels = 16;        // brick edge in voxels (a power of two)
+    int denseBox = -1;           // pool kernel: dense-box tracking; -1 auto (on when the box is a small enough part of the grid), 0 off, 1 on
+    double denseTheta = 0.02;    // a voxel is thin when its attenuation stays below this fraction of the majorant at every energy
     int localMajorant = -1;      // pool kernel: slab-local majorants; -1 auto (on when the table predicts a gain), 0 off, 1 on
     double slabCm = 8.0;         // target slab thickness [cm] (rounded to a power-of-two number of voxel layers; profiles/r02_sweep.txt)
     int serviceWarps = 4;        // pool kernel: warps per block preferring interaction / Rayleigh / refill phases

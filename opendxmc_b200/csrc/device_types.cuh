@@ -113,6 +113,12 @@ struct RunParams {
     // is not below the bound is virtual whatever the voxel holds, so its gather is skipped.  nullptr: no filter.
     const unsigned char* __restrict__ brick; // [bricks * 8]
     int brick_shift, brick_nx, brick_ny;
+    // dense box (pool kernel, DB builds): every voxel that is not thin (air) lies inside the box; inside it the photons are
+    // tracked with mu_max(E), in the rest of the grid with mu_max(E) * db_ratio[band] (flights, transport_pool.cu)
+    float db_lo[3], db_hi[3];  // faces of the box [cm]
+    int db_i0[3], db_n[3];     // first voxel index and extent per axis
+    float db_ratio[16];        // kLmBands energy bands (energy node index >> 5)
+    float db_diag;             // length of the grid's diagonal [cm], rounded up: no path through the grid is longer
     unsigned int hbase_lo, hbase_hi; // mux kernel: global id of the first history of this launch (ids of one launch span < 2^32)
     unsigned long long* __restrict__ work_counter; // global cursor into [local_begin, local_end)
     unsigned long long* __restrict__ stats;        // [5]: steps, interactions, deposits, emitted (2^-16 keV), histories
@@ -157,6 +163,7 @@ struct LaunchConfig {
     int min_blocks; // pool kernel: 5 / 6 = the 48 / 40-register builds (5 / 6 blocks of <= 256 threads per SM), else 64 registers
     bool local_majorant; // pool kernel: the slab-local majorant build
     bool brick_filter;   // pool kernel: the brick pre-filter build of the quad step
+    bool dense_box = false; // pool kernel: the dense-box build of the quad step
 };
 
 } // namespace dxb

@@ -11,10 +11,12 @@ int transportMuxSlots(int mode, bool calib, bool smemTable, int slots); // slot 
 int transportMuxOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem);
 // block-pooled kernel (transport_pool.cu), cfg.slots photon slots per lane class
 cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const LaunchConfig& cfg, cudaStream_t stream);
-int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant = false, bool brickFilter = false);
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant = false, bool brickFilter = false);
+int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant = false, bool brickFilter = false, bool denseBox = false);
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant = false, bool brickFilter = false, bool denseBox = false);
 void setLaunchSmCount(int sms);
 void launchHoleSums(const unsigned long long* tally, const signed char* hole, size_t n, unsigned long long* sums, cudaStream_t s);
+void launchDenseBox(const unsigned int* voxels, int nx, int ny, int nz, const unsigned int* thin, int* box, cudaStream_t s);
+void launchOutsideMax(const unsigned int* voxels, int nx, int ny, int nz, const int* box, unsigned int* out, cudaStream_t s);
 void launchSlabMax(const unsigned int* voxels, size_t layerSize, int nz, int shift, int nslabs, unsigned int* out, cudaStream_t s);
 void launchBrickBound(const unsigned int* voxels, int nx, int ny, int nz, int shift, int nbx, int nby, int nbz, const float* tot,
     const float* majorant, int n_mat, unsigned char* out, cudaStream_t s);

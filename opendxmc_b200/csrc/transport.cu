@@ -470,6 +470,86 @@ __global__ void slabMaxKernel(const unsigned int* __restrict__ voxels, size_t la
             atomicMax(&out[slab * 256 + i], s_max[i]);
 }
 
+// Dense box (transport_pool.cu, DB builds): the bounding box, in voxel indices, of every voxel that is not thin - a voxel of
+// material m is thin when its 24-bit density does not exceed thin[m].  box = {min x, min y, min z, max x, max y, max z}
+// (initialised to {nx, ny, nz, -1, -1, -1} by the caller).  Rows along x are scanned by warps: coalesced, and the row's y / z
+// are warp-uniform.
+__global__ void denseBoxKernel(const unsigned int* __restrict__ voxels, int nx, int ny, int nz, const unsigned int* __restrict__ thin,
+    int* __restrict__ box)
+{
+    __shared__ unsigned int s_thin[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_thin[i] = thin[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t rows = static_cast<size_t>(ny) * nz;
+    int lo[3] = { nx, ny, nz }, hi[3] = { -1, -1, -1 };
+    for (size_t row = warp; row < rows; row += warps) {
+        const int y = static_cast<int>(row % ny), z = static_cast<int>(row / ny);
+        const unsigned int* r = voxels + row * nx;
+        int x0 = nx, x1 = -1;
+        for (int x = lane; x < nx; x += 32) {
+            const unsigned int v = r[x];
+            if ((v & 0xFFFFFF00u) > s_thin[v & 0xFFu]) {
+                x0 = min(x0, x);
+                x1 = max(x1, x);
+            }
+        }
+        if (x1 >= 0) {
+            lo[0] = min(lo[0], x0);
+            hi[0] = max(hi[0], x1);
+            lo[1] = min(lo[1], y);
+            hi[1] = max(hi[1], y);
+            lo[2] = min(lo[2], z);
+            hi[2] = max(hi[2], z);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0 && hi[a] >= 0) {
+            atomicMin(box + a, lo[a]);
+            atomicMax(box + 3 + a, hi[a]);
+        }
+    }
+}
+
+// ... and per material the largest 24-bit density among the voxels OUTSIDE that box: out[material]
+__global__ void outsideMaxKernel(const unsigned int* __restrict__ voxels, int nx, int ny, int nz, const int* __restrict__ box,
+    unsigned int* __restrict__ out)
+{
+    __shared__ unsigned int s_max[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        s_max[i] = 0u;
+    __syncthreads();
+    const int bx0 = box[0], by0 = box[1], bz0 = box[2], bx1 = box[3], by1 = box[4], bz1 = box[5];
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t rows = static_cast<size_t>(ny) * nz;
+    for (size_t row = warp; row < rows; row += warps) {
+        const int y = static_cast<int>(row % ny), z = static_cast<int>(row / ny);
+        const bool rowInside = y >= by0 && y <= by1 && z >= bz0 && z <= bz1;
+        const unsigned int* r = voxels + row * nx;
+        for (int x = lane; x < nx; x += 32) {
+            if (rowInside && x >= bx0 && x <= bx1)
+                continue;
+            const unsigned int v = r[x];
+            atomicMax(&s_max[v & 0xFFu], v & 0xFFFFFF00u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (s_max[i])
+            atomicMax(&out[i], s_max[i]);
+}
+
 // Brick pre-filter table (transport_pool.cu, quad step): one block per brick of 2^shift voxels per edge.  The block finds the
 // largest (24-bit) density per material inside the brick, then for each of the 8 energy octaves the largest ratio
 //   max_m rho_max(m) * tot_m(node) / majorant(node)   over the octave's nodes (both ends included: the kernels interpolate
@@ -903,6 +983,14 @@ void launchSlabMax(const unsigned int* voxels, size_t layerSize, int nz, int shi
 {
     const int parts = max(1, g_streamBlocks / max(nslabs, 1));
     slabMaxKernel<<<nslabs * parts, 256, 0, s>>>(voxels, layerSize, nz, shift, parts, out);
+}
+void launchDenseBox(const unsigned int* voxels, int nx, int ny, int nz, const unsigned int* thin, int* box, cudaStream_t s)
+{
+    denseBoxKernel<<<g_streamBlocks, 256, 0, s>>>(voxels, nx, ny, nz, thin, box);
+}
+void launchOutsideMax(const unsigned int* voxels, int nx, int ny, int nz, const int* box, unsigned int* out, cudaStream_t s)
+{
+    outsideMaxKernel<<<g_streamBlocks, 256, 0, s>>>(voxels, nx, ny, nz, box, out);
 }
 void launchBrickBound(const unsigned int* voxels, int nx, int ny, int nz, int shift, int nbx, int nby, int nbz, const float* tot,
     const float* majorant, int n_mat, unsigned char* out, cudaStream_t s)

@@ -105,6 +105,50 @@ __device__ __forceinline__ bool voxelIndex(const GridDev& G, float x, float y, f
 }
 
 // the same, plus the index of the brick (2^brick_shift voxels per edge) that holds the voxel
+// dense box (DB builds of the pool kernel): the tentative point's voxel, and whether it lies inside the box (which lies inside the grid)
+__device__ __forceinline__ bool voxelIndexBox(const GridDev& G, const RunParams& P, float x, float y, float z, unsigned int& index)
+{
+    const unsigned int ix = static_cast<unsigned int>(__float2int_rd(fmaf(x, G.inv_dx, G.offx)));
+    const unsigned int iy = static_cast<unsigned int>(__float2int_rd(fmaf(y, G.inv_dy, G.offy)));
+    const unsigned int iz = static_cast<unsigned int>(__float2int_rd(fmaf(z, G.inv_dz, G.offz)));
+    index = (iz * G.ny + iy) * G.nx + ix;
+    return ix - static_cast<unsigned int>(P.db_i0[0]) < static_cast<unsigned int>(P.db_n[0])
+        && iy - static_cast<unsigned int>(P.db_i0[1]) < static_cast<unsigned int>(P.db_n[1])
+        && iz - static_cast<unsigned int>(P.db_i0[2]) < static_cast<unsigned int>(P.db_n[2]);
+}
+// distance along (dx, dy, dz) from a point inside the axis-aligned box [lo, hi] to its boundary
+__device__ __forceinline__ float boxExitDistance(float x, float y, float z, float dx, float dy, float dz, float lox, float loy, float loz,
+    float hix, float hiy, float hiz)
+{
+    float t = 3.0e38f;
+    if (dx != 0.0f)
+        t = fminf(t, __fdividef((dx > 0.0f ? hix : lox) - x, dx));
+    if (dy != 0.0f)
+        t = fminf(t, __fdividef((dy > 0.0f ? hiy : loy) - y, dy));
+    if (dz != 0.0f)
+        t = fminf(t, __fdividef((dz > 0.0f ? hiz : loz) - z, dz));
+    return fmaxf(t, 0.0f);
+}
+// distance at which the ray enters the dense box (0 when it starts inside); false on a miss
+__device__ __forceinline__ bool boxEntryDistance(const RunParams& P, float x, float y, float z, float dx, float dy, float dz, float& tin)
+{
+    float tmin = 0.0f, tmax = 3.0e38f;
+    const float p[3] = { x, y, z }, d[3] = { dx, dy, dz };
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (d[a] == 0.0f) {
+            if (p[a] < P.db_lo[a] || p[a] > P.db_hi[a])
+                tmax = -1.0f;
+        } else {
+            const float inv = __fdividef(1.0f, d[a]);
+            const float t0 = (P.db_lo[a] - p[a]) * inv, t1 = (P.db_hi[a] - p[a]) * inv;
+            tmin = fmaxf(tmin, fminf(t0, t1));
+            tmax = fminf(tmax, fmaxf(t0, t1));
+        }
+    }
+    tin = tmin;
+    return tmax > tmin;
+}
 __device__ __forceinline__ bool voxelIndexBrick(const GridDev& G, const RunParams& P, float x, float y, float z, unsigned int& index, unsigned int& brick)
 {
     const unsigned int ix = static_cast<unsigned int>(__float2int_rd(fmaf(x, G.inv_dx, G.offx)));
@@ -359,7 +403,10 @@ __device__ __forceinline__ bool rayleighTry(const TablesDev& tab, int mat, float
 // grid; E and w are valid either way (the caller counts the emitted energy E * w).
 struct SourceSample {
     float px, py, pz, dx, dy, dz, E, w;
+    float chord;  // length of the ray's path through the grid
+    float spareK; // SPARE: word 1 of Philox block 1 as a 24-bit integer (the dense-box build draws its first flight from it)
 };
+template <bool SPARE = false>
 __device__ __forceinline__ bool sampleSource(const RunParams& P, unsigned long long h, SourceSample& q)
 {
     const GridDev& G = P.grid;
@@ -373,6 +420,11 @@ __device__ __forceinline__ bool sampleSource(const RunParams& P, unsigned long l
     const int tube = __ldg(&ex->tube);
     const SpectrumDev& spc = P.spec[tube];
     float E;
+    PhiloxBlock s1;
+    if (SPARE) {
+        s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
+        q.spareK = s1.k(1);
+    }
     if (spc.n <= 1) {
         E = spc.e0;
     } else {
@@ -381,7 +433,8 @@ __device__ __forceinline__ bool sampleSource(const RunParams& P, unsigned long l
             idx = __ldg(spc.alias + idx);
         E = fmaf(static_cast<float>(idx), spc.step, spc.e0);
         if (idx < spc.n - 1) {
-            const PhiloxBlock s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
+            if (!SPARE)
+                s1 = philox4x32_10(P.round_key, qlo, qhi, 1u);
             E = fmaf(s1.u(0), spc.step, E);
         }
     }
@@ -447,6 +500,7 @@ __device__ __forceinline__ bool sampleSource(const RunParams& P, unsigned long l
     q.px = fmaf(q.dx, tmin, q.px);
     q.py = fmaf(q.dy, tmin, q.py);
     q.pz = fmaf(q.dz, tmin, q.pz);
+    q.chord = tmax - tmin;
     return true;
 }
 

@@ -20,6 +20,8 @@ namespace {
 constexpr unsigned int kMetaBlkMask = 0xFFFFFu; // Philox block index of the history (20 bits)
 constexpr int kMetaMatShift = 20;               // material of the pending interaction (8 bits)
 constexpr unsigned int kMetaRetry = 1u << 28;   // Compton already chosen, previous candidate rejected
+constexpr unsigned int kMetaOut = 1u << 29;     // DB builds: the photon is outside the dense box
+constexpr unsigned int kMetaAir = 1u << 30;     // DB builds: it sits on a tentative collision of the outside region that awaits its acceptance number
 
 // A photon slot is three vectors, each stored lane-contiguously so that a warp moves it with one 128-bit (64-bit)
 // shared-memory access per vector, bank-conflict free:
@@ -85,7 +87,13 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
 // anywhere in the grid.  The optical depth drawn for a tentative step is marched through the slabs (piecewise constant
 // majorant), so the estimator stays unbiased.  Pays when the densest material is confined to part of the z range (teeth in
 // a whole-body phantom during a chest scan).
-template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false, bool BF = false>
+// DB: dense-box tracking.  Every voxel that is not thin (air) lies inside an axis-aligned box; inside it the
+// quad step runs at the global majorant, and the rest of the grid - most of a CT volume - is crossed in FLIGHTS at mu_max(E) *
+// db_ratio[band]: one optical depth from the grid's face to the box (refill phase, Philox block 2), one from the box face
+// to the grid's boundary when a tentative step ends beyond the box (its unused acceptance number).  A region boundary is
+// crossed without a collision, so by the memoryless property the walk restarts there with a fresh optical depth.  The
+// rare tentative collision in the outside region is resolved by the next step phase of that photon (kMetaOut / kMetaAir).
+template <int MODE, bool CALIB, bool SMEM_TABLE, int SPC, int LB, bool LM = false, bool BF = false, bool DB = false>
 __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transportKernelPool(const __grid_constant__ RunParams P)
 {
     static_assert(SPC >= 1 && SPC <= 16, "16 status bits per state");
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             }
             const int so = (active ? j : 0) * 32;
             float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, E = 0.f, w = 0.f;
-            unsigned int hlo = 0, hhi = 0, blk = 0;
+            unsigned int hlo = 0, hhi = 0, blk = 0, flags = 0;
             TabPos epos;
             epos.i = 0;
             epos.f = 0.f;
@@ -205,6 +213,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     w = slotC[so].w;
                 hlo = slotC[so].hlo;
                 blk = __float_as_uint(a.w) & kMetaBlkMask;
+                if (DB)
+                    flags = __float_as_uint(a.w) & (kMetaOut | kMetaAir);
                 hhi = P.hbase_hi + (hlo < P.hbase_lo ? 1u : 0u);
                 epos = energyPos(E);
                 const float muMax = lerp(s_maj[epos.i], s_maj[epos.i + 1], epos.f);
@@ -322,6 +332,52 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 // - but not the time: the kernel is bound by instruction issue and dependent latency, not by DRAM, and the
                 // brick lookup costs what the skipped gathers saved (4.83e9 vs 4.92e9 hist/s, profiles/r02_sweep_brickfilter.txt).
                 // Kept as an option (off): it halves the DRAM traffic, which matters when the memory system is shared.
+                if (DB && stepping && (flags & kMetaOut)) {
+                    // ---- a photon outside the dense box (rare here: it collided in the outside region).  One Philox block: the
+                    // acceptance of the waiting tentative collision (word 1), then a flight (word 2; word 0 if nothing waited)
+                    const PhiloxBlock r = philox4x32_10(P.round_key, hlo, hhi, blk);
+                    blk += 1u;
+                    const float outU24 = muMaxU24 * P.db_ratio[epos.i >> 5];
+                    newPhase = kPhDead;
+                    bool fly = true;
+                    float tau = __log2f(fmaf(r.k(0), -kU24, 1.0f)) * -kLn2;
+                    if (flags & kMetaAir) {
+                        tau = __log2f(fmaf(r.k(2), -kU24, 1.0f)) * -kLn2;
+                        unsigned int v;
+                        if (voxelIndex(G, px, py, pz, v)) {
+                            ++nSteps;
+                            const unsigned int cv = loadVoxel(G.voxels + v);
+                            mat = voxelMaterial(cv);
+                            const float* tt = totTable + epos.i;
+                            if (r.k(1) * outU24 < voxelDensity(cv) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f)) {
+                                newPhase = kPhInt;
+                                fly = false;
+                            }
+                        } else {
+                            fly = false; // (rounding put the point outside the grid)
+                        }
+                    }
+                    flags = kMetaOut;
+                    if (fly) {
+                        float tin;
+                        const bool hitBox = boxEntryDistance(P, px, py, pz, dx, dy, dz, tin);
+                        const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
+                        const float need = __fdividef(tau, outU24 * 16777216.0f);
+                        if (need < (hitBox ? tin : tg)) {
+                            px = fmaf(dx, need, px), py = fmaf(dy, need, py), pz = fmaf(dz, need, pz);
+                            flags = kMetaOut | kMetaAir;
+                            newPhase = kPhStep;
+                        } else if (hitBox) {
+                            px = fminf(fmaxf(fmaf(dx, tin, px), P.db_lo[0]), P.db_hi[0]);
+                            py = fminf(fmaxf(fmaf(dy, tin, py), P.db_lo[1]), P.db_hi[1]);
+                            pz = fminf(fmaxf(fmaf(dz, tin, pz), P.db_lo[2]), P.db_hi[2]);
+                            flags = 0u;
+                            ++nHops;
+                            newPhase = kPhStep;
+                        }
+                    }
+                    stepping = false;
+                }
                 if (stepping) {
                     const PhiloxBlock r1 = philox4x32_10(P.round_key, hlo, hhi, blk);
                     const PhiloxBlock r2 = philox4x32_10(P.round_key, hlo, hhi, blk + 1u);
@@ -334,10 +390,13 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     const float x2 = fmaf(dx, s2, x1), y2 = fmaf(dy, s2, y1), z2 = fmaf(dz, s2, z1);
                     const float x3 = fmaf(dx, s3, x2), y3 = fmaf(dy, s3, y2), z3 = fmaf(dz, s3, z2);
                     unsigned int v0, v1, v2, v3, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
-                    const bool in0 = BF ? voxelIndexBrick(G, P, x0, y0, z0, v0, b0) : voxelIndex(G, x0, y0, z0, v0);
-                    const bool in1 = (BF ? voxelIndexBrick(G, P, x1, y1, z1, v1, b1) : voxelIndex(G, x1, y1, z1, v1)) && in0;
-                    const bool in2 = (BF ? voxelIndexBrick(G, P, x2, y2, z2, v2, b2) : voxelIndex(G, x2, y2, z2, v2)) && in1;
-                    const bool in3 = (BF ? voxelIndexBrick(G, P, x3, y3, z3, v3, b3) : voxelIndex(G, x3, y3, z3, v3)) && in2;
+                    // (DB builds: "in" = inside the dense box; a tentative point beyond it ends the walk with a flight)
+                    const bool in0 = DB ? voxelIndexBox(G, P, x0, y0, z0, v0) : BF ? voxelIndexBrick(G, P, x0, y0, z0, v0, b0) : voxelIndex(G, x0, y0, z0, v0);
+                    const bool in1 = (DB ? voxelIndexBox(G, P, x1, y1, z1, v1) : BF ? voxelIndexBrick(G, P, x1, y1, z1, v1, b1) : voxelIndex(G, x1, y1, z1, v1)) && in0;
+                    const bool in2 = (DB ? voxelIndexBox(G, P, x2, y2, z2, v2) : BF ? voxelIndexBrick(G, P, x2, y2, z2, v2, b2) : voxelIndex(G, x2, y2, z2, v2)) && in1;
+                    const bool in3 = (DB ? voxelIndexBox(G, P, x3, y3, z3, v3) : BF ? voxelIndexBrick(G, P, x3, y3, z3, v3, b3) : voxelIndex(G, x3, y3, z3, v3)) && in2;
+                    bool exited = false; // DB: the walk left the box at a sub-step whose acceptance number is exitK
+                    float exitK = 0.0f;
                     // certainly virtual?  (u as a 24-bit integer against q << 16)
                     bool sk0 = false, sk1 = false, sk2 = false, sk3 = false;
                     if (BF) {
@@ -426,8 +485,35 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                                             real = r2.k(3) * muMaxU24 < voxelDensity(c3) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f);
                                         }
                                         newPhase = real ? kPhInt : kPhStep;
+                                    } else if (DB) {
+                                        exited = true;
+                                        exitK = r2.k(3);
                                     }
+                                } else if (DB) {
+                                    exited = true;
+                                    exitK = r2.k(1);
                                 }
+                            }
+                        } else if (DB) {
+                            exited = true;
+                            exitK = r1.k(3);
+                        }
+                    } else if (DB) {
+                        exited = true;
+                        exitK = r1.k(1);
+                    }
+                    if (DB && exited) {
+                        // left the box without a collision: one flight from the box face to the grid's boundary.  No path through
+                        // the grid is longer than its diagonal, so the geometry is only needed for the few flights that could end inside
+                        const float need = __fdividef(__log2f(fmaf(exitK, -kU24, 1.0f)) * -kLn2, muMaxU24 * P.db_ratio[epos.i >> 5] * 16777216.0f);
+                        if (need < P.db_diag) {
+                            const float tb = boxExitDistance(px, py, pz, dx, dy, dz, P.db_lo[0], P.db_lo[1], P.db_lo[2], P.db_hi[0], P.db_hi[1], P.db_hi[2]);
+                            const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
+                            if (need < tg - tb) {
+                                const float t = tb + need;
+                                px = fmaf(dx, t, px), py = fmaf(dy, t, py), pz = fmaf(dz, t, pz);
+                                flags = kMetaOut | kMetaAir;
+                                newPhase = kPhStep;
                             }
                         }
                     }
@@ -507,7 +593,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             }
             if (active) {
                 if (newPhase != kPhDead)
-                    slotA[so] = make_float4(px, py, pz, __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift)));
+                    slotA[so] = make_float4(px, py, pz, __uint_as_float(blk | (static_cast<unsigned int>(mat) << kMetaMatShift) | flags));
                 publishSlot(s_status, newPhase, j);
             }
         } else if (phase == kPhInt || phase == kPhRay) {
@@ -666,12 +752,33 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 const int so = j * 32;
                 if (r < nb && h < P.n_total) {
                     SourceSample q;
-                    hit = sampleSource(P, h, q);
+                    hit = sampleSource<DB>(P, h, q);
                     ++nHistories;
                     emitted += static_cast<unsigned long long>(__float2ll_rn(q.E * q.w * 65536.0f));
+                    const unsigned int meta0 = 2u; // blocks 0-1 belong to the source: the history continues with block 2
+                    unsigned int meta = meta0;
+                    if (DB && hit) {
+                        // the flight from the grid's face to the dense box; its optical depth comes from the spare word of
+                        // the source's second Philox block
+                        const TabPos ep = energyPos(q.E);
+                        const float outMu = lerp(s_maj[ep.i], s_maj[ep.i + 1], ep.f) * kU24 * P.db_ratio[ep.i >> 5] * 16777216.0f;
+                        float tin;
+                        const bool hitBox = boxEntryDistance(P, q.px, q.py, q.pz, q.dx, q.dy, q.dz, tin);
+                        const float need = __fdividef(__log2f(fmaf(q.spareK, -kU24, 1.0f)) * -kLn2, outMu);
+                        if (need < (hitBox ? tin : q.chord)) {
+                            q.px = fmaf(q.dx, need, q.px), q.py = fmaf(q.dy, need, q.py), q.pz = fmaf(q.dz, need, q.pz);
+                            meta |= kMetaOut | kMetaAir;
+                        } else if (hitBox) {
+                            q.px = fminf(fmaxf(fmaf(q.dx, tin, q.px), P.db_lo[0]), P.db_hi[0]);
+                            q.py = fminf(fmaxf(fmaf(q.dy, tin, q.py), P.db_lo[1]), P.db_hi[1]);
+                            q.pz = fminf(fmaxf(fmaf(q.dz, tin, q.pz), P.db_lo[2]), P.db_hi[2]);
+                            ++nHops;
+                        } else {
+                            hit = false; // through the air, past the box, out of the grid
+                        }
+                    }
                     if (hit) {
-                        // blocks 0-1 belong to the source: the history continues with block 2
-                        slotA[so] = make_float4(q.px, q.py, q.pz, __uint_as_float(2u));
+                        slotA[so] = make_float4(q.px, q.py, q.pz, __uint_as_float(meta));
                         slotB[so] = make_float4(q.dx, q.dy, q.dz, q.E);
                         SlotC c;
                         c.w = q.w;
@@ -697,10 +804,10 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
     }
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false, bool DB = false>
 cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t stream)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF, DB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
     if (e != cudaSuccess)
         return e;
@@ -708,10 +815,10 @@ cudaError_t launchPool(const RunParams& p, const LaunchConfig& cfg, cudaStream_t
     return cudaGetLastError();
 }
 
-template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false>
+template <int MODE, bool CALIB, bool SMEM, int M, int LB, bool LM = false, bool BF = false, bool DB = false>
 int occupancyPool(int threads, size_t smem)
 {
-    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF>;
+    auto kern = transportKernelPool<MODE, CALIB, SMEM, M, LB, LM, BF, DB>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -730,6 +837,15 @@ int occupancyPool(int threads, size_t smem)
 #define DXB_POOL_DISPATCH(CALL)                                                  \
     const int md = mode <= 0 ? 0 : (mode == 1 ? 1 : 2);                         \
     const int key = (md << 2) | (calib ? 2 : 0) | (smemTable ? 1 : 0);          \
+    if (denseBox && !brickFilter && !localMajorant && !calib)                   \
+        switch (key) {                                                          \
+        case 0: return CALL(0, false, false, 16, 0, false, false, true);        \
+        case 1: return CALL(0, false, true, 16, 0, false, false, true);         \
+        case 4: return CALL(1, false, false, 16, 0, false, false, true);        \
+        case 5: return CALL(1, false, true, 16, 0, false, false, true);         \
+        case 8: return CALL(2, false, false, 16, 0, false, false, true);        \
+        default: return CALL(2, false, true, 16, 0, false, false, true);        \
+        }                                                                       \
     if (brickFilter && !localMajorant && !calib)                                \
         switch (key) {                                                          \
         case 0: return CALL(0, false, false, 16, 0, false, true);               \
@@ -782,6 +898,7 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
     const bool smemTable = cfg.table_in_smem;
     const bool localMajorant = cfg.local_majorant;
     const bool brickFilter = cfg.brick_filter;
+    const bool denseBox = cfg.dense_box;
     const int slots = cfg.slots;
     const int lb = (cfg.threads <= 256 && (cfg.min_blocks == 5 || cfg.min_blocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? cfg.min_blocks : 0;
 #define DXB_CALL(...) launchPool<__VA_ARGS__>(p, cfg, stream)
@@ -789,17 +906,17 @@ cudaError_t launchTransportPool(const RunParams& p, int mode, bool calib, const 
 #undef DXB_CALL
 }
 
-int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant, bool brickFilter)
+int transportPoolSlots(int mode, bool calib, bool smemTable, int slots, bool localMajorant, bool brickFilter, bool denseBox)
 {
     // must mirror DXB_POOL_DISPATCH: only the production variant is built for several slot counts
-    if ((localMajorant || brickFilter) && !calib)
+    if ((localMajorant || brickFilter || denseBox) && !calib)
         return 16;
     if (mode == 1 && !calib && smemTable && (slots == 6 || slots == 8 || slots == 12))
         return slots;
     return 16;
 }
 
-int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant, bool brickFilter)
+int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int threads, size_t smem, int minBlocks, bool localMajorant, bool brickFilter, bool denseBox)
 {
     const int lb = (threads <= 256 && (minBlocks == 5 || minBlocks == 6) && (slots == 8 || slots == 12 || slots == 16)) ? minBlocks : 0;
 #define DXB_CALL(...) occupancyPool<__VA_ARGS__>(threads, smem)

@@ -116,6 +116,13 @@ struct RandomState {
         return { static_cast<double>(buf[0] >> 8) * (1.0 / 16777216.0), static_cast<double>(buf[1] >> 8) * (1.0 / 16777216.0),
             static_cast<double>(buf[2] >> 8) * (1.0 / 16777216.0), static_cast<double>(buf[3] >> 8) * (1.0 / 16777216.0) };
     }
+    // word `w` of block `b` of this history, as a uniform number (does not advance the stream)
+    double wordOfBlock(uint32_t b, int w) const
+    {
+        uint32_t c[4] = { ctr[0], ctr[1], b, ctr[3] }, out[4];
+        philox(key, c, out);
+        return static_cast<double>(out[w] >> 8) * (1.0 / 16777216.0);
+    }
     double randomUniform()
     {
         if (used == 4) {
@@ -526,6 +533,11 @@ struct AAVoxelGrid {
     // energy band b (= energy node index >> 5) the tracking majorant is majorant(E) * lmRatio[s * 16 + b]
     int lmShift = 0, lmSlabs = 0;
     std::vector<double> lmRatio;
+    // [D] dense-box tracking (transport_pool.cu, DB builds): an axis-aligned box holds every voxel that is not "thin" (air);
+    // inside it the tracking majorant is majorant(E), in the rest of the grid majorant(E) * boxRatio[band]
+    bool boxOn = false;
+    double boxLo[3] = { 0, 0, 0 }, boxHi[3] = { 0, 0, 0 }; // faces [cm] (the device's f32 values)
+    double boxRatio[16] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 };
 
     size_t size() const { return density.size(); }
     double voxelVolume() const { return spacing[0] * spacing[1] * spacing[2]; }
@@ -742,6 +754,138 @@ struct AAVoxelGrid {
         }
     }
 
+    // distance to the exit of the dense box along dir from a point inside it
+    double boxExitDistance(const Particle& p) const
+    {
+        double t = 3.0e38;
+        for (int i = 0; i < 3; ++i) {
+            if (p.dir[i] != 0) {
+                const double plane = p.dir[i] > 0 ? boxHi[i] : boxLo[i];
+                t = std::min(t, (plane - p.pos[i]) / p.dir[i]);
+            }
+        }
+        return std::max(t, 0.0);
+    }
+    // distance at which the ray enters the dense box (0 if it starts inside); false on a miss
+    bool boxIntersect(const Particle& p, double& tmin) const
+    {
+        tmin = 0;
+        double tmax = 3.0e38;
+        for (int i = 0; i < 3; ++i) {
+            if (p.dir[i] == 0) {
+                if (p.pos[i] < boxLo[i] || p.pos[i] > boxHi[i])
+                    return false;
+            } else {
+                const double t0 = (boxLo[i] - p.pos[i]) / p.dir[i], t1 = (boxHi[i] - p.pos[i]) / p.dir[i];
+                tmin = std::max(tmin, std::min(t0, t1));
+                tmax = std::min(tmax, std::max(t0, t1));
+            }
+        }
+        return tmax > tmin;
+    }
+
+    // [D] Woodcock tracking with a dense box.  Outside the box (air around the patient) the majorant is majorant(E) *
+    // boxRatio[band], inside it majorant(E).  A region boundary is crossed without a collision, so by the memoryless
+    // property the flight simply restarts there with a fresh optical depth:
+    //   * the first flight, from the grid's face to the box, draws its optical depth from the spare word 1 of the source's
+    //     second Philox block (block 1) and consumes no block of the transport stream;
+    //   * outside ("flight", one Philox block per flight): tau = -ln(1 - u0); the ray either has its tentative collision
+    //     in the outside region (accepted with mu / (majorant * ratio) by u1 of the NEXT block, after which u2 of that block
+    //     starts the next flight), or reaches the box and continues inside, or leaves the grid;
+    //   * inside: pairs of tentative steps at the global majorant exactly as woodcockTransport; a tentative step that
+    //     ends beyond the box face leaves the box, and the acceptance number of that step (unused otherwise) is the
+    //     optical depth of the flight from the face to the grid's boundary.
+    void woodcockTransportBox(Particle& p, int correction, RandomState& state, WorkerStats& st)
+    {
+        bool out = true;  // the history starts on the grid's face: fly to the box first
+        bool air = false; // a tentative collision in the outside region waits for its acceptance number
+        bool alive = true;
+        bool first = true;
+        while (alive) {
+            const double attMax = majorant(p.energy);
+            const size_t node = std::min<size_t>(static_cast<size_t>(std::max(0.0, materials[0].eCoord(p.energy))), materials[0].nE - 2);
+            const double attOut = g_mirror ? static_cast<double>(static_cast<float>(attMax) * static_cast<float>(boxRatio[node >> 5]))
+                                           : attMax * boxRatio[node >> 5];
+            std::array<double, 4> u { state.wordOfBlock(1, 1), 0, 0, 0 };
+            if (!first)
+                u = state.block();
+            first = false;
+            if (out) {
+                double tau;
+                if (air) {
+                    ++st.steps;
+                    const size_t flat = flatIndex(p.pos);
+                    const uint8_t matInd = materialIndex[flat];
+                    const OMaterial& mat = materials[matInd];
+                    const auto att = mat.attenuationValues(p.energy);
+                    const double attSum = att.sum() * density[flat];
+                    air = false;
+                    if (u[1] * attOut < attSum) {
+                        ++st.interactions;
+                        const auto res = interact(att, p, mat, correction, state);
+                        if (res.energyImparted > 0) {
+                            ++st.deposits;
+                            scoreEnergy(flat, res.energyImparted);
+                        }
+                        alive = res.particleAlive;
+                        continue; // still outside the box: the next block starts a flight
+                    }
+                    tau = -std::log(1.0 - u[2]);
+                } else {
+                    tau = -std::log(1.0 - u[0]);
+                }
+                double tIn = 0;
+                const bool hit = boxIntersect(p, tIn);
+                const double need = tau / attOut;
+                if (need < (hit ? tIn : exitDistance(p))) {
+                    p.translate(need);
+                    air = true;
+                } else if (hit) {
+                    p.translate(tIn);
+                    for (int i = 0; i < 3; ++i)
+                        p.pos[i] = std::min(std::max(p.pos[i], boxLo[i]), boxHi[i]);
+                    out = false;
+                    ++st.hops;
+                } else {
+                    alive = false;
+                }
+                continue;
+            }
+            for (int half = 0; half < 2; ++half) {
+                const double steplen = -std::log(1.0 - u[2 * half]) / attMax;
+                const double tB = boxExitDistance(p);
+                if (!(steplen < tB)) {
+                    const double need = -std::log(1.0 - u[2 * half + 1]) / attOut;
+                    if (need < exitDistance(p) - tB) {
+                        p.translate(tB + need);
+                        out = true;
+                        air = true;
+                    } else {
+                        alive = false;
+                    }
+                    break;
+                }
+                ++st.steps;
+                p.translate(steplen);
+                const size_t flat = flatIndex(p.pos);
+                const uint8_t matInd = materialIndex[flat];
+                const OMaterial& mat = materials[matInd];
+                const auto att = mat.attenuationValues(p.energy);
+                const double attSum = att.sum() * density[flat];
+                if (u[2 * half + 1] * attMax < attSum) {
+                    ++st.interactions;
+                    const auto res = interact(att, p, mat, correction, state);
+                    if (res.energyImparted > 0) {
+                        ++st.deposits;
+                        scoreEnergy(flat, res.energyImparted);
+                    }
+                    alive = res.particleAlive;
+                    break;
+                }
+            }
+        }
+    }
+
     // World::transport: move to the AABB, then track
     void transport(Particle& p, int correction, RandomState& state, WorkerStats& st)
     {
@@ -751,6 +895,8 @@ struct AAVoxelGrid {
         p.translate(tmin);
         if (lmSlabs >= 2 && scoreMaterial < 0)
             woodcockTransportSlabs(p, correction, state, st);
+        else if (boxOn && scoreMaterial < 0)
+            woodcockTransportBox(p, correction, state, st);
         else
             woodcockTransport(p, correction, state, st);
     }
@@ -1361,6 +1507,73 @@ int orc_world_build_local_majorant(orc_world* w, int shift)
         }
     }
     return g.lmSlabs;
+}
+
+// dense-box tracking: the box and outside ratios the device built (dxb_get_dense_box), or none (faces == NULL)
+void orc_world_set_dense_box(orc_world* w, const float* faces, const float* ratio)
+{
+    AAVoxelGrid& g = w->grid;
+    g.boxOn = faces && ratio;
+    if (!g.boxOn)
+        return;
+    for (int i = 0; i < 3; ++i) {
+        g.boxLo[i] = faces[i];
+        g.boxHi[i] = faces[i + 3];
+    }
+    for (int b = 0; b < 16; ++b)
+        g.boxRatio[b] = ratio[b];
+}
+// ... or the oracle's own box in f64 (no GPU needed): a voxel is thin when its attenuation stays below theta x majorant at
+// every energy; the box is the bounding box of all other voxels.  Returns 1 if the box is a proper part of the grid.
+int orc_world_build_dense_box(orc_world* w, double theta)
+{
+    AAVoxelGrid& g = w->grid;
+    g.boxOn = false;
+    const uint32_t nE = g.materials[0].nE;
+    std::vector<double> gm(g.materials.size(), 0.0);
+    for (size_t k = 0; k < g.materials.size(); ++k)
+        for (uint32_t node = 0; node < nE; ++node)
+            gm[k] = std::max(gm[k], (g.materials[k].photo[node] + g.materials[k].incoh[node] + g.materials[k].coh[node]) / g.woodcockStepTable[node]);
+    long lo[3] = { static_cast<long>(g.dim[0]), static_cast<long>(g.dim[1]), static_cast<long>(g.dim[2]) }, hi[3] = { -1, -1, -1 };
+    size_t i = 0;
+    for (long z = 0; z < static_cast<long>(g.dim[2]); ++z)
+        for (long y = 0; y < static_cast<long>(g.dim[1]); ++y)
+            for (long x = 0; x < static_cast<long>(g.dim[0]); ++x, ++i) {
+                if (g.density[i] * gm[g.materialIndex[i]] <= theta)
+                    continue;
+                const long c[3] = { x, y, z };
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = std::min(lo[a], c[a]);
+                    hi[a] = std::max(hi[a], c[a]);
+                }
+            }
+    if (hi[0] < 0)
+        return 0;
+    double vol = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.boxLo[a] = mf(g.aabb[a] + static_cast<double>(lo[a]) * g.spacing[a]);
+        g.boxHi[a] = mf(g.aabb[a] + static_cast<double>(hi[a] + 1) * g.spacing[a]);
+        vol *= static_cast<double>(hi[a] + 1 - lo[a]) / static_cast<double>(g.dim[a]);
+    }
+    std::vector<double> maxDens(g.materials.size(), 0.0);
+    i = 0;
+    for (long z = 0; z < static_cast<long>(g.dim[2]); ++z)
+        for (long y = 0; y < static_cast<long>(g.dim[1]); ++y)
+            for (long x = 0; x < static_cast<long>(g.dim[0]); ++x, ++i)
+                if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2])
+                    maxDens[g.materialIndex[i]] = std::max(maxDens[g.materialIndex[i]], g.density[i]);
+    for (uint32_t band = 0; band < 16; ++band) {
+        double r = 0;
+        for (uint32_t node = band * 32; node <= std::min(band * 32 + 32, nE - 1) && band * 32 < nE; ++node) {
+            double mu = 0;
+            for (size_t k = 0; k < g.materials.size(); ++k)
+                mu = std::max(mu, maxDens[k] * (g.materials[k].photo[node] + g.materials[k].incoh[node] + g.materials[k].coh[node]));
+            r = std::max(r, mu / g.woodcockStepTable[node]);
+        }
+        g.boxRatio[band] = mf(std::min(1.0, std::max(r, 1e-6) * (1.0 + 1e-6)));
+    }
+    g.boxOn = vol < 1.0;
+    return g.boxOn ? 1 : 0;
 }
 
 void orc_set_device_mirroring(int on) { g_mirror = on != 0; }

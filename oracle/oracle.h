@@ -45,6 +45,11 @@ void orc_world_destroy(orc_world*);
  * number of slabs). */
 void orc_world_set_local_majorant(orc_world*, int shift, int n_slabs, const float* ratio);
 int orc_world_build_local_majorant(orc_world*, int shift);
+/* Dense-box tracking (the kernel's DB builds): faces = {x0, y0, z0, x1, y1, z1} [cm] and the 16 outside ratios the device built
+ * (dxb_get_dense_box), NULL switches it off; or the oracle's own box from its f64 tables (thin voxel: attenuation <= theta x
+ * majorant at every energy; returns 1 if the box is a proper part of the grid). */
+void orc_world_set_dense_box(orc_world*, const float* faces, const float* ratio);
+int orc_world_build_dense_box(orc_world*, double theta);
 /* air + PMMA tables for the nested CTDI calibration and the DAP / air-kerma calibrations */
 void orc_world_set_reference_materials(orc_world*, const dxb_material_tables* air, const dxb_material_tables* pmma,
                                        double air_density, double pmma_density);

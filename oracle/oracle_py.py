@@ -46,6 +46,8 @@ def load():
         "orc_world_destroy": (None, [VP]),
         "orc_world_set_local_majorant": (None, [VP, C.c_int, C.c_int, K.c_float_p]),
         "orc_world_build_local_majorant": (C.c_int, [VP, C.c_int]),
+        "orc_world_set_dense_box": (None, [VP, K.c_float_p, K.c_float_p]),
+        "orc_world_build_dense_box": (C.c_int, [VP, C.c_double]),
         "orc_set_device_mirroring": (None, [C.c_int]),
         "orc_get_device_mirroring": (C.c_int, []),
         "orc_world_set_reference_materials": (None, [VP, MT, MT, C.c_double, C.c_double]),
@@ -137,6 +139,19 @@ class OracleWorld:
     def build_local_majorant(self, shift):
         """slab-local majorants from the oracle's own f64 table: slabs of 2**shift voxel layers; returns the slab count"""
         return int(load().orc_world_build_local_majorant(self._h, int(shift)))
+
+    def build_dense_box(self, theta=0.02):
+        """dense-box tracking from the oracle's own f64 tables; True if the box is a proper part of the grid"""
+        return bool(load().orc_world_build_dense_box(self._h, float(theta)))
+
+    def set_dense_box(self, faces, ratio):
+        """track with the box the device built (World.dense_box()); faces None switches it off"""
+        if faces is None:
+            load().orc_world_set_dense_box(self._h, None, None)
+            return
+        f = np.ascontiguousarray(faces, dtype=np.float32)
+        r = np.ascontiguousarray(ratio, dtype=np.float32)
+        load().orc_world_set_dense_box(self._h, f.ctypes.data_as(K.c_float_p), r.ctypes.data_as(K.c_float_p))
 
     def set_local_majorant(self, shift, n_slabs, ratio):
         """track with the table the device built (World.local_majorant()); n_slabs < 2 switches it off"""

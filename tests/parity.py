@@ -70,11 +70,22 @@ def assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, what="", voxel_cm=0.5, 
 
 def mirror_local_majorant(world, oracle_world):
     """The pool kernel tracks with slab-local majorants when the table built with the grid predicts a gain (option
-    local_majorant = -1, the default).  The oracle then has to track with the same table to stay on the same random-number
-    stream.  Returns True if the table was handed over."""
+    local_majorant = -1, the default), or with the dense box when that does (option dense_box = -1).  The oracle then has to
+    track with the same table / box to stay on the same random-number stream: call this AFTER the device run, it follows what
+    that run used (run_stats).  Returns True if a slab table was handed over."""
+    st = world.run_stats()
+    db = world.dense_box()
+    if st["dense_box"]:
+        assert db["built"]
+        oracle_world.set_dense_box(db["faces"], db["ratio"])
+    else:
+        oracle_world.set_dense_box(None, None)
     n, shift, useful, table = world.local_majorant()
-    if n >= 2 and useful:
+    if n >= 2 and (st["local_majorant"] if st["histories"] else useful):
         oracle_world.set_local_majorant(shift, n, table)
         return True
     oracle_world.set_local_majorant(0, 0, None)
     return False
+
+
+mirror_tracking = mirror_local_majorant

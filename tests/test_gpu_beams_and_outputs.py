@@ -540,6 +540,7 @@ def test_slab_local_majorants_on_the_device(dx, orc):
     for lm in (0, -1):
         world = wl.build_world(1, [0])
         world.set_option("local_majorant", lm)
+        world.set_option("dense_box", 0)   # (this test is about the slab table; the dense box has its own below)
         dx.Transport().run_transport(world, wl.beam)
         e, e2, cnt = [a.copy() for a in world.energy_scored()]
         st = world.run_stats()
@@ -574,6 +575,86 @@ def test_slab_local_majorants_on_the_device(dx, orc):
     assert n >= 2 and not useful and 0.0 < table.min() and table.max() <= 1.0
     dx.Transport().run_transport(world, c2.beam)
     assert world.run_stats()["local_majorant"] == 0
+    world.close()
+
+
+def test_dense_box_tracking_on_the_device(dx, orc):
+    """SURVEY §7 step 7 (region-local majorants), as a dense box: most of a CT volume is air around the patient, and the beam
+    is wider than the body.  The pool kernel's DB build crosses that air in flights and runs the quad step only inside the
+    bounding box of the non-thin voxels.  It must (a) follow the oracle on the same box draw for draw - all three physics
+    modes -, (b) take less than half the tentative steps of global tracking and give a statistically equal dose per tissue
+    class, (c) stay GPU-count invariant (shards sum to the whole bit for bit), (d) switch itself off where there is nothing
+    to skip (the CTDI phantom fills its grid) and when the option says so."""
+    wl = dx.workloads.ct_spiral_patient(scale=4, histories=2_000_000, step_deg=5.0)
+    res = {}
+    for db in (0, -1):
+        world = wl.build_world(1, [0])
+        world.set_option("dense_box", db)
+        dx.Transport().run_transport(world, wl.beam)
+        e, e2, cnt = [a.copy() for a in world.energy_scored()]
+        st = world.run_stats()
+        assert st["dense_box"] == (1 if db else 0) and st["local_majorant"] == 0
+        ow = orc.OracleWorld.from_workload(wl)
+        mirror_local_majorant(world, ow)
+        if db:
+            box = world.dense_box()
+            assert box["built"] and box["useful"] and 0 < box["ratio"].max() < 0.01
+            n = [box["box"][a + 3] - box["box"][a] for a in range(3)]
+            assert n[0] < wl.dim[0] and n[1] < wl.dim[1] and n[2] == wl.dim[2]
+            acc = [np.zeros_like(e), np.zeros_like(e2), np.zeros_like(cnt)]
+            for rank in range(3):
+                world.set_history_range(rank, 3)
+                world.set_seed(SEED)
+                dx.Transport().run_transport(world, wl.beam)
+                for a, b in zip(acc, world.energy_scored()):
+                    a += b
+            assert all(np.array_equal(a, b) for a, b in zip(acc, (e, e2, cnt)))
+        oe, oe2, ocnt, ost = ow.run(wl.beam, 1, SEED)
+        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"C2 scale 4 dense_box={db}", voxel_cm=min(wl.spacing))
+        assert abs(st["hops"] - ost["hops"]) <= max(30, 1e-5 * ost["hops"])
+        res[db] = (e, e2, st)
+        world.close()
+    (e0, s0, st0), (e1, s1, st1) = res[0], res[-1]
+    assert st1["hops"] > 0 and st0["hops"] == 0 and st1["steps"] < 0.5 * st0["steps"]
+    assert abs(st0["interactions"] - st1["interactions"]) / st0["interactions"] < 5e-3
+    sigma = np.sqrt(s0.sum() + s1.sum())
+    assert abs(e0.sum() - e1.sum()) / sigma < 4.0
+    for i, name in enumerate(wl.organ_names):
+        m = wl.organ == i
+        s = np.sqrt(s0[m].sum() + s1[m].sum())
+        assert s == 0 or abs(e0[m].sum() - e1[m].sum()) / s < 4.0, name
+    # modes 0 and 2 run their own builds of the kernel
+    small = dx.workloads.ct_spiral_patient(scale=8, histories=1_500_000, step_deg=10.0)
+    for mode in (0, 2):
+        world = small.build_world(mode, [0])
+        dx.Transport().run_transport(world, small.beam)
+        st = world.run_stats()
+        assert st["dense_box"] == 1
+        ow = orc.OracleWorld.from_workload(small)
+        mirror_local_majorant(world, ow)
+        oe, oe2, ocnt, ost = ow.run(small.beam, mode, SEED)
+        e, e2, cnt = world.energy_scored()
+        assert_same_stream_parity(e, cnt, st, oe, ocnt, ost, f"C2 scale 8 dense box mode {mode}", voxel_cm=min(small.spacing))
+        world.close()
+    # the CTDI phantom nearly fills its grid: the flights would cost more than the steps they save, auto mode leaves it alone
+    c1 = dx.workloads.ctdi_body_phantom(n=32, histories=50_000, step_deg=10.0)
+    world = c1.build_world(1, [0])
+    dx.Transport().run_transport(world, c1.beam)
+    box = world.dense_box()
+    assert box["built"] and not box["useful"] and world.run_stats()["dense_box"] == 0
+    world.close()
+    # a grid without thin voxels around its content: nothing to skip, the plain build runs
+    water = dx.Material.byNistName("Water, Liquid")
+    world = dx.World([0])
+    grid = world.addItem(dx.AAVoxelGrid(1))
+    assert grid.setData([24, 24, 24], np.ones(24 ** 3), np.zeros(24 ** 3, dtype=np.uint8), [water])
+    grid.setSpacing([1.0, 1.0, 1.0])
+    world.build()
+    beam = dx.PencilBeam([0.0, 0.0, -30.0], [0, 0, 1], 60.0)
+    beam.setNumberOfExposures(4)
+    beam.setNumberOfParticlesPerExposure(20_000)
+    dx.Transport().run_transport(world, beam)
+    assert world.run_stats()["dense_box"] == 0 and not world.dense_box()["useful"] and world.run_stats()["deposits"] > 0
     world.close()
 
 

@@ -10,7 +10,7 @@ At these sizes the oracle can only follow a few million histories in seconds, so
 import numpy as np
 import pytest
 
-from parity import assert_same_stream_parity
+from parity import assert_same_stream_parity, mirror_local_majorant
 
 pytestmark = pytest.mark.gpu
 
@@ -40,6 +40,8 @@ def test_c2_full_volume_matches_oracle(dx, orc, c2_full):
     e, e2, cnt = world.energy_scored()
     st = world.run_stats()
     ow = orc.OracleWorld.from_workload(wl)
+    mirror_local_majorant(world, ow)   # the kernel tracks this volume with the dense box: so does the oracle
+    assert st["dense_box"] == 1 and st["steps"] < 8 * st["histories"]   # (15.5 tentative steps per history without)
     oe, oe2, ocnt, ost = ow.run(wl.beam, 1, SEED)
     assert st["histories"] == ost["histories"] == wl.beam.numberOfParticles()
     # total deposited energy within 0.5 % (north_star); same Philox streams, so the real difference is f32 rounding
@@ -101,7 +103,8 @@ def test_c2_full_volume_is_deterministic_and_shard_invariant(dx, c2_full):
 def test_c2_full_volume_all_kernel_builds_agree(dx, c2_full):
     wl = c2_full
     ref = None
-    for opts in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 0, "slots_per_lane": 4}, {"pool_slots": 16}, {"pool_slots": 12, "pool_min_blocks": 5}):
+    for opts in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 0, "slots_per_lane": 4}, {"pool_slots": 16, "dense_box": 0},
+                 {"pool_slots": 12, "pool_min_blocks": 5}):
         world = wl.build_world(1, [0])
         for k, v in opts.items():
             world.set_option(k, v)

@@ -61,6 +61,7 @@ def test_c1_energy_and_roi_parity(dx, orc, c1, mode):
     e, e2, cnt = world.energy_scored()
     st = world.run_stats()
     ow = orc.OracleWorld.from_workload(c1)
+    mirror_local_majorant(world, ow)
     oe, oe2, ocnt, ost = ow.run(c1.beam, mode, SEED)
     assert st["histories"] == ost["histories"] == c1.beam.numberOfParticles()
     # total deposited energy within 0.5 %
@@ -121,6 +122,8 @@ def test_c2_small_parity(dx, orc):
     e, e2, cnt = world.energy_scored()
     st = world.run_stats()
     ow = orc.OracleWorld.from_workload(wl)
+    mirror_local_majorant(world, ow)
+    assert st["dense_box"] == 1   # air around the patient: the kernel tracks with the dense box, and so does the oracle
     oe, oe2, ocnt, ost = ow.run(wl.beam, 1, SEED)
     assert st["histories"] == ost["histories"]
     assert abs(e.sum() - oe.sum()) / oe.sum() <= 5e-3
@@ -145,6 +148,7 @@ def test_full_transport_dose_matches_oracle(dx, orc, c1):
     assert tr(world, c1.beam, prog, True)
     d, v, n = world._item.doseArrays()
     ow = orc.OracleWorld.from_workload(c1)
+    mirror_local_majorant(world, ow)
     od, ov, on, ost = ow.transport(c1.beam, 1, True, SEED, 3_600_000)
     f_gpu, f_cpu = world.run_stats()["calibration_factor"], ost["calibration_factor"]
     assert abs(f_gpu - f_cpu) / f_cpu < 0.02, (f_gpu, f_cpu)
@@ -181,7 +185,7 @@ def test_cpp_shim_runs_the_reference_driver(tmp_path):
     assert dose[mat > 0].sum() > 0 and dose[mat == 0].sum() == 0  # delete_air = 1
 
 
-KERNELS = [{"pool_slots": 16}, {"pool_slots": 12, "step_pairs": 1}, {"pool_slots": 8, "step_pairs": 3, "service_warps": 0},
+KERNELS = [{"pool_slots": 16, "dense_box": 0}, {"pool_slots": 12, "step_pairs": 1}, {"pool_slots": 8, "step_pairs": 3, "service_warps": 0},
            {"pool_slots": 6, "refill_threshold": 4, "service_warps": 8},
            {"pool_slots": 0, "slots_per_lane": 4, "step_pairs": 1}, {"pool_slots": 0, "slots_per_lane": 2, "step_pairs": 2},
            {"pool_slots": 0, "slots_per_lane": 6, "step_pairs": 3}]
@@ -217,7 +221,7 @@ def test_kernels_agree_on_calibration_run_and_many_materials(dx):
              dx.workloads.icrp_phantom("AM", scale=4, histories=400_000)]
     for w in cases:
         res = []
-        for o in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 16, "local_majorant": 0}):   # same tracking rule on both sides
+        for o in ({"pool_slots": 0, "slots_per_lane": 0}, {"pool_slots": 16, "local_majorant": 0, "dense_box": 0}):   # same tracking rule on both sides
             world = w.build_world(1, [0])
             world.set_calibration_histories(360_000)
             for k, v in o.items():
@@ -328,6 +332,7 @@ def test_brick_pre_filter_is_bit_exact(dx, brick_voxels):
             world.set_option("brick_filter", filt)
             world.set_option("brick_voxels", brick_voxels)
             world.set_option("local_majorant", 0)
+            world.set_option("dense_box", 0)       # (the filter belongs to the plain quad step)
             world.build()                       # the table is built with the grid
             dx.Transport().run_transport(world, wl.beam)
             out.append((*[a.copy() for a in world.energy_scored()], world.run_stats()))

@@ -338,3 +338,53 @@ def test_slab_local_majorants_leave_the_dose_unchanged(dx, orc):
     masks["lower"] = ~masks["upper"]
     masks["dense"] = wl.density > 1.2
     assert _roi_sigma(e, e2, f, f2, masks) < 4.0
+
+
+@pytest.mark.parametrize("energy", [30.0, 80.0])
+def test_beer_lambert_through_the_dense_box(dx, orc, energy):
+    """Dense-box tracking (flights through the thin voxels around a box that holds everything else, the global majorant
+    inside): the first-collision probability of a pencil beam through air / water / bone / water / air must still be
+    1 - exp(-sum mu t) - the air in front of and behind the box is crossed in flights, not in tentative steps."""
+    water = dx.Material.byNistName("Water, Liquid")
+    bone = dx.Material.byNistName("Bone, Cortical (ICRP)")
+    air = dx.Material.byNistName("Air, Dry (near sea level)")
+    mats, dens = [water, bone, air], [1.0, 1.92, 1.2e-3]
+    n, t = 64, 16.0
+    layer = lambda k: 2 if k < 20 else (0 if k < 32 else (1 if k < 38 else (0 if k < 44 else 2)))
+    beam = dx.PencilBeam([0.0, 0.0, -10.0], [0, 0, 1], energy)
+    beam.setNumberOfExposures(4)
+    beam.setNumberOfParticlesPerExposure(100_000)
+    res = {}
+    for box in (False, True):
+        ow, density, material, spacing = _column_world(dx, orc, mats, dens, layer, n, t)
+        if box:
+            assert ow.build_dense_box(0.02)
+        e, e2, cnt, st = ow.run(beam, 1)
+        res[box] = st
+    thick = t / n
+    tau = sum(dens[layer(k)] * mats[layer(k)].attenuationValues(energy).sum() * thick for k in range(n))
+    expect = 1.0 - math.exp(-tau)
+    nh = res[True]["histories"]
+    for box in (False, True):
+        p = res[box]["interactions"] / nh
+        sigma = math.sqrt(expect * (1 - expect) / nh)
+        assert abs(p - expect) < 4 * sigma + 2e-4, (box, p, expect, sigma)
+    assert res[True]["hops"] > 0 and res[False]["hops"] == 0
+    assert res[True]["steps"] < 0.8 * res[False]["steps"]
+
+
+def test_dense_box_leaves_the_dose_unchanged(dx, orc):
+    """C2-shaped patient (air around an elliptical body) under a spiral beam that is wider than the body: with the dense box
+    the oracle takes less than half the tentative steps and scores a statistically identical dose in every tissue class."""
+    wl = dx.workloads.ct_spiral_patient(scale=4, histories=400_000, step_deg=5.0)
+    a = orc.OracleWorld.from_workload(wl)
+    e, e2, cnt, st = a.run(wl.beam, 1)
+    b = orc.OracleWorld.from_workload(wl)
+    assert b.build_dense_box(0.02)
+    f, f2, fcnt, ft = b.run(wl.beam, 1)
+    assert ft["hops"] > 0 and ft["steps"] < 0.5 * st["steps"]
+    s = math.sqrt(e2.sum() + f2.sum())
+    assert abs(e.sum() - f.sum()) / s < 4.0
+    assert abs(st["interactions"] - ft["interactions"]) / st["interactions"] < 0.01
+    masks = {nm: wl.material.reshape(-1) == i for i, nm in enumerate(["air", "lung", "soft", "bone"])}
+    assert _roi_sigma(e, e2, f, f2, masks) < 4.0
