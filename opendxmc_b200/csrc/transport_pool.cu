@@ -80,6 +80,78 @@ __device__ __forceinline__ void publishSlot(unsigned int* words /* [2] of the cl
     atomicOr(words + phaseWord(phase), 1u << (phaseShift(phase) + j));
 }
 
+// ---- dense-box builds: the rare paths live out of line, so that they do not widen the instruction footprint of the phase loop
+// (the kernel body sits at the edge of the 32 KB instruction cache)
+struct OutsideVisit {
+    float px, py, pz;
+    unsigned int flags, blk;
+    int newPhase, mat;
+    unsigned int steps, hops;
+};
+// A photon outside the dense box is claimed by a step phase (it collided in the outside region).  One Philox block: the
+// acceptance of the waiting tentative collision (word 1), then a flight (word 2; word 0 if nothing waited).
+__device__ __noinline__ OutsideVisit outsideVisit(const RunParams& P, const float* __restrict__ totTable, float px, float py, float pz,
+    float dx, float dy, float dz, unsigned int hlo, unsigned int hhi, unsigned int blk, unsigned int flags, int eposI, float eposF,
+    float muMaxU24)
+{
+    const GridDev& G = P.grid;
+    OutsideVisit o;
+    o.steps = o.hops = 0u;
+    o.mat = 0;
+    const PhiloxBlock r = philox4x32_10(P.round_key, hlo, hhi, blk);
+    o.blk = blk + 1u;
+    const float outU24 = muMaxU24 * P.db_ratio[eposI >> 5];
+    o.newPhase = kPhDead;
+    bool fly = true;
+    float tau = __log2f(fmaf(r.k(0), -kU24, 1.0f)) * -kLn2;
+    if (flags & kMetaAir) {
+        tau = __log2f(fmaf(r.k(2), -kU24, 1.0f)) * -kLn2;
+        unsigned int v;
+        if (voxelIndex(G, px, py, pz, v)) {
+            o.steps = 1u;
+            const unsigned int cv = loadVoxel(G.voxels + v);
+            o.mat = voxelMaterial(cv);
+            const float* tt = totTable + eposI;
+            if (r.k(1) * outU24 < voxelDensity(cv) * lerp(tt[o.mat * kDevNE], tt[o.mat * kDevNE + 1], eposF)) {
+                o.newPhase = kPhInt;
+                fly = false;
+            }
+        } else {
+            fly = false; // (rounding put the point outside the grid)
+        }
+    }
+    o.flags = kMetaOut;
+    if (fly) {
+        float tin;
+        const bool hitBox = boxEntryDistance(P, px, py, pz, dx, dy, dz, tin);
+        const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
+        const float need = __fdividef(tau, outU24 * 16777216.0f);
+        if (need < (hitBox ? tin : tg)) {
+            px = fmaf(dx, need, px), py = fmaf(dy, need, py), pz = fmaf(dz, need, pz);
+            o.flags = kMetaOut | kMetaAir;
+            o.newPhase = kPhStep;
+        } else if (hitBox) {
+            px = fminf(fmaxf(fmaf(dx, tin, px), P.db_lo[0]), P.db_hi[0]);
+            py = fminf(fmaxf(fmaf(dy, tin, py), P.db_lo[1]), P.db_hi[1]);
+            pz = fminf(fmaxf(fmaf(dz, tin, pz), P.db_lo[2]), P.db_hi[2]);
+            o.flags = 0u;
+            o.hops = 1u;
+            o.newPhase = kPhStep;
+        }
+    }
+    o.px = px, o.py = py, o.pz = pz;
+    return o;
+}
+// A flight from the box face towards the grid's boundary whose optical depth `need` [cm at the outside majorant] is shorter
+// than the grid's diagonal: does it end inside the grid?  Returns the distance from (px, py, pz) to that point, or a negative number.
+__device__ __noinline__ float exitFlightEnd(const RunParams& P, float px, float py, float pz, float dx, float dy, float dz, float need)
+{
+    const GridDev& G = P.grid;
+    const float tb = boxExitDistance(px, py, pz, dx, dy, dz, P.db_lo[0], P.db_lo[1], P.db_lo[2], P.db_hi[0], P.db_hi[1], P.db_hi[2]);
+    const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
+    return need < tg - tb ? tb + need : -1.0f;
+}
+
 // LB: register budget through the launch bounds.  0: 64 registers (<= 512 threads per block, 1024 resident threads per SM);
 // 5 / 6: <= 256 threads per block with 5 / 6 resident blocks per SM (48 / 40 registers, a few spilled words).
 // LM: slab-local majorants.  The grid is cut into slabs of 2^lm_shift voxel layers along z; inside a slab the
@@ -190,7 +262,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             // ------------------------------------------------------------ pairs of tentative Woodcock steps
             const int j = claimSlot(s_status + 0, 0, wa, rot);
             const bool active = j >= 0;
-            if (P.diag) {
+            if (!DB && P.diag) {
                 const int n = __popc(__ballot_sync(kFull, active));
                 if (lane == 0) {
                     atomicAdd(P.stats + 8 + kPhStep, 1ull);
@@ -319,7 +391,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     }
                 }
             } else
-            if (!CALIB && P.step_quad) {
+            if (!CALIB && (DB || P.step_quad)) { // (the DB build is only launched for the quad step)
                 // Two step pairs with all four voxel gathers in flight at once: the second pair (block blk + 1) is
                 // speculative and is simply not consumed if the first pair ends in a real collision or outside the grid
                 // (counter-based generator: the same block is regenerated when the history gets there).
@@ -333,49 +405,15 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                 // brick lookup costs what the skipped gathers saved (4.83e9 vs 4.92e9 hist/s, profiles/r02_sweep_brickfilter.txt).
                 // Kept as an option (off): it halves the DRAM traffic, which matters when the memory system is shared.
                 if (DB && stepping && (flags & kMetaOut)) {
-                    // ---- a photon outside the dense box (rare here: it collided in the outside region).  One Philox block: the
-                    // acceptance of the waiting tentative collision (word 1), then a flight (word 2; word 0 if nothing waited)
-                    const PhiloxBlock r = philox4x32_10(P.round_key, hlo, hhi, blk);
-                    blk += 1u;
-                    const float outU24 = muMaxU24 * P.db_ratio[epos.i >> 5];
-                    newPhase = kPhDead;
-                    bool fly = true;
-                    float tau = __log2f(fmaf(r.k(0), -kU24, 1.0f)) * -kLn2;
-                    if (flags & kMetaAir) {
-                        tau = __log2f(fmaf(r.k(2), -kU24, 1.0f)) * -kLn2;
-                        unsigned int v;
-                        if (voxelIndex(G, px, py, pz, v)) {
-                            ++nSteps;
-                            const unsigned int cv = loadVoxel(G.voxels + v);
-                            mat = voxelMaterial(cv);
-                            const float* tt = totTable + epos.i;
-                            if (r.k(1) * outU24 < voxelDensity(cv) * lerp(tt[mat * kDevNE], tt[mat * kDevNE + 1], epos.f)) {
-                                newPhase = kPhInt;
-                                fly = false;
-                            }
-                        } else {
-                            fly = false; // (rounding put the point outside the grid)
-                        }
-                    }
-                    flags = kMetaOut;
-                    if (fly) {
-                        float tin;
-                        const bool hitBox = boxEntryDistance(P, px, py, pz, dx, dy, dz, tin);
-                        const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
-                        const float need = __fdividef(tau, outU24 * 16777216.0f);
-                        if (need < (hitBox ? tin : tg)) {
-                            px = fmaf(dx, need, px), py = fmaf(dy, need, py), pz = fmaf(dz, need, pz);
-                            flags = kMetaOut | kMetaAir;
-                            newPhase = kPhStep;
-                        } else if (hitBox) {
-                            px = fminf(fmaxf(fmaf(dx, tin, px), P.db_lo[0]), P.db_hi[0]);
-                            py = fminf(fmaxf(fmaf(dy, tin, py), P.db_lo[1]), P.db_hi[1]);
-                            pz = fminf(fmaxf(fmaf(dz, tin, pz), P.db_lo[2]), P.db_hi[2]);
-                            flags = 0u;
-                            ++nHops;
-                            newPhase = kPhStep;
-                        }
-                    }
+                    // a photon outside the dense box (rare here: it collided in the outside region)
+                    const OutsideVisit o = outsideVisit(P, totTable, px, py, pz, dx, dy, dz, hlo, hhi, blk, flags, epos.i, epos.f, muMaxU24);
+                    px = o.px, py = o.py, pz = o.pz;
+                    flags = o.flags;
+                    blk = o.blk;
+                    newPhase = o.newPhase;
+                    mat = o.mat;
+                    nSteps += o.steps;
+                    nHops += o.hops;
                     stepping = false;
                 }
                 if (stepping) {
@@ -416,7 +454,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                     // step_quad == 2 (experiment): the speculative second pair is only PREFETCHED into L2 and loaded when the
                     // walk gets there, so that no unconsumed load is outstanding when the slot is published (the release
                     // fence waits for every load in flight)
-                    const bool prefetchOnly = P.step_quad == 2;
+                    const bool prefetchOnly = !DB && P.step_quad == 2;
                     if (in2 && !sk2) {
                         if (prefetchOnly)
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(G.voxels + v2));
@@ -507,10 +545,8 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
                         // the grid is longer than its diagonal, so the geometry is only needed for the few flights that could end inside
                         const float need = __fdividef(__log2f(fmaf(exitK, -kU24, 1.0f)) * -kLn2, muMaxU24 * P.db_ratio[epos.i >> 5] * 16777216.0f);
                         if (need < P.db_diag) {
-                            const float tb = boxExitDistance(px, py, pz, dx, dy, dz, P.db_lo[0], P.db_lo[1], P.db_lo[2], P.db_hi[0], P.db_hi[1], P.db_hi[2]);
-                            const float tg = boxExitDistance(px, py, pz, dx, dy, dz, G.x0, G.y0, G.z0, G.x1, G.y1, G.z1);
-                            if (need < tg - tb) {
-                                const float t = tb + need;
+                            const float t = exitFlightEnd(P, px, py, pz, dx, dy, dz, need);
+                            if (t >= 0.0f) {
                                 px = fmaf(dx, t, px), py = fmaf(dy, t, py), pz = fmaf(dz, t, pz);
                                 flags = kMetaOut | kMetaAir;
                                 newPhase = kPhStep;
@@ -600,7 +636,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             // ------------------------------------------------------------ one sampling try per claimed photon
             const int j = claimSlot(s_status + phaseWord(phase), phaseShift(phase), phase == kPhInt ? wa : wb, rot);
             const bool active = j >= 0;
-            if (P.diag) {
+            if (!DB && P.diag) {
                 const int n = __popc(__ballot_sync(kFull, active));
                 if (lane == 0) {
                     atomicAdd(P.stats + 8 + phase, 1ull);
@@ -720,7 +756,7 @@ __global__ void __launch_bounds__(LB == 0 ? 512 : 256, LB == 0 ? 2 : LB) transpo
             const int j = claimSlot(s_status + 1, 16, wb, rot);
             const unsigned int mGot = __ballot_sync(kFull, j >= 0);
             const int want = __popc(mGot);
-            if (P.diag && lane == 0) {
+            if (!DB && P.diag && lane == 0) {
                 atomicAdd(P.stats + 8 + kPhDead, 1ull);
                 atomicAdd(P.stats + 12 + kPhDead, static_cast<unsigned long long>(want));
             }

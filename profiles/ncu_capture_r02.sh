@@ -10,5 +10,5 @@ ncu --set full --clock-control none --import-source on -k regex:transportKernelP
     python profiles/ncu_target.py c2 > $OUT/r02_pool_target.json 2> $OUT/r02_pool_target.err
 ncu --set full --clock-control none --import-source on -k regex:transportKernelPool -s 1 -c 1 -o $OUT/r02_pool_lm -f \
     python profiles/ncu_target.py c3 > $OUT/r02_pool_lm_target.json 2> $OUT/r02_pool_lm_target.err
-tail -2 $OUT/r02_pool_target.json $OUT/r02_pool_lm_target.json
+tail -n 2 $OUT/r02_pool_target.json; tail -n 2 $OUT/r02_pool_lm_target.json
 ls -la $OUT/*.ncu-rep
