@@ -911,11 +911,6 @@ int initDevice(dxb_ctx* c, DeviceState& d)
 // ============================================================================ C ABI
 extern "C" {
 
-#ifndef DXB_KERNEL_BUILD_ID
-#define DXB_KERNEL_BUILD_ID "unknown"
-#endif
-const char* dxb_kernel_build_id(void) { return DXB_KERNEL_BUILD_ID; }
-
 int dxb_device_count(void)
 {
     int n = 0;

@@ -961,3 +961,11 @@ int transportPoolOccupancy(int mode, bool calib, bool smemTable, int slots, int 
 }
 
 } // namespace dxb
+
+// Identity of the shipped transport kernel: hash of this file, transport_common.cuh, device_types.cuh and the nvcc flags
+// (Makefile: KERNEL_ID).  Defined HERE so that it cannot be older than the kernel it names; bench.py reports a measured
+// DRAM traffic only from an ncu capture whose id equals this one.
+#ifndef DXB_KERNEL_BUILD_ID
+#define DXB_KERNEL_BUILD_ID "unknown"
+#endif
+extern "C" const char* dxb_kernel_build_id(void) { return DXB_KERNEL_BUILD_ID; }

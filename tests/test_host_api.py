@@ -508,3 +508,17 @@ def test_icrp_import_golden_from_the_reference(dx):
         assert media_names == case["media_names"]
         for c, rc in zip(comps, case["media_composition"]):
             assert c == {int(z): w for z, w in rc.items()}
+
+
+def test_kernel_build_id_names_the_kernel_sources():
+    """dxb_kernel_build_id() keys the ncu traffic capture bench.py is allowed to quote (profiles/*traffic*.json): it is the
+    hash of the transport kernel's sources + nvcc flags, compiled into the kernel's own translation unit - a library built
+    from other kernel sources must report another id."""
+    import hashlib
+    import os
+    from opendxmc_b200 import _capi as K
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha256()
+    for f in ("transport_pool.cu", "transport_common.cuh", "device_types.cuh"):
+        h.update(open(os.path.join(root, "opendxmc_b200", "csrc", f), "rb").read())
+    assert K.load().dxb_kernel_build_id().decode().split("-")[0] == h.hexdigest()[:16]
