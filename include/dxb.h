@@ -328,7 +328,10 @@ uint64_t dxb_shard_local_count(uint64_t n_total, uint64_t rank, uint64_t world);
 uint64_t dxb_shard_history_id(uint64_t local_index, uint64_t rank, uint64_t world);
 int dxb_set_calibration_histories(dxb_ctx*, uint64_t n);      /* nested CTDI run size */
 int dxb_set_stream(dxb_ctx*, void* cuda_stream);              /* launch on a caller-owned stream (device 0 of the ctx) */
-int dxb_set_option(dxb_ctx*, const char* key, double value);  /* tuning knobs, see DESIGN.md */
+/* Tuning knobs; none changes a result except the four that select the tracking variant - "dense_box" and
+ * "local_majorant" (-1 auto, 0 off, 1 on), "dense_theta", "slab_cm" - which change the random walk, not its expectation
+ * (0 / 0 = plain Woodcock tracking with one majorant, the reference's rule).  Unknown keys return DXB_EINVAL. */
+int dxb_set_option(dxb_ctx*, const char* key, double value);
 
 /* Transport::operator()(world, beam, progress, useBeamCalibration) — R:src/libopendxmc/simulationpipeline.cpp:165.
  * Blocking. Clears the energy tallies, runs all histories of the beam, reduces across the
