@@ -325,7 +325,9 @@ def cpu_oracle_rate(args, wl, target_seconds):
             "sample": "%d histories (%d per exposure x %d exposures) of the same beam through the full volume, %.1f s" % (
                 st["histories"], s["ppe"], s["nexp"], st["seconds"]),
             "steps_per_history": st["steps"] / st["histories"], "deposits_per_history": st["deposits"] / st["histories"],
-            "deposited_kev_per_history": s["deposited_per_history"]}
+            "deposited_kev_per_history": s["deposited_per_history"],
+            "tracking": "Woodcock tracking with one global majorant, the reference's rule (the GPU arm may track the air around the "
+                        "patient in flights, roofline.tracking: same expectation, fewer tentative steps)"}
 
 
 def run_reference(args):
