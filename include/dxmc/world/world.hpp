@@ -51,6 +51,26 @@ public:
             const int rc = dxb_create(&m_ctx, devs.empty() ? nullptr : devs.data(), static_cast<int>(devs.size()));
             if (rc != DXB_OK)
                 throw std::runtime_error("dxmc::World::build: dxb_create failed (no CUDA device? there is no CPU fallback)");
+            // DXMC_B200_OPTIONS="key=value,key=value": dxb_set_option for an application that cannot be recompiled, e.g.
+            // "dense_box=0,local_majorant=0" = plain Woodcock tracking with one majorant (the reference's rule)
+            if (const char* opts = std::getenv("DXMC_B200_OPTIONS")) {
+                std::string tok;
+                for (char ch : std::string(opts) + ",") {
+                    if (ch != ',') {
+                        tok.push_back(ch);
+                        continue;
+                    }
+                    const auto eq = tok.find('=');
+                    if (eq != std::string::npos && eq > 0) {
+                        const std::string key = tok.substr(0, eq);
+                        if (dxb_set_option(m_ctx, key.c_str(), std::atof(tok.c_str() + eq + 1)) != DXB_OK)
+                            throw std::runtime_error("dxmc::World::build: DXMC_B200_OPTIONS: " + std::string(dxb_last_error(m_ctx)));
+                    } else if (!tok.empty()) {
+                        throw std::runtime_error("dxmc::World::build: DXMC_B200_OPTIONS: expected key=value, got '" + tok + "'");
+                    }
+                    tok.clear();
+                }
+            }
         }
         const int rc = m_item->upload(m_ctx);
         if (rc != DXB_OK)

@@ -647,3 +647,13 @@ def test_second_start_simulation_on_the_same_pipeline(tmp_path):
     assert r.returncode == 0, (r.stdout, r.stderr)
     meta = json.load(open(prefix + ".json"))
     assert meta["second_run_identical"] == 1
+
+
+def test_world_shim_rejects_a_malformed_options_variable(tmp_path):
+    """DXMC_B200_OPTIONS="key=value,..." lets an application that cannot be recompiled reach dxb_set_option (e.g. the reference's
+    tracking rule: dense_box=0,local_majorant=0); a malformed entry must stop the run loudly, not be ignored."""
+    env = dict(os.environ, DXMC_B200_OPTIONS="nonsense")
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "opendxmc_ref_cpu"), "run", "1", "1", "600", str(tmp_path / "opt"), "1.0", "sequential"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode != 0
+    assert "DXMC_B200_OPTIONS: expected key=value" in r.stderr
