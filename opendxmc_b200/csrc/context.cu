@@ -113,6 +113,8 @@ int uploadTables(dxb_ctx* c, World& w, const std::vector<std::shared_ptr<Materia
     return DXB_OK;
 }
 
+constexpr int kRefNode = 378; // energy node of 60 keV: the auto rules of the slab table and of the dense box look at this energy
+
 // Slab-local majorants (transport_pool.cu, LM builds).  Slabs of 2^shift voxel layers along z, about opt.slabCm thick.  The
 // device finds, per slab and material, the largest density (exact integer maxima of the 24-bit densities); the small table
 //   ratio(slab, band) = max over the band's energy nodes of [ max_m rho_max(slab, m) * tot_m(node) / majorant(node) ]
@@ -144,7 +146,7 @@ int buildLocalMajorant(dxb_ctx* c, World& w, cudaStream_t s)
     CUDA_TRY(c, cudaStreamSynchronize(s));
     w.lmHost.assign(static_cast<size_t>(slabs) * kLmBands, 1.0f);
     double meanRatio = 0;
-    const int refBand = 378 >> 5; // the band of 60 keV (node 378): where a diagnostic spectrum has most of its photons
+    const int refBand = kRefNode >> 5; // the band of 60 keV: where a diagnostic spectrum has most of its photons
     for (int sl = 0; sl < slabs; ++sl) {
         for (int b = 0; b < kLmBands; ++b) {
             const int n0 = b * 32, n1 = std::min(b * 32 + 32, kDevNE - 1);
@@ -228,7 +230,7 @@ int buildDenseBox(dxb_ctx* c, World& w, cudaStream_t s)
         w.dbFaces[a + 3] = std::fmaf(static_cast<float>(w.dbBox[a + 3]), d, lo);
         part *= static_cast<double>(w.dbBox[a + 3] - w.dbBox[a]) / static_cast<double>(w.dim[a]);
     }
-    const int refBand = 378 >> 5;
+    const int refBand = kRefNode >> 5;
     for (int b = 0; b < kLmBands; ++b) {
         const int n0 = b * 32, n1 = std::min(b * 32 + 32, kDevNE - 1);
         float r = 0.0f;
@@ -254,7 +256,7 @@ int buildDenseBox(dxb_ctx* c, World& w, cudaStream_t s)
     for (int a = 0; a < 3; ++a)
         vol *= static_cast<double>(w.dim[a]) * w.spacing[a];
     const double outsidePath = std::cbrt(vol) - std::cbrt(vol * part);
-    const double savedSteps = static_cast<double>(maj[378]) * outsidePath;
+    const double savedSteps = static_cast<double>(maj[kRefNode]) * outsidePath;
     w.dbUseful = part < 0.85 && w.dbRatio[refBand] < 0.25f && savedSteps >= 2.5;
     return DXB_OK;
 }
