@@ -388,3 +388,27 @@ def test_dense_box_leaves_the_dose_unchanged(dx, orc):
     assert abs(st["interactions"] - ft["interactions"]) / st["interactions"] < 0.01
     masks = {nm: wl.material.reshape(-1) == i for i, nm in enumerate(["air", "lung", "soft", "bone"])}
     assert _roi_sigma(e, e2, f, f2, masks) < 4.0
+
+
+@pytest.mark.parametrize("case", ["dx_cone_child", "dual_source_thorax_mode2"])
+def test_dense_box_other_beams_and_modes(dx, orc, case):
+    """The dense box under beams that enter and leave through other faces than a fan beam does (a radiography cone on a
+    child phantom: photons enter through the front face and leave through the back and the sides; a dual-source spiral in
+    physics mode 2): fewer tentative steps, statistically the same deposited energy in every density class."""
+    if case == "dx_cone_child":
+        wl, mode = dx.workloads.icrp_phantom("10M", scale=6, histories=300_000, beam_kind="dx"), 1
+    else:
+        wl, mode = dx.workloads.ct_dual_source_thorax(scale=8, histories=300_000, step_deg=10.0), 2
+    a = orc.OracleWorld.from_workload(wl)
+    e, e2, cnt, st = a.run(wl.beam, mode)
+    b = orc.OracleWorld.from_workload(wl)
+    assert b.build_dense_box(0.02)
+    f, f2, fcnt, ft = b.run(wl.beam, mode)
+    assert ft["hops"] > 0 and ft["steps"] < 0.9 * st["steps"]
+    assert abs(st["interactions"] - ft["interactions"]) / st["interactions"] < 0.015
+    s = math.sqrt(e2.sum() + f2.sum())
+    assert abs(e.sum() - f.sum()) / s < 4.0
+    rho = np.asarray(wl.density).reshape(-1)
+    masks = {"thin": rho <= 0.05, "lung-like": (rho > 0.05) & (rho <= 0.6), "soft": (rho > 0.6) & (rho <= 1.2), "dense": rho > 1.2}
+    masks = {k: m for k, m in masks.items() if m.any() and e[m].sum() > 0}
+    assert _roi_sigma(e, e2, f, f2, masks) < 4.0
